@@ -1,0 +1,856 @@
+// oracle/ts_oracle.cpp
+// =====================================================================================
+// TEST INFRASTRUCTURE ONLY.  CPU restatement (C++17) of the hot path of
+// EmbarkStudios/texture-synthesis: the per-pixel nearest-neighbour patch search
+// (`Generator::resolve`, lib/src/ms.rs:702-1052, and what it calls) plus the pyramid
+// builder that feeds it (lib/src/img_pyramid.rs:7-37).
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+// legs may load this library.  The product (texture-synthesis_b200/csrc) never links,
+// includes or calls anything in this directory.
+//
+// PARITY STATUS: "parity unpinned" against the real Rust binary.  No Rust toolchain and
+// no crate sources exist in the build container, so the reference cannot be compiled
+// or run here.  What IS pinned:
+//   * Pcg32 (rand_pcg 0.3.1 Lcg64Xsh32) against the two published known-answer
+//     vectors (tests/test_oracle_rng.py),
+//   * the CoordinateTransform byte format against lib/src/lib.rs:212-325.
+// What is restated from the published algorithm of un-vendored crates and cannot be
+// cross-checked offline: rand_core 0.6.3 `seed_from_u64`, rand 0.8.5 `gen_range`
+// (UniformInt::sample_single_inclusive), image 0.23.12 `imageops::resize`.
+// rstar 0.7.1's order among equidistant neighbours is unspecified in the reference;
+// this oracle defines the CANONICAL order: ascending (d^2, dy, dx).
+//
+// Every function cites the reference file:line it follows (paths relative to the
+// reference checkout, lib/src/...).
+// =====================================================================================
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace {
+
+// ------------------------------------------------------------------------------------
+// RNG: rand_pcg 0.3.1 Lcg64Xsh32 (= Pcg32), rand_core 0.6.3 seed_from_u64,
+// rand 0.8.5 gen_range.  Call sites: ms.rs:386,454-458,549-564,616-627,804.
+// ------------------------------------------------------------------------------------
+constexpr uint64_t PCG_MUL = 6364136223846793005ULL;
+
+struct Pcg32 {
+    uint64_t state, inc;
+    // Lcg64Xsh32::from_state_incr: state += inc; step()
+    static Pcg32 from_state_incr(uint64_t s, uint64_t inc) {
+        Pcg32 r{s + inc, inc};
+        r.step();
+        return r;
+    }
+    // Lcg64Xsh32::new(state, stream): increment = (stream << 1) | 1
+    static Pcg32 with_stream(uint64_t s, uint64_t stream) { return from_state_incr(s, (stream << 1) | 1); }
+    // Lcg64Xsh32::from_seed([u8;16]): two LE u64 -> from_state_incr(a, b | 1)
+    static Pcg32 from_seed(const uint8_t seed[16]) {
+        uint64_t a = 0, b = 0;
+        for (int i = 7; i >= 0; --i) { a = (a << 8) | seed[i]; b = (b << 8) | seed[8 + i]; }
+        return from_state_incr(a, b | 1);
+    }
+    // rand_core::SeedableRng::seed_from_u64 default impl (PCG32 fill, inc 11634580027462260723)
+    static Pcg32 seed_from_u64(uint64_t st) {
+        uint8_t seed[16];
+        for (int c = 0; c < 4; ++c) {
+            st = st * PCG_MUL + 11634580027462260723ULL;
+            uint32_t xs = (uint32_t)(((st >> 18) ^ st) >> 27);
+            uint32_t rot = (uint32_t)(st >> 59);
+            uint32_t x = (xs >> rot) | (xs << ((32 - rot) & 31));
+            seed[4 * c + 0] = (uint8_t)x; seed[4 * c + 1] = (uint8_t)(x >> 8);
+            seed[4 * c + 2] = (uint8_t)(x >> 16); seed[4 * c + 3] = (uint8_t)(x >> 24);
+        }
+        return from_seed(seed);
+    }
+    void step() { state = state * PCG_MUL + inc; }
+    uint32_t next_u32() {
+        uint64_t s = state;
+        step();
+        uint32_t rot = (uint32_t)(s >> 59);
+        uint32_t xs = (uint32_t)(((s >> 18) ^ s) >> 27);
+        return (xs >> rot) | (xs << ((32 - rot) & 31));
+    }
+    // impls::next_u64_via_u32: low word first
+    uint64_t next_u64() {
+        uint64_t lo = next_u32();
+        uint64_t hi = next_u32();
+        return (hi << 32) | lo;
+    }
+    // UniformInt<u32>::sample_single_inclusive(0, n-1): zone = (n << lz(n)) - 1
+    uint32_t gen_range_u32(uint32_t n) {
+        uint32_t zone = (n << __builtin_clz(n)) - 1;
+        for (;;) {
+            uint64_t m = (uint64_t)next_u32() * (uint64_t)n;
+            if ((uint32_t)m <= zone) return (uint32_t)(m >> 32);
+        }
+    }
+    // UniformInt<usize>::sample_single_inclusive on a 64-bit target (64-bit draws)
+    uint64_t gen_range_usize(uint64_t n) {
+        uint64_t zone = (n << __builtin_clzll(n)) - 1;
+        for (;;) {
+            unsigned __int128 m = (unsigned __int128)next_u64() * (unsigned __int128)n;
+            if ((uint64_t)m <= zone) return (uint64_t)(m >> 64);
+        }
+    }
+    // UniformInt<u8>::sample_single_inclusive(lo, hi-1): u32 draws, modulus zone
+    uint8_t gen_range_u8(uint8_t lo, uint8_t hi_excl) {
+        uint32_t range = (uint32_t)(uint8_t)(hi_excl - 1 - lo) + 1;
+        uint32_t ints_to_reject = (0xFFFFFFFFu - range + 1) % range;
+        uint32_t zone = 0xFFFFFFFFu - ints_to_reject;
+        for (;;) {
+            uint64_t m = (uint64_t)next_u32() * (uint64_t)range;
+            if ((uint32_t)m <= zone) return (uint8_t)(lo + (uint8_t)(m >> 32));
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------
+// image 0.23.12 imageops::resize (vertical_sample then horizontal_sample, u8
+// intermediate, un-normalised weights divided by their sum, truncating f32->u8).
+// Call sites: img_pyramid.rs:27-32 (Gaussian), ms.rs:244-260 (Triangle),
+// utils.rs:67-72 (CatmullRom).
+// ------------------------------------------------------------------------------------
+enum Filter { F_TRIANGLE = 0, F_CATMULLROM = 1, F_GAUSSIAN = 2 };
+
+static float kernel_eval(int f, float x) {
+    switch (f) {
+    case F_TRIANGLE: {
+        float a = std::fabs(x);
+        return a < 1.0f ? 1.0f - a : 0.0f;
+    }
+    case F_CATMULLROM: {  // bc_cubic_spline(x, 0.0, 0.5)
+        const float b = 0.0f, c = 0.5f;
+        float a = std::fabs(x);
+        float k;
+        if (a < 1.0f)
+            k = (12.0f - 9.0f * b - 6.0f * c) * (a * a * a) + (-18.0f + 12.0f * b + 6.0f * c) * (a * a) + (6.0f - 2.0f * b);
+        else if (a < 2.0f)
+            k = (-b - 6.0f * c) * (a * a * a) + (6.0f * b + 30.0f * c) * (a * a) + (-12.0f * b - 48.0f * c) * a + (8.0f * b + 24.0f * c);
+        else
+            k = 0.0f;
+        return k / 6.0f;
+    }
+    default: {  // gaussian(x, 0.5)
+        const float r = 0.5f;
+        float norm = 1.0f / (std::sqrt(2.0f * 3.14159265358979323846f) * r);
+        return norm * std::exp(-(x * x) / (2.0f * (r * r)));
+    }
+    }
+}
+static float kernel_support(int f) { return f == F_TRIANGLE ? 1.0f : (f == F_CATMULLROM ? 2.0f : 3.0f); }
+
+struct Taps { int left; std::vector<float> w; float sum; };
+
+static Taps make_taps(int in_sz, int out_sz, int o, int filter) {
+    float ratio = (float)in_sz / (float)out_sz;
+    float sratio = ratio < 1.0f ? 1.0f : ratio;
+    float support = kernel_support(filter) * sratio;
+    float inputx = ((float)o + 0.5f) * ratio;
+    int64_t left = (int64_t)std::floor(inputx - support);
+    left = std::min<int64_t>(std::max<int64_t>(left, 0), (int64_t)in_sz - 1);
+    int64_t right = (int64_t)std::ceil(inputx + support);
+    right = std::min<int64_t>(std::max<int64_t>(right, left + 1), (int64_t)in_sz);
+    inputx = inputx - 0.5f;
+    Taps t;
+    t.left = (int)left;
+    t.sum = 0.0f;
+    for (int64_t i = left; i < right; ++i) {
+        float w = kernel_eval(filter, ((float)i - inputx) / sratio);
+        t.w.push_back(w);
+        t.sum += w;
+    }
+    return t;
+}
+
+static inline uint8_t f32_to_u8_trunc(float v) {
+    v = v < 0.0f ? 0.0f : (v > 255.0f ? 255.0f : v);
+    return (uint8_t)v;  // NumCast f32->u8 truncates
+}
+
+static void resize_rgba(const uint8_t* src, int w, int h, uint8_t* dst, int nw, int nh, int filter) {
+    std::vector<uint8_t> tmp((size_t)w * nh * 4);
+    for (int oy = 0; oy < nh; ++oy) {  // vertical_sample
+        Taps t = make_taps(h, nh, oy, filter);
+        for (int x = 0; x < w; ++x) {
+            float acc[4] = {0, 0, 0, 0};
+            for (size_t i = 0; i < t.w.size(); ++i) {
+                const uint8_t* p = src + ((size_t)(t.left + (int)i) * w + x) * 4;
+                for (int c = 0; c < 4; ++c) acc[c] += (float)p[c] * t.w[i];
+            }
+            uint8_t* o = tmp.data() + ((size_t)oy * w + x) * 4;
+            for (int c = 0; c < 4; ++c) o[c] = f32_to_u8_trunc(acc[c] / t.sum);
+        }
+    }
+    for (int ox = 0; ox < nw; ++ox) {  // horizontal_sample
+        Taps t = make_taps(w, nw, ox, filter);
+        for (int y = 0; y < nh; ++y) {
+            float acc[4] = {0, 0, 0, 0};
+            for (size_t i = 0; i < t.w.size(); ++i) {
+                const uint8_t* p = tmp.data() + ((size_t)y * w + (t.left + (int)i)) * 4;
+                for (int c = 0; c < 4; ++c) acc[c] += (float)p[c] * t.w[i];
+            }
+            uint8_t* o = dst + ((size_t)y * nw + ox) * 4;
+            for (int c = 0; c < 4; ++c) o[c] = f32_to_u8_trunc(acc[c] / t.sum);
+        }
+    }
+}
+
+// img_pyramid.rs:20-37 build_gaussian: level 0 = blurriest ... level L-1 = input copy.
+static void pyramid_build(const uint8_t* src, int w, int h, uint32_t levels, uint8_t* out) {
+    size_t img = (size_t)w * h * 4;
+    size_t n = 0;
+    for (uint32_t i = levels > 0 ? levels - 1 : 0; i >= 1; --i) {
+        uint32_t p = 1u << i;
+        int sw = (int)((uint32_t)w / p), sh = (int)((uint32_t)h / p);
+        std::vector<uint8_t> small((size_t)std::max(sw, 0) * std::max(sh, 0) * 4);
+        resize_rgba(src, w, h, small.data(), sw, sh, F_GAUSSIAN);
+        resize_rgba(small.data(), sw, sh, out + n * img, w, h, F_GAUSSIAN);
+        ++n;
+    }
+    std::memcpy(out + n * img, src, img);
+}
+
+// ------------------------------------------------------------------------------------
+// Generator state (ms.rs:207-217) and helpers
+// ------------------------------------------------------------------------------------
+struct Image {
+    int w = 0, h = 0;
+    const uint8_t* d = nullptr;
+    bool in_bounds(int x, int y) const { return x >= 0 && y >= 0 && x < w && y < h; }
+    const uint8_t* px(int x, int y) const { return d + ((size_t)y * w + x) * 4; }
+};
+
+enum { METHOD_ALL = 0, METHOD_IGNORE = 1, METHOD_IMAGE = 2 };
+
+static inline int modulo(int a, int b) { int r = a % b; return r < 0 ? r + b : r; }  // ms.rs:84-91
+
+// k-NN over the resolved set.  The reference uses a grid of rstar R*-trees
+// (ms.rs:1313-1531); with a single tree the query is exact, ordered by squared
+// distance (i32/i64), tie order unspecified.  Here: 8x8-pixel cells as 64-bit masks,
+// ring search, canonical order (d^2, dy, dx).
+struct KnnGrid {
+    int ox = 0, oy = 0, gw = 0, gh = 0;
+    std::unique_ptr<std::atomic<uint64_t>[]> cells;
+    void init(int W, int H, int mx, int my) {
+        ox = mx; oy = my;
+        gw = (W + 2 * mx + 7) / 8; gh = (H + 2 * my + 7) / 8;
+        cells.reset(new std::atomic<uint64_t>[(size_t)gw * gh]);
+        for (size_t i = 0; i < (size_t)gw * gh; ++i) cells[i].store(0, std::memory_order_relaxed);
+    }
+    void insert(int x, int y) {
+        int X = x + ox, Y = y + oy;
+        cells[(size_t)(Y >> 3) * gw + (X >> 3)].fetch_or(1ULL << (((Y & 7) << 3) | (X & 7)), std::memory_order_relaxed);
+    }
+    static inline uint64_t key(int64_t d2, int dy, int dx) {
+        return ((uint64_t)d2 << 32) | ((uint64_t)(uint32_t)(dy + 32768) << 16) | (uint64_t)(uint32_t)(dx + 32768);
+    }
+    void visit(int cx, int cy, int x, int y, std::vector<uint64_t>& keys) const {
+        if (cx < 0 || cy < 0 || cx >= gw || cy >= gh) return;
+        uint64_t m = cells[(size_t)cy * gw + cx].load(std::memory_order_relaxed);
+        while (m) {
+            int b = __builtin_ctzll(m);
+            m &= m - 1;
+            int px = cx * 8 + (b & 7) - ox, py = cy * 8 + (b >> 3) - oy;
+            int dx = px - x, dy = py - y;
+            keys.push_back(key((int64_t)dx * dx + (int64_t)dy * dy, dy, dx));
+        }
+    }
+    // out: up to k (x,y) pairs, canonical order
+    void query(int x, int y, int k, std::vector<uint64_t>& keys, std::vector<int>& out) const {
+        keys.clear(); out.clear();
+        int cx = (x + ox) >> 3, cy = (y + oy) >> 3;
+        int rmax = std::max(std::max(cx, gw - 1 - cx), std::max(cy, gh - 1 - cy));
+        for (int r = 0; r <= rmax; ++r) {
+            if (r == 0) visit(cx, cy, x, y, keys);
+            else {
+                for (int i = -r; i <= r; ++i) { visit(cx + i, cy - r, x, y, keys); visit(cx + i, cy + r, x, y, keys); }
+                for (int i = -r + 1; i <= r - 1; ++i) { visit(cx - r, cy + i, x, y, keys); visit(cx + r, cy + i, x, y, keys); }
+            }
+            if ((int)keys.size() >= k) {
+                std::nth_element(keys.begin(), keys.begin() + (k - 1), keys.end());
+                int64_t kd2 = (int64_t)(keys[k - 1] >> 32);
+                int64_t bound = (int64_t)(8 * r + 1) * (8 * r + 1);
+                if (kd2 < bound) break;
+            }
+        }
+        size_t n = std::min<size_t>(keys.size(), (size_t)k);
+        std::partial_sort(keys.begin(), keys.begin() + n, keys.end());
+        for (size_t i = 0; i < n; ++i) {
+            int dy = (int)((keys[i] >> 16) & 0xFFFF) - 32768, dx = (int)(keys[i] & 0xFFFF) - 32768;
+            out.push_back(x + dx); out.push_back(y + dy);
+        }
+    }
+};
+
+struct Params {  // mirrors ms.rs:18-42 GeneratorParams; same layout as tsb_params
+    uint32_t nearest_neighbors;
+    uint32_t _pad0;
+    uint64_t random_sample_locations;
+    float cauchy_dispersion;
+    float p;
+    int32_t p_stages;
+    float alpha;
+    uint64_t seed;
+    uint64_t max_thread_count;
+    int32_t tiling_mode;
+    int32_t _pad1;
+};
+
+struct EvalOut {  // one pixel resolution, not committed
+    int n_neigh = 0;
+    int n_cand = 0;
+    int best_idx = 0;
+    int best_x = 0, best_y = 0, best_map = 0;
+    uint32_t best_patch = 0;
+    float score = 0.f;
+    bool random = false;  // resolve_at_random path
+};
+
+struct Candidate { int x, y; uint32_t map, patch; int sign; };  // sign: +1 coherence, -1 random (ms.rs:534 vs 588)
+
+struct Gen {
+    int W = 0, H = 0;
+    std::vector<uint8_t> color;        // W*H*4        (ms.rs:208)
+    std::vector<uint32_t> coord;       // W*H*3 x,y,map (ms.rs:209)
+    std::vector<uint32_t> idm;         // W*H*2 patch,map (ms.rs:210)
+    std::vector<uint32_t> unresolved;  // ms.rs:212
+    std::vector<std::pair<uint32_t, float>> resolved;  // ms.rs:213
+    KnnGrid grid;                      // ms.rs:214
+    std::vector<int> tree_points;      // every (x,y) ever inserted, incl. mirrors (for state export)
+    size_t locked = 0;                 // ms.rs:215
+    std::mutex unresolved_mx;
+
+    // inputs (borrowed)
+    int levels = 0;
+    std::vector<std::vector<Image>> ex;       // [example][level]  (all examples, incl. ignored)
+    std::vector<int> methods;
+    std::vector<Image> smask;                 // [example] RGBA sampling mask (METHOD_IMAGE)
+    bool has_guides = false;
+    std::vector<Image> tguide;                // [level]
+    std::vector<std::vector<Image>> exg;      // [example][level] (NOT filtered, ms.rs:67-81)
+
+    // trace (optional)
+    std::vector<uint32_t> tr_pixel;
+    std::vector<int32_t> tr_best, tr_ncand, tr_nneigh;
+    std::vector<float> tr_score;
+    bool trace = false;
+    double last_resolve_seconds = 0.0;
+
+    void put_color(uint32_t flat, const uint8_t* px) { std::memcpy(&color[(size_t)flat * 4], px, 4); }
+
+    // ms.rs:296-331 flush_resolved (tree part)
+    void tree_insert(int x, int y, bool tiling) {
+        grid.insert(x, y);
+        if (trace_points) { tree_points.push_back(x); tree_points.push_back(y); }
+        if (tiling) {
+            int x_l = (int)((float)W * 0.05f), x_r = W - x_l;
+            int y_b = (int)((float)H * 0.05f), y_t = H - y_b;
+            if (x < x_l) { grid.insert(x + W, y); if (trace_points) { tree_points.push_back(x + W); tree_points.push_back(y); } }
+            else if (x > x_r) { grid.insert(x - W, y); if (trace_points) { tree_points.push_back(x - W); tree_points.push_back(y); } }
+            if (y < y_b) { grid.insert(x, y + H); if (trace_points) { tree_points.push_back(x); tree_points.push_back(y + H); } }
+            else if (y > y_t) { grid.insert(x, y - H); if (trace_points) { tree_points.push_back(x); tree_points.push_back(y - H); } }
+        }
+    }
+    bool trace_points = true;
+};
+
+struct StageCtx {
+    int level;
+    std::vector<Image> ex;            // filtered (non-ignored) examples at this level  (ms.rs:1552-1563)
+    std::vector<int> methods;         // filtered
+    std::vector<Image> smask;         // filtered
+    bool guided;
+    Image tguide;
+    std::vector<Image> exg;           // unfiltered (ms.rs:67-81)
+    float lut_my[256], lut_guide[256];  // indexed by |a-b| (ms.rs:1290-1311: 256x256 table depends on |a-b| only)
+    uint32_t k;
+    uint64_t m;
+    bool tiling;
+};
+
+static void build_luts(StageCtx& s, float cauchy_dispersion, float adaptive_alpha) {
+    // ms.rs:739-742, 853-858, 1110-1120
+    float sig2 = cauchy_dispersion * cauchy_dispersion;
+    for (int d = 0; d < 256; ++d) {
+        float x = ((float)d - 0.0f) / 255.0f;  // (f32(a) - f32(b)) / 255 with a-b = +-d: x*x is sign-symmetric
+        float x2 = x * x;
+        float cauchy = log1pf(x2 / sig2);
+        float l2 = x2;
+        if (s.guided) {
+            s.lut_guide[d] = adaptive_alpha * l2;
+            s.lut_my[d] = (1.0f - adaptive_alpha) * cauchy;
+        } else {
+            s.lut_guide[d] = 0.0f;
+            s.lut_my[d] = cauchy;
+        }
+    }
+}
+
+static void make_stage(const Gen& g, StageCtx& s, int level, const Params& prm) {
+    s.level = level;
+    s.ex.clear(); s.methods.clear(); s.smask.clear(); s.exg.clear();
+    for (size_t e = 0; e < g.ex.size(); ++e) {
+        if (g.methods[e] == METHOD_IGNORE) continue;
+        s.ex.push_back(g.ex[e][level]);
+        s.methods.push_back(g.methods[e]);
+        s.smask.push_back(g.smask[e]);
+    }
+    s.guided = g.has_guides;
+    if (g.has_guides) {
+        s.tguide = g.tguide[level];
+        for (size_t e = 0; e < g.exg.size(); ++e) s.exg.push_back(g.exg[e][level]);
+    }
+    s.k = prm.nearest_neighbors;
+    s.m = prm.random_sample_locations;
+    s.tiling = prm.tiling_mode != 0;
+}
+
+// ms.rs:1534-1549
+static inline bool check_coord_validity(const StageCtx& s, int x, int y, uint32_t map) {
+    if (!s.ex[map].in_bounds(x, y)) return false;
+    if (s.methods[map] == METHOD_IMAGE) return s.smask[map].px(x, y)[0] != 0;
+    return true;
+}
+
+struct Scratch {
+    std::vector<uint64_t> keys;
+    std::vector<int> neigh;      // x,y pairs
+    std::vector<double> dist;    // one per neighbour (the x4 duplication is applied in the sum)
+    std::vector<float> gauss;
+    std::vector<uint8_t> pat, gpat;
+    std::vector<Candidate> cands;
+};
+
+// One pixel resolution without the commit: ms.rs:917-986 (steps 2-4).
+static void eval_pixel(const Gen& g, const StageCtx& s, int px, int py, uint64_t loop_seed, uint64_t p_stage_seed,
+                       Scratch& sc, EvalOut& out, int* neigh_out /*nullable, 2*k ints*/) {
+    const int W = g.W, H = g.H;
+    // 2. k nearest resolved neighbours (ms.rs:926-930 -> 1363-1530)
+    g.grid.query(px, py, (int)s.k, sc.keys, sc.neigh);
+    const int kk = (int)sc.neigh.size() / 2;
+    out = EvalOut();
+    out.n_neigh = kk;
+    if (neigh_out) for (int i = 0; i < 2 * kk; ++i) neigh_out[i] = sc.neigh[i];
+    if (kk == 0) {
+        // ms.rs:1002-1009 -> 447-475 resolve_at_random(seed = p_stage_seed): three fresh RNGs
+        out.random = true;
+        uint32_t rmap = (uint32_t)Pcg32::seed_from_u64(p_stage_seed).gen_range_usize(s.ex.size());
+        uint32_t rx = Pcg32::seed_from_u64(p_stage_seed).gen_range_u32((uint32_t)s.ex[rmap].w);
+        uint32_t ry = Pcg32::seed_from_u64(p_stage_seed).gen_range_u32((uint32_t)s.ex[rmap].h);
+        out.best_x = (int)rx; out.best_y = (int)ry; out.best_map = (int)rmap;
+        out.best_patch = (uint32_t)py * (uint32_t)W + (uint32_t)px;
+        out.score = 0.0f;
+        return;
+    }
+    // 2.1 distances (ms.rs:405-425), f64, true fma, divided by the mean of the x4-duplicated list
+    sc.dist.resize(kk);
+    {
+        double dimx = (double)W, dimy = (double)H;
+        double x2 = (double)px / dimx, y2 = (double)py / dimy;
+        double sum = 0.0;
+        for (int j = 0; j < kk; ++j) {
+            double x1 = (double)sc.neigh[2 * j] / dimx, y1 = (double)sc.neigh[2 * j + 1] / dimy;
+            double d = std::fma(x1 - x2, x1 - x2, (y1 - y2) * (y1 - y2));
+            sc.dist[j] = d;
+            sum += d; sum += d; sum += d; sum += d;  // iter().sum() over [d,d,d,d,...]
+        }
+        double avg = sum / (double)(kk * 4);
+        for (int j = 0; j < kk; ++j) sc.dist[j] /= avg;
+    }
+    // 3. candidates (ms.rs:478-602)
+    sc.cands.clear();
+    for (int j = 0; j < kk; ++j) {
+        int nx = sc.neigh[2 * j], ny = sc.neigh[2 * j + 1];
+        int sx = px - nx, sy = py - ny;
+        size_t nflat = (size_t)modulo(ny, H) * W + modulo(nx, W);
+        int ox = (int)g.coord[nflat * 3 + 0], oy = (int)g.coord[nflat * 3 + 1];
+        uint32_t patch = g.idm[nflat * 2 + 0], map = g.idm[nflat * 2 + 1];
+        int cx = ox + sx, cy = oy + sy;
+        if (check_coord_validity(s, cx, cy, map)) sc.cands.push_back({cx, cy, map, patch, +1});
+    }
+    {
+        Pcg32 rng = Pcg32::seed_from_u64(loop_seed + 1);
+        for (uint32_t r = 0; r < (uint32_t)s.m; ++r) {
+            uint32_t map = (uint32_t)rng.gen_range_usize(s.ex.size());
+            uint32_t dw = (uint32_t)s.ex[map].w, dh = (uint32_t)s.ex[map].h;
+            int rx, ry;
+            for (;;) {
+                rx = (int)rng.gen_range_u32(dw);
+                ry = (int)rng.gen_range_u32(dh);
+                if (check_coord_validity(s, rx, ry, map)) break;
+            }
+            sc.cands.push_back({rx, ry, map, (uint32_t)ry * dw + (uint32_t)rx, -1});
+        }
+    }
+    out.n_cand = (int)sc.cands.size();
+    // target pattern (ms.rs:948-966, 1151-1181)
+    sc.pat.resize((size_t)kk * 4);
+    sc.gpat.resize((size_t)kk * 4);
+    static const uint8_t outside[4] = {0, 0, 0, 255};
+    for (int j = 0; j < kk; ++j) {
+        int nx = sc.neigh[2 * j], ny = sc.neigh[2 * j + 1];
+        if (s.tiling) { nx = modulo(nx, W); ny = modulo(ny, H); }
+        bool inb = nx >= 0 && ny >= 0 && nx < W && ny < H;
+        std::memcpy(&sc.pat[(size_t)j * 4], inb ? &g.color[((size_t)ny * W + nx) * 4] : outside, 4);
+        if (s.guided) {
+            int gx = sc.neigh[2 * j], gy = sc.neigh[2 * j + 1];
+            if (s.tiling) { gx = modulo(gx, s.tguide.w); gy = modulo(gy, s.tguide.h); }
+            std::memcpy(&sc.gpat[(size_t)j * 4], s.tguide.in_bounds(gx, gy) ? s.tguide.px(gx, gy) : outside, 4);
+        }
+    }
+    // 4. find_best_match (ms.rs:1184-1224) / better_match (ms.rs:1227-1288)
+    sc.gauss.resize(kk);
+    for (int j = 0; j < kk; ++j) sc.gauss[j] = (float)std::exp(-1.0 * sc.dist[j]);
+    int best = 0;
+    float lowest = std::numeric_limits<float>::max();
+    for (int a = 0; a < (int)sc.cands.size(); ++a) {
+        const Candidate& c = sc.cands[a];
+        float score = 0.0f;
+        bool rejected = false;
+        for (int j = 0; j < kk; ++j) {
+            int ox = sc.neigh[2 * j] - px, oy = sc.neigh[2 * j + 1] - py;
+            int ex_ = c.x + c.sign * ox, ey_ = c.y + c.sign * oy;
+            const Image& im = s.ex[c.map];
+            const uint8_t* e = im.in_bounds(ex_, ey_) ? im.px(ex_, ey_) : outside;
+            float nps = 0.0f;
+            for (int ch = 0; ch < 4; ++ch) {
+                int d = (int)sc.pat[(size_t)j * 4 + ch] - (int)e[ch];
+                nps += s.lut_my[d < 0 ? -d : d];
+            }
+            if (s.guided) {
+                const Image& gi = s.exg[c.map];
+                const uint8_t* ge = gi.in_bounds(ex_, ey_) ? gi.px(ex_, ey_) : outside;
+                for (int ch = 0; ch < 4; ++ch) {
+                    int d = (int)sc.gpat[(size_t)j * 4 + ch] - (int)ge[ch];
+                    nps += s.lut_guide[d < 0 ? -d : d];
+                }
+            }
+            score += nps * sc.gauss[j];
+            if (score >= lowest) { rejected = true; break; }
+        }
+        if (!rejected) { lowest = score; best = a; }
+    }
+    const Candidate& b = sc.cands[best];
+    out.best_idx = best;
+    out.best_x = b.x; out.best_y = b.y; out.best_map = (int)b.map; out.best_patch = b.patch;
+    out.score = lowest;
+}
+
+// ms.rs:334-377 update
+static void commit_pixel(Gen& g, const StageCtx& s, int px, int py, const EvalOut& r, bool is_new,
+                         std::vector<std::pair<uint32_t, float>>& my_resolved, bool tiling_flag) {
+    uint32_t flat = (uint32_t)py * (uint32_t)g.W + (uint32_t)px;
+    g.coord[(size_t)flat * 3 + 0] = (uint32_t)r.best_x;
+    g.coord[(size_t)flat * 3 + 1] = (uint32_t)r.best_y;
+    g.coord[(size_t)flat * 3 + 2] = (uint32_t)r.best_map;
+    g.idm[(size_t)flat * 2 + 0] = r.best_patch;
+    g.idm[(size_t)flat * 2 + 1] = (uint32_t)r.best_map;
+    g.put_color(flat, s.ex[r.best_map].px(r.best_x, r.best_y));
+    if (is_new) {
+        g.tree_insert(px, py, tiling_flag);
+        my_resolved.emplace_back(flat, r.score);
+    }
+}
+
+// ms.rs:702-1052.  max_items < 0: run everything; otherwise stop after that many work items
+// (counted across stages) leaving the state frozen for snapshot tests.
+static void resolve(Gen& g, const Params& prm, int64_t max_items) {
+    auto t0 = std::chrono::steady_clock::now();
+    const size_t total = g.unresolved.size();  // ms.rs:710
+    g.trace_points = prm.max_thread_count <= 1;  // the point log is not thread-safe
+    const bool tiling = prm.tiling_mode != 0;
+    int pyramid_level = 0;
+    // ms.rs:747-779: rebuild the tree grid and re-insert pre-resolved pixels (+ mirrors)
+    {
+        int mx = (int)((float)g.W * 0.05f) + 1, my = (int)((float)g.H * 0.05f) + 1;
+        g.grid.init(g.W, g.H, mx, my);
+        g.tree_points.clear();
+        for (auto& r : g.resolved) g.tree_insert((int)(r.first % (uint32_t)g.W), (int)(r.first / (uint32_t)g.W), tiling);
+    }
+    int64_t done_items = 0;
+    for (int p_stage = prm.p_stages; p_stage >= 0; --p_stage) {
+        StageCtx s;
+        make_stage(g, s, pyramid_level, prm);
+        if (pyramid_level > 0) {  // ms.rs:687-700 next_pyramid_level
+            for (auto& r : g.resolved) {
+                size_t f = r.first;
+                g.put_color((uint32_t)f, s.ex[g.coord[f * 3 + 2]].px((int)g.coord[f * 3 + 0], (int)g.coord[f * 3 + 1]));
+            }
+        }
+        pyramid_level += 1;
+        pyramid_level = std::min(pyramid_level, prm.p_stages - 1);  // ms.rs:800 (q9)
+        const uint64_t p_stage_seed = (uint64_t)Pcg32::seed_from_u64(prm.seed + (uint64_t)p_stage).next_u32();  // ms.rs:803
+        float fp = powf(prm.p, (float)p_stage) * (float)total;  // ms.rs:733-735
+        size_t pixels_to_resolve = fp <= 0.0f ? 0 : (fp >= 18446744073709551615.0f ? SIZE_MAX : (size_t)fp);
+        const size_t redo_count = g.resolved.size() - g.locked;  // ms.rs:812
+        const size_t n_workers = redo_count < 1000 ? 1 : (size_t)std::max<uint64_t>(1, prm.max_thread_count);  // ms.rs:815
+        float adaptive_alpha = 0.0f;  // ms.rs:846-851
+        if (g.has_guides && p_stage > 0) {
+            float tr = (float)g.resolved.size();
+            float v = prm.alpha * (1.0f - (tr / (float)total));
+            adaptive_alpha = v * (v * v);
+        }
+        build_luts(s, prm.cauchy_dispersion, adaptive_alpha);
+
+        std::atomic<size_t> processed{0};
+        std::vector<std::vector<std::pair<uint32_t, float>>> per_thread(n_workers);
+        const int64_t stage_cap = max_items < 0 ? -1 : std::max<int64_t>(0, max_items - done_items);
+        auto worker = [&](size_t tid) {
+            Scratch sc;
+            EvalOut r;
+            auto& mine = per_thread[tid];
+            for (;;) {
+                size_t i = processed.fetch_add(1, std::memory_order_relaxed);  // ms.rs:889
+                if (i >= pixels_to_resolve) break;
+                if (stage_cap >= 0 && (int64_t)i >= stage_cap) break;
+                uint64_t loop_seed = p_stage_seed + (uint64_t)i;  // ms.rs:902
+                uint32_t flat;
+                bool is_new;
+                if (i < redo_count) {  // ms.rs:905-907
+                    is_new = false;
+                    flat = g.resolved[i + g.locked].first;
+                } else {  // ms.rs:909-915 -> 380-389
+                    is_new = true;
+                    std::lock_guard<std::mutex> lk(g.unresolved_mx);
+                    if (g.unresolved.empty()) break;
+                    size_t idx = (size_t)Pcg32::seed_from_u64(loop_seed).gen_range_usize(g.unresolved.size());
+                    flat = g.unresolved[idx];
+                    g.unresolved[idx] = g.unresolved.back();
+                    g.unresolved.pop_back();
+                }
+                int px = (int)(flat % (uint32_t)g.W), py = (int)(flat / (uint32_t)g.W);
+                eval_pixel(g, s, px, py, loop_seed, p_stage_seed, sc, r, nullptr);
+                if (g.trace && n_workers == 1) {
+                    g.tr_pixel.push_back(flat); g.tr_best.push_back(r.random ? -1 : r.best_idx);
+                    g.tr_ncand.push_back(r.n_cand); g.tr_nneigh.push_back(r.n_neigh); g.tr_score.push_back(r.score);
+                }
+                if (r.random) {
+                    // resolve_at_random: update(.., true, Score(0), (PatchId(flat), MapId), is_tiling=false)  ms.rs:460-474
+                    commit_pixel(g, s, px, py, r, true, mine, false);
+                } else {
+                    commit_pixel(g, s, px, py, r, is_new, mine, tiling);
+                }
+            }
+        };
+        if (n_workers == 1) worker(0);
+        else {
+            std::vector<std::thread> th;
+            for (size_t t = 0; t < n_workers; ++t) th.emplace_back(worker, t);
+            for (auto& t : th) t.join();
+        }
+        for (auto& v : per_thread) g.resolved.insert(g.resolved.end(), v.begin(), v.end());  // ms.rs:1043-1049
+        size_t did = std::min(processed.load(), pixels_to_resolve);
+        if (stage_cap >= 0) did = std::min<size_t>(did, (size_t)stage_cap);
+        done_items += (int64_t)did;
+        if (max_items >= 0 && done_items >= max_items) break;
+    }
+    g.last_resolve_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// ms.rs:427-445 resolve_random_batch; session.rs:42-52 passes pyramid[len-1] of ALL examples (q7)
+static void random_init(Gen& g, uint64_t steps, uint64_t seed) {
+    std::vector<Image> imgs;
+    for (auto& e : g.ex) imgs.push_back(e[g.levels - 1]);
+    for (uint64_t i = 0; i < steps; ++i) {
+        if (g.unresolved.empty()) continue;
+        size_t idx = (size_t)Pcg32::seed_from_u64(seed + i).gen_range_usize(g.unresolved.size());
+        uint32_t flat = g.unresolved[idx];
+        g.unresolved[idx] = g.unresolved.back();
+        g.unresolved.pop_back();
+        uint64_t s2 = seed + i + (uint64_t)flat;
+        uint32_t rmap = (uint32_t)Pcg32::seed_from_u64(s2).gen_range_usize(imgs.size());
+        uint32_t rx = Pcg32::seed_from_u64(s2).gen_range_u32((uint32_t)imgs[rmap].w);
+        uint32_t ry = Pcg32::seed_from_u64(s2).gen_range_u32((uint32_t)imgs[rmap].h);
+        g.coord[(size_t)flat * 3 + 0] = rx; g.coord[(size_t)flat * 3 + 1] = ry; g.coord[(size_t)flat * 3 + 2] = rmap;
+        g.idm[(size_t)flat * 2 + 0] = flat; g.idm[(size_t)flat * 2 + 1] = rmap;
+        g.put_color(flat, imgs[rmap].px((int)rx, (int)ry));
+        g.resolved.emplace_back(flat, 0.0f);
+        // tree insert into the pre-resolve grid is superseded by the rebuild at ms.rs:747-779
+    }
+    g.locked += (size_t)steps;  // ms.rs:444
+}
+
+}  // namespace
+
+// =====================================================================================
+// C entry points (ctypes)
+// =====================================================================================
+extern "C" {
+
+// ---- RNG known-answer helpers -------------------------------------------------------
+void orc_pcg32_new_stream(uint64_t state, uint64_t stream, uint32_t n, uint32_t* out) {
+    Pcg32 r = Pcg32::with_stream(state, stream);
+    for (uint32_t i = 0; i < n; ++i) out[i] = r.next_u32();
+}
+uint64_t orc_pcg32_from_seed_next_u64(const uint8_t* seed16) {
+    Pcg32 r = Pcg32::from_seed(seed16);
+    return r.next_u64();
+}
+void orc_pcg32_seed_from_u64(uint64_t seed, uint32_t n, uint32_t* out) {
+    Pcg32 r = Pcg32::seed_from_u64(seed);
+    for (uint32_t i = 0; i < n; ++i) out[i] = r.next_u32();
+}
+// kind: 0 = u32 range, 1 = usize range, 2 = u8 range [0, n)
+void orc_gen_range_seq(uint64_t seed, int kind, uint64_t n, uint32_t count, uint64_t* out) {
+    Pcg32 r = Pcg32::seed_from_u64(seed);
+    for (uint32_t i = 0; i < count; ++i)
+        out[i] = kind == 0 ? r.gen_range_u32((uint32_t)n) : (kind == 1 ? r.gen_range_usize(n) : r.gen_range_u8(0, (uint8_t)n));
+}
+
+// ---- resampling / pyramid -------------------------------------------------------------
+void orc_resize(const uint8_t* src, int w, int h, uint8_t* dst, int nw, int nh, int filter) {
+    resize_rgba(src, w, h, dst, nw, nh, filter);
+}
+void orc_pyramid_build(const uint8_t* rgba, int w, int h, uint32_t levels, uint8_t* out) {
+    pyramid_build(rgba, w, h, levels == 0 ? 1 : levels, out);
+}
+
+// ---- generator ------------------------------------------------------------------------
+// ms.rs:220-293.  mask/colour must already be at output size (caller-side Triangle resize via orc_resize).
+void* orc_gen_create(int w, int h, const uint8_t* inpaint_mask, const uint8_t* inpaint_color, int inpaint_index) {
+    Gen* g = new Gen();
+    g->W = w; g->H = h;
+    size_t s = (size_t)w * h;
+    g->color.assign(s * 4, 0);
+    g->coord.assign(s * 3, 0);
+    g->idm.assign(s * 2, 0);
+    if (!inpaint_mask) {
+        g->unresolved.resize(s);
+        for (size_t i = 0; i < s; ++i) g->unresolved[i] = (uint32_t)i;
+    } else {
+        std::memcpy(g->color.data(), inpaint_color, s * 4);
+        for (size_t i = 0; i < s; ++i) {
+            if (inpaint_mask[i * 4] < 255) g->unresolved.push_back((uint32_t)i);
+            else {
+                g->resolved.emplace_back((uint32_t)i, 0.0f);
+                g->coord[i * 3 + 0] = (uint32_t)(i % (size_t)w);
+                g->coord[i * 3 + 1] = (uint32_t)(i / (size_t)w);
+                g->coord[i * 3 + 2] = (uint32_t)inpaint_index;
+            }
+        }
+        g->locked = g->resolved.size();
+    }
+    g->grid.init(w, h, (int)((float)w * 0.05f) + 1, (int)((float)h * 0.05f) + 1);
+    return g;
+}
+void orc_gen_destroy(void* h) { delete (Gen*)h; }
+
+// pyr[e]: levels*w*h*4 bytes (level 0 = blurriest).  masks[e]: RGBA w*h or NULL.  Borrowed until destroy.
+void orc_gen_set_examples(void* h, int n, int levels, const int* w, const int* hh, const uint8_t* const* pyr,
+                          const int* methods, const uint8_t* const* masks) {
+    Gen* g = (Gen*)h;
+    g->levels = levels;
+    g->ex.assign(n, {});
+    g->methods.assign(methods, methods + n);
+    g->smask.assign(n, Image());
+    for (int e = 0; e < n; ++e) {
+        for (int l = 0; l < levels; ++l) {
+            Image im; im.w = w[e]; im.h = hh[e]; im.d = pyr[e] + (size_t)l * w[e] * hh[e] * 4;
+            g->ex[e].push_back(im);
+        }
+        if (masks && masks[e]) { g->smask[e].w = w[e]; g->smask[e].h = hh[e]; g->smask[e].d = masks[e]; }
+    }
+}
+// target: levels*W*H*4 at output size; exg[e]: levels*gw[e]*gh[e]*4 for EVERY example (unfiltered)
+void orc_gen_set_guides(void* h, const uint8_t* target, int tw, int th, int n, const int* gw, const int* gh,
+                        const uint8_t* const* exg) {
+    Gen* g = (Gen*)h;
+    g->has_guides = true;
+    g->tguide.clear();
+    for (int l = 0; l < g->levels; ++l) { Image im; im.w = tw; im.h = th; im.d = target + (size_t)l * tw * th * 4; g->tguide.push_back(im); }
+    g->exg.assign(n, {});
+    for (int e = 0; e < n; ++e)
+        for (int l = 0; l < g->levels; ++l) { Image im; im.w = gw[e]; im.h = gh[e]; im.d = exg[e] + (size_t)l * gw[e] * gh[e] * 4; g->exg[e].push_back(im); }
+}
+void orc_gen_random_init(void* h, uint64_t count, uint64_t seed) { random_init(*(Gen*)h, count, seed); }
+void orc_gen_set_trace(void* h, int on) { ((Gen*)h)->trace = on != 0; }
+void orc_gen_resolve(void* h, const Params* prm, int64_t max_items) { resolve(*(Gen*)h, *prm, max_items); }
+double orc_gen_last_seconds(void* h) { return ((Gen*)h)->last_resolve_seconds; }
+
+void orc_gen_read_color(void* h, uint8_t* dst) { Gen* g = (Gen*)h; std::memcpy(dst, g->color.data(), g->color.size()); }
+void orc_gen_read_coord(void* h, uint32_t* dst) { Gen* g = (Gen*)h; std::memcpy(dst, g->coord.data(), g->coord.size() * 4); }
+void orc_gen_read_id(void* h, uint32_t* dst) { Gen* g = (Gen*)h; std::memcpy(dst, g->idm.data(), g->idm.size() * 4); }
+uint64_t orc_gen_resolved_count(void* h) { return ((Gen*)h)->resolved.size(); }
+uint64_t orc_gen_locked_count(void* h) { return ((Gen*)h)->locked; }
+void orc_gen_read_resolved(void* h, uint32_t* flat, float* score) {
+    Gen* g = (Gen*)h;
+    for (size_t i = 0; i < g->resolved.size(); ++i) { flat[i] = g->resolved[i].first; score[i] = g->resolved[i].second; }
+}
+uint64_t orc_gen_tree_point_count(void* h) { return ((Gen*)h)->tree_points.size() / 2; }
+void orc_gen_read_tree_points(void* h, int32_t* xy) { Gen* g = (Gen*)h; std::memcpy(xy, g->tree_points.data(), g->tree_points.size() * 4); }
+uint64_t orc_gen_trace_count(void* h) { return ((Gen*)h)->tr_pixel.size(); }
+void orc_gen_read_trace(void* h, uint32_t* pixel, int32_t* best, int32_t* ncand, int32_t* nneigh, float* score) {
+    Gen* g = (Gen*)h;
+    size_t n = g->tr_pixel.size();
+    std::memcpy(pixel, g->tr_pixel.data(), n * 4); std::memcpy(best, g->tr_best.data(), n * 4);
+    std::memcpy(ncand, g->tr_ncand.data(), n * 4); std::memcpy(nneigh, g->tr_nneigh.data(), n * 4);
+    std::memcpy(score, g->tr_score.data(), n * 4);
+}
+
+// Frozen-snapshot evaluation: for each item (pixel, loop_seed) compute the k-NN list, candidates and
+// argmin against the CURRENT state without committing.  level/adaptive_alpha select the stage context.
+// neigh: n*2*k int32 (x,y, unused tail = INT32_MIN); res: n*8 int32
+// [n_neigh, n_cand, best_idx, best_x, best_y, best_map, best_patch, random]; score: n floats.
+void orc_gen_eval_items(void* h, const Params* prm, int level, float adaptive_alpha, uint64_t p_stage_seed, uint32_t n,
+                        const uint32_t* pixel_flat, const uint64_t* loop_seed, int32_t* neigh, int32_t* res, float* score) {
+    Gen* g = (Gen*)h;
+    StageCtx s;
+    make_stage(*g, s, level, *prm);
+    build_luts(s, prm->cauchy_dispersion, adaptive_alpha);
+    Scratch sc;
+    const int k = (int)prm->nearest_neighbors;
+    for (uint32_t i = 0; i < n; ++i) {
+        EvalOut r;
+        int px = (int)(pixel_flat[i] % (uint32_t)g->W), py = (int)(pixel_flat[i] / (uint32_t)g->W);
+        int32_t* no = neigh ? neigh + (size_t)i * 2 * k : nullptr;
+        if (no) for (int j = 0; j < 2 * k; ++j) no[j] = INT32_MIN;
+        eval_pixel(*g, s, px, py, loop_seed[i], p_stage_seed, sc, r, no);
+        int32_t* ro = res + (size_t)i * 8;
+        ro[0] = r.n_neigh; ro[1] = r.n_cand; ro[2] = r.best_idx; ro[3] = r.best_x; ro[4] = r.best_y;
+        ro[5] = r.best_map; ro[6] = (int32_t)r.best_patch; ro[7] = r.random ? 1 : 0;
+        score[i] = r.score;
+    }
+}
+
+// ---- read-outs that the reference derives from the maps (ms.rs:605-684) --------------------
+void orc_uncertainty_map(void* h, uint8_t* dst) {  // ms.rs:635-653
+    Gen* g = (Gen*)h;
+    std::memset(dst, 0, (size_t)g->W * g->H * 4);
+    for (auto& r : g->resolved) {
+        float v = std::min(r.second, 1.0f) * 255.0f;
+        uint8_t s = (uint8_t)(v < 0.0f ? 0.0f : (v > 255.0f ? 255.0f : v));  // `as u8` saturates, NaN -> 0
+        uint8_t* o = dst + (size_t)r.first * 4;
+        o[0] = s; o[1] = (uint8_t)(255 - s); o[2] = 0; o[3] = 255;
+    }
+}
+void orc_id_maps(void* h, uint8_t* patch_map, uint8_t* map_map) {  // ms.rs:605-633
+    Gen* g = (Gen*)h;
+    size_t s = (size_t)g->W * g->H;
+    for (size_t i = 0; i < s; ++i) {
+        uint32_t pid = g->idm[i * 2 + 0], mid = g->idm[i * 2 + 1];
+        uint8_t* a = patch_map + i * 4;
+        a[0] = Pcg32::seed_from_u64((uint64_t)pid).gen_range_u8(0, 255);
+        a[1] = Pcg32::seed_from_u64((uint64_t)(uint32_t)(pid * 5u + 21u)).gen_range_u8(0, 255);
+        a[2] = Pcg32::seed_from_u64((uint64_t)(pid / 4u + 12u)).gen_range_u8(0, 255);
+        a[3] = 255;
+        uint8_t* b = map_map + i * 4;
+        b[0] = Pcg32::seed_from_u64((uint64_t)mid * 200ULL).gen_range_u8(0, 255);
+        b[1] = Pcg32::seed_from_u64((uint64_t)(uint32_t)(mid * 5u + 341u)).gen_range_u8(0, 255);
+        b[2] = Pcg32::seed_from_u64((uint64_t)(uint32_t)(mid * 1200u - 35412u)).gen_range_u8(0, 255);  // u32 wrap in release
+        b[3] = 255;
+    }
+}
+
+}  // extern "C"

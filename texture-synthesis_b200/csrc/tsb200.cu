@@ -1,0 +1,1164 @@
+// tsb200.cu -- host side of the C ABI in include/tsb200.h: device memory, the exact wave schedule
+// (stage plan, pixel order, dependency phases, rounds) and the read-outs.
+//
+// Reference call stack being replaced: Session::run (lib/src/session.rs:37-66) ->
+// Generator::resolve_random_batch (ms.rs:427-445) + Generator::resolve (ms.rs:702-1052).
+#include "../../include/tsb200.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "tsb_device.cuh"
+
+using namespace tsb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            return fail(TSB_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__)); \
+    } while (0)
+#define TRY(call)                 \
+    do {                          \
+        int r__ = (call);         \
+        if (r__ != 0) return r__; \
+    } while (0)
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    int ensure(size_t count) {
+        if (count <= n) return 0;
+        release();
+        CU(cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T)));
+        n = count;
+        return 0;
+    }
+    int upload(const T* h, size_t count, cudaStream_t s) {
+        TRY(ensure(count));
+        if (count) CU(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+        return 0;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// image 0.23.12 imageops::resize tap tables (vertical_sample / horizontal_sample share the formula).
+// ---------------------------------------------------------------------------------------------
+float kernel_eval(int f, float x) {
+    switch (f) {
+    case TSB_FILTER_TRIANGLE: {
+        float a = fabsf(x);
+        return a < 1.0f ? 1.0f - a : 0.0f;
+    }
+    case TSB_FILTER_CATMULLROM: {  // bc_cubic_spline(x, b = 0, c = 0.5)
+        const float b = 0.0f, c = 0.5f;
+        float a = fabsf(x), k;
+        if (a < 1.0f) k = (12.0f - 9.0f * b - 6.0f * c) * (a * a * a) + (-18.0f + 12.0f * b + 6.0f * c) * (a * a) + (6.0f - 2.0f * b);
+        else if (a < 2.0f) k = (-b - 6.0f * c) * (a * a * a) + (6.0f * b + 30.0f * c) * (a * a) + (-12.0f * b - 48.0f * c) * a + (8.0f * b + 24.0f * c);
+        else k = 0.0f;
+        return k / 6.0f;
+    }
+    default: {  // gaussian(x, r = 0.5)
+        const float r = 0.5f;
+        float norm = 1.0f / (sqrtf(2.0f * 3.14159265358979323846f) * r);
+        return norm * expf(-(x * x) / (2.0f * (r * r)));
+    }
+    }
+}
+
+struct HostTaps {
+    std::vector<int> left, count, offset;
+    std::vector<float> sum, weights;
+};
+
+void build_taps(int in_sz, int out_sz, int filter, HostTaps& t) {
+    t = HostTaps();
+    const float support0 = filter == TSB_FILTER_TRIANGLE ? 1.0f : (filter == TSB_FILTER_CATMULLROM ? 2.0f : 3.0f);
+    const float ratio = (float)in_sz / (float)out_sz;
+    const float sratio = ratio < 1.0f ? 1.0f : ratio;
+    const float support = support0 * sratio;
+    for (int o = 0; o < out_sz; ++o) {
+        float inputx = ((float)o + 0.5f) * ratio;
+        long long left = (long long)floorf(inputx - support);
+        left = std::min<long long>(std::max<long long>(left, 0), (long long)in_sz - 1);
+        long long right = (long long)ceilf(inputx + support);
+        right = std::min<long long>(std::max<long long>(right, left + 1), (long long)in_sz);
+        inputx = inputx - 0.5f;
+        t.left.push_back((int)left);
+        t.count.push_back((int)(right - left));
+        t.offset.push_back((int)t.weights.size());
+        float sum = 0.0f;
+        for (long long i = left; i < right; ++i) {
+            float w = kernel_eval(filter, ((float)i - inputx) / sratio);
+            t.weights.push_back(w);
+            sum += w;
+        }
+        t.sum.push_back(sum);
+    }
+}
+
+struct DevTaps {
+    DevBuf<int> left, count, offset;
+    DevBuf<float> sum, weights;
+    TapTable table() const { return TapTable{left.p, count.p, offset.p, sum.p, weights.p}; }
+    int upload(const HostTaps& h, cudaStream_t s) {
+        TRY(left.upload(h.left.data(), h.left.size(), s));
+        TRY(count.upload(h.count.data(), h.count.size(), s));
+        TRY(offset.upload(h.offset.data(), h.offset.size(), s));
+        TRY(sum.upload(h.sum.data(), h.sum.size(), s));
+        TRY(weights.upload(h.weights.data(), h.weights.size(), s));
+        return 0;
+    }
+};
+
+// resize on device buffers: src (w x h) -> dst (nw x nh); tmp must hold w*nh pixels.
+int device_resize(const uint32_t* src, int w, int h, uint32_t* dst, int nw, int nh, int filter, uint32_t* tmp, cudaStream_t s) {
+    if (nw <= 0 || nh <= 0) return 0;
+    HostTaps hv, hh;
+    build_taps(h, nh, filter, hv);
+    build_taps(w, nw, filter, hh);
+    DevTaps dv, dh;
+    TRY(dv.upload(hv, s));
+    TRY(dh.upload(hh, s));
+    dim3 b(128, 1);
+    k_resample_v<<<dim3((w + 127) / 128, nh), b, 0, s>>>(src, w, h, tmp, nh, dv.table());
+    k_resample_h<<<dim3((nw + 127) / 128, nh), b, 0, s>>>(tmp, w, nh, dst, nw, dh.table());
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s));  // tap tables are freed on return
+    return 0;
+}
+
+struct SpiralHost {
+    std::vector<short2> off;
+    std::vector<uint32_t> cntLE;
+    int RT2;
+};
+
+SpiralHost build_spiral(int RT) {
+    SpiralHost sp;
+    sp.RT2 = RT * RT;
+    struct E { int d2, dy, dx; };
+    std::vector<E> v;
+    for (int dy = -RT; dy <= RT; ++dy)
+        for (int dx = -RT; dx <= RT; ++dx) {
+            int d2 = dx * dx + dy * dy;
+            if (d2 <= sp.RT2) v.push_back({d2, dy, dx});
+        }
+    std::sort(v.begin(), v.end(), [](const E& a, const E& b) {
+        if (a.d2 != b.d2) return a.d2 < b.d2;
+        if (a.dy != b.dy) return a.dy < b.dy;
+        return a.dx < b.dx;
+    });
+    sp.cntLE.assign(sp.RT2 + 1, 0);
+    for (auto& e : v) {
+        sp.off.push_back(make_short2((short)e.dx, (short)e.dy));
+        sp.cntLE[e.d2] += 1;
+    }
+    for (int i = 1; i <= sp.RT2; ++i) sp.cntLE[i] += sp.cntLE[i - 1];
+    return sp;
+}
+
+constexpr int SPIRAL_RT = 48;
+constexpr uint32_t PAIR_MAX = 4096;   // phases up to this size use the all-pairs dependency test
+constexpr int ROUNDS_PER_SYNC = 4;
+
+struct StagePlan {
+    int p_stage, level;
+    bool recolour;
+    uint64_t seed;
+    size_t pixels_to_resolve, redo_count, n_redo, n_new, pick_base, resolved_before;
+    float adaptive_alpha;
+};
+
+}  // namespace
+
+struct tsb_generator {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int W = 0, H = 0;
+    bool inpaint = false;
+    uint32_t inpaint_index = 0;
+    // host mirrors of the order-defining state (ms.rs:212-215)
+    std::vector<uint32_t> unresolved0;       // as created
+    std::vector<uint32_t> resolved0;         // locked inpaint pixels, as created
+    std::vector<uint32_t> unresolved;        // current
+    std::vector<uint32_t> resolved_order;    // `resolved` flat coords in resolution order
+    size_t locked = 0, inpaint_locked = 0;
+    std::vector<int32_t> loaded_points;      // load_state: explicit tree points
+    bool have_loaded_points = false;
+
+    // device state
+    DevBuf<uint4> d_state;
+    DevBuf<float> d_score;
+    DevBuf<uint32_t> d_mask;
+    DevBuf<uint32_t> d_inp_mask, d_inp_color;
+    int mx = 0, my = 0, wpr = 0, mrows = 0;
+    DevBuf<short2> d_spiral;
+    DevBuf<uint32_t> d_cntLE;
+    int spiralN = 0, RT2 = 0;
+
+    // inputs (device resident)
+    bool inputs_ready = false;
+    int n_levels = 0, n_ex_all = 0, n_ex = 0;
+    std::vector<int> ex_w, ex_h, ex_kind;           // all examples
+    std::vector<int> filt;                          // filtered index -> all index
+    std::vector<DevBuf<uint32_t>> d_ex;             // per (all) example: levels*w*h
+    std::vector<DevBuf<uint8_t>> d_smask;           // per (all) example
+    DevBuf<DevEx> d_exdesc;                         // [levels][n_ex] filtered
+    bool guided = false;
+    int tgw = 0, tgh = 0;
+    DevBuf<uint32_t> d_tguide;                      // levels*tgw*tgh
+    std::vector<DevBuf<uint32_t>> d_exg;
+    std::vector<int> exg_w, exg_h;
+    DevBuf<DevGuide> d_exgdesc;                     // [levels][n_ex_all]
+    DevBuf<float> d_luts;                           // 512 floats
+    DevBuf<unsigned long long> d_counters;
+
+    // per-run buffers
+    DevBuf<uint32_t> d_item_pixel, d_item_R2, d_pred_cnt, d_preds, d_done, d_pend0, d_pend1, d_ctrl, d_pmap;
+    DevBuf<uint32_t> d_rand_xy, d_pick_idx, d_tmp_u32;
+    DevBuf<uint8_t> d_rand_map;
+    uint32_t* h_ctrl = nullptr;  // pinned, 8 words
+    bool pmap_ready = false;
+
+    // trace
+    bool trace = false;
+    DevBuf<int32_t> d_tr_best, d_tr_ncand, d_tr_nneigh;
+    DevBuf<float> d_tr_score;
+    std::vector<uint32_t> tr_pixel;
+    std::vector<int32_t> tr_fix_best;  // host-resolved (random) items: index list
+    std::vector<uint64_t> tr_fix_idx;
+    uint64_t trace_n = 0;
+
+    tsb_stats stats{};
+    int max_ctas = 0;
+
+    ~tsb_generator() {
+        if (h_ctrl) cudaFreeHost(h_ctrl);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+int set_device(tsb_generator* g) { CU(cudaSetDevice(g->device)); return 0; }
+
+void fill_stage_geometry(tsb_generator* g, StageDev& S, bool tiling) {
+    memset(&S, 0, sizeof(S));
+    S.state = g->d_state.p; S.mask = g->d_mask.p; S.score = g->d_score.p;
+    S.W = g->W; S.H = g->H;
+    S.mx = g->mx; S.my = g->my; S.wpr = g->wpr; S.mrows = g->mrows;
+    S.tiling = tiling ? 1 : 0;
+    S.x_l = (int)((float)g->W * 0.05f); S.x_r = g->W - S.x_l;   // ms.rs:308-311
+    S.y_b = (int)((float)g->H * 0.05f); S.y_t = g->H - S.y_b;
+    S.spiral = g->d_spiral.p; S.cntLE = g->d_cntLE.p; S.spiralN = g->spiralN; S.RT2 = g->RT2;
+    S.k = 1; S.m = 0; S.r2_hint = 16;
+    S.counters = nullptr;
+}
+
+int init_state(tsb_generator* g) {
+    const uint32_t n = (uint32_t)g->W * (uint32_t)g->H;
+    cudaStream_t s = g->stream;
+    if (g->inpaint)
+        k_state_init_inpaint<<<(n + 255) / 256, 256, 0, s>>>(g->d_state.p, g->d_score.p, g->d_inp_mask.p, g->d_inp_color.p, g->W, n, g->inpaint_index);
+    else
+        k_state_init<<<(n + 255) / 256, 256, 0, s>>>(g->d_state.p, g->d_score.p, n);
+    CU(cudaGetLastError());
+    CU(cudaMemsetAsync(g->d_mask.p, 0, (size_t)g->wpr * g->mrows * 4, s));
+    g->unresolved = g->unresolved0;
+    g->resolved_order = g->resolved0;
+    g->locked = g->inpaint_locked = g->resolved0.size();
+    g->have_loaded_points = false;
+    return 0;
+}
+
+// upload one pyramid (levels*w*h RGBA) into a device buffer
+int upload_pyramid(const tsb_pyramid& p, DevBuf<uint32_t>& d, cudaStream_t s) {
+    size_t n = (size_t)p.n_levels * p.width * p.height;
+    return d.upload((const uint32_t*)p.levels, n, s);
+}
+
+int upload_inputs(tsb_generator* g, const tsb_pyramid* examples, uint32_t n_examples, const tsb_guides* guides, const tsb_sampling* sampling) {
+    if (!examples || n_examples == 0) return fail(TSB_ERR_INVALID, "at least one example is required");
+    cudaStream_t s = g->stream;
+    g->inputs_ready = false;
+    g->n_ex_all = (int)n_examples;
+    g->n_levels = (int)examples[0].n_levels;
+    g->ex_w.clear(); g->ex_h.clear(); g->ex_kind.clear(); g->filt.clear();
+    g->d_ex.clear(); g->d_smask.clear();
+    g->d_ex.resize(n_examples); g->d_smask.resize(n_examples);
+    for (uint32_t e = 0; e < n_examples; ++e) {
+        const tsb_pyramid& p = examples[e];
+        if (!p.levels || p.width == 0 || p.height == 0 || p.n_levels == 0) return fail(TSB_ERR_INVALID, "example %u is empty", e);
+        if ((int)p.n_levels != g->n_levels) return fail(TSB_ERR_INVALID, "all example pyramids must have the same number of levels");
+        if (p.width > 32767 || p.height > 32767) return fail(TSB_ERR_UNSUPPORTED, "example dimensions above 32767 are not supported");
+        int kind = sampling ? sampling[e].kind : TSB_SAMPLE_ALL;
+        g->ex_w.push_back((int)p.width); g->ex_h.push_back((int)p.height); g->ex_kind.push_back(kind);
+        TRY(upload_pyramid(p, g->d_ex[e], s));
+        if (kind == TSB_SAMPLE_IMAGE) {
+            if (!sampling[e].rgba) return fail(TSB_ERR_INVALID, "sampling mask %u is null", e);
+            std::vector<uint8_t> r((size_t)p.width * p.height);
+            bool any = false;
+            for (size_t i = 0; i < r.size(); ++i) { r[i] = sampling[e].rgba[i * 4]; any |= r[i] != 0; }
+            if (!any) return fail(TSB_ERR_INVALID, "sampling mask %u allows no pixel (the reference would loop forever, ms.rs:562-574)", e);
+            TRY(g->d_smask[e].upload(r.data(), r.size(), s));
+            CU(cudaStreamSynchronize(s));
+        }
+        if (kind != TSB_SAMPLE_IGNORE) g->filt.push_back((int)e);
+    }
+    g->n_ex = (int)g->filt.size();
+    if (g->n_ex == 0) return fail(TSB_ERR_INVALID, "at least one example must not be ignored (session.rs:501-524)");
+    if (g->n_ex > 255) return fail(TSB_ERR_UNSUPPORTED, "more than 255 examples");
+    // descriptors per level, filtered (get_single_example_level, ms.rs:1552-1563)
+    std::vector<DevEx> desc((size_t)g->n_levels * g->n_ex);
+    for (int l = 0; l < g->n_levels; ++l)
+        for (int f = 0; f < g->n_ex; ++f) {
+            int e = g->filt[f];
+            DevEx d;
+            d.w = g->ex_w[e]; d.h = g->ex_h[e];
+            d.px = g->d_ex[e].p + (size_t)l * d.w * d.h;
+            d.smask = g->ex_kind[e] == TSB_SAMPLE_IMAGE ? g->d_smask[e].p : nullptr;
+            desc[(size_t)l * g->n_ex + f] = d;
+        }
+    TRY(g->d_exdesc.upload(desc.data(), desc.size(), s));
+    g->guided = guides != nullptr;
+    g->d_exg.clear(); g->exg_w.clear(); g->exg_h.clear();
+    if (guides) {
+        if (guides->n_examples != n_examples) return fail(TSB_ERR_INVALID, "guides must be given for all examples or none (session.rs:501-524)");
+        if ((int)guides->target.n_levels != g->n_levels) return fail(TSB_ERR_INVALID, "target guide pyramid level count mismatch");
+        g->tgw = (int)guides->target.width; g->tgh = (int)guides->target.height;
+        TRY(upload_pyramid(guides->target, g->d_tguide, s));
+        g->d_exg.resize(n_examples);
+        std::vector<DevGuide> gd((size_t)g->n_levels * n_examples);
+        for (uint32_t e = 0; e < n_examples; ++e) {
+            const tsb_pyramid& p = guides->examples[e];
+            if ((int)p.n_levels != g->n_levels) return fail(TSB_ERR_INVALID, "example guide %u level count mismatch", e);
+            TRY(upload_pyramid(p, g->d_exg[e], s));
+            g->exg_w.push_back((int)p.width); g->exg_h.push_back((int)p.height);
+            for (int l = 0; l < g->n_levels; ++l) {
+                DevGuide d;
+                d.w = (int)p.width; d.h = (int)p.height;
+                d.px = g->d_exg[e].p + (size_t)l * d.w * d.h;
+                gd[(size_t)l * n_examples + e] = d;
+            }
+        }
+        TRY(g->d_exgdesc.upload(gd.data(), gd.size(), s));
+    }
+    CU(cudaStreamSynchronize(s));
+    g->inputs_ready = true;
+    return 0;
+}
+
+int check_params(const tsb_generator* g, const tsb_params* p) {
+    // session.rs:450-499
+    if (!(p->cauchy_dispersion >= 0.0f && p->cauchy_dispersion <= 1.0f)) return fail(TSB_ERR_INVALID, "cauchy_dispersion must be in [0,1]");
+    if (!(p->p >= 0.0f && p->p <= 1.0f)) return fail(TSB_ERR_INVALID, "backtrack_percent must be in [0,1]");
+    if (!(p->alpha >= 0.0f && p->alpha <= 1.0f)) return fail(TSB_ERR_INVALID, "guide_alpha must be in [0,1]");
+    if (p->max_thread_count == 0) return fail(TSB_ERR_INVALID, "max_thread_count must be >= 1");
+    if (p->random_sample_locations == 0) return fail(TSB_ERR_INVALID, "random_sample_locations must be >= 1");
+    if (p->p_stages < 0) return fail(TSB_ERR_INVALID, "backtrack_stages must be >= 0");
+    if (p->nearest_neighbors == 0 || p->nearest_neighbors > (uint32_t)KMAX) return fail(TSB_ERR_UNSUPPORTED, "nearest_neighbors must be in [1,%d]", KMAX);
+    if (p->nearest_neighbors + p->random_sample_locations > (uint64_t)CANDMAX)
+        return fail(TSB_ERR_UNSUPPORTED, "nearest_neighbors + random_sample_locations must be <= %d", CANDMAX);
+    if (p->cauchy_dispersion == 0.0f) return fail(TSB_ERR_UNSUPPORTED, "cauchy_dispersion == 0 yields NaN costs in the reference (quirk q14); not supported");
+    int need_levels = p->p_stages == 0 ? 1 : p->p_stages;
+    if (g->n_levels < need_levels) return fail(TSB_ERR_INVALID, "example pyramids have %d levels, %d needed", g->n_levels, need_levels);
+    return 0;
+}
+
+void stage_inputs(tsb_generator* g, StageDev& S, int level, const tsb_params* p) {
+    S.ex = g->d_exdesc.p + (size_t)level * g->n_ex;
+    S.n_ex = g->n_ex;
+    S.exg = g->guided ? g->d_exgdesc.p + (size_t)level * g->n_ex_all : nullptr;
+    S.n_exg = g->guided ? g->n_ex_all : 0;
+    S.tguide = g->guided ? g->d_tguide.p + (size_t)level * g->tgw * g->tgh : nullptr;
+    S.tgw = g->tgw; S.tgh = g->tgh;
+    S.lut_my = g->d_luts.p; S.lut_guide = g->d_luts.p + 256;
+    S.k = (int)p->nearest_neighbors; S.m = (int)p->random_sample_locations;
+}
+
+// PrerenderedU8Function tables (ms.rs:739-742, 853-858, 1110-1120) reduced to |a-b| (256 entries)
+int upload_luts(tsb_generator* g, const tsb_params* p, float adaptive_alpha) {
+    float h[512];
+    float sig2 = p->cauchy_dispersion * p->cauchy_dispersion;
+    for (int d = 0; d < 256; ++d) {
+        float x = (float)d / 255.0f;
+        float x2 = x * x;
+        float cauchy = log1pf(x2 / sig2);
+        if (g->guided) { h[d] = (1.0f - adaptive_alpha) * cauchy; h[256 + d] = adaptive_alpha * x2; }
+        else { h[d] = cauchy; h[256 + d] = 0.0f; }
+    }
+    CU(cudaMemcpyAsync(g->d_luts.p, h, sizeof(h), cudaMemcpyHostToDevice, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    return 0;
+}
+
+uint32_t r2_hint_for(const tsb_generator* g, size_t resolved_now, uint32_t k) {
+    double area = (double)g->W * (double)g->H;
+    double r2 = 1.5 * (double)k * area / (3.14159265358979 * (double)std::max<size_t>(resolved_now, 1));
+    double cap = 4.0e9;
+    return (uint32_t)std::min(std::max(r2, 8.0), cap);
+}
+
+template <typename K, typename... Args>
+int launch_resolve_kernel(tsb_generator* g, K kernel, int grid, Args... args) {
+    kernel<<<grid, CTA_THREADS, sizeof(CtaSmem), g->stream>>>(args...);
+    CU(cudaGetLastError());
+    g->stats.kernel_launches++;
+    return 0;
+}
+
+int grid_for(const tsb_generator* g, uint32_t items) {
+    int need = (int)((items + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+    return std::max(1, std::min(need, g->max_ctas));
+}
+
+struct PhaseTimers {
+    cudaEvent_t a0, a1, r0, r1;
+};
+
+// Execute work items [i0, i0+n) of the current stage.
+int run_phase(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, bool is_new, bool analyze, uint64_t trace_base) {
+    cudaStream_t s = g->stream;
+    PhaseDev P;
+    memset(&P, 0, sizeof(P));
+    P.item_pixel = g->d_item_pixel.p + i0;
+    P.item_R2 = g->d_item_R2.p; P.pred_cnt = g->d_pred_cnt.p; P.preds = g->d_preds.p; P.done = g->d_done.p;
+    P.pending[0] = g->d_pend0.p; P.pending[1] = g->d_pend1.p;
+    P.cnt = g->d_ctrl.p; P.minpend = g->d_ctrl.p + 4;
+    P.pmap = g->d_pmap.p;
+    P.rand_xy = g->d_rand_xy.p; P.rand_map = g->d_rand_map.p;
+    P.n = n; P.stage_base = i0; P.is_new = is_new ? 1u : 0u;
+    if (g->trace) { P.tr_best = g->d_tr_best.p; P.tr_ncand = g->d_tr_ncand.p; P.tr_nneigh = g->d_tr_nneigh.p; P.tr_score = g->d_tr_score.p; }
+    P.trace_base = trace_base;
+    g->stats.phases++;
+
+    cudaEvent_t e0, e1, e2;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventCreate(&e2));
+    CU(cudaEventRecord(e0, s));
+    uint32_t ctrl[8] = {n, 0, 0, 0, 0, NONE32, NONE32, NONE32};
+    memcpy(g->h_ctrl, ctrl, sizeof(ctrl));
+    CU(cudaMemcpyAsync(g->d_ctrl.p, g->h_ctrl, sizeof(ctrl), cudaMemcpyHostToDevice, s));
+    if (analyze) {
+        TRY(launch_resolve_kernel(g, k_radius, grid_for(g, n), S, P));
+        if (n <= PAIR_MAX) k_preds_pairs<<<grid_for(g, n), CTA_THREADS, 0, s>>>(S, P);
+        else k_preds_scan<<<grid_for(g, n), CTA_THREADS, 0, s>>>(S, P);
+        CU(cudaGetLastError());
+        g->stats.kernel_launches++;
+    } else {
+        // single serial item: no predecessors, unbounded neighbour search
+        g->h_ctrl[8] = R2_INF;
+        CU(cudaMemcpyAsync(g->d_item_R2.p, g->h_ctrl + 8, 4, cudaMemcpyHostToDevice, s));
+        CU(cudaMemsetAsync(g->d_pred_cnt.p, 0, 4, s));
+        CU(cudaMemsetAsync(g->d_done.p, 0, 4, s));
+        CU(cudaMemsetAsync(g->d_pend0.p, 0, 4, s));
+    }
+    CU(cudaEventRecord(e1, s));
+    uint32_t known = n, round = 0;
+    while (known > 0) {
+        int grid = grid_for(g, known);
+        for (int r = 0; r < ROUNDS_PER_SYNC; ++r) {
+            if (g->guided) TRY(launch_resolve_kernel(g, k_round<true>, grid, S, P, round));
+            else TRY(launch_resolve_kernel(g, k_round<false>, grid, S, P, round));
+            ++round;
+            g->stats.rounds++;
+            if (n == 1) break;
+        }
+        CU(cudaMemcpyAsync(g->h_ctrl, g->d_ctrl.p + (round & 3), 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        known = g->h_ctrl[0];
+        if (round > 4u * n + 16u) return fail(TSB_ERR_INTERNAL, "dependency rounds did not converge (phase of %u items)", n);
+    }
+    if (analyze) {
+        k_pmap_clear<<<(n + 255) / 256, 256, 0, s>>>(P);
+        CU(cudaGetLastError());
+        g->stats.kernel_launches++;
+    }
+    CU(cudaEventRecord(e2, s));
+    CU(cudaEventSynchronize(e2));
+    float ma = 0.f, mr = 0.f;
+    cudaEventElapsedTime(&ma, e0, e1);
+    cudaEventElapsedTime(&mr, e1, e2);
+    g->stats.gpu_ms_analysis += ma;
+    g->stats.gpu_ms_resolve += mr;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    return 0;
+}
+
+int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, void* user) {
+    if (!g->inputs_ready) return fail(TSB_ERR_INVALID, "inputs have not been uploaded");
+    TRY(check_params(g, prm));
+    TRY(set_device(g));
+    const double t_start = now_ms();
+    cudaStream_t s = g->stream;
+    memset(&g->stats, 0, sizeof(g->stats));
+    const bool tiling = prm->tiling_mode != 0;
+    const uint32_t k = prm->nearest_neighbors;
+    const int m = (int)prm->random_sample_locations;
+    const size_t total = g->unresolved.size();  // ms.rs:710
+    const size_t npix = (size_t)g->W * g->H;
+
+    // ---- stage plan (ms.rs:786-812): everything that defines the pixel order is known up front ----
+    const double t_plan0 = now_ms();
+    std::vector<StagePlan> plan;
+    size_t resolved_n = g->resolved_order.size(), unresolved_n = total, n_picks = 0, max_stage_items = 1, max_phase = 1, total_items = 0;
+    {
+        int pyramid_level = 0;
+        for (int p_stage = prm->p_stages; p_stage >= 0; --p_stage) {
+            StagePlan sp;
+            sp.p_stage = p_stage;
+            sp.level = pyramid_level;
+            sp.recolour = pyramid_level > 0;
+            pyramid_level = std::min(pyramid_level + 1, prm->p_stages - 1);
+            sp.seed = (uint64_t)Pcg32::seed_from_u64(prm->seed + (uint64_t)p_stage).next_u32();
+            float fp = powf(prm->p, (float)p_stage) * (float)total;
+            sp.pixels_to_resolve = fp <= 0.0f ? 0 : (size_t)fp;
+            sp.redo_count = resolved_n - g->locked;
+            sp.n_redo = std::min(sp.redo_count, sp.pixels_to_resolve);
+            sp.n_new = std::min(sp.pixels_to_resolve - sp.n_redo, unresolved_n);
+            sp.pick_base = n_picks;
+            sp.resolved_before = resolved_n;
+            sp.adaptive_alpha = 0.0f;
+            if (g->guided && p_stage > 0) {  // ms.rs:846-851
+                float v = prm->alpha * (1.0f - ((float)resolved_n / (float)total));
+                sp.adaptive_alpha = v * (v * v);
+            }
+            n_picks += sp.n_new;
+            unresolved_n -= sp.n_new;
+            resolved_n += sp.n_new;
+            max_stage_items = std::max(max_stage_items, sp.n_redo + sp.n_new);
+            max_phase = std::max(max_phase, std::max(sp.n_redo, sp.n_new));
+            total_items += sp.n_redo + sp.n_new;
+            plan.push_back(sp);
+        }
+    }
+    if (max_stage_items > 0xFFFFFFF0ull) return fail(TSB_ERR_UNSUPPORTED, "output too large");
+
+    // ---- pixel order: pick_random_unresolved (ms.rs:380-389) for every new pixel of every stage ----
+    std::vector<uint32_t> picks(n_picks);
+    {
+        TRY(g->d_pick_idx.ensure(std::max<size_t>(n_picks, 1)));
+        size_t un = total;
+        for (auto& sp : plan) {
+            if (sp.n_new) {
+                uint32_t nn = (uint32_t)sp.n_new;
+                k_pick_indices<<<(nn + 255) / 256, 256, 0, s>>>(sp.seed + (uint64_t)sp.redo_count, (uint64_t)un, nn, g->d_pick_idx.p + sp.pick_base);
+                CU(cudaGetLastError());
+                g->stats.kernel_launches++;
+            }
+            un -= sp.n_new;
+        }
+        std::vector<uint32_t> idx(n_picks);
+        if (n_picks) CU(cudaMemcpyAsync(idx.data(), g->d_pick_idx.p, n_picks * 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        std::vector<uint32_t>& v = g->unresolved;  // swap_remove chain
+        size_t len = v.size();
+        for (size_t t = 0; t < n_picks; ++t) {
+            uint32_t j = idx[t];
+            picks[t] = v[j];
+            v[j] = v[len - 1];
+            --len;
+        }
+        v.resize(len);
+    }
+    g->stats.host_ms_schedule = now_ms() - t_plan0;
+
+    // ---- buffers ----
+    TRY(g->d_item_pixel.ensure(max_stage_items));
+    TRY(g->d_item_R2.ensure(max_phase));
+    TRY(g->d_pred_cnt.ensure(max_phase));
+    TRY(g->d_preds.ensure(max_phase * (size_t)PRED_CAP));
+    TRY(g->d_done.ensure(max_phase));
+    TRY(g->d_pend0.ensure(max_phase));
+    TRY(g->d_pend1.ensure(max_phase));
+    TRY(g->d_ctrl.ensure(8));
+    TRY(g->d_rand_xy.ensure(max_stage_items * (size_t)m));
+    TRY(g->d_rand_map.ensure(max_stage_items * (size_t)m));
+    TRY(g->d_luts.ensure(512));
+    TRY(g->d_counters.ensure(4));
+    CU(cudaMemsetAsync(g->d_counters.p, 0, 4 * sizeof(unsigned long long), s));
+    if (!g->pmap_ready) {
+        TRY(g->d_pmap.ensure(npix));
+        CU(cudaMemsetAsync(g->d_pmap.p, 0xFF, npix * 4, s));
+        g->pmap_ready = true;
+    }
+    g->trace_n = 0;
+    g->tr_pixel.clear(); g->tr_fix_idx.clear();
+    if (g->trace) {
+        TRY(g->d_tr_best.ensure(total_items)); TRY(g->d_tr_ncand.ensure(total_items));
+        TRY(g->d_tr_nneigh.ensure(total_items)); TRY(g->d_tr_score.ensure(total_items));
+    }
+
+    // ---- rebuild the resolved set with tiling mirrors (ms.rs:747-779) ----
+    StageDev S;
+    fill_stage_geometry(g, S, tiling);
+    S.counters = g->d_counters.p;
+    CU(cudaMemsetAsync(g->d_mask.p, 0, (size_t)g->wpr * g->mrows * 4, s));
+    if (g->have_loaded_points) {
+        TRY(g->d_tmp_u32.upload((const uint32_t*)g->loaded_points.data(), g->loaded_points.size(), s));
+        uint32_t np = (uint32_t)(g->loaded_points.size() / 2);
+        if (np) k_mask_insert_points<<<(np + 255) / 256, 256, 0, s>>>(S, (const int32_t*)g->d_tmp_u32.p, np);
+    } else if (!g->resolved_order.empty()) {
+        TRY(g->d_tmp_u32.upload(g->resolved_order.data(), g->resolved_order.size(), s));
+        uint32_t np = (uint32_t)g->resolved_order.size();
+        k_mask_insert_flat<<<(np + 255) / 256, 256, 0, s>>>(S, g->d_tmp_u32.p, np, tiling ? 1 : 0);
+    }
+    CU(cudaGetLastError());
+
+    uint64_t overall_total = 0, overall_current = 0;
+    for (auto& sp : plan) overall_total += sp.pixels_to_resolve;
+    uint32_t last_pcnt = 0;
+    std::vector<uint8_t> progress_img;
+    uint64_t trace_base = 0;
+    std::vector<uint32_t> stage_pixels;
+
+    for (auto& sp : plan) {
+        stage_inputs(g, S, sp.level, prm);
+        TRY(upload_luts(g, prm, sp.adaptive_alpha));
+        if (sp.recolour) {  // next_pyramid_level, ms.rs:687-700
+            k_recolour<<<(uint32_t)((npix + 255) / 256), 256, 0, s>>>(S);
+            CU(cudaGetLastError());
+            g->stats.kernel_launches++;
+        }
+        const size_t n_items = sp.n_redo + sp.n_new;
+        if (n_items == 0) continue;
+        stage_pixels.resize(n_items);
+        for (size_t i = 0; i < sp.n_redo; ++i) stage_pixels[i] = g->resolved_order[g->locked + i];  // ms.rs:905-907
+        for (size_t t = 0; t < sp.n_new; ++t) stage_pixels[sp.n_redo + t] = picks[sp.pick_base + t];
+        CU(cudaMemcpyAsync(g->d_item_pixel.p, stage_pixels.data(), n_items * 4, cudaMemcpyHostToDevice, s));
+        if (g->trace) g->tr_pixel.insert(g->tr_pixel.end(), stage_pixels.begin(), stage_pixels.end());
+        // random candidates of every item of the stage: rng seeded with loop_seed + 1 = stage seed + i + 1 (ms.rs:902,945)
+        k_rand_candidates<<<(uint32_t)((n_items + 127) / 128), 128, 0, s>>>(S.ex, S.n_ex, m, sp.seed + 1ull, (uint32_t)n_items,
+                                                                          g->d_rand_xy.p, g->d_rand_map.p);
+        CU(cudaGetLastError());
+        g->stats.kernel_launches++;
+
+        size_t resolved_now = sp.resolved_before;
+        // ---- redo phase: the resolved set is static, radii are exact ----
+        if (sp.n_redo) {
+            S.r2_hint = r2_hint_for(g, resolved_now, k);
+            TRY(run_phase(g, S, 0, (uint32_t)sp.n_redo, false, true, trace_base));
+        }
+        // ---- new pixels, in epochs over which the resolved count at most doubles ----
+        size_t cur = sp.n_redo;
+        while (cur < n_items) {
+            if (resolved_now == 0) {
+                // no resolved neighbour at all: resolve_at_random(seed = p_stage_seed), ms.rs:1002-1009 -> 447-475
+                uint32_t flat = stage_pixels[cur];
+                uint32_t rmap = (uint32_t)Pcg32::seed_from_u64(sp.seed).gen_range_usize((uint64_t)g->n_ex);
+                int e = g->filt[rmap];
+                uint32_t rx = Pcg32::seed_from_u64(sp.seed).gen_range_u32((uint32_t)g->ex_w[e]);
+                uint32_t ry = Pcg32::seed_from_u64(sp.seed).gen_range_u32((uint32_t)g->ex_h[e]);
+                uint32_t item[4] = {flat, rx, ry, rmap};
+                TRY(g->d_tmp_u32.upload(item, 4, s));
+                k_commit_fixed<<<1, 32, 0, s>>>(S, S.ex, g->d_tmp_u32.p, 1, 1);
+                CU(cudaGetLastError());
+                CU(cudaStreamSynchronize(s));
+                g->stats.kernel_launches++;
+                if (g->trace) g->tr_fix_idx.push_back(trace_base + cur);
+                cur += 1; resolved_now += 1;
+                continue;
+            }
+            size_t base = resolved_now - g->inpaint_locked;
+            size_t n_e = base < 2 * (size_t)k ? 1 : std::min(n_items - cur, base);
+            S.r2_hint = r2_hint_for(g, resolved_now, k);
+            TRY(run_phase(g, S, (uint32_t)cur, (uint32_t)n_e, true, n_e > 1, trace_base));
+            cur += n_e; resolved_now += n_e;
+            if (cb) {
+                uint64_t cur_total = overall_current + cur;
+                uint32_t pcnt = (uint32_t)lroundf((float)cur_total / (float)overall_total * 100.0f);
+                if (pcnt != last_pcnt) {
+                    last_pcnt = pcnt;
+                    progress_img.resize(npix * 4);
+                    TRY(g->d_tmp_u32.ensure(npix));
+                    k_unpack_state<<<(uint32_t)((npix + 255) / 256), 256, 0, s>>>(g->d_state.p, (uint32_t)npix, g->d_tmp_u32.p, nullptr, nullptr);
+                    CU(cudaMemcpyAsync(progress_img.data(), g->d_tmp_u32.p, npix * 4, cudaMemcpyDeviceToHost, s));
+                    CU(cudaStreamSynchronize(s));
+                    cb(user, progress_img.data(), (uint32_t)g->W, (uint32_t)g->H, cur_total, overall_total, cur, sp.pixels_to_resolve);
+                }
+            }
+        }
+        // ms.rs:1043-1049: newly resolved pixels join `resolved` in processing order
+        for (size_t t = 0; t < sp.n_new; ++t) g->resolved_order.push_back(picks[sp.pick_base + t]);
+        overall_current += sp.pixels_to_resolve;
+        trace_base += n_items;
+    }
+    g->trace_n = g->trace ? trace_base : 0;
+    unsigned long long cnt[4];
+    CU(cudaMemcpyAsync(cnt, g->d_counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    g->stats.texels_fetched = cnt[0]; g->stats.texels_nominal = cnt[1]; g->stats.candidates = cnt[2];
+    g->stats.work_items = total_items;
+    g->stats.wall_ms_total = now_ms() - t_start;
+    g->stats.gpu_ms_other = 0.0;
+    g->have_loaded_points = false;
+    return 0;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char* tsb_last_error(void) { return g_err.c_str(); }
+
+int tsb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int tsb_resize(const uint8_t* rgba, uint32_t w, uint32_t h, uint8_t* out, uint32_t nw, uint32_t nh, int filter) {
+    if (!rgba || !out || w == 0 || h == 0) return fail(TSB_ERR_INVALID, "tsb_resize: empty image");
+    if (filter < 0 || filter > 2) return fail(TSB_ERR_INVALID, "tsb_resize: unknown filter");
+    if (nw == 0 || nh == 0) return 0;
+    cudaStream_t s = nullptr;
+    DevBuf<uint32_t> src, tmp, dst;
+    TRY(src.upload((const uint32_t*)rgba, (size_t)w * h, s));
+    TRY(tmp.ensure((size_t)w * nh));
+    TRY(dst.ensure((size_t)nw * nh));
+    TRY(device_resize(src.p, (int)w, (int)h, dst.p, (int)nw, (int)nh, filter, tmp.p, s));
+    CU(cudaMemcpy(out, dst.p, (size_t)nw * nh * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int tsb_pyramid_build(const uint8_t* rgba, uint32_t w, uint32_t h, uint32_t levels, uint8_t* out) {
+    if (!rgba || !out || w == 0 || h == 0) return fail(TSB_ERR_INVALID, "tsb_pyramid_build: empty image");
+    if (levels == 0) levels = 1;  // (1..0) is empty: only the original is pushed (img_pyramid.rs:25,35)
+    cudaStream_t s = nullptr;
+    const size_t img = (size_t)w * h;
+    DevBuf<uint32_t> src, small, tmp, lvl;
+    TRY(src.upload((const uint32_t*)rgba, img, s));
+    TRY(small.ensure(img)); TRY(tmp.ensure(img)); TRY(lvl.ensure(img));
+    size_t n = 0;
+    for (uint32_t i = levels - 1; i >= 1; --i) {
+        if (i >= 32) return fail(TSB_ERR_INVALID, "too many pyramid levels");
+        uint32_t p = 1u << i;
+        int sw = (int)(w / p), sh = (int)(h / p);
+        if (sw == 0 || sh == 0) return fail(TSB_ERR_INVALID, "image too small for %u pyramid levels (the reference would produce an empty image)", levels);
+        TRY(device_resize(src.p, (int)w, (int)h, small.p, sw, sh, TSB_FILTER_GAUSSIAN, tmp.p, s));
+        TRY(device_resize(small.p, sw, sh, lvl.p, (int)w, (int)h, TSB_FILTER_GAUSSIAN, tmp.p, s));
+        CU(cudaMemcpy(out + n * img * 4, lvl.p, img * 4, cudaMemcpyDeviceToHost));
+        ++n;
+    }
+    memcpy(out + n * img * 4, rgba, img * 4);
+    return 0;
+}
+
+int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
+    if (!desc || !out) return fail(TSB_ERR_INVALID, "null argument");
+    if (desc->out_width == 0 || desc->out_height == 0) return fail(TSB_ERR_INVALID, "empty output size");
+    if (desc->out_width > 16384 || desc->out_height > 16384) return fail(TSB_ERR_UNSUPPORTED, "output dimensions above 16384 are not supported");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (ndev == 0) return fail(TSB_ERR_CUDA, "no CUDA device");
+    tsb_generator* g = new tsb_generator();
+    int dev = desc->device;
+    if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+    g->device = dev;
+    auto bail = [&](int code) { delete g; return code; };
+    if (cudaSetDevice(dev) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "cudaSetDevice(%d) failed", dev));
+    if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "stream creation failed"));
+    if (cudaMallocHost((void**)&g->h_ctrl, 64) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "pinned allocation failed"));
+    g->W = (int)desc->out_width; g->H = (int)desc->out_height;
+    const size_t npix = (size_t)g->W * g->H;
+    // mask geometry: room for the tiling mirror copies on every side (ms.rs:308-327)
+    int x_l = (int)((float)g->W * 0.05f), y_b = (int)((float)g->H * 0.05f);
+    g->mx = ((x_l + 1 + 31) / 32) * 32; g->my = y_b + 1;
+    g->wpr = (g->W + 2 * g->mx + 31) / 32; g->mrows = g->H + 2 * g->my;
+    int rc = 0;
+    if ((rc = g->d_state.ensure(npix)) || (rc = g->d_score.ensure(npix)) || (rc = g->d_mask.ensure((size_t)g->wpr * g->mrows))) return bail(rc);
+    SpiralHost sp = build_spiral(SPIRAL_RT);
+    g->spiralN = (int)sp.off.size(); g->RT2 = sp.RT2;
+    if ((rc = g->d_spiral.upload(sp.off.data(), sp.off.size(), g->stream)) || (rc = g->d_cntLE.upload(sp.cntLE.data(), sp.cntLE.size(), g->stream))) return bail(rc);
+    if (desc->inpaint_mask) {
+        if (!desc->inpaint_color) return bail(fail(TSB_ERR_INVALID, "inpaint_color is required with inpaint_mask"));
+        g->inpaint = true;
+        g->inpaint_index = desc->inpaint_example_index;
+        if ((rc = g->d_inp_mask.upload((const uint32_t*)desc->inpaint_mask, npix, g->stream)) ||
+            (rc = g->d_inp_color.upload((const uint32_t*)desc->inpaint_color, npix, g->stream))) return bail(rc);
+        for (size_t i = 0; i < npix; ++i) {  // ms.rs:271-279
+            if (desc->inpaint_mask[i * 4] < 255) g->unresolved0.push_back((uint32_t)i);
+            else g->resolved0.push_back((uint32_t)i);
+        }
+    } else {
+        g->unresolved0.resize(npix);
+        for (size_t i = 0; i < npix; ++i) g->unresolved0[i] = (uint32_t)i;
+    }
+    int per_sm = 0;
+    cudaFuncSetAttribute(k_round<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
+    cudaFuncSetAttribute(k_round<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
+    cudaFuncSetAttribute(k_eval_items<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
+    cudaFuncSetAttribute(k_eval_items<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
+    cudaFuncSetAttribute(k_radius, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_round<false>, CTA_THREADS, sizeof(CtaSmem)) != cudaSuccess || per_sm < 1) per_sm = 1;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "cudaGetDeviceProperties failed"));
+    g->max_ctas = prop.multiProcessorCount * per_sm;
+    if ((rc = init_state(g))) return bail(rc);
+    if (cudaStreamSynchronize(g->stream) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "generator initialisation failed: %s", cudaGetErrorString(cudaGetLastError())));
+    *out = g;
+    return 0;
+}
+
+void tsb_generator_destroy(tsb_generator* g) {
+    if (!g) return;
+    cudaSetDevice(g->device);
+    delete g;
+}
+
+int tsb_generator_reset(tsb_generator* g) {
+    if (!g) return fail(TSB_ERR_INVALID, "null generator");
+    TRY(set_device(g));
+    TRY(init_state(g));
+    CU(cudaStreamSynchronize(g->stream));
+    return 0;
+}
+
+int tsb_generator_random_init(tsb_generator* g, uint64_t count, const tsb_image* top, uint32_t n, uint64_t seed) {
+    if (!g || !top || n == 0) return fail(TSB_ERR_INVALID, "null argument");
+    TRY(set_device(g));
+    cudaStream_t s = g->stream;
+    // upload the images (pyramid[len-1] of EVERY example, session.rs:42-48)
+    std::vector<DevBuf<uint32_t>> imgs(n);
+    std::vector<DevEx> desc(n);
+    for (uint32_t e = 0; e < n; ++e) {
+        TRY(imgs[e].upload((const uint32_t*)top[e].rgba, (size_t)top[e].width * top[e].height, s));
+        desc[e].px = imgs[e].p; desc[e].smask = nullptr; desc[e].w = (int)top[e].width; desc[e].h = (int)top[e].height;
+    }
+    DevBuf<DevEx> d_desc;
+    TRY(d_desc.upload(desc.data(), n, s));
+    std::vector<uint32_t> items;
+    for (uint64_t i = 0; i < count; ++i) {  // ms.rs:433-443
+        if (g->unresolved.empty()) continue;
+        size_t idx = (size_t)Pcg32::seed_from_u64(seed + i).gen_range_usize((uint64_t)g->unresolved.size());
+        uint32_t flat = g->unresolved[idx];
+        g->unresolved[idx] = g->unresolved.back();
+        g->unresolved.pop_back();
+        uint64_t s2 = seed + i + (uint64_t)flat;
+        uint32_t rmap = (uint32_t)Pcg32::seed_from_u64(s2).gen_range_usize((uint64_t)n);
+        uint32_t rx = Pcg32::seed_from_u64(s2).gen_range_u32(top[rmap].width);
+        uint32_t ry = Pcg32::seed_from_u64(s2).gen_range_u32(top[rmap].height);
+        items.push_back(flat); items.push_back(rx); items.push_back(ry); items.push_back(rmap);
+        g->resolved_order.push_back(flat);
+    }
+    g->locked += (size_t)count;  // ms.rs:444
+    if (!items.empty()) {
+        StageDev S;
+        fill_stage_geometry(g, S, false);
+        DevBuf<uint32_t> d_items;
+        TRY(d_items.upload(items.data(), items.size(), s));
+        uint32_t ni = (uint32_t)(items.size() / 4);
+        k_commit_fixed<<<(ni + 127) / 128, 128, 0, s>>>(S, d_desc.p, d_items.p, ni, 0);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(s));
+    }
+    return 0;
+}
+
+int tsb_generator_upload_inputs(tsb_generator* g, const tsb_pyramid* examples, uint32_t n_examples, const tsb_guides* guides, const tsb_sampling* sampling) {
+    if (!g) return fail(TSB_ERR_INVALID, "null generator");
+    TRY(set_device(g));
+    return upload_inputs(g, examples, n_examples, guides, sampling);
+}
+
+int tsb_generator_resolve_resident(tsb_generator* g, const tsb_params* params, tsb_progress_fn cb, void* user) {
+    if (!g || !params) return fail(TSB_ERR_INVALID, "null argument");
+    return resolve_impl(g, params, cb, user);
+}
+
+int tsb_generator_resolve(tsb_generator* g, const tsb_params* params, const tsb_pyramid* examples, uint32_t n_examples,
+                          const tsb_guides* guides, const tsb_sampling* sampling, tsb_progress_fn cb, void* user) {
+    if (!g || !params) return fail(TSB_ERR_INVALID, "null argument");
+    TRY(set_device(g));
+    TRY(upload_inputs(g, examples, n_examples, guides, sampling));
+    return resolve_impl(g, params, cb, user);
+}
+
+static int read_unpacked(tsb_generator* g, uint32_t* color, uint32_t* coord, uint32_t* idm) {
+    TRY(set_device(g));
+    const size_t npix = (size_t)g->W * g->H;
+    DevBuf<uint32_t> dc, dco, di;
+    if (color) TRY(dc.ensure(npix));
+    if (coord) TRY(dco.ensure(npix * 3));
+    if (idm) TRY(di.ensure(npix * 2));
+    k_unpack_state<<<(uint32_t)((npix + 255) / 256), 256, 0, g->stream>>>(g->d_state.p, (uint32_t)npix, dc.p, dco.p, di.p);
+    CU(cudaGetLastError());
+    if (color) CU(cudaMemcpyAsync(color, dc.p, npix * 4, cudaMemcpyDeviceToHost, g->stream));
+    if (coord) CU(cudaMemcpyAsync(coord, dco.p, npix * 12, cudaMemcpyDeviceToHost, g->stream));
+    if (idm) CU(cudaMemcpyAsync(idm, di.p, npix * 8, cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    return 0;
+}
+
+int tsb_generator_read_color(tsb_generator* g, uint8_t* rgba) {
+    if (!g || !rgba) return fail(TSB_ERR_INVALID, "null argument");
+    return read_unpacked(g, (uint32_t*)rgba, nullptr, nullptr);
+}
+int tsb_generator_read_coord(tsb_generator* g, uint32_t* xym) {
+    if (!g || !xym) return fail(TSB_ERR_INVALID, "null argument");
+    return read_unpacked(g, nullptr, xym, nullptr);
+}
+int tsb_generator_read_id(tsb_generator* g, uint32_t* pm) {
+    if (!g || !pm) return fail(TSB_ERR_INVALID, "null argument");
+    return read_unpacked(g, nullptr, nullptr, pm);
+}
+int tsb_generator_resolved_count(tsb_generator* g, uint64_t* n, uint64_t* locked) {
+    if (!g) return fail(TSB_ERR_INVALID, "null generator");
+    if (n) *n = g->resolved_order.size();
+    if (locked) *locked = g->locked;
+    return 0;
+}
+int tsb_generator_read_resolved(tsb_generator* g, uint32_t* flat, float* score) {
+    if (!g) return fail(TSB_ERR_INVALID, "null generator");
+    TRY(set_device(g));
+    size_t n = g->resolved_order.size();
+    if (flat) memcpy(flat, g->resolved_order.data(), n * 4);
+    if (score && n) {
+        DevBuf<uint32_t> df;
+        DevBuf<float> ds;
+        TRY(df.upload(g->resolved_order.data(), n, g->stream));
+        TRY(ds.ensure(n));
+        k_gather_scores<<<(uint32_t)((n + 255) / 256), 256, 0, g->stream>>>(g->d_score.p, df.p, (uint32_t)n, ds.p);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(score, ds.p, n * 4, cudaMemcpyDeviceToHost, g->stream));
+        CU(cudaStreamSynchronize(g->stream));
+    }
+    return 0;
+}
+int tsb_generator_read_uncertainty(tsb_generator* g, uint8_t* rgba) {
+    if (!g || !rgba) return fail(TSB_ERR_INVALID, "null argument");
+    TRY(set_device(g));
+    const size_t npix = (size_t)g->W * g->H;
+    StageDev S;
+    fill_stage_geometry(g, S, false);
+    DevBuf<uint32_t> d;
+    TRY(d.ensure(npix));
+    k_uncertainty<<<(uint32_t)((npix + 255) / 256), 256, 0, g->stream>>>(S, d.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(rgba, d.p, npix * 4, cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    return 0;
+}
+int tsb_generator_read_id_maps(tsb_generator* g, uint8_t* patch_rgba, uint8_t* map_rgba) {
+    if (!g || !patch_rgba || !map_rgba) return fail(TSB_ERR_INVALID, "null argument");
+    TRY(set_device(g));
+    const size_t npix = (size_t)g->W * g->H;
+    DevBuf<uint32_t> a, b;
+    TRY(a.ensure(npix)); TRY(b.ensure(npix));
+    k_id_maps<<<(uint32_t)((npix + 255) / 256), 256, 0, g->stream>>>(g->d_state.p, (uint32_t)npix, a.p, b.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(patch_rgba, a.p, npix * 4, cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaMemcpyAsync(map_rgba, b.p, npix * 4, cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    return 0;
+}
+int tsb_generator_get_stats(tsb_generator* g, tsb_stats* out) {
+    if (!g || !out) return fail(TSB_ERR_INVALID, "null argument");
+    *out = g->stats;
+    return 0;
+}
+
+// ---- test-only ---------------------------------------------------------------------------------
+int tsb_generator_load_state(tsb_generator* g, const uint8_t* color, const uint32_t* coord, const uint32_t* idm,
+                             const int32_t* tree_xy, uint64_t n_tree, const uint32_t* resolved_flat,
+                             const float* resolved_score, uint64_t n_resolved, uint64_t locked) {
+    if (!g || !color || !coord || !idm) return fail(TSB_ERR_INVALID, "null argument");
+    TRY(set_device(g));
+    cudaStream_t s = g->stream;
+    const size_t npix = (size_t)g->W * g->H;
+    DevBuf<uint32_t> dc, dco, di;
+    TRY(dc.upload((const uint32_t*)color, npix, s));
+    TRY(dco.upload(coord, npix * 3, s));
+    TRY(di.upload(idm, npix * 2, s));
+    k_pack_state<<<(uint32_t)((npix + 255) / 256), 256, 0, s>>>(g->d_state.p, (uint32_t)npix, dc.p, dco.p, di.p);
+    CU(cudaGetLastError());
+    CU(cudaMemsetAsync(g->d_mask.p, 0, (size_t)g->wpr * g->mrows * 4, s));
+    StageDev S;
+    fill_stage_geometry(g, S, false);
+    DevBuf<uint32_t> dp;
+    if (n_tree) {
+        TRY(dp.upload((const uint32_t*)tree_xy, n_tree * 2, s));
+        k_mask_insert_points<<<(uint32_t)((n_tree + 255) / 256), 256, 0, s>>>(S, (const int32_t*)dp.p, (uint32_t)n_tree);
+        CU(cudaGetLastError());
+    }
+    g->loaded_points.assign(tree_xy, tree_xy + n_tree * 2);
+    g->have_loaded_points = true;
+    g->resolved_order.assign(resolved_flat, resolved_flat + n_resolved);
+    g->locked = (size_t)locked;
+    if (n_resolved && resolved_score) {
+        DevBuf<uint32_t> df;
+        DevBuf<float> ds;
+        TRY(df.upload(resolved_flat, n_resolved, s));
+        TRY(ds.upload(resolved_score, n_resolved, s));
+        k_scatter_scores<<<(uint32_t)((n_resolved + 255) / 256), 256, 0, s>>>(g->d_score.p, df.p, ds.p, (uint32_t)n_resolved);
+        CU(cudaGetLastError());
+    }
+    // unresolved = every pixel not in the resolved list, in ascending order (order only matters for later picks)
+    std::vector<uint8_t> isres(npix, 0);
+    for (uint64_t i = 0; i < n_resolved; ++i) isres[resolved_flat[i]] = 1;
+    g->unresolved.clear();
+    for (size_t i = 0; i < npix; ++i) if (!isres[i]) g->unresolved.push_back((uint32_t)i);
+    CU(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int tsb_generator_eval_items(tsb_generator* g, const tsb_params* prm, int32_t level, float adaptive_alpha, uint64_t p_stage_seed,
+                             uint32_t n, const uint32_t* pixel_flat, const uint64_t* loop_seed, int32_t* neigh, int32_t* res, float* score) {
+    if (!g || !prm || !pixel_flat || !loop_seed || !neigh || !res || !score) return fail(TSB_ERR_INVALID, "null argument");
+    if (!g->inputs_ready) return fail(TSB_ERR_INVALID, "inputs have not been uploaded");
+    TRY(check_params(g, prm));
+    TRY(set_device(g));
+    (void)p_stage_seed;
+    if (level < 0 || level >= g->n_levels) return fail(TSB_ERR_INVALID, "level out of range");
+    cudaStream_t s = g->stream;
+    const int k = (int)prm->nearest_neighbors, m = (int)prm->random_sample_locations;
+    TRY(g->d_luts.ensure(512));
+    StageDev S;
+    fill_stage_geometry(g, S, prm->tiling_mode != 0);
+    stage_inputs(g, S, level, prm);
+    TRY(upload_luts(g, prm, adaptive_alpha));
+    S.r2_hint = r2_hint_for(g, g->resolved_order.size(), (uint32_t)k);
+    DevBuf<uint32_t> dpix, dxy;
+    DevBuf<uint8_t> dmap;
+    DevBuf<int32_t> dneigh, dres;
+    DevBuf<float> dscore;
+    TRY(dpix.upload(pixel_flat, n, s));
+    TRY(dxy.ensure((size_t)n * m)); TRY(dmap.ensure((size_t)n * m));
+    TRY(dneigh.ensure((size_t)n * 2 * k)); TRY(dres.ensure((size_t)n * 8)); TRY(dscore.ensure(n));
+    // items carry arbitrary loop seeds: generate their random candidates one launch per run of consecutive seeds
+    uint32_t i = 0;
+    while (i < n) {
+        uint32_t j = i + 1;
+        while (j < n && loop_seed[j] == loop_seed[j - 1] + 1) ++j;
+        k_rand_candidates<<<(j - i + 127) / 128, 128, 0, s>>>(S.ex, S.n_ex, m, loop_seed[i] + 1ull, j - i, dxy.p + (size_t)i * m, dmap.p + (size_t)i * m);
+        CU(cudaGetLastError());
+        i = j;
+    }
+    int grid = grid_for(g, n);
+    if (g->guided) k_eval_items<true><<<grid, CTA_THREADS, sizeof(CtaSmem), s>>>(S, n, dpix.p, dxy.p, dmap.p, dneigh.p, dres.p, dscore.p);
+    else k_eval_items<false><<<grid, CTA_THREADS, sizeof(CtaSmem), s>>>(S, n, dpix.p, dxy.p, dmap.p, dneigh.p, dres.p, dscore.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(neigh, dneigh.p, (size_t)n * 2 * k * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(res, dres.p, (size_t)n * 8 * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(score, dscore.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    // items without any resolved neighbour take the resolve_at_random path (ms.rs:1002-1009): host draws
+    for (uint32_t t = 0; t < n; ++t) {
+        int32_t* ro = res + (size_t)t * 8;
+        if (ro[7]) {
+            uint32_t rmap = (uint32_t)Pcg32::seed_from_u64(p_stage_seed).gen_range_usize((uint64_t)g->n_ex);
+            int e = g->filt[rmap];
+            ro[3] = (int32_t)Pcg32::seed_from_u64(p_stage_seed).gen_range_u32((uint32_t)g->ex_w[e]);
+            ro[4] = (int32_t)Pcg32::seed_from_u64(p_stage_seed).gen_range_u32((uint32_t)g->ex_h[e]);
+            ro[5] = (int32_t)rmap; ro[6] = (int32_t)pixel_flat[t]; ro[1] = 0; ro[2] = 0;
+            score[t] = 0.f;
+        }
+    }
+    return 0;
+}
+
+int tsb_generator_set_trace(tsb_generator* g, int on) {
+    if (!g) return fail(TSB_ERR_INVALID, "null generator");
+    g->trace = on != 0;
+    return 0;
+}
+int tsb_generator_trace_count(tsb_generator* g, uint64_t* n) {
+    if (!g || !n) return fail(TSB_ERR_INVALID, "null argument");
+    *n = g->trace_n;
+    return 0;
+}
+int tsb_generator_read_trace(tsb_generator* g, uint32_t* pixel, int32_t* best, int32_t* ncand, int32_t* nneigh, float* score) {
+    if (!g) return fail(TSB_ERR_INVALID, "null generator");
+    TRY(set_device(g));
+    size_t n = (size_t)g->trace_n;
+    if (!n) return 0;
+    memcpy(pixel, g->tr_pixel.data(), n * 4);
+    CU(cudaMemcpy(best, g->d_tr_best.p, n * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(ncand, g->d_tr_ncand.p, n * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(nneigh, g->d_tr_nneigh.p, n * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(score, g->d_tr_score.p, n * 4, cudaMemcpyDeviceToHost));
+    for (uint64_t idx : g->tr_fix_idx) { best[idx] = -1; ncand[idx] = 0; nneigh[idx] = 0; score[idx] = 0.f; }
+    return 0;
+}
+
+int tsb_microbench_gather(uint64_t bytes, int mode, int iters, double* useful_gbs, double* gathers_per_s) {
+    int w = 512;
+    int h = (int)(bytes / 4 / (uint64_t)w);
+    if (h < 32) return fail(TSB_ERR_INVALID, "window too small");
+    DevBuf<uint32_t> img, sink;
+    std::vector<uint32_t> host((size_t)w * h);
+    for (size_t i = 0; i < host.size(); ++i) host[i] = (uint32_t)(i * 2654435761u);
+    TRY(img.upload(host.data(), host.size(), nullptr));
+    TRY(sink.ensure(1));
+    cudaDeviceProp prop;
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaGetDeviceProperties(&prop, dev));
+    const int threads = 256, blocks = prop.multiProcessorCount * 8 * 4, steps = 50;
+    cudaTextureObject_t tex = 0;
+    if (mode == 1) {
+        cudaResourceDesc rd;
+        memset(&rd, 0, sizeof(rd));
+        rd.resType = cudaResourceTypePitch2D;
+        rd.res.pitch2D.devPtr = img.p;
+        rd.res.pitch2D.desc = cudaCreateChannelDesc<uchar4>();
+        rd.res.pitch2D.width = (size_t)w; rd.res.pitch2D.height = (size_t)h; rd.res.pitch2D.pitchInBytes = (size_t)w * 4;
+        cudaTextureDesc td;
+        memset(&td, 0, sizeof(td));
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        CU(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+    }
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    for (int it = -2; it < iters; ++it) {
+        if (it == 0) CU(cudaEventRecord(e0));
+        if (mode == 1) k_gather_bench_tex<<<blocks, threads>>>(tex, w, h, steps, (uint32_t)it, sink.p);
+        else k_gather_bench<<<blocks, threads>>>(img.p, w, h, steps, (uint32_t)it, sink.p);
+    }
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    CU(cudaGetLastError());
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    double gathers = (double)iters * (double)blocks * threads * 8.0 * steps;
+    if (gathers_per_s) *gathers_per_s = gathers / (ms * 1e-3);
+    if (useful_gbs) *useful_gbs = gathers * 4.0 / (ms * 1e-3) / 1e9;
+    if (tex) cudaDestroyTextureObject(tex);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return 0;
+}
+
+}  // extern "C"

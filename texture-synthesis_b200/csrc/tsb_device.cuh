@@ -1,0 +1,890 @@
+// tsb_device.cuh -- sm_100a kernels of the texture-synthesis hot path.
+//
+// One warp performs one "pixel resolution" (reference lib/src/ms.rs:887-1011):
+//   K2  k nearest resolved neighbours  : spiral walk / disc scan over a bit-packed resolved mask
+//                                         (replaces TreeGrid + rstar, ms.rs:1313-1531)
+//   K3  candidates                      : coherence candidates from the neighbours' source coordinates
+//                                         (ms.rs:496-547) + pre-generated PCG-exact random ones (ms.rs:549-599)
+//   K4  cost + argmin                   : one lane per candidate, strict f32 order (ms.rs:1184-1288)
+//   K5  commit                          : ms.rs:334-377 / 296-331
+// Rounds of mutually independent work items are executed in the exact serial order semantics of
+// the single-threaded reference: an item runs once every lower-index item inside its conflict
+// radius has committed (see DESIGN.md "Exact wave schedule").
+#pragma once
+#include <cuda_runtime.h>
+#include <cfloat>
+#include <cstdint>
+#include "tsb_rng.cuh"
+
+namespace tsb {
+
+constexpr int KMAX = 128;         // max nearest_neighbors
+constexpr int CANDMAX = 256;      // max nearest_neighbors + random_sample_locations
+constexpr int KBUF = 256;         // key buffer of the general k-NN path
+constexpr int PRED_CAP = 160;     // predecessor list capacity per work item
+constexpr int WARPS_PER_CTA = 8;
+constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
+constexpr uint32_t NONE32 = 0xFFFFFFFFu;
+constexpr uint32_t R2_INF = 0xFFFFFFFFu;
+constexpr uint32_t OUTSIDE_RGBA = 0xFF000000u;  // image::Rgba([0,0,0,255]) little-endian (ms.rs:950)
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+struct DevEx {  // one (non-ignored) example at the current pyramid level
+    const uint32_t* px;
+    const uint8_t* smask;  // R channel of the sampling mask or nullptr (SamplingMethod::All)
+    int w, h;
+};
+struct DevGuide {  // one example guide at the current level (NOT filtered, ms.rs:67-81)
+    const uint32_t* px;
+    int w, h;
+};
+
+struct StageDev {
+    // synthesis state
+    uint4* state;     // per output pixel {colour RGBA, src x|y<<16, patch id, id_map.map | coord_map.map<<16}
+    uint32_t* mask;   // resolved set, bit packed, extended by the tiling margins
+    float* score;     // first-resolution score per pixel (ms.rs:365: never updated on redo)
+    int W, H;
+    int mx, my, wpr, mrows;  // mask geometry: bit (x+mx, y+my), wpr words per row, mrows rows
+    int tiling, x_l, x_r, y_b, y_t;  // ms.rs:308-311
+    // inputs at this level
+    const DevEx* ex;
+    int n_ex;
+    const DevGuide* exg;
+    int n_exg;
+    const uint32_t* tguide;
+    int tgw, tgh;
+    const float* lut_my;     // 256 entries indexed by |a-b|
+    const float* lut_guide;  // 256
+    // spiral table: offsets sorted by (d^2, dy, dx); cntLE[r2] = #offsets with d^2 <= r2
+    const short2* spiral;
+    const uint32_t* cntLE;
+    int spiralN, RT2;
+    int k, m;
+    uint32_t r2_hint;  // starting radius^2 of the general k-NN search
+    unsigned long long* counters;  // [0] texels fetched, [1] texels nominal, [2] candidates, [3] items
+};
+
+struct PhaseDev {
+    const uint32_t* item_pixel;  // [n] flat output pixel of local item
+    uint32_t* item_R2;           // [n] conflict radius^2 (k-th neighbour distance at phase start)
+    uint32_t* pred_cnt;          // [n]
+    uint32_t* preds;             // [n][PRED_CAP] local indices of lower items that must commit first
+    uint32_t* done;              // [n]
+    uint32_t* pending[2];        // ping-pong pending lists
+    uint32_t* cnt;               // [4] pending counts ring (round r reads r&3, appends (r+1)&3, clears (r+2)&3)
+    uint32_t* minpend;           // [4] min pending local index ring
+    uint32_t* pmap;              // W*H: local item index or NONE32
+    const uint32_t* rand_xy;     // [n_stage][m] pre-generated random candidates (x | y<<16)
+    const uint8_t* rand_map;     // [n_stage][m]
+    uint32_t n;                  // items in phase
+    uint32_t stage_base;         // work-item index (within the stage) of local item 0
+    uint32_t is_new;             // 1: new pixels (insert into the resolved set), 0: redo
+    // trace (optional, indexed by stage work-item index + trace_base)
+    int32_t* tr_best; int32_t* tr_ncand; int32_t* tr_nneigh; float* tr_score;
+    uint64_t trace_base;
+};
+
+struct __align__(16) WarpScratch {
+    union {
+        unsigned long long keys[KBUF];  // general k-NN path (dead once the neighbour list is built)
+        struct { uint32_t cxy[CANDMAX]; uint32_t cpatch[CANDMAX]; } c;
+    } u;
+    double d[KMAX];
+    uint16_t cmeta[CANDMAX];  // map id | 0x8000 for random candidates (mirrored pattern, ms.rs:588)
+    short2 off[KMAX];         // neighbour offsets n_j - p, canonical order
+    float g[KMAX];
+    uint32_t tcol[KMAX];
+    uint32_t gcol[KMAX];
+    int cnt;
+    int pad[3];
+};
+
+struct ItemOut {
+    int kk, ncand, best;
+    int bx, by, bmap;
+    uint32_t bpatch;
+    float score;
+};
+
+__device__ __forceinline__ int imod(int a, int b) { int r = a % b; return r < 0 ? r + b : r; }
+
+__device__ __forceinline__ int isqrt_u32(uint32_t v) {
+    int r = (int)sqrtf((float)v);
+    while ((unsigned long long)r * (unsigned long long)r > v) --r;
+    while ((unsigned long long)(r + 1) * (unsigned long long)(r + 1) <= v) ++r;
+    return r;
+}
+
+__device__ __forceinline__ bool mask_test(const StageDev& S, int x, int y) {
+    int X = x + S.mx, Y = y + S.my;
+    if ((unsigned)X >= (unsigned)(S.wpr * 32) || (unsigned)Y >= (unsigned)S.mrows) return false;
+    return (__ldcg(S.mask + (size_t)Y * S.wpr + (X >> 5)) >> (X & 31)) & 1u;
+}
+__device__ __forceinline__ void mask_set(const StageDev& S, int x, int y) {
+    int X = x + S.mx, Y = y + S.my;
+    if ((unsigned)X >= (unsigned)(S.wpr * 32) || (unsigned)Y >= (unsigned)S.mrows) return;
+    atomicOr(S.mask + (size_t)Y * S.wpr + (X >> 5), 1u << (X & 31));
+}
+// flush_resolved, ms.rs:296-331 (tree part): the pixel plus its tiling mirror copies (no diagonal copy)
+__device__ __forceinline__ void mask_insert(const StageDev& S, int x, int y, bool mirrors) {
+    mask_set(S, x, y);
+    if (mirrors) {
+        if (x < S.x_l) mask_set(S, x + S.W, y);
+        else if (x > S.x_r) mask_set(S, x - S.W, y);
+        if (y < S.y_b) mask_set(S, x, y + S.H);
+        else if (y > S.y_t) mask_set(S, x, y - S.H);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// General disc scan over the bit mask (any radius).  COLLECT=false: count bits with d^2 <= R2.
+// COLLECT=true: append keys (d^2<<32 | (dy+32768)<<16 | (dx+32768)) to ws.u.keys (ws.cnt).
+// ---------------------------------------------------------------------------------------------
+template <bool COLLECT>
+__device__ uint32_t scan_disc(const StageDev& S, WarpScratch& ws, int lane, int x, int y, uint32_t R2) {
+    int r = isqrt_u32(R2);
+    int ylo = max(y - r, -S.my), yhi = min(y + r, S.mrows - 1 - S.my);
+    uint32_t cnt = 0;
+    for (int yy = ylo + lane; yy <= yhi; yy += 32) {
+        int dy = yy - y;
+        int w = isqrt_u32(R2 - (uint32_t)(dy * dy));
+        int xlo = max(x - w, -S.mx), xhi = min(x + w, S.wpr * 32 - 1 - S.mx);
+        if (xlo > xhi) continue;
+        int Xlo = xlo + S.mx, Xhi = xhi + S.mx;
+        const uint32_t* row = S.mask + (size_t)(yy + S.my) * S.wpr;
+        for (int wd = Xlo >> 5; wd <= (Xhi >> 5); ++wd) {
+            uint32_t bits = __ldcg(row + wd);
+            if (wd == (Xlo >> 5)) bits &= 0xFFFFFFFFu << (Xlo & 31);
+            if (wd == (Xhi >> 5)) bits &= 0xFFFFFFFFu >> (31 - (Xhi & 31));
+            if (!COLLECT) cnt += __popc(bits);
+            else {
+                while (bits) {
+                    int b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    int dx = (wd * 32 + b - S.mx) - x;
+                    unsigned long long key = ((unsigned long long)(uint32_t)(dx * dx + dy * dy) << 32) |
+                                             ((unsigned long long)(uint32_t)(dy + 32768) << 16) |
+                                             (unsigned long long)(uint32_t)(dx + 32768);
+                    int slot = atomicAdd(&ws.cnt, 1);
+                    if (slot < KBUF) ws.u.keys[slot] = key;
+                }
+            }
+        }
+    }
+    if (!COLLECT) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
+        return cnt;
+    }
+    __syncwarp();
+    return (uint32_t)ws.cnt;
+}
+
+__device__ void sort_keys(WarpScratch& ws, int lane, int n) {
+    int n2 = 32;
+    while (n2 < n) n2 <<= 1;
+    for (int i = n + lane; i < n2; i += 32) ws.u.keys[i] = ~0ull;
+    __syncwarp();
+    for (int size = 2; size <= n2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = lane; t < (n2 >> 1); t += 32) {
+                int i = 2 * t - (t & (stride - 1));
+                int j = i + stride;
+                bool up = (i & size) == 0;
+                unsigned long long a = ws.u.keys[i], b = ws.u.keys[j];
+                if ((a > b) == up) { ws.u.keys[i] = b; ws.u.keys[j] = a; }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// k nearest resolved points of (x,y) in canonical order (d^2, dy, dx) -> ws.off[0..kk).
+// R2bound: if != R2_INF, the caller guarantees that the disc d^2 <= R2bound holds at least k points.
+// Returns kk; *r2_out = d^2 of the k-th neighbour (R2_INF if fewer than k points exist).
+__device__ int knn_search(const StageDev& S, WarpScratch& ws, int lane, int x, int y, uint32_t R2bound, uint32_t* r2_out) {
+    const int k = S.k;
+    const unsigned lt = (1u << lane) - 1u;
+    // ---- path A: spiral walk over the fixed-offset table ----
+    bool bounded = (R2bound != R2_INF) && (R2bound <= (uint32_t)S.RT2);
+    if (bounded || R2bound == R2_INF) {
+        int limit = bounded ? (int)__ldg(S.cntLE + R2bound) : S.spiralN;
+        // unbounded search: do not walk the whole table when the hint says the set is sparse
+        if (!bounded && S.r2_hint > (uint32_t)S.RT2) limit = 0;
+        int cnt = 0;
+        for (int base = 0; base < limit && cnt < k; base += 32) {
+            int idx = base + lane;
+            bool hit = false;
+            short2 o = make_short2(0, 0);
+            if (idx < limit) {
+                o = __ldg(S.spiral + idx);
+                hit = mask_test(S, x + o.x, y + o.y);
+            }
+            unsigned b = __ballot_sync(FULL, hit);
+            int pos = cnt + __popc(b & lt);
+            if (hit && pos < k) ws.off[pos] = o;
+            cnt += __popc(b);
+        }
+        if (cnt >= k) {
+            __syncwarp();
+            short2 last = ws.off[k - 1];
+            *r2_out = (uint32_t)(last.x * last.x + last.y * last.y);
+            return k;
+        }
+    }
+    // ---- path B: disc scan + sort ----
+    uint32_t extw = (uint32_t)(S.wpr * 32), exth = (uint32_t)S.mrows;
+    const uint32_t R2max = extw * extw + exth * exth;
+    uint32_t R2 = R2bound;
+    uint32_t c = 0;
+    bool need_search = true;
+    if (R2bound != R2_INF) {
+        c = scan_disc<false>(S, ws, lane, x, y, R2);
+        need_search = (c > (uint32_t)KBUF) || (c < (uint32_t)k);
+    }
+    if (need_search) {
+        uint32_t lo = 0;
+        R2 = max(S.r2_hint, 4u);
+        if (R2 > R2max) R2 = R2max;
+        for (;;) {
+            c = scan_disc<false>(S, ws, lane, x, y, R2);
+            if (c >= (uint32_t)k || R2 >= R2max) break;
+            lo = R2;
+            uint32_t nx = R2 + (R2 >> 1) + 1;
+            R2 = (nx > R2max || nx < R2) ? R2max : nx;
+        }
+        if (c > (uint32_t)KBUF) {
+            uint32_t hi = R2;
+            while (hi - lo > 1) {
+                uint32_t mid = lo + ((hi - lo) >> 1);
+                c = scan_disc<false>(S, ws, lane, x, y, mid);
+                if (c >= (uint32_t)k) { hi = mid; if (c <= (uint32_t)KBUF) break; }
+                else lo = mid;
+            }
+            R2 = hi;
+        }
+    }
+    if (lane == 0) ws.cnt = 0;
+    __syncwarp();
+    int n = (int)scan_disc<true>(S, ws, lane, x, y, R2);
+    if (n > KBUF) n = KBUF;  // only reachable with > KBUF exact ties on one circle
+    sort_keys(ws, lane, n);
+    int kk = n < k ? n : k;
+    unsigned long long kth = kk > 0 ? ws.u.keys[kk - 1] : 0ull;
+    __syncwarp();
+    for (int j = lane; j < kk; j += 32) {
+        unsigned long long key = ws.u.keys[j];
+        ws.off[j] = make_short2((short)((int)(key & 0xFFFF) - 32768), (short)((int)((key >> 16) & 0xFFFF) - 32768));
+    }
+    __syncwarp();
+    *r2_out = (kk == k) ? (uint32_t)(kth >> 32) : R2_INF;
+    return kk;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One pixel resolution (steps 2-4 of ms.rs:917-986) by one warp.  No commit.
+// ---------------------------------------------------------------------------------------------
+template <bool GUIDED>
+__device__ void resolve_item(const StageDev& S, WarpScratch& ws, const float* __restrict__ s_lut,
+                             const float* __restrict__ s_lutg, int lane, int x, int y, uint32_t R2bound,
+                             const uint32_t* __restrict__ rand_xy, const uint8_t* __restrict__ rand_map, ItemOut& out) {
+    const unsigned lt = (1u << lane) - 1u;
+    uint32_t r2;
+    const int kk = knn_search(S, ws, lane, x, y, R2bound, &r2);
+    out.kk = kk;
+    out.ncand = 0; out.best = 0; out.bx = out.by = out.bmap = 0; out.bpatch = 0; out.score = 0.f;
+    if (kk == 0) return;
+    const int W = S.W, H = S.H;
+    // ---- neighbour state, distances (ms.rs:405-425), coherence candidates (ms.rs:496-547) ----
+    const double dimx = (double)W, dimy = (double)H;
+    const double x2 = __ddiv_rn((double)x, dimx), y2 = __ddiv_rn((double)y, dimy);
+    int ncand = 0;
+    for (int base = 0; base < kk; base += 32) {
+        int j = base + lane;
+        bool valid = false;
+        uint32_t cxy = 0, cpatch = 0;
+        uint16_t cmeta = 0;
+        if (j < kk) {
+            short2 o = ws.off[j];
+            int nx = x + o.x, ny = y + o.y;
+            int qx = nx, qy = ny;
+            if (S.tiling) { qx = imod(nx, W); qy = imod(ny, H); }
+            uint4 st = __ldcg(S.state + (size_t)qy * W + qx);
+            ws.tcol[j] = st.x;  // ms.rs:1151-1181 target pattern from the output colour map
+            if (GUIDED) {
+                int gx = nx, gy = ny;
+                if (S.tiling) { gx = imod(nx, S.tgw); gy = imod(ny, S.tgh); }
+                ws.gcol[j] = ((unsigned)gx < (unsigned)S.tgw && (unsigned)gy < (unsigned)S.tgh)
+                                 ? __ldg(S.tguide + (size_t)gy * S.tgw + gx) : OUTSIDE_RGBA;
+            }
+            double x1 = __ddiv_rn((double)nx, dimx), y1 = __ddiv_rn((double)ny, dimy);
+            double ddx = __dsub_rn(x1, x2), ddy = __dsub_rn(y1, y2);
+            ws.d[j] = __fma_rn(ddx, ddx, __dmul_rn(ddy, ddy));
+            int sx = (int)(st.y & 0xFFFFu), sy = (int)(st.y >> 16);
+            uint32_t map = st.w & 0xFFFFu;  // id_map's MapId (ms.rs:510-511)
+            int cx = sx - o.x, cy = sy - o.y;  // source of the neighbour + (p - n)
+            if (map < (uint32_t)S.n_ex) {
+                DevEx e = S.ex[map];
+                if ((unsigned)cx < (unsigned)e.w && (unsigned)cy < (unsigned)e.h)
+                    valid = e.smask ? (__ldg(e.smask + (size_t)cy * e.w + cx) != 0) : true;
+            }
+            cxy = (uint32_t)cx | ((uint32_t)cy << 16);
+            cpatch = st.z;
+            cmeta = (uint16_t)map;
+        }
+        unsigned b = __ballot_sync(FULL, valid);
+        if (valid) {
+            int pos = ncand + __popc(b & lt);
+            ws.u.c.cxy[pos] = cxy; ws.u.c.cpatch[pos] = cpatch; ws.cmeta[pos] = cmeta;
+        }
+        ncand += __popc(b);
+    }
+    __syncwarp();
+    // ---- weights: mean over the x4-duplicated list, sequential f64 sum (ms.rs:417-423, 1198-1203) ----
+    {
+        double sum = 0.0;
+        for (int j = 0; j < kk; ++j) {
+            double d = ws.d[j];
+            sum = __dadd_rn(sum, d); sum = __dadd_rn(sum, d); sum = __dadd_rn(sum, d); sum = __dadd_rn(sum, d);
+        }
+        double avg = __ddiv_rn(sum, (double)(kk * 4));
+        for (int j = lane; j < kk; j += 32) ws.g[j] = (float)exp(-__ddiv_rn(ws.d[j], avg));
+    }
+    // ---- random candidates (ms.rs:549-599), pre-generated by k_rand_candidates ----
+    for (int r = lane; r < S.m; r += 32) {
+        uint32_t xy = __ldg(rand_xy + r);
+        uint32_t map = __ldg(rand_map + r);
+        int pos = ncand + r;
+        ws.u.c.cxy[pos] = xy;
+        ws.u.c.cpatch[pos] = (xy >> 16) * (uint32_t)S.ex[map].w + (xy & 0xFFFFu);  // ms.rs:577
+        ws.cmeta[pos] = (uint16_t)(map | 0x8000u);
+    }
+    ncand += S.m;
+    __syncwarp();
+    out.ncand = ncand;
+    // ---- find_best_match / better_match (ms.rs:1184-1288): one lane per candidate ----
+    float best = FLT_MAX;
+    int besti = 0;
+    uint32_t fetched = 0;
+    for (int base = 0; base < ncand; base += 32) {
+        int a = base + lane;
+        float s = 0.f;
+        bool ok = false;
+        if (a < ncand) {
+            uint32_t cxy = ws.u.c.cxy[a];
+            uint32_t meta = ws.cmeta[a];
+            int cx = (int)(cxy & 0xFFFFu), cy = (int)(cxy >> 16);
+            int sgn = (meta & 0x8000u) ? -1 : 1;
+            uint32_t map = meta & 0x7FFFu;
+            DevEx e = S.ex[map];
+            DevGuide ge;
+            if (GUIDED) ge = S.exg[map];
+            ok = true;
+            for (int j = 0; j < kk; ++j) {
+                short2 o = ws.off[j];
+                int X = cx + sgn * o.x, Y = cy + sgn * o.y;
+                uint32_t tex = OUTSIDE_RGBA;
+                if ((unsigned)X < (unsigned)e.w && (unsigned)Y < (unsigned)e.h) tex = __ldg(e.px + (size_t)Y * e.w + X);
+                uint32_t dd = __vabsdiffu4(ws.tcol[j], tex);
+                float t = s_lut[dd & 0xFFu];
+                t = __fadd_rn(t, s_lut[(dd >> 8) & 0xFFu]);
+                t = __fadd_rn(t, s_lut[(dd >> 16) & 0xFFu]);
+                t = __fadd_rn(t, s_lut[dd >> 24]);
+                if (GUIDED) {
+                    uint32_t gtex = OUTSIDE_RGBA;
+                    if ((unsigned)X < (unsigned)ge.w && (unsigned)Y < (unsigned)ge.h) gtex = __ldg(ge.px + (size_t)Y * ge.w + X);
+                    uint32_t dg = __vabsdiffu4(ws.gcol[j], gtex);
+                    t = __fadd_rn(t, s_lutg[dg & 0xFFu]);
+                    t = __fadd_rn(t, s_lutg[(dg >> 8) & 0xFFu]);
+                    t = __fadd_rn(t, s_lutg[(dg >> 16) & 0xFFu]);
+                    t = __fadd_rn(t, s_lutg[dg >> 24]);
+                }
+                s = __fadd_rn(s, __fmul_rn(t, ws.g[j]));
+                ++fetched;
+                if (s >= best) { ok = false; break; }  // early-out vs. the best of earlier rounds (ms.rs:1281)
+            }
+        }
+        bool win = ok && (s < best);
+        float ms = win ? s : INFINITY;
+        int ma = a;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float os = __shfl_xor_sync(FULL, ms, o);
+            int oa = __shfl_xor_sync(FULL, ma, o);
+            if (os < ms || (os == ms && oa < ma)) { ms = os; ma = oa; }
+        }
+        if (ms < best) { best = ms; besti = ma; }  // first strict minimum wins (q11)
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) fetched += __shfl_xor_sync(FULL, fetched, o);
+    if (lane == 0 && S.counters) {
+        atomicAdd(S.counters + 0, (unsigned long long)fetched * (GUIDED ? 2ull : 1ull));
+        atomicAdd(S.counters + 1, (unsigned long long)ncand * (unsigned long long)kk * (GUIDED ? 2ull : 1ull));
+        atomicAdd(S.counters + 2, (unsigned long long)ncand);
+        atomicAdd(S.counters + 3, 1ull);
+    }
+    uint32_t bxy = ws.u.c.cxy[besti];
+    out.best = besti;
+    out.bx = (int)(bxy & 0xFFFFu);
+    out.by = (int)(bxy >> 16);
+    out.bmap = (int)(ws.cmeta[besti] & 0x7FFFu);
+    out.bpatch = ws.u.c.cpatch[besti];
+    out.score = best;
+    __syncwarp();
+}
+
+__device__ __forceinline__ void load_luts(const StageDev& S, float* s_lut, float* s_lutg) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { s_lut[i] = S.lut_my[i]; s_lutg[i] = S.lut_guide[i]; }
+    __syncthreads();
+}
+
+struct __align__(16) CtaSmem {
+    float lut[256];
+    float lutg[256];
+    WarpScratch ws[WARPS_PER_CTA];
+};
+
+// ---------------------------------------------------------------------------------------------
+// Round kernel: every pending item whose predecessors have committed is resolved and committed.
+// ---------------------------------------------------------------------------------------------
+template <bool GUIDED>
+__global__ void __launch_bounds__(CTA_THREADS) k_round(StageDev S, PhaseDev P, uint32_t round) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CtaSmem& sm = *reinterpret_cast<CtaSmem*>(smem_raw);
+    load_luts(S, sm.lut, sm.lutg);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpScratch& ws = sm.ws[warp];
+    const uint32_t npend = P.cnt[round & 3];
+    const uint32_t minprev = P.minpend[round & 3];
+    if (blockIdx.x == 0 && threadIdx.x == 0) { P.cnt[(round + 2) & 3] = 0; P.minpend[(round + 2) & 3] = NONE32; }
+    const uint32_t* pend = P.pending[round & 1];
+    uint32_t* next = P.pending[(round + 1) & 1];
+    const uint32_t nwarps = gridDim.x * WARPS_PER_CTA;
+    for (uint32_t w = blockIdx.x * WARPS_PER_CTA + warp; w < npend; w += nwarps) {
+        const uint32_t it = pend[w];
+        const uint32_t pc = P.pred_cnt[it];
+        bool ready = true;
+        if (pc > (uint32_t)PRED_CAP) ready = (it == minprev);  // overflowed list: wait for every lower item
+        else {
+            const uint32_t* pl = P.preds + (size_t)it * PRED_CAP;
+            for (uint32_t base = 0; base < pc; base += 32) {
+                uint32_t j = base + lane;
+                bool nd = false;
+                if (j < pc) nd = *((volatile uint32_t*)(P.done + pl[j])) == 0u;
+                if (__any_sync(FULL, nd)) { ready = false; break; }
+            }
+        }
+        if (!ready) {
+            if (lane == 0) {
+                uint32_t pos = atomicAdd(P.cnt + ((round + 1) & 3), 1u);
+                next[pos] = it;
+                atomicMin(P.minpend + ((round + 1) & 3), it);
+            }
+            continue;
+        }
+        __threadfence();  // acquire: predecessors' commits are visible below
+        const uint32_t flat = P.item_pixel[it];
+        const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
+        const uint32_t si = P.stage_base + it;
+        ItemOut o;
+        resolve_item<GUIDED>(S, ws, sm.lut, sm.lutg, lane, x, y, P.item_R2[it], P.rand_xy + (size_t)si * S.m,
+                             P.rand_map + (size_t)si * S.m, o);
+        if (lane == 0) {
+            if (o.kk > 0) {  // ms.rs:334-377 update
+                DevEx e = S.ex[o.bmap];
+                uint32_t col = __ldg(e.px + (size_t)o.by * e.w + o.bx);
+                S.state[flat] = make_uint4(col, (uint32_t)o.bx | ((uint32_t)o.by << 16), o.bpatch,
+                                           (uint32_t)o.bmap | ((uint32_t)o.bmap << 16));
+                if (P.is_new) {
+                    S.score[flat] = o.score;
+                    mask_insert(S, x, y, S.tiling != 0);
+                }
+            }
+            if (P.tr_best) {
+                size_t ti = (size_t)(P.trace_base + si);
+                P.tr_best[ti] = o.kk > 0 ? o.best : -1;
+                P.tr_ncand[ti] = o.ncand; P.tr_nneigh[ti] = o.kk; P.tr_score[ti] = o.score;
+            }
+            __threadfence();  // release
+            *((volatile uint32_t*)(P.done + it)) = 1u;
+        }
+        __syncwarp();
+    }
+}
+
+// Frozen-snapshot evaluation (test harness): resolve without committing.
+template <bool GUIDED>
+__global__ void __launch_bounds__(CTA_THREADS) k_eval_items(StageDev S, uint32_t n, const uint32_t* pixel_flat,
+                                                             const uint32_t* rand_xy, const uint8_t* rand_map,
+                                                             int32_t* neigh, int32_t* res, float* score) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CtaSmem& sm = *reinterpret_cast<CtaSmem*>(smem_raw);
+    load_luts(S, sm.lut, sm.lutg);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpScratch& ws = sm.ws[warp];
+    const uint32_t nwarps = gridDim.x * WARPS_PER_CTA;
+    for (uint32_t it = blockIdx.x * WARPS_PER_CTA + warp; it < n; it += nwarps) {
+        const uint32_t flat = pixel_flat[it];
+        const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
+        ItemOut o;
+        resolve_item<GUIDED>(S, ws, sm.lut, sm.lutg, lane, x, y, R2_INF, rand_xy + (size_t)it * S.m,
+                             rand_map + (size_t)it * S.m, o);
+        int32_t* no = neigh + (size_t)it * 2 * S.k;
+        for (int j = lane; j < S.k; j += 32) {
+            if (j < o.kk) { short2 of = ws.off[j]; no[2 * j] = x + of.x; no[2 * j + 1] = y + of.y; }
+            else { no[2 * j] = INT32_MIN; no[2 * j + 1] = INT32_MIN; }
+        }
+        if (lane == 0) {
+            int32_t* ro = res + (size_t)it * 8;
+            ro[0] = o.kk; ro[1] = o.ncand; ro[2] = o.best; ro[3] = o.bx; ro[4] = o.by; ro[5] = o.bmap;
+            ro[6] = (int32_t)o.bpatch; ro[7] = o.kk == 0 ? 1 : 0;
+            score[it] = o.score;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dependency analysis
+// ---------------------------------------------------------------------------------------------
+// Conflict radius of every item: distance^2 of its k-th nearest resolved point at phase start.
+__global__ void __launch_bounds__(CTA_THREADS) k_radius(StageDev S, PhaseDev P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CtaSmem& sm = *reinterpret_cast<CtaSmem*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpScratch& ws = sm.ws[warp];
+    const uint32_t nwarps = gridDim.x * WARPS_PER_CTA;
+    for (uint32_t it = blockIdx.x * WARPS_PER_CTA + warp; it < P.n; it += nwarps) {
+        const uint32_t flat = P.item_pixel[it];
+        const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
+        uint32_t r2;
+        knn_search(S, ws, lane, x, y, R2_INF, &r2);
+        if (lane == 0) {
+            P.item_R2[it] = r2;
+            P.pred_cnt[it] = 0;
+            P.done[it] = 0;
+            P.pending[0][it] = it;
+            P.pmap[flat] = it;
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void k_pmap_clear(PhaseDev P) {
+    uint32_t it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it < P.n) P.pmap[P.item_pixel[it]] = NONE32;
+}
+
+__device__ __forceinline__ void pred_visit(const StageDev& S, const PhaseDev& P, uint32_t it, uint32_t R2i, int qx, int qy, uint32_t D) {
+    if (S.tiling) { qx = imod(qx, S.W); qy = imod(qy, S.H); }  // conservative: treat the canvas as a torus
+    else if ((unsigned)qx >= (unsigned)S.W || (unsigned)qy >= (unsigned)S.H) return;
+    uint32_t j = P.pmap[(size_t)qy * S.W + qx];
+    if (j == NONE32 || j == it) return;
+    if (j < it) {
+        uint32_t slot = atomicAdd(P.pred_cnt + it, 1u);
+        if (slot < (uint32_t)PRED_CAP) P.preds[(size_t)it * PRED_CAP + slot] = j;
+    } else if (D > P.item_R2[j]) {  // j does not see `it` from its side: register the edge for it
+        uint32_t slot = atomicAdd(P.pred_cnt + j, 1u);
+        if (slot < (uint32_t)PRED_CAP) P.preds[(size_t)j * PRED_CAP + slot] = it;
+    }
+    (void)R2i;
+}
+
+// Edges i -> j (i < j) for every pair with dist^2 <= max(R_i^2, R_j^2), found by scanning the dense
+// pending-index map over each item's own disc.
+__global__ void __launch_bounds__(CTA_THREADS) k_preds_scan(StageDev S, PhaseDev P) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nwarps = gridDim.x * WARPS_PER_CTA;
+    for (uint32_t it = blockIdx.x * WARPS_PER_CTA + warp; it < P.n; it += nwarps) {
+        const uint32_t flat = P.item_pixel[it];
+        const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
+        const uint32_t R2 = P.item_R2[it];
+        if (R2 <= (uint32_t)S.RT2) {
+            int limit = (int)__ldg(S.cntLE + R2);
+            for (int idx = lane; idx < limit; idx += 32) {
+                short2 o = __ldg(S.spiral + idx);
+                pred_visit(S, P, it, R2, x + o.x, y + o.y, (uint32_t)(o.x * o.x + o.y * o.y));
+            }
+        } else {
+            int rmaxx = S.tiling ? S.W / 2 : S.W, rmaxy = S.tiling ? S.H / 2 : S.H;
+            int r = isqrt_u32(R2);
+            int ry = min(r, rmaxy);
+            for (int dy = -ry; dy <= ry; ++dy) {
+                int w = min(isqrt_u32(R2 - (uint32_t)(dy * dy)), rmaxx);
+                for (int dx = -w + lane; dx <= w; dx += 32)
+                    pred_visit(S, P, it, R2, x + dx, y + dy, (uint32_t)(dx * dx + dy * dy));
+            }
+        }
+    }
+}
+
+// Small phases: all-pairs test.
+__global__ void __launch_bounds__(CTA_THREADS) k_preds_pairs(StageDev S, PhaseDev P) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint32_t nwarps = gridDim.x * WARPS_PER_CTA;
+    for (uint32_t it = blockIdx.x * WARPS_PER_CTA + warp; it < P.n; it += nwarps) {
+        const uint32_t flat = P.item_pixel[it];
+        const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
+        const uint32_t R2 = P.item_R2[it];
+        uint32_t cnt = 0;
+        for (uint32_t base = 0; base < it; base += 32) {
+            uint32_t j = base + lane;
+            bool edge = false;
+            if (j < it) {
+                uint32_t fj = P.item_pixel[j];
+                int dx = abs((int)(fj % (uint32_t)S.W) - x), dy = abs((int)(fj / (uint32_t)S.W) - y);
+                if (S.tiling) { dx = min(dx, S.W - dx); dy = min(dy, S.H - dy); }
+                unsigned long long D = (unsigned long long)dx * dx + (unsigned long long)dy * dy;
+                uint32_t Rm = max(R2, P.item_R2[j]);
+                edge = (Rm == R2_INF) || (D <= (unsigned long long)Rm);
+            }
+            unsigned b = __ballot_sync(FULL, edge);
+            if (edge) {
+                uint32_t slot = cnt + __popc(b & lt);
+                if (slot < (uint32_t)PRED_CAP) P.preds[(size_t)it * PRED_CAP + slot] = j;
+            }
+            cnt += __popc(b);
+        }
+        if (lane == 0) P.pred_cnt[it] = cnt;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Random candidates (ms.rs:549-599): rng = Pcg32::seed_from_u64(loop_seed + 1); per candidate one usize draw
+// for the map, then (x, y) u32 draws until the sampling mask accepts.  One thread per work item; the
+// stream depends only on (stage seed, work-item index) so a whole stage is generated ahead of the rounds.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_rand_candidates(const DevEx* ex, int n_ex, int m, uint64_t seed_base, uint32_t n,
+                                  uint32_t* rand_xy, uint8_t* rand_map) {
+    uint32_t it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= n) return;
+    Pcg32 rng = Pcg32::seed_from_u64(seed_base + (uint64_t)it);
+    uint32_t* oxy = rand_xy + (size_t)it * m;
+    uint8_t* om = rand_map + (size_t)it * m;
+    for (int r = 0; r < m; ++r) {
+        uint32_t map = (uint32_t)rng.gen_range_usize((uint64_t)n_ex);
+        DevEx e = ex[map];
+        uint32_t rx, ry;
+        for (;;) {
+            rx = rng.gen_range_u32((uint32_t)e.w);
+            ry = rng.gen_range_u32((uint32_t)e.h);
+            if (!e.smask || e.smask[(size_t)ry * e.w + rx] != 0) break;
+        }
+        oxy[r] = rx | (ry << 16);
+        om[r] = (uint8_t)map;
+    }
+}
+
+// pick_random_unresolved's index draw (ms.rs:386): idx[t] = Pcg32::seed_from_u64(seed_base + t).gen_range(0..len0 - t)
+__global__ void k_pick_indices(uint64_t seed_base, uint64_t len0, uint32_t n, uint32_t* idx) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    idx[t] = (uint32_t)Pcg32::seed_from_u64(seed_base + (uint64_t)t).gen_range_usize(len0 - (uint64_t)t);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small state kernels
+// ---------------------------------------------------------------------------------------------
+// next_pyramid_level, ms.rs:687-700: recolour every resolved pixel from the new level through coord_map
+__global__ void k_recolour(StageDev S) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (uint32_t)(S.W * S.H)) return;
+    int x = (int)(p % (uint32_t)S.W), y = (int)(p / (uint32_t)S.W);
+    if (!mask_test(S, x, y)) return;
+    uint4 st = S.state[p];
+    uint32_t map = st.w >> 16;  // coord_map's MapId
+    if (map >= (uint32_t)S.n_ex) return;
+    DevEx e = S.ex[map];
+    int sx = (int)(st.y & 0xFFFFu), sy = (int)(st.y >> 16);
+    if (sx < e.w && sy < e.h) S.state[p].x = e.px[(size_t)sy * e.w + sx];
+}
+
+// (re)insert resolved pixels into the mask with their tiling mirrors (ms.rs:764-778)
+__global__ void k_mask_insert_flat(StageDev S, const uint32_t* flat, uint32_t n, int mirrors) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    mask_insert(S, (int)(flat[i] % (uint32_t)S.W), (int)(flat[i] / (uint32_t)S.W), mirrors != 0);
+}
+__global__ void k_mask_insert_points(StageDev S, const int32_t* xy, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    mask_set(S, xy[2 * i], xy[2 * i + 1]);
+}
+
+// resolve_at_random (ms.rs:447-475) with host-drawn coordinates: items = [flat, x, y, map]
+__global__ void k_commit_fixed(StageDev S, const DevEx* imgs, const uint32_t* items, uint32_t n, int insert) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t flat = items[4 * i], sx = items[4 * i + 1], sy = items[4 * i + 2], map = items[4 * i + 3];
+    DevEx e = imgs[map];
+    S.state[flat] = make_uint4(e.px[(size_t)sy * e.w + sx], sx | (sy << 16), flat, map | (map << 16));
+    S.score[flat] = 0.f;
+    if (insert) mask_set(S, (int)(flat % (uint32_t)S.W), (int)(flat / (uint32_t)S.W));  // is_tiling_mode = false (ms.rs:473)
+}
+
+__global__ void k_state_init(uint4* state, float* score, uint32_t n) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    state[p] = make_uint4(0, 0, 0, 0);
+    score[p] = 0.f;
+}
+// new_from_inpaint, ms.rs:265-293
+__global__ void k_state_init_inpaint(uint4* state, float* score, const uint32_t* mask_rgba, const uint32_t* color, int W,
+                                     uint32_t n, uint32_t example_index) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    bool locked = (mask_rgba[p] & 0xFFu) == 255u;
+    uint32_t x = p % (uint32_t)W, y = p / (uint32_t)W;
+    state[p] = locked ? make_uint4(color[p], x | (y << 16), 0u, example_index << 16) : make_uint4(color[p], 0, 0, 0);
+    score[p] = 0.f;
+}
+__global__ void k_unpack_state(const uint4* state, uint32_t n, uint32_t* color, uint32_t* coord, uint32_t* idm) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint4 st = state[p];
+    if (color) color[p] = st.x;
+    if (coord) { coord[3 * p] = st.y & 0xFFFFu; coord[3 * p + 1] = st.y >> 16; coord[3 * p + 2] = st.w >> 16; }
+    if (idm) { idm[2 * p] = st.z; idm[2 * p + 1] = st.w & 0xFFFFu; }
+}
+__global__ void k_pack_state(uint4* state, uint32_t n, const uint32_t* color, const uint32_t* coord, const uint32_t* idm) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    state[p] = make_uint4(color[p], coord[3 * p] | (coord[3 * p + 1] << 16), idm[2 * p], idm[2 * p + 1] | (coord[3 * p + 2] << 16));
+}
+__global__ void k_gather_scores(const float* score, const uint32_t* flat, uint32_t n, float* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = score[flat[i]];
+}
+__global__ void k_scatter_scores(float* score, const uint32_t* flat, const float* in, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) score[flat[i]] = in[i];
+}
+
+// get_uncertainty_map (ms.rs:635-653) and get_id_maps (ms.rs:605-633)
+__global__ void k_uncertainty(StageDev S, uint32_t* out) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (uint32_t)(S.W * S.H)) return;
+    uint32_t v = 0;
+    if (mask_test(S, (int)(p % (uint32_t)S.W), (int)(p / (uint32_t)S.W))) {
+        float f = __fmul_rn(fminf(S.score[p], 1.0f), 255.0f);
+        uint32_t s = (uint32_t)(f < 0.f ? 0.f : (f > 255.f ? 255.f : f));  // `as u8` saturates, NaN -> 0
+        if (!(f == f)) s = 0;
+        v = s | ((255u - s) << 8) | 0xFF000000u;
+    }
+    out[p] = v;
+}
+__global__ void k_id_maps(const uint4* state, uint32_t n, uint32_t* patch_rgba, uint32_t* map_rgba) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint4 st = state[p];
+    uint32_t pid = st.z, mid = st.w & 0xFFFFu;
+    uint32_t a0 = Pcg32::seed_from_u64((uint64_t)pid).gen_range_u8(255);
+    uint32_t a1 = Pcg32::seed_from_u64((uint64_t)(uint32_t)(pid * 5u + 21u)).gen_range_u8(255);
+    uint32_t a2 = Pcg32::seed_from_u64((uint64_t)(pid / 4u + 12u)).gen_range_u8(255);
+    patch_rgba[p] = a0 | (a1 << 8) | (a2 << 16) | 0xFF000000u;
+    uint32_t b0 = Pcg32::seed_from_u64((uint64_t)mid * 200ull).gen_range_u8(255);
+    uint32_t b1 = Pcg32::seed_from_u64((uint64_t)(uint32_t)(mid * 5u + 341u)).gen_range_u8(255);
+    uint32_t b2 = Pcg32::seed_from_u64((uint64_t)(uint32_t)(mid * 1200u - 35412u)).gen_range_u8(255);  // wraps like release Rust
+    map_rgba[p] = b0 | (b1 << 8) | (b2 << 16) | 0xFF000000u;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: separable resampling (image 0.23.12 imageops::resize): vertical pass then horizontal pass,
+// u8 intermediate, per-output-index tap tables built on the host (same libm as the reference build).
+// ---------------------------------------------------------------------------------------------
+struct TapTable {
+    const int* left;     // [out]
+    const int* count;    // [out]
+    const int* offset;   // [out] into weights
+    const float* sum;    // [out]
+    const float* weights;
+};
+
+__device__ __forceinline__ uint32_t resample_finish(float a0, float a1, float a2, float a3, float sum) {
+    float v[4] = {__fdiv_rn(a0, sum), __fdiv_rn(a1, sum), __fdiv_rn(a2, sum), __fdiv_rn(a3, sum)};
+    uint32_t r = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float f = v[c] < 0.f ? 0.f : (v[c] > 255.f ? 255.f : v[c]);
+        r |= ((uint32_t)f & 0xFFu) << (8 * c);  // truncating cast
+    }
+    return r;
+}
+
+__global__ void k_resample_v(const uint32_t* __restrict__ src, int w, int h, uint32_t* __restrict__ dst, int nh, TapTable t) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
+    if (x >= w || oy >= nh) return;
+    (void)h;
+    int left = t.left[oy], n = t.count[oy];
+    const float* wt = t.weights + t.offset[oy];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int i = 0; i < n; ++i) {
+        uint32_t p = __ldg(src + (size_t)(left + i) * w + x);
+        float wv = wt[i];
+        a0 = __fadd_rn(a0, __fmul_rn((float)(p & 0xFFu), wv));
+        a1 = __fadd_rn(a1, __fmul_rn((float)((p >> 8) & 0xFFu), wv));
+        a2 = __fadd_rn(a2, __fmul_rn((float)((p >> 16) & 0xFFu), wv));
+        a3 = __fadd_rn(a3, __fmul_rn((float)(p >> 24), wv));
+    }
+    dst[(size_t)oy * w + x] = resample_finish(a0, a1, a2, a3, t.sum[oy]);
+}
+
+__global__ void k_resample_h(const uint32_t* __restrict__ src, int w, int h, uint32_t* __restrict__ dst, int nw, TapTable t) {
+    int ox = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (ox >= nw || y >= h) return;
+    int left = t.left[ox], n = t.count[ox];
+    const float* wt = t.weights + t.offset[ox];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const uint32_t* row = src + (size_t)y * w + left;
+    for (int i = 0; i < n; ++i) {
+        uint32_t p = __ldg(row + i);
+        float wv = wt[i];
+        a0 = __fadd_rn(a0, __fmul_rn((float)(p & 0xFFu), wv));
+        a1 = __fadd_rn(a1, __fmul_rn((float)((p >> 8) & 0xFFu), wv));
+        a2 = __fadd_rn(a2, __fmul_rn((float)((p >> 16) & 0xFFu), wv));
+        a3 = __fadd_rn(a3, __fmul_rn((float)(p >> 24), wv));
+    }
+    dst[(size_t)y * nw + ox] = resample_finish(a0, a1, a2, a3, t.sum[ox]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gather microbenchmark: the scoring kernel's access pattern without the arithmetic.  Every lane
+// owns a random window origin and walks `steps` pseudo-neighbour offsets inside a 13x13 window.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_gather_bench(const uint32_t* __restrict__ img, int w, int h, int steps, uint32_t seed, uint32_t* sink) {
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t s = tid * 2654435761u + seed;
+    uint32_t acc = 0;
+    for (int rep = 0; rep < 8; ++rep) {
+        s = s * 1664525u + 1013904223u;
+        int cx = 8 + (int)((s >> 8) % (uint32_t)(w - 16)), cy = 8 + (int)((s >> 4) % (uint32_t)(h - 16));
+        uint32_t o = s;
+        for (int j = 0; j < steps; ++j) {
+            o = o * 1664525u + 1013904223u;
+            int X = cx + (int)((o >> 10) % 13u) - 6, Y = cy + (int)((o >> 20) % 13u) - 6;
+            acc += __ldg(img + (size_t)Y * w + X);
+        }
+    }
+    if (acc == 0x12345678u) sink[0] = acc;
+}
+__global__ void k_gather_bench_tex(cudaTextureObject_t tex, int w, int h, int steps, uint32_t seed, uint32_t* sink) {
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t s = tid * 2654435761u + seed;
+    uint32_t acc = 0;
+    for (int rep = 0; rep < 8; ++rep) {
+        s = s * 1664525u + 1013904223u;
+        int cx = 8 + (int)((s >> 8) % (uint32_t)(w - 16)), cy = 8 + (int)((s >> 4) % (uint32_t)(h - 16));
+        uint32_t o = s;
+        for (int j = 0; j < steps; ++j) {
+            o = o * 1664525u + 1013904223u;
+            int X = cx + (int)((o >> 10) % 13u) - 6, Y = cy + (int)((o >> 20) % 13u) - 6;
+            uchar4 v = tex2D<uchar4>(tex, (float)X + 0.5f, (float)Y + 0.5f);
+            acc += v.x + v.y + v.z + v.w;
+        }
+    }
+    if (acc == 0x12345678u) sink[0] = acc;
+}
+
+}  // namespace tsb
