@@ -1,0 +1,256 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the texture-synthesis hot path on B200.
+
+One "step" = one complete `Session::run()`-equivalent (reference lib/src/session.rs:37-66: Generator::resolve
+over all backtrack stages) of a 2048x2048 output from a synthetic 512x512 example with default parameters
+(k=50, m=50, cauchy 1.0, backtrack 0.5 x 5 stages, seed 0) -- the configuration BASELINE.json's metric is
+quoted on.  Metric: output pixels per second.
+
+  python bench.py --gpus 1 --steps 3 --warmup 3                     (our arm: CUDA path through the C ABI)
+  python bench.py --impl reference --gpus 1 --steps 1 --warmup 0    (CPU arm: the oracle port on all host cores)
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N   (one independent session per GPU)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+OUT, EX = 2048, 512
+WORKLOAD = f"{OUT}x{OUT} output from synthetic {EX}x{EX} example (synth_texture seed 1), k=50 m=50 cauchy=1.0 backtrack=0.5x5 seed=0"
+CPU_SAMPLE_OUT = 512  # bounded CPU sample: same example and parameters, 512x512 output
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], False
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([c.strip() for c in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for i, nm in enumerate(names):
+                if len(r) > 4 + i and r[4 + i].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def build_inputs():
+    from texture_synthesis_b200.synth import synth_texture
+    ex = synth_texture(EX, EX, 1)
+    return ex
+
+
+def cpu_oracle_run(ex, out, threads):
+    """The reference's CPU path as restated by the oracle, timed around the equivalent of Session::run()."""
+    from oracle import ts_oracle as O
+    pyr = O.pyramid_build(ex, 5)
+    g = O.Generator(out, out)
+    g.set_examples([pyr])
+    secs = g.resolve(O.make_params(seed=0, threads=threads))
+    return out * out / secs, secs
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    ex = build_inputs()
+    cores = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        cpu_oracle_run(ex, 128, cores)
+    vals, secs = [], []
+    for _ in range(max(1, args.steps)):
+        v, s = cpu_oracle_run(ex, CPU_SAMPLE_OUT, cores)
+        vals.append(v)
+        secs.append(s)
+    v = float(np.mean(vals))
+    sample = f"{CPU_SAMPLE_OUT}x{CPU_SAMPLE_OUT} output (same example/parameters) per step; px/s is size-independent to first order"
+    line = {
+        "impl": "reference", "metric": "output px/s", "value": v, "unit": "px/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "C++ restatement of lib/src/ms.rs (oracle port; no Rust toolchain in the image), "
+                   "reference threading model: atomic work counter, serial while redo_count < 1000"},
+        "cpu_baseline": {"value": v, "unit": "px/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "px/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from texture_synthesis_b200 import capi
+    if not torch.cuda.is_available() or capi.device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist_.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ex = build_inputs()
+    pyr = capi.pyramid_build(ex, 5)            # K1 (img_pyramid.rs:20-37) on the GPU; outside the timed region like Session::build()
+    pinned = torch.empty(pyr.shape, dtype=torch.uint8, pin_memory=True)
+    pinned.numpy()[...] = pyr
+    pyr_pinned = pinned.numpy()
+    params = capi.make_params(seed=0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    g = capi.Generator(OUT, OUT, device=local_rank)
+    g.upload_inputs([pyr])
+    out_host = torch.empty((OUT, OUT, 4), dtype=torch.uint8, pin_memory=True).numpy()
+
+    def step_resident():
+        g.reset()
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        g.resolve_resident(params)
+        return g.stats()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    stats = []
+    with ClockSampler(local_rank) as clk:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            stats.append(step_resident())
+        barrier()
+        t1 = time.perf_counter()
+    # device-timed step: CUDA events recorded by the library on its own stream around the whole call
+    ms = np.array([s["gpu_ms_total"] for s in stats])
+    t_local = float(ms.sum()) * 1e-3
+    if dist is not None:
+        tt = torch.tensor([t_local], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_max = float(tt.item())
+    else:
+        t_max = t_local
+    value = world * args.steps * OUT * OUT / t_max
+
+    # end to end through the public C-ABI call with HOST buffers: H2D of the example pyramid and D2H of the result inside
+    e2e_t = []
+    for _ in range(max(1, args.steps)):
+        g.reset()
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        a = time.perf_counter()
+        g.resolve(params, [pyr_pinned])
+        capi._check(g.L.tsb_generator_read_color(g.h, out_host.ctypes.data))
+        e2e_t.append(time.perf_counter() - a)
+    e2e_local = float(np.sum(e2e_t))
+    if dist is not None:
+        tt = torch.tensor([e2e_local], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_local = float(tt.item())
+    e2e_value = world * len(e2e_t) * OUT * OUT / e2e_local
+
+    if rank != 0:
+        return
+    st = stats[-1]
+    peaks, peak_src = measured_peaks()
+    # dominant kernel: k_round (K2+K3+K4+K5 fused).  Algorithmic bytes per launch set = texels actually gathered x 4 B
+    # + per pixel-resolution k*4 B target pattern + k*16 B neighbour state + 16 B written.
+    k = 50
+    alg_bytes = st["texels_fetched"] * 4 + st["work_items"] * (k * 4 + k * 16 + 16)
+    kern_s = st["gpu_ms_resolve"] * 1e-3
+    achieved = alg_bytes / kern_s / 1e9
+    try:
+        l2_gbs, l2_gps = capi.microbench_gather(EX * EX * 4, 0, 20)
+    except Exception:
+        l2_gbs, l2_gps = None, None
+    cores = os.cpu_count() or 1
+    cpu_v, cpu_s = cpu_oracle_run(ex, CPU_SAMPLE_OUT, cores) if world == 1 else (None, None)
+    line = {
+        "metric": "output px/s", "value": value, "unit": "px/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": float(ms.mean()), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "parallelism": "1 session per GPU (independent sessions, no collective)" if world > 1 else "1 GPU",
+                   "l2": "256 MiB flush buffer written between timed iterations", "schedule": "exact 1-thread order (dependency rounds)",
+                   "pixel_resolutions_per_step": int(st["work_items"]), "candidate_evals_per_s": st["candidates"] / (float(ms.mean()) * 1e-3),
+                   "host_wall_ms_per_step": (t1 - t0) * 1e3 / args.steps},
+        "clocks": clk.summary(),
+        "e2e": {"value": e2e_value, "unit": "px/s", "h2d_bytes_per_step": int(pyr.nbytes), "d2h_bytes_per_step": int(out_host.nbytes)},
+        "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                     "traffic": None, "peak_source": peak_src, "kernel": "k_round", "kernel_ms_per_step": st["gpu_ms_resolve"],
+                     "texels_fetched": int(st["texels_fetched"]), "texels_nominal": int(st["texels_nominal"]),
+                     "l2_gather": {"note": "example level is L2 resident: own microbenchmark of random 4-byte gathers over a 1 MiB window",
+                                   "peak_gathers_per_s": l2_gps, "peak_useful_gbs": l2_gbs,
+                                   "achieved_gathers_per_s": st["texels_fetched"] / kern_s,
+                                   "frac": (st["texels_fetched"] / kern_s / l2_gps) if l2_gps else None}},
+    }
+    if cpu_v is not None:
+        line["cpu_baseline"] = {"value": cpu_v, "unit": "px/s", "cores": cores, "kind": "port",
+                                "sample": f"{CPU_SAMPLE_OUT}x{CPU_SAMPLE_OUT} output, same example and parameters, {cpu_s:.1f} s"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

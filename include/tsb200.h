@@ -111,6 +111,7 @@ typedef struct {
     double gpu_ms_other;        /* candidate pre-generation, recolour, uploads */
     double host_ms_schedule;    /* host time spent planning the pixel order */
     double wall_ms_total;       /* wall time of the call */
+    double gpu_ms_total;        /* CUDA-event time from the first to the last operation of the call on its stream */
 } tsb_stats;
 
 enum { TSB_FILTER_TRIANGLE = 0, TSB_FILTER_CATMULLROM = 1, TSB_FILTER_GAUSSIAN = 2 };

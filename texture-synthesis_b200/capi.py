@@ -58,7 +58,8 @@ class Stats(C.Structure):
     _fields_ = [("work_items", C.c_uint64), ("candidates", C.c_uint64), ("texels_fetched", C.c_uint64),
                 ("texels_nominal", C.c_uint64), ("rounds", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("phases", C.c_uint64), ("gpu_ms_resolve", C.c_double), ("gpu_ms_analysis", C.c_double),
-                ("gpu_ms_other", C.c_double), ("host_ms_schedule", C.c_double), ("wall_ms_total", C.c_double)]
+                ("gpu_ms_other", C.c_double), ("host_ms_schedule", C.c_double), ("wall_ms_total", C.c_double),
+                ("gpu_ms_total", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

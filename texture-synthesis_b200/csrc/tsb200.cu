@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -217,9 +218,9 @@ struct tsb_generator {
     // device state
     DevBuf<uint4> d_state;
     DevBuf<float> d_score;
-    DevBuf<uint32_t> d_mask;
+    DevBuf<uint32_t> d_mask, d_mask1;
     DevBuf<uint32_t> d_inp_mask, d_inp_color;
-    int mx = 0, my = 0, wpr = 0, mrows = 0;
+    int mx = 0, my = 0, wpr = 0, mrows = 0, wpr1 = 0;
     DevBuf<short2> d_spiral;
     DevBuf<uint32_t> d_cntLE;
     int spiralN = 0, RT2 = 0;
@@ -272,7 +273,8 @@ int set_device(tsb_generator* g) { CU(cudaSetDevice(g->device)); return 0; }
 
 void fill_stage_geometry(tsb_generator* g, StageDev& S, bool tiling) {
     memset(&S, 0, sizeof(S));
-    S.state = g->d_state.p; S.mask = g->d_mask.p; S.score = g->d_score.p;
+    S.state = g->d_state.p; S.mask = g->d_mask.p; S.mask1 = g->d_mask1.p; S.score = g->d_score.p;
+    S.wpr1 = g->wpr1; S.n_points_max = 0xFFFFFFFFu;
     S.W = g->W; S.H = g->H;
     S.mx = g->mx; S.my = g->my; S.wpr = g->wpr; S.mrows = g->mrows;
     S.tiling = tiling ? 1 : 0;
@@ -292,6 +294,7 @@ int init_state(tsb_generator* g) {
         k_state_init<<<(n + 255) / 256, 256, 0, s>>>(g->d_state.p, g->d_score.p, n);
     CU(cudaGetLastError());
     CU(cudaMemsetAsync(g->d_mask.p, 0, (size_t)g->wpr * g->mrows * 4, s));
+    CU(cudaMemsetAsync(g->d_mask1.p, 0, (size_t)g->wpr1 * g->mrows * 4, s));
     g->unresolved = g->unresolved0;
     g->resolved_order = g->resolved0;
     g->locked = g->inpaint_locked = g->resolved0.size();
@@ -428,8 +431,8 @@ uint32_t r2_hint_for(const tsb_generator* g, size_t resolved_now, uint32_t k) {
 }
 
 template <typename K, typename... Args>
-int launch_resolve_kernel(tsb_generator* g, K kernel, int grid, Args... args) {
-    kernel<<<grid, CTA_THREADS, sizeof(CtaSmem), g->stream>>>(args...);
+int launch_resolve_kernel(tsb_generator* g, K kernel, int grid, size_t smem, Args... args) {
+    kernel<<<grid, CTA_THREADS, smem, g->stream>>>(args...);
     CU(cudaGetLastError());
     g->stats.kernel_launches++;
     return 0;
@@ -467,7 +470,7 @@ int run_phase(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, bool
     memcpy(g->h_ctrl, ctrl, sizeof(ctrl));
     CU(cudaMemcpyAsync(g->d_ctrl.p, g->h_ctrl, sizeof(ctrl), cudaMemcpyHostToDevice, s));
     if (analyze) {
-        TRY(launch_resolve_kernel(g, k_radius, grid_for(g, n), S, P));
+        TRY(launch_resolve_kernel(g, k_radius, grid_for(g, n), sizeof(CtaSmem), S, P));
         if (n <= PAIR_MAX) k_preds_pairs<<<grid_for(g, n), CTA_THREADS, 0, s>>>(S, P);
         else k_preds_scan<<<grid_for(g, n), CTA_THREADS, 0, s>>>(S, P);
         CU(cudaGetLastError());
@@ -485,8 +488,8 @@ int run_phase(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, bool
     while (known > 0) {
         int grid = grid_for(g, known);
         for (int r = 0; r < ROUNDS_PER_SYNC; ++r) {
-            if (g->guided) TRY(launch_resolve_kernel(g, k_round<true>, grid, S, P, round));
-            else TRY(launch_resolve_kernel(g, k_round<false>, grid, S, P, round));
+            if (g->guided) TRY(launch_resolve_kernel(g, k_round<true>, grid, sizeof(RoundSmem), S, P, round));
+            else TRY(launch_resolve_kernel(g, k_round<false>, grid, sizeof(RoundSmem), S, P, round));
             ++round;
             g->stats.rounds++;
             if (n == 1) break;
@@ -508,6 +511,9 @@ int run_phase(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, bool
     cudaEventElapsedTime(&mr, e1, e2);
     g->stats.gpu_ms_analysis += ma;
     g->stats.gpu_ms_resolve += mr;
+    if (getenv("TSB_DEBUG_PHASES"))
+        fprintf(stderr, "[tsb] phase i0=%u n=%u new=%d analyze=%d rounds=%u analysis_ms=%.3f resolve_ms=%.3f\n", i0, n, (int)is_new,
+                (int)analyze, round, ma, mr);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     return 0;
 }
@@ -519,6 +525,9 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
     const double t_start = now_ms();
     cudaStream_t s = g->stream;
     memset(&g->stats, 0, sizeof(g->stats));
+    cudaEvent_t ev_begin, ev_end;
+    CU(cudaEventCreate(&ev_begin)); CU(cudaEventCreate(&ev_end));
+    CU(cudaEventRecord(ev_begin, s));
     const bool tiling = prm->tiling_mode != 0;
     const uint32_t k = prm->nearest_neighbors;
     const int m = (int)prm->random_sample_locations;
@@ -602,8 +611,8 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
     TRY(g->d_rand_xy.ensure(max_stage_items * (size_t)m));
     TRY(g->d_rand_map.ensure(max_stage_items * (size_t)m));
     TRY(g->d_luts.ensure(512));
-    TRY(g->d_counters.ensure(4));
-    CU(cudaMemsetAsync(g->d_counters.p, 0, 4 * sizeof(unsigned long long), s));
+    TRY(g->d_counters.ensure(ST_COUNT));
+    CU(cudaMemsetAsync(g->d_counters.p, 0, ST_COUNT * sizeof(unsigned long long), s));
     if (!g->pmap_ready) {
         TRY(g->d_pmap.ensure(npix));
         CU(cudaMemsetAsync(g->d_pmap.p, 0xFF, npix * 4, s));
@@ -621,6 +630,7 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
     fill_stage_geometry(g, S, tiling);
     S.counters = g->d_counters.p;
     CU(cudaMemsetAsync(g->d_mask.p, 0, (size_t)g->wpr * g->mrows * 4, s));
+    CU(cudaMemsetAsync(g->d_mask1.p, 0, (size_t)g->wpr1 * g->mrows * 4, s));
     if (g->have_loaded_points) {
         TRY(g->d_tmp_u32.upload((const uint32_t*)g->loaded_points.data(), g->loaded_points.size(), s));
         uint32_t np = (uint32_t)(g->loaded_points.size() / 2);
@@ -664,6 +674,7 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
         // ---- redo phase: the resolved set is static, radii are exact ----
         if (sp.n_redo) {
             S.r2_hint = r2_hint_for(g, resolved_now, k);
+            S.n_points_max = (uint32_t)std::min<size_t>(3 * resolved_now, 0xFFFFFFFFull);
             TRY(run_phase(g, S, 0, (uint32_t)sp.n_redo, false, true, trace_base));
         }
         // ---- new pixels, in epochs over which the resolved count at most doubles ----
@@ -689,6 +700,7 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
             size_t base = resolved_now - g->inpaint_locked;
             size_t n_e = base < 2 * (size_t)k ? 1 : std::min(n_items - cur, base);
             S.r2_hint = r2_hint_for(g, resolved_now, k);
+            S.n_points_max = (uint32_t)std::min<size_t>(3 * (resolved_now + n_e), 0xFFFFFFFFull);
             TRY(run_phase(g, S, (uint32_t)cur, (uint32_t)n_e, true, n_e > 1, trace_base));
             cur += n_e; resolved_now += n_e;
             if (cb) {
@@ -711,13 +723,24 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
         trace_base += n_items;
     }
     g->trace_n = g->trace ? trace_base : 0;
-    unsigned long long cnt[4];
+    unsigned long long cnt[ST_COUNT];
     CU(cudaMemcpyAsync(cnt, g->d_counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    g->stats.texels_fetched = cnt[0]; g->stats.texels_nominal = cnt[1]; g->stats.candidates = cnt[2];
+    g->stats.texels_fetched = cnt[ST_FETCHED]; g->stats.texels_nominal = cnt[ST_NOMINAL]; g->stats.candidates = cnt[ST_CANDS];
+    if (getenv("TSB_DEBUG_PHASES") && cnt[ST_ITEMS])
+        fprintf(stderr, "[tsb] cycles/item: ready %.0f knn %.0f neigh %.0f weight+rand %.0f score %.0f commit %.0f (items %llu)\n",
+                (double)cnt[ST_CYC_READY] / cnt[ST_ITEMS], (double)cnt[ST_CYC_KNN] / cnt[ST_ITEMS], (double)cnt[ST_CYC_NEIGH] / cnt[ST_ITEMS],
+                (double)cnt[ST_CYC_WEIGHT] / cnt[ST_ITEMS], (double)cnt[ST_CYC_SCORE] / cnt[ST_ITEMS], (double)cnt[ST_CYC_COMMIT] / cnt[ST_ITEMS],
+                cnt[ST_ITEMS]);
     g->stats.work_items = total_items;
+    CU(cudaEventRecord(ev_end, s));
+    CU(cudaEventSynchronize(ev_end));
+    float ms_total = 0.f;
+    cudaEventElapsedTime(&ms_total, ev_begin, ev_end);
+    cudaEventDestroy(ev_begin); cudaEventDestroy(ev_end);
+    g->stats.gpu_ms_total = ms_total;
     g->stats.wall_ms_total = now_ms() - t_start;
-    g->stats.gpu_ms_other = 0.0;
+    g->stats.gpu_ms_other = ms_total - g->stats.gpu_ms_resolve - g->stats.gpu_ms_analysis;
     g->have_loaded_points = false;
     return 0;
 }
@@ -795,8 +818,10 @@ int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
     int x_l = (int)((float)g->W * 0.05f), y_b = (int)((float)g->H * 0.05f);
     g->mx = ((x_l + 1 + 31) / 32) * 32; g->my = y_b + 1;
     g->wpr = (g->W + 2 * g->mx + 31) / 32; g->mrows = g->H + 2 * g->my;
+    g->wpr1 = (g->wpr + 31) / 32;
     int rc = 0;
-    if ((rc = g->d_state.ensure(npix)) || (rc = g->d_score.ensure(npix)) || (rc = g->d_mask.ensure((size_t)g->wpr * g->mrows))) return bail(rc);
+    if ((rc = g->d_state.ensure(npix)) || (rc = g->d_score.ensure(npix)) || (rc = g->d_mask.ensure((size_t)g->wpr * g->mrows)) ||
+        (rc = g->d_mask1.ensure((size_t)g->wpr1 * g->mrows))) return bail(rc);
     SpiralHost sp = build_spiral(SPIRAL_RT);
     g->spiralN = (int)sp.off.size(); g->RT2 = sp.RT2;
     if ((rc = g->d_spiral.upload(sp.off.data(), sp.off.size(), g->stream)) || (rc = g->d_cntLE.upload(sp.cntLE.data(), sp.cntLE.size(), g->stream))) return bail(rc);
@@ -815,12 +840,12 @@ int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
         for (size_t i = 0; i < npix; ++i) g->unresolved0[i] = (uint32_t)i;
     }
     int per_sm = 0;
-    cudaFuncSetAttribute(k_round<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
-    cudaFuncSetAttribute(k_round<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
+    cudaFuncSetAttribute(k_round<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
+    cudaFuncSetAttribute(k_round<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
     cudaFuncSetAttribute(k_eval_items<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
     cudaFuncSetAttribute(k_eval_items<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
     cudaFuncSetAttribute(k_radius, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_round<false>, CTA_THREADS, sizeof(CtaSmem)) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_round<false>, CTA_THREADS, sizeof(RoundSmem)) != cudaSuccess || per_sm < 1) per_sm = 1;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "cudaGetDeviceProperties failed"));
     g->max_ctas = prop.multiProcessorCount * per_sm;
@@ -1003,6 +1028,7 @@ int tsb_generator_load_state(tsb_generator* g, const uint8_t* color, const uint3
     k_pack_state<<<(uint32_t)((npix + 255) / 256), 256, 0, s>>>(g->d_state.p, (uint32_t)npix, dc.p, dco.p, di.p);
     CU(cudaGetLastError());
     CU(cudaMemsetAsync(g->d_mask.p, 0, (size_t)g->wpr * g->mrows * 4, s));
+    CU(cudaMemsetAsync(g->d_mask1.p, 0, (size_t)g->wpr1 * g->mrows * 4, s));
     StageDev S;
     fill_stage_geometry(g, S, false);
     DevBuf<uint32_t> dp;

@@ -43,9 +43,12 @@ struct StageDev {
     // synthesis state
     uint4* state;     // per output pixel {colour RGBA, src x|y<<16, patch id, id_map.map | coord_map.map<<16}
     uint32_t* mask;   // resolved set, bit packed, extended by the tiling margins
+    uint32_t* mask1;  // summary: bit w of row r set iff mask word (r, w) is non-zero (sparse-regime scans skip empty words)
     float* score;     // first-resolution score per pixel (ms.rs:365: never updated on redo)
     int W, H;
     int mx, my, wpr, mrows;  // mask geometry: bit (x+mx, y+my), wpr words per row, mrows rows
+    int wpr1;                // summary words per row
+    uint32_t n_points_max;   // upper bound of points in the mask (incl. mirror copies)
     int tiling, x_l, x_r, y_b, y_t;  // ms.rs:308-311
     // inputs at this level
     const DevEx* ex;
@@ -62,7 +65,7 @@ struct StageDev {
     int spiralN, RT2;
     int k, m;
     uint32_t r2_hint;  // starting radius^2 of the general k-NN search
-    unsigned long long* counters;  // [0] texels fetched, [1] texels nominal, [2] candidates, [3] items
+    unsigned long long* counters;  // [ST_COUNT] run statistics (see enum below), flushed once per CTA
 };
 
 struct PhaseDev {
@@ -100,7 +103,13 @@ struct __align__(16) WarpScratch {
     int pad[3];
 };
 
+// statistics accumulated per warp in registers, per CTA in shared memory, flushed once per CTA
+enum { ST_FETCHED = 0, ST_NOMINAL, ST_CANDS, ST_ITEMS, ST_CYC_READY, ST_CYC_KNN, ST_CYC_NEIGH, ST_CYC_WEIGHT,
+       ST_CYC_SCORE, ST_CYC_COMMIT, ST_COUNT };
+
 struct ItemOut {
+    unsigned long long fetched, nominal;
+    long long c_knn, c_neigh, c_weight, c_score;
     int kk, ncand, best;
     int bx, by, bmap;
     uint32_t bpatch;
@@ -125,6 +134,11 @@ __device__ __forceinline__ void mask_set(const StageDev& S, int x, int y) {
     int X = x + S.mx, Y = y + S.my;
     if ((unsigned)X >= (unsigned)(S.wpr * 32) || (unsigned)Y >= (unsigned)S.mrows) return;
     atomicOr(S.mask + (size_t)Y * S.wpr + (X >> 5), 1u << (X & 31));
+    // the summary bit is published by every writer that does not already SEE it (a plain "first writer
+    // sets it" rule would let a reader observe the detail bit before the summary bit)
+    uint32_t* s1 = S.mask1 + (size_t)Y * S.wpr1 + (X >> 10);
+    uint32_t b1 = 1u << ((X >> 5) & 31);
+    if (!(__ldcg(s1) & b1)) atomicOr(s1, b1);
 }
 // flush_resolved, ms.rs:296-331 (tree part): the pixel plus its tiling mirror copies (no diagonal copy)
 __device__ __forceinline__ void mask_insert(const StageDev& S, int x, int y, bool mirrors) {
@@ -142,7 +156,7 @@ __device__ __forceinline__ void mask_insert(const StageDev& S, int x, int y, boo
 // COLLECT=true: append keys (d^2<<32 | (dy+32768)<<16 | (dx+32768)) to ws.u.keys (ws.cnt).
 // ---------------------------------------------------------------------------------------------
 template <bool COLLECT>
-__device__ uint32_t scan_disc(const StageDev& S, WarpScratch& ws, int lane, int x, int y, uint32_t R2) {
+__device__ __forceinline__ uint32_t scan_disc(const StageDev& S, WarpScratch& ws, int lane, int x, int y, uint32_t R2) {
     int r = isqrt_u32(R2);
     int ylo = max(y - r, -S.my), yhi = min(y + r, S.mrows - 1 - S.my);
     uint32_t cnt = 0;
@@ -153,21 +167,30 @@ __device__ uint32_t scan_disc(const StageDev& S, WarpScratch& ws, int lane, int 
         if (xlo > xhi) continue;
         int Xlo = xlo + S.mx, Xhi = xhi + S.mx;
         const uint32_t* row = S.mask + (size_t)(yy + S.my) * S.wpr;
-        for (int wd = Xlo >> 5; wd <= (Xhi >> 5); ++wd) {
-            uint32_t bits = __ldcg(row + wd);
-            if (wd == (Xlo >> 5)) bits &= 0xFFFFFFFFu << (Xlo & 31);
-            if (wd == (Xhi >> 5)) bits &= 0xFFFFFFFFu >> (31 - (Xhi & 31));
-            if (!COLLECT) cnt += __popc(bits);
-            else {
-                while (bits) {
-                    int b = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    int dx = (wd * 32 + b - S.mx) - x;
-                    unsigned long long key = ((unsigned long long)(uint32_t)(dx * dx + dy * dy) << 32) |
-                                             ((unsigned long long)(uint32_t)(dy + 32768) << 16) |
-                                             (unsigned long long)(uint32_t)(dx + 32768);
-                    int slot = atomicAdd(&ws.cnt, 1);
-                    if (slot < KBUF) ws.u.keys[slot] = key;
+        const uint32_t* row1 = S.mask1 + (size_t)(yy + S.my) * S.wpr1;
+        const int w0 = Xlo >> 5, w1 = Xhi >> 5;
+        for (int sw = w0 >> 5; sw <= (w1 >> 5); ++sw) {
+            uint32_t b1 = __ldcg(row1 + sw);
+            if (sw == (w0 >> 5)) b1 &= 0xFFFFFFFFu << (w0 & 31);
+            if (sw == (w1 >> 5)) b1 &= 0xFFFFFFFFu >> (31 - (w1 & 31));
+            while (b1) {
+                int wd = sw * 32 + __ffs(b1) - 1;
+                b1 &= b1 - 1;
+                uint32_t bits = __ldcg(row + wd);
+                if (wd == w0) bits &= 0xFFFFFFFFu << (Xlo & 31);
+                if (wd == w1) bits &= 0xFFFFFFFFu >> (31 - (Xhi & 31));
+                if (!COLLECT) cnt += __popc(bits);
+                else {
+                    while (bits) {
+                        int b = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        int dx = (wd * 32 + b - S.mx) - x;
+                        unsigned long long key = ((unsigned long long)(uint32_t)(dx * dx + dy * dy) << 32) |
+                                                 ((unsigned long long)(uint32_t)(dy + 32768) << 16) |
+                                                 (unsigned long long)(uint32_t)(dx + 32768);
+                        int slot = atomicAdd(&ws.cnt, 1);
+                        if (slot < KBUF) ws.u.keys[slot] = key;
+                    }
                 }
             }
         }
@@ -181,7 +204,7 @@ __device__ uint32_t scan_disc(const StageDev& S, WarpScratch& ws, int lane, int 
     return (uint32_t)ws.cnt;
 }
 
-__device__ void sort_keys(WarpScratch& ws, int lane, int n) {
+__device__ __noinline__ void sort_keys(WarpScratch& ws, int lane, int n) {
     int n2 = 32;
     while (n2 < n) n2 <<= 1;
     for (int i = n + lane; i < n2; i += 32) ws.u.keys[i] = ~0ull;
@@ -203,7 +226,7 @@ __device__ void sort_keys(WarpScratch& ws, int lane, int n) {
 // k nearest resolved points of (x,y) in canonical order (d^2, dy, dx) -> ws.off[0..kk).
 // R2bound: if != R2_INF, the caller guarantees that the disc d^2 <= R2bound holds at least k points.
 // Returns kk; *r2_out = d^2 of the k-th neighbour (R2_INF if fewer than k points exist).
-__device__ int knn_search(const StageDev& S, WarpScratch& ws, int lane, int x, int y, uint32_t R2bound, uint32_t* r2_out) {
+__device__ __forceinline__ int knn_search(const StageDev& S, WarpScratch& ws, int lane, int x, int y, uint32_t R2bound, uint32_t* r2_out) {
     const int k = S.k;
     const unsigned lt = (1u << lane) - 1u;
     // ---- path A: spiral walk over the fixed-offset table ----
@@ -213,18 +236,26 @@ __device__ int knn_search(const StageDev& S, WarpScratch& ws, int lane, int x, i
         // unbounded search: do not walk the whole table when the hint says the set is sparse
         if (!bounded && S.r2_hint > (uint32_t)S.RT2) limit = 0;
         int cnt = 0;
-        for (int base = 0; base < limit && cnt < k; base += 32) {
-            int idx = base + lane;
-            bool hit = false;
-            short2 o = make_short2(0, 0);
-            if (idx < limit) {
-                o = __ldg(S.spiral + idx);
-                hit = mask_test(S, x + o.x, y + o.y);
+        for (int base = 0; base < limit && cnt < k; base += 128) {
+            short2 o[4];
+            bool hit[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int idx = base + 32 * u + lane;
+                hit[u] = false;
+                o[u] = make_short2(0, 0);
+                if (idx < limit) {
+                    o[u] = __ldg(S.spiral + idx);
+                    hit[u] = mask_test(S, x + o[u].x, y + o[u].y);
+                }
             }
-            unsigned b = __ballot_sync(FULL, hit);
-            int pos = cnt + __popc(b & lt);
-            if (hit && pos < k) ws.off[pos] = o;
-            cnt += __popc(b);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                unsigned b = __ballot_sync(FULL, hit[u]);
+                int pos = cnt + __popc(b & lt);
+                if (hit[u] && pos < k) ws.off[pos] = o[u];
+                cnt += __popc(b);
+            }
         }
         if (cnt >= k) {
             __syncwarp();
@@ -238,12 +269,15 @@ __device__ int knn_search(const StageDev& S, WarpScratch& ws, int lane, int x, i
     const uint32_t R2max = extw * extw + exth * exth;
     uint32_t R2 = R2bound;
     uint32_t c = 0;
-    bool need_search = true;
-    if (R2bound != R2_INF) {
-        c = scan_disc<false>(S, ws, lane, x, y, R2);
-        need_search = (c > (uint32_t)KBUF) || (c < (uint32_t)k);
+    int n = -1;
+    if (S.n_points_max <= (uint32_t)KBUF) R2 = R2max;  // the whole set fits the key buffer: take everything
+    if (R2 != R2_INF) {
+        if (lane == 0) ws.cnt = 0;
+        __syncwarp();
+        n = (int)scan_disc<true>(S, ws, lane, x, y, R2);
+        if (n > KBUF || (n < k && R2 < R2max)) n = -1;  // overflow (or a stale bound): search below
     }
-    if (need_search) {
+    if (n < 0) {
         uint32_t lo = 0;
         R2 = max(S.r2_hint, 4u);
         if (R2 > R2max) R2 = R2max;
@@ -264,10 +298,10 @@ __device__ int knn_search(const StageDev& S, WarpScratch& ws, int lane, int x, i
             }
             R2 = hi;
         }
+        if (lane == 0) ws.cnt = 0;
+        __syncwarp();
+        n = (int)scan_disc<true>(S, ws, lane, x, y, R2);
     }
-    if (lane == 0) ws.cnt = 0;
-    __syncwarp();
-    int n = (int)scan_disc<true>(S, ws, lane, x, y, R2);
     if (n > KBUF) n = KBUF;  // only reachable with > KBUF exact ties on one circle
     sort_keys(ws, lane, n);
     int kk = n < k ? n : k;
@@ -286,12 +320,15 @@ __device__ int knn_search(const StageDev& S, WarpScratch& ws, int lane, int x, i
 // One pixel resolution (steps 2-4 of ms.rs:917-986) by one warp.  No commit.
 // ---------------------------------------------------------------------------------------------
 template <bool GUIDED>
-__device__ void resolve_item(const StageDev& S, WarpScratch& ws, const float* __restrict__ s_lut,
+__device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws, const float* __restrict__ s_lut,
                              const float* __restrict__ s_lutg, int lane, int x, int y, uint32_t R2bound,
                              const uint32_t* __restrict__ rand_xy, const uint8_t* __restrict__ rand_map, ItemOut& out) {
     const unsigned lt = (1u << lane) - 1u;
     uint32_t r2;
+    long long t0 = clock64();
     const int kk = knn_search(S, ws, lane, x, y, R2bound, &r2);
+    long long t1 = clock64();
+    out.c_knn = t1 - t0; out.c_neigh = out.c_weight = out.c_score = 0; out.fetched = out.nominal = 0;
     out.kk = kk;
     out.ncand = 0; out.best = 0; out.bx = out.by = out.bmap = 0; out.bpatch = 0; out.score = 0.f;
     if (kk == 0) return;
@@ -341,6 +378,7 @@ __device__ void resolve_item(const StageDev& S, WarpScratch& ws, const float* __
         ncand += __popc(b);
     }
     __syncwarp();
+    long long t2 = clock64();
     // ---- weights: mean over the x4-duplicated list, sequential f64 sum (ms.rs:417-423, 1198-1203) ----
     {
         double sum = 0.0;
@@ -362,6 +400,7 @@ __device__ void resolve_item(const StageDev& S, WarpScratch& ws, const float* __
     }
     ncand += S.m;
     __syncwarp();
+    long long t3 = clock64();
     out.ncand = ncand;
     // ---- find_best_match / better_match (ms.rs:1184-1288): one lane per candidate ----
     float best = FLT_MAX;
@@ -381,28 +420,44 @@ __device__ void resolve_item(const StageDev& S, WarpScratch& ws, const float* __
             DevGuide ge;
             if (GUIDED) ge = S.exg[map];
             ok = true;
-            for (int j = 0; j < kk; ++j) {
-                short2 o = ws.off[j];
-                int X = cx + sgn * o.x, Y = cy + sgn * o.y;
-                uint32_t tex = OUTSIDE_RGBA;
-                if ((unsigned)X < (unsigned)e.w && (unsigned)Y < (unsigned)e.h) tex = __ldg(e.px + (size_t)Y * e.w + X);
-                uint32_t dd = __vabsdiffu4(ws.tcol[j], tex);
-                float t = s_lut[dd & 0xFFu];
-                t = __fadd_rn(t, s_lut[(dd >> 8) & 0xFFu]);
-                t = __fadd_rn(t, s_lut[(dd >> 16) & 0xFFu]);
-                t = __fadd_rn(t, s_lut[dd >> 24]);
-                if (GUIDED) {
-                    uint32_t gtex = OUTSIDE_RGBA;
-                    if ((unsigned)X < (unsigned)ge.w && (unsigned)Y < (unsigned)ge.h) gtex = __ldg(ge.px + (size_t)Y * ge.w + X);
-                    uint32_t dg = __vabsdiffu4(ws.gcol[j], gtex);
-                    t = __fadd_rn(t, s_lutg[dg & 0xFFu]);
-                    t = __fadd_rn(t, s_lutg[(dg >> 8) & 0xFFu]);
-                    t = __fadd_rn(t, s_lutg[(dg >> 16) & 0xFFu]);
-                    t = __fadd_rn(t, s_lutg[dg >> 24]);
+            for (int j0 = 0; j0 < kk; j0 += 8) {
+                uint32_t tex[8], gtex[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {  // issue the gathers of the chunk first (memory-level parallelism)
+                    int j = j0 + u;
+                    tex[u] = OUTSIDE_RGBA;
+                    gtex[u] = OUTSIDE_RGBA;
+                    if (j < kk) {
+                        short2 o = ws.off[j];
+                        int X = cx + sgn * o.x, Y = cy + sgn * o.y;
+                        if ((unsigned)X < (unsigned)e.w && (unsigned)Y < (unsigned)e.h) { tex[u] = __ldg(e.px + (size_t)Y * e.w + X); ++fetched; }
+                        if (GUIDED) {
+                            if ((unsigned)X < (unsigned)ge.w && (unsigned)Y < (unsigned)ge.h) { gtex[u] = __ldg(ge.px + (size_t)Y * ge.w + X); ++fetched; }
+                        }
+                    }
                 }
-                s = __fadd_rn(s, __fmul_rn(t, ws.g[j]));
-                ++fetched;
-                if (s >= best) { ok = false; break; }  // early-out vs. the best of earlier rounds (ms.rs:1281)
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {  // strict left-to-right f32 accumulation (ms.rs:1259-1280)
+                    int j = j0 + u;
+                    if (j < kk) {
+                        uint32_t dd = __vabsdiffu4(ws.tcol[j], tex[u]);
+                        float t = s_lut[dd & 0xFFu];
+                        t = __fadd_rn(t, s_lut[(dd >> 8) & 0xFFu]);
+                        t = __fadd_rn(t, s_lut[(dd >> 16) & 0xFFu]);
+                        t = __fadd_rn(t, s_lut[dd >> 24]);
+                        if (GUIDED) {
+                            uint32_t dg = __vabsdiffu4(ws.gcol[j], gtex[u]);
+                            t = __fadd_rn(t, s_lutg[dg & 0xFFu]);
+                            t = __fadd_rn(t, s_lutg[(dg >> 8) & 0xFFu]);
+                            t = __fadd_rn(t, s_lutg[(dg >> 16) & 0xFFu]);
+                            t = __fadd_rn(t, s_lutg[dg >> 24]);
+                        }
+                        s = __fadd_rn(s, __fmul_rn(t, ws.g[j]));
+                    }
+                }
+                // early-out vs. the best of earlier rounds (ms.rs:1281); all terms are >= 0, so testing the
+                // prefix only at chunk ends rejects exactly the same candidates
+                if (s >= best) { ok = false; break; }
             }
         }
         bool win = ok && (s < best);
@@ -418,12 +473,10 @@ __device__ void resolve_item(const StageDev& S, WarpScratch& ws, const float* __
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) fetched += __shfl_xor_sync(FULL, fetched, o);
-    if (lane == 0 && S.counters) {
-        atomicAdd(S.counters + 0, (unsigned long long)fetched * (GUIDED ? 2ull : 1ull));
-        atomicAdd(S.counters + 1, (unsigned long long)ncand * (unsigned long long)kk * (GUIDED ? 2ull : 1ull));
-        atomicAdd(S.counters + 2, (unsigned long long)ncand);
-        atomicAdd(S.counters + 3, 1ull);
-    }
+    long long t4 = clock64();
+    out.fetched = fetched;
+    out.nominal = (unsigned long long)ncand * (unsigned long long)kk * (GUIDED ? 2ull : 1ull);
+    out.c_neigh = t2 - t1; out.c_weight = t3 - t2; out.c_score = t4 - t3;
     uint32_t bxy = ws.u.c.cxy[besti];
     out.best = besti;
     out.bx = (int)(bxy & 0xFFFFu);
@@ -439,10 +492,18 @@ __device__ __forceinline__ void load_luts(const StageDev& S, float* s_lut, float
     __syncthreads();
 }
 
+constexpr int REQ_CAP = 1024;  // per-CTA staging of re-queued items (one global atomic per CTA and round)
+
 struct __align__(16) CtaSmem {
     float lut[256];
     float lutg[256];
     WarpScratch ws[WARPS_PER_CTA];
+};
+struct __align__(16) RoundSmem {
+    CtaSmem c;
+    uint32_t req[REQ_CAP];
+    unsigned long long stat[ST_COUNT];
+    uint32_t req_cnt, req_min, req_base, pad;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -451,8 +512,14 @@ struct __align__(16) CtaSmem {
 template <bool GUIDED>
 __global__ void __launch_bounds__(CTA_THREADS) k_round(StageDev S, PhaseDev P, uint32_t round) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    CtaSmem& sm = *reinterpret_cast<CtaSmem*>(smem_raw);
+    RoundSmem& rs = *reinterpret_cast<RoundSmem*>(smem_raw);
+    CtaSmem& sm = rs.c;
+    if (threadIdx.x == 0) { rs.req_cnt = 0; rs.req_min = NONE32; }
+    if (threadIdx.x < ST_COUNT) rs.stat[threadIdx.x] = 0ull;
     load_luts(S, sm.lut, sm.lutg);
+    unsigned long long st_acc[ST_COUNT];
+#pragma unroll
+    for (int i = 0; i < ST_COUNT; ++i) st_acc[i] = 0ull;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpScratch& ws = sm.ws[warp];
     const uint32_t npend = P.cnt[round & 3];
@@ -462,6 +529,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_round(StageDev S, PhaseDev P, u
     uint32_t* next = P.pending[(round + 1) & 1];
     const uint32_t nwarps = gridDim.x * WARPS_PER_CTA;
     for (uint32_t w = blockIdx.x * WARPS_PER_CTA + warp; w < npend; w += nwarps) {
+        long long tr0 = clock64();
         const uint32_t it = pend[w];
         const uint32_t pc = P.pred_cnt[it];
         bool ready = true;
@@ -477,19 +545,22 @@ __global__ void __launch_bounds__(CTA_THREADS) k_round(StageDev S, PhaseDev P, u
         }
         if (!ready) {
             if (lane == 0) {
-                uint32_t pos = atomicAdd(P.cnt + ((round + 1) & 3), 1u);
-                next[pos] = it;
-                atomicMin(P.minpend + ((round + 1) & 3), it);
+                uint32_t slot = atomicAdd(&rs.req_cnt, 1u);
+                if (slot < (uint32_t)REQ_CAP) rs.req[slot] = it;
+                else next[atomicAdd(P.cnt + ((round + 1) & 3), 1u)] = it;  // staging full: direct append
+                atomicMin(&rs.req_min, it);
             }
             continue;
         }
         __threadfence();  // acquire: predecessors' commits are visible below
+        st_acc[ST_CYC_READY] += (unsigned long long)(clock64() - tr0);
         const uint32_t flat = P.item_pixel[it];
         const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
         const uint32_t si = P.stage_base + it;
         ItemOut o;
         resolve_item<GUIDED>(S, ws, sm.lut, sm.lutg, lane, x, y, P.item_R2[it], P.rand_xy + (size_t)si * S.m,
                              P.rand_map + (size_t)si * S.m, o);
+        long long tc0 = clock64();
         if (lane == 0) {
             if (o.kk > 0) {  // ms.rs:334-377 update
                 DevEx e = S.ex[o.bmap];
@@ -510,7 +581,26 @@ __global__ void __launch_bounds__(CTA_THREADS) k_round(StageDev S, PhaseDev P, u
             *((volatile uint32_t*)(P.done + it)) = 1u;
         }
         __syncwarp();
+        st_acc[ST_FETCHED] += o.fetched; st_acc[ST_NOMINAL] += o.nominal; st_acc[ST_CANDS] += (unsigned long long)o.ncand;
+        st_acc[ST_ITEMS] += 1ull;
+        st_acc[ST_CYC_KNN] += (unsigned long long)o.c_knn; st_acc[ST_CYC_NEIGH] += (unsigned long long)o.c_neigh;
+        st_acc[ST_CYC_WEIGHT] += (unsigned long long)o.c_weight; st_acc[ST_CYC_SCORE] += (unsigned long long)o.c_score;
+        st_acc[ST_CYC_COMMIT] += (unsigned long long)(clock64() - tc0);
     }
+    if (lane == 0 && S.counters) {
+#pragma unroll
+        for (int i = 0; i < ST_COUNT; ++i) if (st_acc[i]) atomicAdd(&rs.stat[i], st_acc[i]);
+    }
+    // flush the staged re-queue list with one global atomic per CTA
+    __syncthreads();
+    const uint32_t nreq = min(rs.req_cnt, (uint32_t)REQ_CAP);
+    if (threadIdx.x == 0 && nreq) {
+        rs.req_base = atomicAdd(P.cnt + ((round + 1) & 3), nreq);
+        atomicMin(P.minpend + ((round + 1) & 3), rs.req_min);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < nreq; i += blockDim.x) next[rs.req_base + i] = rs.req[i];
+    if (S.counters && threadIdx.x < ST_COUNT && rs.stat[threadIdx.x]) atomicAdd(S.counters + threadIdx.x, rs.stat[threadIdx.x]);
 }
 
 // Frozen-snapshot evaluation (test harness): resolve without committing.
