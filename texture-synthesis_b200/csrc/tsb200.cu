@@ -15,6 +15,8 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_scan.cuh>
+
 #include "tsb_device.cuh"
 
 using namespace tsb;
@@ -246,6 +248,10 @@ struct tsb_generator {
     DevBuf<uint32_t> d_item_pixel, d_item_R2, d_pred_cnt, d_preds, d_done, d_pend0, d_pend1, d_ctrl, d_pmap;
     DevBuf<uint32_t> d_rand_xy, d_pick_idx, d_tmp_u32;
     DevBuf<uint8_t> d_rand_map;
+    DevBuf<uint32_t> d_npred, d_nsucc, d_succ_off, d_succ_cur, d_succ, d_queue, d_fctl;
+    DevBuf<uint8_t> d_cub_temp;
+    int max_ctas_flow = 0;
+    bool use_rounds = false;
     uint32_t* h_ctrl = nullptr;  // pinned, 8 words
     bool pmap_ready = false;
 
@@ -470,7 +476,9 @@ int run_phase(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, bool
     memcpy(g->h_ctrl, ctrl, sizeof(ctrl));
     CU(cudaMemcpyAsync(g->d_ctrl.p, g->h_ctrl, sizeof(ctrl), cudaMemcpyHostToDevice, s));
     if (analyze) {
-        TRY(launch_resolve_kernel(g, k_radius, grid_for(g, n), sizeof(CtaSmem), S, P));
+        FlowDev F0;
+        memset(&F0, 0, sizeof(F0));
+        TRY(launch_resolve_kernel(g, k_radius, grid_for(g, n), sizeof(CtaSmem), S, P, F0));
         if (n <= PAIR_MAX) k_preds_pairs<<<grid_for(g, n), CTA_THREADS, 0, s>>>(S, P);
         else k_preds_scan<<<grid_for(g, n), CTA_THREADS, 0, s>>>(S, P);
         CU(cudaGetLastError());
@@ -515,6 +523,103 @@ int run_phase(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, bool
         fprintf(stderr, "[tsb] phase i0=%u n=%u new=%d analyze=%d rounds=%u analysis_ms=%.3f resolve_ms=%.3f\n", i0, n, (int)is_new,
                 (int)analyze, round, ma, mr);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    return 0;
+}
+
+
+PhaseDev make_phase(tsb_generator* g, uint32_t i0, uint32_t n, bool is_new, uint64_t trace_base) {
+    PhaseDev P;
+    memset(&P, 0, sizeof(P));
+    P.item_pixel = g->d_item_pixel.p + i0;
+    P.item_R2 = g->d_item_R2.p; P.pred_cnt = g->d_pred_cnt.p; P.preds = g->d_preds.p; P.done = g->d_done.p;
+    P.pending[0] = g->d_pend0.p; P.pending[1] = g->d_pend1.p;
+    P.cnt = g->d_ctrl.p; P.minpend = g->d_ctrl.p + 4;
+    P.pmap = g->d_pmap.p;
+    P.rand_xy = g->d_rand_xy.p; P.rand_map = g->d_rand_map.p;
+    P.n = n; P.stage_base = i0; P.is_new = is_new ? 1u : 0u;
+    if (g->trace) { P.tr_best = g->d_tr_best.p; P.tr_ncand = g->d_tr_ncand.p; P.tr_nneigh = g->d_tr_nneigh.p; P.tr_score = g->d_tr_score.p; }
+    P.trace_base = trace_base;
+    return P;
+}
+
+struct PhaseClock {
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+    int begin(cudaStream_t s) { CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventCreate(&e2)); CU(cudaEventRecord(e0, s)); return 0; }
+    int mid(cudaStream_t s) { CU(cudaEventRecord(e1, s)); return 0; }
+    int end(tsb_generator* g, cudaStream_t s, const char* what, uint32_t i0, uint32_t n, bool is_new, uint64_t extra) {
+        CU(cudaEventRecord(e2, s));
+        CU(cudaEventSynchronize(e2));
+        float ma = 0.f, mr = 0.f;
+        cudaEventElapsedTime(&ma, e0, e1);
+        cudaEventElapsedTime(&mr, e1, e2);
+        g->stats.gpu_ms_analysis += ma;
+        g->stats.gpu_ms_resolve += mr;
+        if (getenv("TSB_DEBUG_PHASES"))
+            fprintf(stderr, "[tsb] %s i0=%u n=%u new=%d extra=%llu analysis_ms=%.3f resolve_ms=%.3f\n", what, i0, n, (int)is_new,
+                    (unsigned long long)extra, ma, mr);
+        return 0;
+    }
+    ~PhaseClock() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); if (e2) cudaEventDestroy(e2); }
+};
+
+// Items [i0, i0+n) one after the other on one warp (start of a synthesis; fallback for degenerate phases).
+int run_serial(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, bool is_new, uint64_t trace_base) {
+    cudaStream_t s = g->stream;
+    PhaseDev P = make_phase(g, i0, n, is_new, trace_base);
+    g->stats.phases++;
+    PhaseClock clk;
+    TRY(clk.begin(s));
+    TRY(clk.mid(s));
+    if (g->guided) k_serial<true><<<1, CTA_THREADS, sizeof(RoundSmem), s>>>(S, P);
+    else k_serial<false><<<1, CTA_THREADS, sizeof(RoundSmem), s>>>(S, P);
+    CU(cudaGetLastError());
+    g->stats.kernel_launches++;
+    g->stats.rounds++;
+    return clk.end(g, s, "serial", i0, n, is_new, 0);
+}
+
+// Items [i0, i0+n) in dataflow order: radius -> CSR dependency graph -> persistent kernel.
+int run_phase_flow(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, bool is_new, uint64_t trace_base) {
+    cudaStream_t s = g->stream;
+    PhaseDev P = make_phase(g, i0, n, is_new, trace_base);
+    FlowDev F;
+    F.npred = g->d_npred.p; F.nsucc = g->d_nsucc.p; F.succ_off = g->d_succ_off.p; F.succ_cur = g->d_succ_cur.p;
+    F.succ = g->d_succ.p; F.queue = g->d_queue.p; F.ctl = g->d_fctl.p;
+    g->stats.phases++;
+    PhaseClock clk;
+    TRY(clk.begin(s));
+    const int ga = grid_for(g, n);
+    k_radius<<<ga, CTA_THREADS, sizeof(CtaSmem), s>>>(S, P, F);
+    if (n <= PAIR_MAX) k_edges_pairs<0><<<ga, CTA_THREADS, 0, s>>>(S, P, F);
+    else k_edges_scan<0><<<ga, CTA_THREADS, 0, s>>>(S, P, F);
+    CU(cudaGetLastError());
+    size_t temp_bytes = g->d_cub_temp.n;
+    CU(cub::DeviceScan::ExclusiveSum(g->d_cub_temp.p, temp_bytes, F.nsucc, F.succ_off, (int)(n + 1), s));
+    CU(cudaMemcpyAsync(g->h_ctrl, F.succ_off + n, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    const uint64_t edges = g->h_ctrl[0];
+    g->stats.kernel_launches += 3;
+    if (edges > 400ull * n + (64ull << 20)) {  // degenerate conflict graph: run the phase serially instead
+        k_pmap_clear<<<(n + 255) / 256, 256, 0, s>>>(P);
+        CU(cudaGetLastError());
+        return run_serial(g, S, i0, n, is_new, trace_base);
+    }
+    if (edges > g->d_succ.n) { TRY(g->d_succ.ensure(edges + edges / 4 + 1024)); F.succ = g->d_succ.p; }
+    if (n <= PAIR_MAX) k_edges_pairs<1><<<ga, CTA_THREADS, 0, s>>>(S, P, F);
+    else k_edges_scan<1><<<ga, CTA_THREADS, 0, s>>>(S, P, F);
+    k_seed_queue<<<(n + 255) / 256, 256, 0, s>>>(P, F);
+    CU(cudaGetLastError());
+    TRY(clk.mid(s));
+    const int gf = std::max(1, std::min((int)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), g->max_ctas_flow));
+    if (g->guided) k_flow<true><<<gf, CTA_THREADS, sizeof(RoundSmem), s>>>(S, P, F);
+    else k_flow<false><<<gf, CTA_THREADS, sizeof(RoundSmem), s>>>(S, P, F);
+    k_pmap_clear<<<(n + 255) / 256, 256, 0, s>>>(P);
+    CU(cudaGetLastError());
+    g->stats.kernel_launches += 4;
+    g->stats.rounds++;
+    CU(cudaMemcpyAsync(g->h_ctrl, F.ctl, 12, cudaMemcpyDeviceToHost, s));
+    TRY(clk.end(g, s, "flow", i0, n, is_new, edges));
+    if (g->h_ctrl[FC_ABORT]) return fail(TSB_ERR_INTERNAL, "dataflow phase of %u items stalled (head %u tail %u)", n, g->h_ctrl[0], g->h_ctrl[1]);
     return 0;
 }
 
@@ -603,11 +708,20 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
     TRY(g->d_item_pixel.ensure(max_stage_items));
     TRY(g->d_item_R2.ensure(max_phase));
     TRY(g->d_pred_cnt.ensure(max_phase));
-    TRY(g->d_preds.ensure(max_phase * (size_t)PRED_CAP));
+    if (getenv("TSB_MODE") && !strcmp(getenv("TSB_MODE"), "rounds")) TRY(g->d_preds.ensure(max_phase * (size_t)PRED_CAP));
     TRY(g->d_done.ensure(max_phase));
     TRY(g->d_pend0.ensure(max_phase));
     TRY(g->d_pend1.ensure(max_phase));
     TRY(g->d_ctrl.ensure(8));
+    TRY(g->d_npred.ensure(max_phase + 1)); TRY(g->d_nsucc.ensure(max_phase + 1)); TRY(g->d_succ_off.ensure(max_phase + 1));
+    TRY(g->d_succ_cur.ensure(max_phase + 1)); TRY(g->d_queue.ensure(max_phase + 1)); TRY(g->d_fctl.ensure(4));
+    TRY(g->d_succ.ensure(max_phase * 40 + 1024));
+    {
+        size_t tb = 0;
+        CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, g->d_nsucc.p, g->d_succ_off.p, (int)(max_phase + 1), s));
+        TRY(g->d_cub_temp.ensure(tb + 256));
+    }
+    g->use_rounds = getenv("TSB_MODE") && !strcmp(getenv("TSB_MODE"), "rounds");
     TRY(g->d_rand_xy.ensure(max_stage_items * (size_t)m));
     TRY(g->d_rand_map.ensure(max_stage_items * (size_t)m));
     TRY(g->d_luts.ensure(512));
@@ -675,7 +789,8 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
         if (sp.n_redo) {
             S.r2_hint = r2_hint_for(g, resolved_now, k);
             S.n_points_max = (uint32_t)std::min<size_t>(3 * resolved_now, 0xFFFFFFFFull);
-            TRY(run_phase(g, S, 0, (uint32_t)sp.n_redo, false, true, trace_base));
+            if (g->use_rounds) TRY(run_phase(g, S, 0, (uint32_t)sp.n_redo, false, true, trace_base));
+            else TRY(run_phase_flow(g, S, 0, (uint32_t)sp.n_redo, false, trace_base));
         }
         // ---- new pixels, in epochs over which the resolved count at most doubles ----
         size_t cur = sp.n_redo;
@@ -698,10 +813,13 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
                 continue;
             }
             size_t base = resolved_now - g->inpaint_locked;
-            size_t n_e = base < 2 * (size_t)k ? 1 : std::min(n_items - cur, base);
+            const bool serial = base < 2 * (size_t)k;  // every item still depends on (almost) all earlier ones
+            size_t n_e = serial ? (g->use_rounds ? 1 : std::min(n_items - cur, 2 * (size_t)k - base)) : std::min(n_items - cur, base);
             S.r2_hint = r2_hint_for(g, resolved_now, k);
             S.n_points_max = (uint32_t)std::min<size_t>(3 * (resolved_now + n_e), 0xFFFFFFFFull);
-            TRY(run_phase(g, S, (uint32_t)cur, (uint32_t)n_e, true, n_e > 1, trace_base));
+            if (g->use_rounds) TRY(run_phase(g, S, (uint32_t)cur, (uint32_t)n_e, true, n_e > 1, trace_base));
+            else if (serial) TRY(run_serial(g, S, (uint32_t)cur, (uint32_t)n_e, true, trace_base));
+            else TRY(run_phase_flow(g, S, (uint32_t)cur, (uint32_t)n_e, true, trace_base));
             cur += n_e; resolved_now += n_e;
             if (cb) {
                 uint64_t cur_total = overall_current + cur;
@@ -845,10 +963,18 @@ int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
     cudaFuncSetAttribute(k_eval_items<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
     cudaFuncSetAttribute(k_eval_items<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
     cudaFuncSetAttribute(k_radius, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
+    cudaFuncSetAttribute(k_flow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
+    cudaFuncSetAttribute(k_flow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
+    cudaFuncSetAttribute(k_serial<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
+    cudaFuncSetAttribute(k_serial<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_round<false>, CTA_THREADS, sizeof(RoundSmem)) != cudaSuccess || per_sm < 1) per_sm = 1;
+    int per_sm_flow = 0, per_sm_flow_g = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_flow, k_flow<false>, CTA_THREADS, sizeof(RoundSmem)) != cudaSuccess || per_sm_flow < 1) per_sm_flow = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_flow_g, k_flow<true>, CTA_THREADS, sizeof(RoundSmem)) != cudaSuccess || per_sm_flow_g < 1) per_sm_flow_g = 1;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "cudaGetDeviceProperties failed"));
     g->max_ctas = prop.multiProcessorCount * per_sm;
+    g->max_ctas_flow = prop.multiProcessorCount * std::min(per_sm_flow, per_sm_flow_g);  // persistent grid: co-resident CTAs only
     if ((rc = init_state(g))) return bail(rc);
     if (cudaStreamSynchronize(g->stream) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "generator initialisation failed: %s", cudaGetErrorString(cudaGetLastError())));
     *out = g;

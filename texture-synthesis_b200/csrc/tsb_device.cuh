@@ -88,6 +88,19 @@ struct PhaseDev {
     uint64_t trace_base;
 };
 
+// Dataflow execution of one phase: CSR successor lists + a ready queue (every item is enqueued exactly once,
+// so the queue is a plain array of n slots; NONE32 = slot not yet published).
+struct FlowDev {
+    uint32_t* npred;     // [n]   predecessors that have not committed yet
+    uint32_t* nsucc;     // [n+1] successor counts (entry n is 0 so that the scan yields the edge total)
+    uint32_t* succ_off;  // [n+1] exclusive scan of nsucc
+    uint32_t* succ_cur;  // [n]   fill cursors
+    uint32_t* succ;      // [edges]
+    uint32_t* queue;     // [n]
+    uint32_t* ctl;       // [0] head  [1] tail  [2] abort flag
+};
+enum { FC_HEAD = 0, FC_TAIL = 1, FC_ABORT = 2 };
+
 struct __align__(16) WarpScratch {
     union {
         unsigned long long keys[KBUF];  // general k-NN path (dead once the neighbour list is built)
@@ -95,6 +108,7 @@ struct __align__(16) WarpScratch {
     } u;
     double d[KMAX];
     uint16_t cmeta[CANDMAX];  // map id | 0x8000 for random candidates (mirrored pattern, ms.rs:588)
+    uint8_t corig[CANDMAX];   // index of the candidate in the reference's (un-deduplicated) candidate list
     short2 off[KMAX];         // neighbour offsets n_j - p, canonical order
     float g[KMAX];
     uint32_t tcol[KMAX];
@@ -389,6 +403,51 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws,
         double avg = __ddiv_rn(sum, (double)(kk * 4));
         for (int j = lane; j < kk; j += 32) ws.g[j] = (float)exp(-__ddiv_rn(ws.d[j], avg));
     }
+    const int kk8 = (kk + 7) & ~7;
+    // pad to a multiple of 8 with zero-weight neighbours: t * 0 = +0 and s + 0 = s, so the sum is unchanged
+    if (lane < kk8 - kk) { int j = kk + lane; ws.off[j] = make_short2(0, 0); ws.g[j] = 0.f; ws.tcol[j] = 0u; ws.gcol[j] = 0u; }
+    __syncwarp();
+    // ---- exact de-duplication of coherence candidates: the same (source coord, map) proposed by several
+    // neighbours has the same neighbourhood and therefore the same score; the first one wins the tie (q11) ----
+    const int ncoh = ncand;
+    {
+        unsigned long long* dk = reinterpret_cast<unsigned long long*>(ws.d);  // distances are dead from here on
+        for (int a = lane; a < ncoh; a += 32) dk[a] = (unsigned long long)ws.u.c.cxy[a] | ((unsigned long long)ws.cmeta[a] << 32);
+        __syncwarp();
+        unsigned long long key[KMAX / 32];
+        uint32_t pat[KMAX / 32];
+        bool keep[KMAX / 32];
+#pragma unroll
+        for (int c = 0; c < KMAX / 32; ++c) {
+            int a = c * 32 + lane;
+            keep[c] = a < ncoh;
+            key[c] = keep[c] ? dk[a] : 0ull;
+            pat[c] = keep[c] ? ws.u.c.cpatch[a] : 0u;
+        }
+        for (int b = 0; b + 1 < ncoh; ++b) {
+            unsigned long long kb = dk[b];
+#pragma unroll
+            for (int c = 0; c < KMAX / 32; ++c)
+                if (kb == key[c] && b < c * 32 + lane) keep[c] = false;
+        }
+        __syncwarp();
+        int nuniq = 0;
+#pragma unroll
+        for (int c = 0; c < KMAX / 32; ++c) {
+            if (c * 32 < ncoh) {
+                unsigned bm = __ballot_sync(FULL, keep[c]);
+                if (keep[c]) {
+                    int pos = nuniq + __popc(bm & lt);
+                    ws.u.c.cxy[pos] = (uint32_t)key[c]; ws.cmeta[pos] = (uint16_t)(key[c] >> 32);
+                    ws.u.c.cpatch[pos] = pat[c]; ws.corig[pos] = (uint8_t)(c * 32 + lane);
+                }
+                nuniq += __popc(bm);
+                __syncwarp();
+            }
+        }
+        ncand = nuniq;
+    }
+    const int nuniq_coh = ncand;
     // ---- random candidates (ms.rs:549-599), pre-generated by k_rand_candidates ----
     for (int r = lane; r < S.m; r += 32) {
         uint32_t xy = __ldg(rand_xy + r);
@@ -397,20 +456,24 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws,
         ws.u.c.cxy[pos] = xy;
         ws.u.c.cpatch[pos] = (xy >> 16) * (uint32_t)S.ex[map].w + (xy & 0xFFFFu);  // ms.rs:577
         ws.cmeta[pos] = (uint16_t)(map | 0x8000u);
+        ws.corig[pos] = (uint8_t)(ncoh + r);
     }
     ncand += S.m;
     __syncwarp();
     long long t3 = clock64();
-    out.ncand = ncand;
+    out.ncand = ncoh + S.m;  // the reference's candidate count
     // ---- find_best_match / better_match (ms.rs:1184-1288): one lane per candidate ----
     float best = FLT_MAX;
     int besti = 0;
     uint32_t fetched = 0;
-    for (int base = 0; base < ncand; base += 32) {
+    // coherence candidates get their own round(s) first: they establish `best`, so the random candidates
+    // (higher indices, so ties still go to the earlier candidate) early-out after a chunk or two
+    for (int base = 0; base < ncand; base = (base < nuniq_coh && base + 32 >= nuniq_coh) ? nuniq_coh : base + 32) {
+        const int lim = base < nuniq_coh ? nuniq_coh : ncand;
         int a = base + lane;
         float s = 0.f;
         bool ok = false;
-        if (a < ncand) {
+        if (a < lim) {
             uint32_t cxy = ws.u.c.cxy[a];
             uint32_t meta = ws.cmeta[a];
             int cx = (int)(cxy & 0xFFFFu), cy = (int)(cxy >> 16);
@@ -420,40 +483,37 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws,
             DevGuide ge;
             if (GUIDED) ge = S.exg[map];
             ok = true;
-            for (int j0 = 0; j0 < kk; j0 += 8) {
+            for (int j0 = 0; j0 < kk8; j0 += 8) {
                 uint32_t tex[8], gtex[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {  // issue the gathers of the chunk first (memory-level parallelism)
-                    int j = j0 + u;
+                    const int j = j0 + u;
+                    short2 o = ws.off[j];
+                    int X = cx + sgn * o.x, Y = cy + sgn * o.y;
                     tex[u] = OUTSIDE_RGBA;
                     gtex[u] = OUTSIDE_RGBA;
-                    if (j < kk) {
-                        short2 o = ws.off[j];
-                        int X = cx + sgn * o.x, Y = cy + sgn * o.y;
-                        if ((unsigned)X < (unsigned)e.w && (unsigned)Y < (unsigned)e.h) { tex[u] = __ldg(e.px + (size_t)Y * e.w + X); ++fetched; }
-                        if (GUIDED) {
-                            if ((unsigned)X < (unsigned)ge.w && (unsigned)Y < (unsigned)ge.h) { gtex[u] = __ldg(ge.px + (size_t)Y * ge.w + X); ++fetched; }
-                        }
+                    if ((unsigned)X < (unsigned)e.w && (unsigned)Y < (unsigned)e.h) tex[u] = __ldg(e.px + (size_t)Y * e.w + X);
+                    if (GUIDED) {
+                        if ((unsigned)X < (unsigned)ge.w && (unsigned)Y < (unsigned)ge.h) gtex[u] = __ldg(ge.px + (size_t)Y * ge.w + X);
                     }
                 }
+                fetched += (uint32_t)min(8, kk - j0);
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {  // strict left-to-right f32 accumulation (ms.rs:1259-1280)
-                    int j = j0 + u;
-                    if (j < kk) {
-                        uint32_t dd = __vabsdiffu4(ws.tcol[j], tex[u]);
-                        float t = s_lut[dd & 0xFFu];
-                        t = __fadd_rn(t, s_lut[(dd >> 8) & 0xFFu]);
-                        t = __fadd_rn(t, s_lut[(dd >> 16) & 0xFFu]);
-                        t = __fadd_rn(t, s_lut[dd >> 24]);
-                        if (GUIDED) {
-                            uint32_t dg = __vabsdiffu4(ws.gcol[j], gtex[u]);
-                            t = __fadd_rn(t, s_lutg[dg & 0xFFu]);
-                            t = __fadd_rn(t, s_lutg[(dg >> 8) & 0xFFu]);
-                            t = __fadd_rn(t, s_lutg[(dg >> 16) & 0xFFu]);
-                            t = __fadd_rn(t, s_lutg[dg >> 24]);
-                        }
-                        s = __fadd_rn(s, __fmul_rn(t, ws.g[j]));
+                    const int j = j0 + u;
+                    uint32_t dd = __vabsdiffu4(ws.tcol[j], tex[u]);
+                    float t = s_lut[dd & 0xFFu];
+                    t = __fadd_rn(t, s_lut[(dd >> 8) & 0xFFu]);
+                    t = __fadd_rn(t, s_lut[(dd >> 16) & 0xFFu]);
+                    t = __fadd_rn(t, s_lut[dd >> 24]);
+                    if (GUIDED) {
+                        uint32_t dg = __vabsdiffu4(ws.gcol[j], gtex[u]);
+                        t = __fadd_rn(t, s_lutg[dg & 0xFFu]);
+                        t = __fadd_rn(t, s_lutg[(dg >> 8) & 0xFFu]);
+                        t = __fadd_rn(t, s_lutg[(dg >> 16) & 0xFFu]);
+                        t = __fadd_rn(t, s_lutg[dg >> 24]);
                     }
+                    s = __fadd_rn(s, __fmul_rn(t, ws.g[j]));
                 }
                 // early-out vs. the best of earlier rounds (ms.rs:1281); all terms are >= 0, so testing the
                 // prefix only at chunk ends rejects exactly the same candidates
@@ -474,11 +534,11 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws,
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) fetched += __shfl_xor_sync(FULL, fetched, o);
     long long t4 = clock64();
-    out.fetched = fetched;
-    out.nominal = (unsigned long long)ncand * (unsigned long long)kk * (GUIDED ? 2ull : 1ull);
+    out.fetched = (unsigned long long)fetched * (GUIDED ? 2ull : 1ull);  // neighbour positions evaluated (example + guide texel each)
+    out.nominal = (unsigned long long)out.ncand * (unsigned long long)kk * (GUIDED ? 2ull : 1ull);
     out.c_neigh = t2 - t1; out.c_weight = t3 - t2; out.c_score = t4 - t3;
     uint32_t bxy = ws.u.c.cxy[besti];
-    out.best = besti;
+    out.best = (int)ws.corig[besti];
     out.bx = (int)(bxy & 0xFFFFu);
     out.by = (int)(bxy >> 16);
     out.bmap = (int)(ws.cmeta[besti] & 0x7FFFu);
@@ -505,6 +565,24 @@ struct __align__(16) RoundSmem {
     unsigned long long stat[ST_COUNT];
     uint32_t req_cnt, req_min, req_base, pad;
 };
+
+// update(), ms.rs:334-377 (+ flush_resolved's tree insert, ms.rs:296-331); called by lane 0
+__device__ __forceinline__ void commit_item(const StageDev& S, const PhaseDev& P, uint32_t si, uint32_t flat, int x, int y, const ItemOut& o) {
+    if (o.kk > 0) {
+        DevEx e = S.ex[o.bmap];
+        uint32_t col = __ldg(e.px + (size_t)o.by * e.w + o.bx);
+        S.state[flat] = make_uint4(col, (uint32_t)o.bx | ((uint32_t)o.by << 16), o.bpatch, (uint32_t)o.bmap | ((uint32_t)o.bmap << 16));
+        if (P.is_new) {
+            S.score[flat] = o.score;
+            mask_insert(S, x, y, S.tiling != 0);
+        }
+    }
+    if (P.tr_best) {
+        size_t ti = (size_t)(P.trace_base + si);
+        P.tr_best[ti] = o.kk > 0 ? o.best : -1;
+        P.tr_ncand[ti] = o.ncand; P.tr_nneigh[ti] = o.kk; P.tr_score[ti] = o.score;
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // Round kernel: every pending item whose predecessors have committed is resolved and committed.
@@ -562,21 +640,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_round(StageDev S, PhaseDev P, u
                              P.rand_map + (size_t)si * S.m, o);
         long long tc0 = clock64();
         if (lane == 0) {
-            if (o.kk > 0) {  // ms.rs:334-377 update
-                DevEx e = S.ex[o.bmap];
-                uint32_t col = __ldg(e.px + (size_t)o.by * e.w + o.bx);
-                S.state[flat] = make_uint4(col, (uint32_t)o.bx | ((uint32_t)o.by << 16), o.bpatch,
-                                           (uint32_t)o.bmap | ((uint32_t)o.bmap << 16));
-                if (P.is_new) {
-                    S.score[flat] = o.score;
-                    mask_insert(S, x, y, S.tiling != 0);
-                }
-            }
-            if (P.tr_best) {
-                size_t ti = (size_t)(P.trace_base + si);
-                P.tr_best[ti] = o.kk > 0 ? o.best : -1;
-                P.tr_ncand[ti] = o.ncand; P.tr_nneigh[ti] = o.kk; P.tr_score[ti] = o.score;
-            }
+            commit_item(S, P, si, flat, x, y, o);
             __threadfence();  // release
             *((volatile uint32_t*)(P.done + it)) = 1u;
         }
@@ -601,6 +665,114 @@ __global__ void __launch_bounds__(CTA_THREADS) k_round(StageDev S, PhaseDev P, u
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < nreq; i += blockDim.x) next[rs.req_base + i] = rs.req[i];
     if (S.counters && threadIdx.x < ST_COUNT && rs.stat[threadIdx.x]) atomicAdd(S.counters + threadIdx.x, rs.stat[threadIdx.x]);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Persistent dataflow kernel: one launch per phase.  Warps claim queue slots in order; a slot is
+// published when the last predecessor of an item commits.  Grid = co-resident CTAs only.
+// ---------------------------------------------------------------------------------------------
+template <bool GUIDED>
+__global__ void __launch_bounds__(CTA_THREADS) k_flow(StageDev S, PhaseDev P, FlowDev F) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RoundSmem& rs = *reinterpret_cast<RoundSmem*>(smem_raw);
+    CtaSmem& sm = rs.c;
+    if (threadIdx.x < ST_COUNT) rs.stat[threadIdx.x] = 0ull;
+    load_luts(S, sm.lut, sm.lutg);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpScratch& ws = sm.ws[warp];
+    unsigned long long st_acc[ST_COUNT];
+#pragma unroll
+    for (int i = 0; i < ST_COUNT; ++i) st_acc[i] = 0ull;
+    volatile uint32_t* vq = F.queue;
+    volatile uint32_t* vctl = F.ctl;
+    for (;;) {
+        long long tr0 = clock64();
+        uint32_t slot = 0;
+        if (lane == 0) slot = atomicAdd(F.ctl + FC_HEAD, 1u);
+        slot = __shfl_sync(FULL, slot, 0);
+        if (slot >= P.n) break;
+        uint32_t it = NONE32;
+        if (lane == 0) {
+            unsigned spins = 0, ns = 32;
+            while ((it = vq[slot]) == NONE32) {
+                __nanosleep(ns);
+                if (ns < 1024) ns <<= 1;
+                if ((++spins & 1023u) == 0u) {
+                    if (vctl[FC_ABORT]) break;
+                    if (spins > (1u << 22)) { atomicExch(F.ctl + FC_ABORT, 1u); break; }  // watchdog: never hang the device
+                }
+            }
+        }
+        it = __shfl_sync(FULL, it, 0);
+        if (it == NONE32) break;
+        __threadfence();  // acquire: commits of all predecessors are visible below
+        st_acc[ST_CYC_READY] += (unsigned long long)(clock64() - tr0);
+        const uint32_t flat = P.item_pixel[it];
+        const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
+        const uint32_t si = P.stage_base + it;
+        ItemOut o;
+        resolve_item<GUIDED>(S, ws, sm.lut, sm.lutg, lane, x, y, P.item_R2[it], P.rand_xy + (size_t)si * S.m,
+                             P.rand_map + (size_t)si * S.m, o);
+        long long tc0 = clock64();
+        if (lane == 0) {
+            commit_item(S, P, si, flat, x, y, o);
+            __threadfence();  // release
+        }
+        __syncwarp();
+        // notify successors; the one that drops a counter to zero publishes the item
+        const uint32_t s0 = F.succ_off[it], s1 = F.succ_off[it + 1];
+        for (uint32_t e = s0 + lane; e < s1; e += 32) {
+            uint32_t sc = F.succ[e];
+            if (atomicSub(F.npred + sc, 1u) == 1u) {
+                __threadfence();
+                uint32_t pos = atomicAdd(F.ctl + FC_TAIL, 1u);
+                vq[pos] = sc;
+            }
+        }
+        st_acc[ST_FETCHED] += o.fetched; st_acc[ST_NOMINAL] += o.nominal; st_acc[ST_CANDS] += (unsigned long long)o.ncand;
+        st_acc[ST_ITEMS] += 1ull;
+        st_acc[ST_CYC_KNN] += (unsigned long long)o.c_knn; st_acc[ST_CYC_NEIGH] += (unsigned long long)o.c_neigh;
+        st_acc[ST_CYC_WEIGHT] += (unsigned long long)o.c_weight; st_acc[ST_CYC_SCORE] += (unsigned long long)o.c_score;
+        st_acc[ST_CYC_COMMIT] += (unsigned long long)(clock64() - tc0);
+    }
+    if (lane == 0 && S.counters) {
+#pragma unroll
+        for (int i = 0; i < ST_COUNT; ++i) if (st_acc[i]) atomicAdd(&rs.stat[i], st_acc[i]);
+    }
+    __syncthreads();
+    if (S.counters && threadIdx.x < ST_COUNT && rs.stat[threadIdx.x]) atomicAdd(S.counters + threadIdx.x, rs.stat[threadIdx.x]);
+}
+
+// Strictly serial execution of items [0, n) by one warp: the start of a synthesis, where every item
+// depends on all earlier ones (the reference itself is serial there, ms.rs:815).
+template <bool GUIDED>
+__global__ void __launch_bounds__(CTA_THREADS) k_serial(StageDev S, PhaseDev P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RoundSmem& rs = *reinterpret_cast<RoundSmem*>(smem_raw);
+    CtaSmem& sm = rs.c;
+    load_luts(S, sm.lut, sm.lutg);
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    WarpScratch& ws = sm.ws[0];
+    unsigned long long fetched = 0, nominal = 0, cands = 0;
+    for (uint32_t it = 0; it < P.n; ++it) {
+        const uint32_t flat = P.item_pixel[it];
+        const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
+        const uint32_t si = P.stage_base + it;
+        ItemOut o;
+        resolve_item<GUIDED>(S, ws, sm.lut, sm.lutg, lane, x, y, R2_INF, P.rand_xy + (size_t)si * S.m, P.rand_map + (size_t)si * S.m, o);
+        if (lane == 0) {
+            commit_item(S, P, si, flat, x, y, o);
+            __threadfence();
+        }
+        __syncwarp();
+        fetched += o.fetched; nominal += o.nominal; cands += (unsigned long long)o.ncand;
+    }
+    if (lane == 0 && S.counters) {
+        atomicAdd(S.counters + ST_FETCHED, fetched); atomicAdd(S.counters + ST_NOMINAL, nominal);
+        atomicAdd(S.counters + ST_CANDS, cands); atomicAdd(S.counters + ST_ITEMS, (unsigned long long)P.n);
+    }
 }
 
 // Frozen-snapshot evaluation (test harness): resolve without committing.
@@ -639,7 +811,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_eval_items(StageDev S, uint32_t
 // Dependency analysis
 // ---------------------------------------------------------------------------------------------
 // Conflict radius of every item: distance^2 of its k-th nearest resolved point at phase start.
-__global__ void __launch_bounds__(CTA_THREADS) k_radius(StageDev S, PhaseDev P) {
+__global__ void __launch_bounds__(CTA_THREADS) k_radius(StageDev S, PhaseDev P, FlowDev F) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CtaSmem& sm = *reinterpret_cast<CtaSmem*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -656,6 +828,10 @@ __global__ void __launch_bounds__(CTA_THREADS) k_radius(StageDev S, PhaseDev P) 
             P.done[it] = 0;
             P.pending[0][it] = it;
             P.pmap[flat] = it;
+            if (F.npred) {
+                F.npred[it] = 0; F.nsucc[it] = 0; F.succ_cur[it] = 0; F.queue[it] = NONE32;
+                if (it == 0) { F.nsucc[P.n] = 0; F.ctl[FC_HEAD] = 0; F.ctl[FC_TAIL] = 0; F.ctl[FC_ABORT] = 0; }
+            }
         }
         __syncwarp();
     }
@@ -739,6 +915,76 @@ __global__ void __launch_bounds__(CTA_THREADS) k_preds_pairs(StageDev S, PhaseDe
         }
         if (lane == 0) P.pred_cnt[it] = cnt;
     }
+}
+
+
+// ---- CSR dependency graph for the dataflow kernel: edge a -> b (a < b) for every pair with
+// dist^2 <= max(R_a^2, R_b^2).  PASS 0 counts, PASS 1 fills (after an exclusive scan of nsucc). ----
+template <int PASS>
+__device__ __forceinline__ void edge_emit(const FlowDev& F, uint32_t a, uint32_t b) {
+    if (PASS == 0) { atomicAdd(F.nsucc + a, 1u); atomicAdd(F.npred + b, 1u); }
+    else { uint32_t slot = atomicAdd(F.succ_cur + a, 1u); F.succ[F.succ_off[a] + slot] = b; }
+}
+template <int PASS>
+__device__ __forceinline__ void edge_visit(const StageDev& S, const PhaseDev& P, const FlowDev& F, uint32_t it, int qx, int qy, uint32_t D) {
+    if (S.tiling) { qx = imod(qx, S.W); qy = imod(qy, S.H); }  // conservative: treat the canvas as a torus
+    else if ((unsigned)qx >= (unsigned)S.W || (unsigned)qy >= (unsigned)S.H) return;
+    uint32_t j = P.pmap[(size_t)qy * S.W + qx];
+    if (j == NONE32 || j == it) return;
+    if (j < it) edge_emit<PASS>(F, j, it);                       // `it` sees j from its own disc
+    else if (D > P.item_R2[j]) edge_emit<PASS>(F, it, j);        // j does not see `it`: registered from this side
+}
+template <int PASS>
+__global__ void __launch_bounds__(CTA_THREADS) k_edges_scan(StageDev S, PhaseDev P, FlowDev F) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nwarps = gridDim.x * WARPS_PER_CTA;
+    for (uint32_t it = blockIdx.x * WARPS_PER_CTA + warp; it < P.n; it += nwarps) {
+        const uint32_t flat = P.item_pixel[it];
+        const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
+        const uint32_t R2 = P.item_R2[it];
+        if (R2 <= (uint32_t)S.RT2) {
+            int limit = (int)__ldg(S.cntLE + R2);
+            for (int idx = lane; idx < limit; idx += 32) {
+                short2 o = __ldg(S.spiral + idx);
+                edge_visit<PASS>(S, P, F, it, x + o.x, y + o.y, (uint32_t)(o.x * o.x + o.y * o.y));
+            }
+        } else {
+            int rmaxx = S.tiling ? S.W / 2 : S.W, rmaxy = S.tiling ? S.H / 2 : S.H;
+            int r = isqrt_u32(R2);
+            int ry = min(r, rmaxy);
+            for (int dy = -ry; dy <= ry; ++dy) {
+                int w = min(isqrt_u32(R2 - (uint32_t)(dy * dy)), rmaxx);
+                for (int dx = -w + lane; dx <= w; dx += 32)
+                    edge_visit<PASS>(S, P, F, it, x + dx, y + dy, (uint32_t)(dx * dx + dy * dy));
+            }
+        }
+    }
+}
+template <int PASS>
+__global__ void __launch_bounds__(CTA_THREADS) k_edges_pairs(StageDev S, PhaseDev P, FlowDev F) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nwarps = gridDim.x * WARPS_PER_CTA;
+    for (uint32_t it = blockIdx.x * WARPS_PER_CTA + warp; it < P.n; it += nwarps) {
+        const uint32_t flat = P.item_pixel[it];
+        const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
+        const uint32_t R2 = P.item_R2[it];
+        for (uint32_t base = 0; base < it; base += 32) {
+            uint32_t j = base + lane;
+            if (j < it) {
+                uint32_t fj = P.item_pixel[j];
+                int dx = abs((int)(fj % (uint32_t)S.W) - x), dy = abs((int)(fj / (uint32_t)S.W) - y);
+                if (S.tiling) { dx = min(dx, S.W - dx); dy = min(dy, S.H - dy); }
+                unsigned long long D = (unsigned long long)dx * dx + (unsigned long long)dy * dy;
+                uint32_t Rm = max(R2, P.item_R2[j]);
+                if ((Rm == R2_INF) || (D <= (unsigned long long)Rm)) edge_emit<PASS>(F, j, it);
+            }
+        }
+    }
+}
+__global__ void k_seed_queue(PhaseDev P, FlowDev F) {
+    uint32_t it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= P.n) return;
+    if (F.npred[it] == 0u) F.queue[atomicAdd(F.ctl + FC_TAIL, 1u)] = it;
 }
 
 // ---------------------------------------------------------------------------------------------
