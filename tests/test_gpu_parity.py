@@ -156,3 +156,18 @@ def test_session_mirror_runs_like_reference_example_01():
     go.set_examples([case_pyr])
     go.resolve(O.make_params(seed=120))
     assert (go.color() == img).all()
+
+
+@pytest.mark.parametrize("env", [{"TSB_MODE": "csr"}, {"TSB_MODE": "rounds"}, {"TSB_SUCC_STRIDE": "6"}], ids=["csr", "rounds", "stride_overflow"])
+def test_alternative_schedulers_give_the_same_result(env, monkeypatch):
+    """The dependency scheduler has three interchangeable implementations (fixed-stride successor lists, CSR
+    fallback on overflow, host-visible rounds): all must reproduce the serial order exactly."""
+    case = Case("sched", 96, 80, [(64, 48)], seed=17, tiling=True).build()
+    ref = case.run_gpu()
+    for k_, v in env.items():
+        monkeypatch.setenv(k_, v)
+    alt = case.run_gpu()
+    assert (ref.coord() == alt.coord()).all() and (ref.color() == alt.color()).all()
+    fa, sa = ref.resolved()
+    fb, sb = alt.resolved()
+    assert (fa == fb).all() and (sa.view(np.uint32) == sb.view(np.uint32)).all()

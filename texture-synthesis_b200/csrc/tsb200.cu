@@ -6,6 +6,8 @@
 #include "../../include/tsb200.h"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -67,6 +69,21 @@ struct DevBuf {
     int upload(const T* h, size_t count, cudaStream_t s) {
         TRY(ensure(count));
         if (count) CU(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+        return 0;
+    }
+};
+
+template <typename T>
+struct PinnedBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+    int ensure(size_t count) {
+        if (count <= n) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; n = 0;
+        CU(cudaMallocHost((void**)&p, std::max<size_t>(count, 1) * sizeof(T)));
+        n = count;
         return 0;
     }
 };
@@ -191,6 +208,7 @@ SpiralHost build_spiral(int RT) {
 constexpr int SPIRAL_RT = 48;
 constexpr uint32_t PAIR_MAX = 4096;   // phases up to this size use the all-pairs dependency test
 constexpr int ROUNDS_PER_SYNC = 4;
+constexpr size_t SUCC_STRIDE = 160;   // fixed-stride successor lists (single analysis pass); overflow falls back to CSR
 
 struct StagePlan {
     int p_stage, level;
@@ -251,8 +269,10 @@ struct tsb_generator {
     DevBuf<uint32_t> d_npred, d_nsucc, d_succ_off, d_succ_cur, d_succ, d_queue, d_fctl;
     DevBuf<uint8_t> d_cub_temp;
     int max_ctas_flow = 0;
-    bool use_rounds = false;
-    uint32_t* h_ctrl = nullptr;  // pinned, 8 words
+    bool use_rounds = false, force_csr = false;
+    size_t succ_stride = SUCC_STRIDE;
+    uint32_t* h_ctrl = nullptr;  // pinned, 16 words
+    PinnedBuf<uint32_t> h_idx, h_items;  // pick indices (D2H) and per-stage work-item pixels (H2D)
     bool pmap_ready = false;
 
     // trace
@@ -584,39 +604,55 @@ int run_phase_flow(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n,
     PhaseDev P = make_phase(g, i0, n, is_new, trace_base);
     FlowDev F;
     F.npred = g->d_npred.p; F.nsucc = g->d_nsucc.p; F.succ_off = g->d_succ_off.p; F.succ_cur = g->d_succ_cur.p;
-    F.succ = g->d_succ.p; F.queue = g->d_queue.p; F.ctl = g->d_fctl.p;
+    F.succ = g->d_succ.p; F.queue = g->d_queue.p; F.ctl = g->d_fctl.p; F.stride = 0;
     g->stats.phases++;
     PhaseClock clk;
     TRY(clk.begin(s));
     const int ga = grid_for(g, n);
-    k_radius<<<ga, CTA_THREADS, sizeof(CtaSmem), s>>>(S, P, F);
-    if (n <= PAIR_MAX) k_edges_pairs<0><<<ga, CTA_THREADS, 0, s>>>(S, P, F);
-    else k_edges_scan<0><<<ga, CTA_THREADS, 0, s>>>(S, P, F);
-    CU(cudaGetLastError());
-    size_t temp_bytes = g->d_cub_temp.n;
-    CU(cub::DeviceScan::ExclusiveSum(g->d_cub_temp.p, temp_bytes, F.nsucc, F.succ_off, (int)(n + 1), s));
-    CU(cudaMemcpyAsync(g->h_ctrl, F.succ_off + n, 4, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    const uint64_t edges = g->h_ctrl[0];
-    g->stats.kernel_launches += 3;
-    if (edges > 400ull * n + (64ull << 20)) {  // degenerate conflict graph: run the phase serially instead
+    const int gf = std::max(1, std::min((int)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), g->max_ctas_flow));
+    uint64_t edges = 0;
+    bool use_csr = g->force_csr || (size_t)n * g->succ_stride > g->d_succ.n;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        F.stride = use_csr ? 0u : (uint32_t)g->succ_stride;
+        k_radius<<<ga, CTA_THREADS, sizeof(CtaSmem), s>>>(S, P, F);
+        CU(cudaGetLastError());
+        g->stats.kernel_launches++;
+        if (use_csr) {
+            if (n <= PAIR_MAX) k_edges_pairs<0><<<ga, CTA_THREADS, 0, s>>>(S, P, F);
+            else k_edges_scan<0><<<ga, CTA_THREADS, 0, s>>>(S, P, F);
+            CU(cudaGetLastError());
+            size_t temp_bytes = g->d_cub_temp.n;
+            CU(cub::DeviceScan::ExclusiveSum(g->d_cub_temp.p, temp_bytes, F.nsucc, F.succ_off, (int)(n + 1), s));
+            CU(cudaMemcpyAsync(g->h_ctrl, F.succ_off + n, 4, cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));
+            edges = g->h_ctrl[0];
+            g->stats.kernel_launches += 3;
+            if (edges > 400ull * n + (64ull << 20)) {  // degenerate conflict graph: run the phase serially instead
+                k_pmap_clear<<<(n + 255) / 256, 256, 0, s>>>(P);
+                CU(cudaGetLastError());
+                return run_serial(g, S, i0, n, is_new, trace_base);
+            }
+            if (edges > g->d_succ.n) { TRY(g->d_succ.ensure(edges + edges / 4 + 1024)); F.succ = g->d_succ.p; }
+            if (n <= PAIR_MAX) k_edges_pairs<1><<<ga, CTA_THREADS, 0, s>>>(S, P, F);
+            else k_edges_scan<1><<<ga, CTA_THREADS, 0, s>>>(S, P, F);
+        } else {
+            if (n <= PAIR_MAX) k_edges_pairs<2><<<ga, CTA_THREADS, 0, s>>>(S, P, F);
+            else k_edges_scan<2><<<ga, CTA_THREADS, 0, s>>>(S, P, F);
+        }
+        k_seed_queue<<<(n + 255) / 256, 256, 0, s>>>(P, F);
+        CU(cudaGetLastError());
+        if (attempt == 0) TRY(clk.mid(s));
+        if (g->guided) k_flow<true><<<gf, CTA_THREADS, sizeof(RoundSmem), s>>>(S, P, F);
+        else k_flow<false><<<gf, CTA_THREADS, sizeof(RoundSmem), s>>>(S, P, F);
         k_pmap_clear<<<(n + 255) / 256, 256, 0, s>>>(P);
         CU(cudaGetLastError());
-        return run_serial(g, S, i0, n, is_new, trace_base);
+        g->stats.kernel_launches += 4;
+        g->stats.rounds++;
+        CU(cudaMemcpyAsync(g->h_ctrl, F.ctl, 16, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        if (!use_csr && g->h_ctrl[FC_OVERFLOW]) { use_csr = true; continue; }  // a successor list overflowed: nothing ran, redo with CSR
+        break;
     }
-    if (edges > g->d_succ.n) { TRY(g->d_succ.ensure(edges + edges / 4 + 1024)); F.succ = g->d_succ.p; }
-    if (n <= PAIR_MAX) k_edges_pairs<1><<<ga, CTA_THREADS, 0, s>>>(S, P, F);
-    else k_edges_scan<1><<<ga, CTA_THREADS, 0, s>>>(S, P, F);
-    k_seed_queue<<<(n + 255) / 256, 256, 0, s>>>(P, F);
-    CU(cudaGetLastError());
-    TRY(clk.mid(s));
-    const int gf = std::max(1, std::min((int)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), g->max_ctas_flow));
-    if (g->guided) k_flow<true><<<gf, CTA_THREADS, sizeof(RoundSmem), s>>>(S, P, F);
-    else k_flow<false><<<gf, CTA_THREADS, sizeof(RoundSmem), s>>>(S, P, F);
-    k_pmap_clear<<<(n + 255) / 256, 256, 0, s>>>(P);
-    CU(cudaGetLastError());
-    g->stats.kernel_launches += 4;
-    g->stats.rounds++;
     CU(cudaMemcpyAsync(g->h_ctrl, F.ctl, 12, cudaMemcpyDeviceToHost, s));
     TRY(clk.end(g, s, "flow", i0, n, is_new, edges));
     if (g->h_ctrl[FC_ABORT]) return fail(TSB_ERR_INTERNAL, "dataflow phase of %u items stalled (head %u tail %u)", n, g->h_ctrl[0], g->h_ctrl[1]);
@@ -675,8 +711,27 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
     }
     if (max_stage_items > 0xFFFFFFF0ull) return fail(TSB_ERR_UNSUPPORTED, "output too large");
 
-    // ---- pixel order: pick_random_unresolved (ms.rs:380-389) for every new pixel of every stage ----
-    std::vector<uint32_t> picks(n_picks);
+    // ---- rebuild the resolved set with tiling mirrors (ms.rs:747-779) ----
+    StageDev S;
+    fill_stage_geometry(g, S, tiling);
+    CU(cudaMemsetAsync(g->d_mask.p, 0, (size_t)g->wpr * g->mrows * 4, s));
+    CU(cudaMemsetAsync(g->d_mask1.p, 0, (size_t)g->wpr1 * g->mrows * 4, s));
+    if (g->have_loaded_points) {
+        TRY(g->d_tmp_u32.upload((const uint32_t*)g->loaded_points.data(), g->loaded_points.size(), s));
+        uint32_t np = (uint32_t)(g->loaded_points.size() / 2);
+        if (np) k_mask_insert_points<<<(np + 255) / 256, 256, 0, s>>>(S, (const int32_t*)g->d_tmp_u32.p, np);
+    } else if (!g->resolved_order.empty()) {
+        TRY(g->d_tmp_u32.upload(g->resolved_order.data(), g->resolved_order.size(), s));
+        uint32_t np = (uint32_t)g->resolved_order.size();
+        k_mask_insert_flat<<<(np + 255) / 256, 256, 0, s>>>(S, g->d_tmp_u32.p, np, tiling ? 1 : 0);
+    }
+    CU(cudaGetLastError());
+
+    // ---- pixel order: pick_random_unresolved (ms.rs:380-389) for every new pixel of every stage.  The index
+    // draws run on the GPU; the swap_remove chain and the per-stage work-item lists are produced by a host
+    // worker thread that runs ahead of the GPU (stage s+1 is planned while stage s executes). ----
+    TRY(g->h_idx.ensure(std::max<size_t>(n_picks, 1)));
+    TRY(g->h_items.ensure(std::max<size_t>(total_items, 1)));
     {
         TRY(g->d_pick_idx.ensure(std::max<size_t>(n_picks, 1)));
         size_t un = total;
@@ -689,19 +744,34 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
             }
             un -= sp.n_new;
         }
-        std::vector<uint32_t> idx(n_picks);
-        if (n_picks) CU(cudaMemcpyAsync(idx.data(), g->d_pick_idx.p, n_picks * 4, cudaMemcpyDeviceToHost, s));
+        if (n_picks) CU(cudaMemcpyAsync(g->h_idx.p, g->d_pick_idx.p, n_picks * 4, cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
+    }
+    std::vector<size_t> stage_item_base(plan.size() + 1, 0);
+    for (size_t i = 0; i < plan.size(); ++i) stage_item_base[i + 1] = stage_item_base[i] + plan[i].n_redo + plan[i].n_new;
+    std::atomic<int> stages_planned{0};
+    std::thread planner([&]() {
         std::vector<uint32_t>& v = g->unresolved;  // swap_remove chain
         size_t len = v.size();
-        for (size_t t = 0; t < n_picks; ++t) {
-            uint32_t j = idx[t];
-            picks[t] = v[j];
-            v[j] = v[len - 1];
-            --len;
+        const uint32_t* idx = g->h_idx.p;
+        for (size_t si = 0; si < plan.size(); ++si) {
+            const StagePlan& sp = plan[si];
+            uint32_t* items = g->h_items.p + stage_item_base[si];
+            for (size_t i = 0; i < sp.n_redo; ++i) items[i] = g->resolved_order[g->locked + i];  // ms.rs:905-907
+            uint32_t* fresh = items + sp.n_redo;
+            for (size_t t = 0; t < sp.n_new; ++t) {
+                uint32_t j = idx[sp.pick_base + t];
+                fresh[t] = v[j];
+                v[j] = v[len - 1];
+                --len;
+            }
+            // ms.rs:1043-1049: newly resolved pixels join `resolved` in processing order
+            g->resolved_order.insert(g->resolved_order.end(), fresh, fresh + sp.n_new);
+            stages_planned.store((int)si + 1, std::memory_order_release);
         }
         v.resize(len);
-    }
+    });
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{planner};
     g->stats.host_ms_schedule = now_ms() - t_plan0;
 
     // ---- buffers ----
@@ -715,13 +785,15 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
     TRY(g->d_ctrl.ensure(8));
     TRY(g->d_npred.ensure(max_phase + 1)); TRY(g->d_nsucc.ensure(max_phase + 1)); TRY(g->d_succ_off.ensure(max_phase + 1));
     TRY(g->d_succ_cur.ensure(max_phase + 1)); TRY(g->d_queue.ensure(max_phase + 1)); TRY(g->d_fctl.ensure(4));
-    TRY(g->d_succ.ensure(max_phase * 40 + 1024));
+    TRY(g->d_succ.ensure(max_phase * SUCC_STRIDE + 1024));
     {
         size_t tb = 0;
         CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, g->d_nsucc.p, g->d_succ_off.p, (int)(max_phase + 1), s));
         TRY(g->d_cub_temp.ensure(tb + 256));
     }
     g->use_rounds = getenv("TSB_MODE") && !strcmp(getenv("TSB_MODE"), "rounds");
+    g->force_csr = getenv("TSB_MODE") && !strcmp(getenv("TSB_MODE"), "csr");
+    g->succ_stride = getenv("TSB_SUCC_STRIDE") ? std::max(1, atoi(getenv("TSB_SUCC_STRIDE"))) : SUCC_STRIDE;
     TRY(g->d_rand_xy.ensure(max_stage_items * (size_t)m));
     TRY(g->d_rand_map.ensure(max_stage_items * (size_t)m));
     TRY(g->d_luts.ensure(512));
@@ -739,29 +811,12 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
         TRY(g->d_tr_nneigh.ensure(total_items)); TRY(g->d_tr_score.ensure(total_items));
     }
 
-    // ---- rebuild the resolved set with tiling mirrors (ms.rs:747-779) ----
-    StageDev S;
-    fill_stage_geometry(g, S, tiling);
     S.counters = g->d_counters.p;
-    CU(cudaMemsetAsync(g->d_mask.p, 0, (size_t)g->wpr * g->mrows * 4, s));
-    CU(cudaMemsetAsync(g->d_mask1.p, 0, (size_t)g->wpr1 * g->mrows * 4, s));
-    if (g->have_loaded_points) {
-        TRY(g->d_tmp_u32.upload((const uint32_t*)g->loaded_points.data(), g->loaded_points.size(), s));
-        uint32_t np = (uint32_t)(g->loaded_points.size() / 2);
-        if (np) k_mask_insert_points<<<(np + 255) / 256, 256, 0, s>>>(S, (const int32_t*)g->d_tmp_u32.p, np);
-    } else if (!g->resolved_order.empty()) {
-        TRY(g->d_tmp_u32.upload(g->resolved_order.data(), g->resolved_order.size(), s));
-        uint32_t np = (uint32_t)g->resolved_order.size();
-        k_mask_insert_flat<<<(np + 255) / 256, 256, 0, s>>>(S, g->d_tmp_u32.p, np, tiling ? 1 : 0);
-    }
-    CU(cudaGetLastError());
-
     uint64_t overall_total = 0, overall_current = 0;
     for (auto& sp : plan) overall_total += sp.pixels_to_resolve;
     uint32_t last_pcnt = 0;
     std::vector<uint8_t> progress_img;
     uint64_t trace_base = 0;
-    std::vector<uint32_t> stage_pixels;
 
     for (auto& sp : plan) {
         stage_inputs(g, S, sp.level, prm);
@@ -773,11 +828,15 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
         }
         const size_t n_items = sp.n_redo + sp.n_new;
         if (n_items == 0) continue;
-        stage_pixels.resize(n_items);
-        for (size_t i = 0; i < sp.n_redo; ++i) stage_pixels[i] = g->resolved_order[g->locked + i];  // ms.rs:905-907
-        for (size_t t = 0; t < sp.n_new; ++t) stage_pixels[sp.n_redo + t] = picks[sp.pick_base + t];
-        CU(cudaMemcpyAsync(g->d_item_pixel.p, stage_pixels.data(), n_items * 4, cudaMemcpyHostToDevice, s));
-        if (g->trace) g->tr_pixel.insert(g->tr_pixel.end(), stage_pixels.begin(), stage_pixels.end());
+        const size_t stage_idx = (size_t)(&sp - &plan[0]);
+        {
+            const double tw = now_ms();
+            while (stages_planned.load(std::memory_order_acquire) <= (int)stage_idx) std::this_thread::yield();
+            g->stats.host_ms_schedule += now_ms() - tw;  // time the GPU had to wait for the planner
+        }
+        const uint32_t* stage_pixels = g->h_items.p + stage_item_base[stage_idx];
+        CU(cudaMemcpyAsync(g->d_item_pixel.p, stage_pixels, n_items * 4, cudaMemcpyHostToDevice, s));
+        if (g->trace) g->tr_pixel.insert(g->tr_pixel.end(), stage_pixels, stage_pixels + n_items);
         // random candidates of every item of the stage: rng seeded with loop_seed + 1 = stage seed + i + 1 (ms.rs:902,945)
         k_rand_candidates<<<(uint32_t)((n_items + 127) / 128), 128, 0, s>>>(S.ex, S.n_ex, m, sp.seed + 1ull, (uint32_t)n_items,
                                                                           g->d_rand_xy.p, g->d_rand_map.p);
@@ -835,8 +894,6 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
                 }
             }
         }
-        // ms.rs:1043-1049: newly resolved pixels join `resolved` in processing order
-        for (size_t t = 0; t < sp.n_new; ++t) g->resolved_order.push_back(picks[sp.pick_base + t]);
         overall_current += sp.pixels_to_resolve;
         trace_base += n_items;
     }

@@ -97,9 +97,10 @@ struct FlowDev {
     uint32_t* succ_cur;  // [n]   fill cursors
     uint32_t* succ;      // [edges]
     uint32_t* queue;     // [n]
-    uint32_t* ctl;       // [0] head  [1] tail  [2] abort flag
+    uint32_t* ctl;       // [0] head  [1] tail  [2] abort flag  [3] successor-list overflow (fixed-stride mode)
+    uint32_t stride;     // > 0: successors of item a live in succ[a*stride ..] (single analysis pass); 0: CSR
 };
-enum { FC_HEAD = 0, FC_TAIL = 1, FC_ABORT = 2 };
+enum { FC_HEAD = 0, FC_TAIL = 1, FC_ABORT = 2, FC_OVERFLOW = 3 };
 
 struct __align__(16) WarpScratch {
     union {
@@ -686,7 +687,8 @@ __global__ void __launch_bounds__(CTA_THREADS) k_flow(StageDev S, PhaseDev P, Fl
     for (int i = 0; i < ST_COUNT; ++i) st_acc[i] = 0ull;
     volatile uint32_t* vq = F.queue;
     volatile uint32_t* vctl = F.ctl;
-    for (;;) {
+    const bool skip = F.stride && vctl[FC_OVERFLOW];  // incomplete successor lists: do nothing, the host re-plans the phase
+    for (; !skip;) {
         long long tr0 = clock64();
         uint32_t slot = 0;
         if (lane == 0) slot = atomicAdd(F.ctl + FC_HEAD, 1u);
@@ -721,7 +723,8 @@ __global__ void __launch_bounds__(CTA_THREADS) k_flow(StageDev S, PhaseDev P, Fl
         }
         __syncwarp();
         // notify successors; the one that drops a counter to zero publishes the item
-        const uint32_t s0 = F.succ_off[it], s1 = F.succ_off[it + 1];
+        const uint32_t s0 = F.stride ? it * F.stride : F.succ_off[it];
+        const uint32_t s1 = F.stride ? s0 + F.nsucc[it] : F.succ_off[it + 1];
         for (uint32_t e = s0 + lane; e < s1; e += 32) {
             uint32_t sc = F.succ[e];
             if (atomicSub(F.npred + sc, 1u) == 1u) {
@@ -830,7 +833,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_radius(StageDev S, PhaseDev P, 
             P.pmap[flat] = it;
             if (F.npred) {
                 F.npred[it] = 0; F.nsucc[it] = 0; F.succ_cur[it] = 0; F.queue[it] = NONE32;
-                if (it == 0) { F.nsucc[P.n] = 0; F.ctl[FC_HEAD] = 0; F.ctl[FC_TAIL] = 0; F.ctl[FC_ABORT] = 0; }
+                if (it == 0) { F.nsucc[P.n] = 0; F.ctl[FC_HEAD] = 0; F.ctl[FC_TAIL] = 0; F.ctl[FC_ABORT] = 0; F.ctl[FC_OVERFLOW] = 0; }
             }
         }
         __syncwarp();
@@ -923,7 +926,13 @@ __global__ void __launch_bounds__(CTA_THREADS) k_preds_pairs(StageDev S, PhaseDe
 template <int PASS>
 __device__ __forceinline__ void edge_emit(const FlowDev& F, uint32_t a, uint32_t b) {
     if (PASS == 0) { atomicAdd(F.nsucc + a, 1u); atomicAdd(F.npred + b, 1u); }
-    else { uint32_t slot = atomicAdd(F.succ_cur + a, 1u); F.succ[F.succ_off[a] + slot] = b; }
+    else if (PASS == 1) { uint32_t slot = atomicAdd(F.succ_cur + a, 1u); F.succ[F.succ_off[a] + slot] = b; }
+    else {  // PASS 2: single pass into fixed-stride lists; an overflow makes the host redo the phase with the CSR passes
+        uint32_t slot = atomicAdd(F.nsucc + a, 1u);
+        if (slot < F.stride) F.succ[(size_t)a * F.stride + slot] = b;
+        else F.ctl[FC_OVERFLOW] = 1u;
+        atomicAdd(F.npred + b, 1u);
+    }
 }
 template <int PASS>
 __device__ __forceinline__ void edge_visit(const StageDev& S, const PhaseDev& P, const FlowDev& F, uint32_t it, int qx, int qy, uint32_t D) {
