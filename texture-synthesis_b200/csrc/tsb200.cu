@@ -285,7 +285,7 @@ struct tsb_generator {
     uint64_t trace_n = 0;
 
     tsb_stats stats{};
-    int max_ctas = 0;
+    int max_ctas = 0, n_sms = 0;
 
     ~tsb_generator() {
         if (h_ctrl) cudaFreeHost(h_ctrl);
@@ -464,6 +464,12 @@ int launch_resolve_kernel(tsb_generator* g, K kernel, int grid, size_t smem, Arg
     return 0;
 }
 
+// kernels without shared memory (dependency scans) are latency bound: allow twice as many resident CTAs
+int grid_light(const tsb_generator* g, uint32_t items) {
+    int need = (int)((items + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+    return std::max(1, std::min(need, g->n_sms * 8));
+}
+
 int grid_for(const tsb_generator* g, uint32_t items) {
     int need = (int)((items + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
     return std::max(1, std::min(need, g->max_ctas));
@@ -608,7 +614,7 @@ int run_phase_flow(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n,
     g->stats.phases++;
     PhaseClock clk;
     TRY(clk.begin(s));
-    const int ga = grid_for(g, n);
+    const int ga = grid_for(g, n), gl = grid_light(g, n);
     const int gf = std::max(1, std::min((int)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), g->max_ctas_flow));
     uint64_t edges = 0;
     bool use_csr = g->force_csr || (size_t)n * g->succ_stride > g->d_succ.n;
@@ -619,7 +625,7 @@ int run_phase_flow(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n,
         g->stats.kernel_launches++;
         if (use_csr) {
             if (n <= PAIR_MAX) k_edges_pairs<0><<<ga, CTA_THREADS, 0, s>>>(S, P, F);
-            else k_edges_scan<0><<<ga, CTA_THREADS, 0, s>>>(S, P, F);
+            else k_edges_scan<0><<<gl, CTA_THREADS, 0, s>>>(S, P, F);
             CU(cudaGetLastError());
             size_t temp_bytes = g->d_cub_temp.n;
             CU(cub::DeviceScan::ExclusiveSum(g->d_cub_temp.p, temp_bytes, F.nsucc, F.succ_off, (int)(n + 1), s));
@@ -634,10 +640,10 @@ int run_phase_flow(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n,
             }
             if (edges > g->d_succ.n) { TRY(g->d_succ.ensure(edges + edges / 4 + 1024)); F.succ = g->d_succ.p; }
             if (n <= PAIR_MAX) k_edges_pairs<1><<<ga, CTA_THREADS, 0, s>>>(S, P, F);
-            else k_edges_scan<1><<<ga, CTA_THREADS, 0, s>>>(S, P, F);
+            else k_edges_scan<1><<<gl, CTA_THREADS, 0, s>>>(S, P, F);
         } else {
             if (n <= PAIR_MAX) k_edges_pairs<2><<<ga, CTA_THREADS, 0, s>>>(S, P, F);
-            else k_edges_scan<2><<<ga, CTA_THREADS, 0, s>>>(S, P, F);
+            else k_edges_scan<2><<<gl, CTA_THREADS, 0, s>>>(S, P, F);
         }
         k_seed_queue<<<(n + 255) / 256, 256, 0, s>>>(P, F);
         CU(cudaGetLastError());
@@ -847,7 +853,7 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
         // ---- redo phase: the resolved set is static, radii are exact ----
         if (sp.n_redo) {
             S.r2_hint = r2_hint_for(g, resolved_now, k);
-            S.n_points_max = (uint32_t)std::min<size_t>(3 * resolved_now, 0xFFFFFFFFull);
+            S.n_points_max = (uint32_t)std::min<size_t>((tiling ? 3 : 1) * resolved_now, 0xFFFFFFFFull);
             if (g->use_rounds) TRY(run_phase(g, S, 0, (uint32_t)sp.n_redo, false, true, trace_base));
             else TRY(run_phase_flow(g, S, 0, (uint32_t)sp.n_redo, false, trace_base));
         }
@@ -875,7 +881,17 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
             const bool serial = base < 2 * (size_t)k;  // every item still depends on (almost) all earlier ones
             size_t n_e = serial ? (g->use_rounds ? 1 : std::min(n_items - cur, 2 * (size_t)k - base)) : std::min(n_items - cur, base);
             S.r2_hint = r2_hint_for(g, resolved_now, k);
-            S.n_points_max = (uint32_t)std::min<size_t>(3 * (resolved_now + n_e), 0xFFFFFFFFull);
+            S.n_points_max = (uint32_t)std::min<size_t>((tiling ? 3 : 1) * (resolved_now + n_e), 0xFFFFFFFFull);
+            if (serial && tiling && resolved_now + n_e <= (size_t)KBUF) {
+                // exact upper bound of the point count (pixels + their mirror copies, ms.rs:306-327) so that the
+                // serial kernel can keep the whole set as a list; pixels resolved before this stage count 3x
+                size_t cnt = 3 * sp.resolved_before;
+                for (size_t i = sp.n_redo; i < cur + n_e; ++i) {
+                    int x = (int)(stage_pixels[i] % (uint32_t)g->W), y = (int)(stage_pixels[i] / (uint32_t)g->W);
+                    cnt += 1 + ((x < S.x_l || x > S.x_r) ? 1 : 0) + ((y < S.y_b || y > S.y_t) ? 1 : 0);
+                }
+                S.n_points_max = (uint32_t)cnt;
+            }
             if (g->use_rounds) TRY(run_phase(g, S, (uint32_t)cur, (uint32_t)n_e, true, n_e > 1, trace_base));
             else if (serial) TRY(run_serial(g, S, (uint32_t)cur, (uint32_t)n_e, true, trace_base));
             else TRY(run_phase_flow(g, S, (uint32_t)cur, (uint32_t)n_e, true, trace_base));
@@ -1030,6 +1046,7 @@ int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_flow_g, k_flow<true>, CTA_THREADS, sizeof(RoundSmem)) != cudaSuccess || per_sm_flow_g < 1) per_sm_flow_g = 1;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "cudaGetDeviceProperties failed"));
+    g->n_sms = prop.multiProcessorCount;
     g->max_ctas = prop.multiProcessorCount * per_sm;
     g->max_ctas_flow = prop.multiProcessorCount * std::min(per_sm_flow, per_sm_flow_g);  // persistent grid: co-resident CTAs only
     if ((rc = init_state(g))) return bail(rc);

@@ -331,17 +331,40 @@ __device__ __forceinline__ int knn_search(const StageDev& S, WarpScratch& ws, in
     return kk;
 }
 
+// k nearest among an explicit point list held in shared memory (serial start of a synthesis, where the
+// resolved set is tiny and scanning the mask would cost more than looking at every point)
+__device__ __forceinline__ int knn_points(const StageDev& S, WarpScratch& ws, int lane, int x, int y, const short2* pts, int npts, uint32_t* r2_out) {
+    for (int i = lane; i < npts; i += 32) {
+        int dx = pts[i].x - x, dy = pts[i].y - y;
+        ws.u.keys[i] = ((unsigned long long)(uint32_t)(dx * dx + dy * dy) << 32) | ((unsigned long long)(uint32_t)(dy + 32768) << 16) |
+                       (unsigned long long)(uint32_t)(dx + 32768);
+    }
+    __syncwarp();
+    sort_keys(ws, lane, npts);
+    const int kk = npts < S.k ? npts : S.k;
+    unsigned long long kth = kk > 0 ? ws.u.keys[kk - 1] : 0ull;
+    __syncwarp();
+    for (int j = lane; j < kk; j += 32) {
+        unsigned long long key = ws.u.keys[j];
+        ws.off[j] = make_short2((short)((int)(key & 0xFFFF) - 32768), (short)((int)((key >> 16) & 0xFFFF) - 32768));
+    }
+    __syncwarp();
+    *r2_out = (kk == S.k) ? (uint32_t)(kth >> 32) : R2_INF;
+    return kk;
+}
+
 // ---------------------------------------------------------------------------------------------
 // One pixel resolution (steps 2-4 of ms.rs:917-986) by one warp.  No commit.
 // ---------------------------------------------------------------------------------------------
 template <bool GUIDED>
 __device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws, const float* __restrict__ s_lut,
                              const float* __restrict__ s_lutg, int lane, int x, int y, uint32_t R2bound,
-                             const uint32_t* __restrict__ rand_xy, const uint8_t* __restrict__ rand_map, ItemOut& out) {
+                             const uint32_t* __restrict__ rand_xy, const uint8_t* __restrict__ rand_map, ItemOut& out,
+                             const short2* pts = nullptr, int npts = 0) {
     const unsigned lt = (1u << lane) - 1u;
     uint32_t r2;
     long long t0 = clock64();
-    const int kk = knn_search(S, ws, lane, x, y, R2bound, &r2);
+    const int kk = pts ? knn_points(S, ws, lane, x, y, pts, npts, &r2) : knn_search(S, ws, lane, x, y, R2bound, &r2);
     long long t1 = clock64();
     out.c_knn = t1 - t0; out.c_neigh = out.c_weight = out.c_score = 0; out.fetched = out.nominal = 0;
     out.kk = kk;
@@ -415,36 +438,27 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws,
         unsigned long long* dk = reinterpret_cast<unsigned long long*>(ws.d);  // distances are dead from here on
         for (int a = lane; a < ncoh; a += 32) dk[a] = (unsigned long long)ws.u.c.cxy[a] | ((unsigned long long)ws.cmeta[a] << 32);
         __syncwarp();
-        unsigned long long key[KMAX / 32];
-        uint32_t pat[KMAX / 32];
-        bool keep[KMAX / 32];
-#pragma unroll
-        for (int c = 0; c < KMAX / 32; ++c) {
-            int a = c * 32 + lane;
-            keep[c] = a < ncoh;
-            key[c] = keep[c] ? dk[a] : 0ull;
-            pat[c] = keep[c] ? ws.u.c.cpatch[a] : 0u;
-        }
-        for (int b = 0; b + 1 < ncoh; ++b) {
-            unsigned long long kb = dk[b];
-#pragma unroll
-            for (int c = 0; c < KMAX / 32; ++c)
-                if (kb == key[c] && b < c * 32 + lane) keep[c] = false;
-        }
-        __syncwarp();
+        // chunk by chunk: __match_any groups equal keys inside the chunk (the lowest lane is the first occurrence),
+        // then the survivors are checked against the unique keys of earlier chunks (dk[0..nuniq), compacted in place)
         int nuniq = 0;
-#pragma unroll
-        for (int c = 0; c < KMAX / 32; ++c) {
-            if (c * 32 < ncoh) {
-                unsigned bm = __ballot_sync(FULL, keep[c]);
-                if (keep[c]) {
-                    int pos = nuniq + __popc(bm & lt);
-                    ws.u.c.cxy[pos] = (uint32_t)key[c]; ws.cmeta[pos] = (uint16_t)(key[c] >> 32);
-                    ws.u.c.cpatch[pos] = pat[c]; ws.corig[pos] = (uint8_t)(c * 32 + lane);
-                }
-                nuniq += __popc(bm);
-                __syncwarp();
+        for (int base = 0; base < ncoh; base += 32) {
+            const int a = base + lane;
+            const bool valid = a < ncoh;
+            const unsigned long long key = valid ? dk[a] : (0xFFFF000000000000ull | (unsigned long long)lane);  // distinct dummies
+            const uint32_t pat = valid ? ws.u.c.cpatch[a] : 0u;
+            const unsigned grp = __match_any_sync(FULL, key);
+            bool keep = valid && ((int)(__ffs(grp) - 1) == lane);
+            for (int u = 0; u < nuniq; ++u) keep = keep && (dk[u] != key);
+            __syncwarp();
+            const unsigned bm = __ballot_sync(FULL, keep);
+            if (keep) {
+                const int pos = nuniq + __popc(bm & lt);
+                dk[pos] = key;
+                ws.u.c.cxy[pos] = (uint32_t)key; ws.cmeta[pos] = (uint16_t)(key >> 32);
+                ws.u.c.cpatch[pos] = pat; ws.corig[pos] = (uint8_t)a;
             }
+            nuniq += __popc(bm);
+            __syncwarp();
         }
         ncand = nuniq;
     }
@@ -759,15 +773,46 @@ __global__ void __launch_bounds__(CTA_THREADS) k_serial(StageDev S, PhaseDev P) 
     const int lane = threadIdx.x;
     WarpScratch& ws = sm.ws[0];
     unsigned long long fetched = 0, nominal = 0, cands = 0;
+    // While the whole resolved set fits the key buffer, keep it as a point list (read once from the mask,
+    // extended with every commit) instead of scanning the mask for every item.
+    short2* pts = reinterpret_cast<short2*>(rs.req);  // the re-queue staging area is unused by this kernel
+    const bool use_list = S.n_points_max <= (uint32_t)KBUF;
+    int npts = 0;
+    if (use_list) {
+        if (lane == 0) ws.cnt = 0;
+        __syncwarp();
+        uint32_t extw = (uint32_t)(S.wpr * 32), exth = (uint32_t)S.mrows;
+        npts = min((int)scan_disc<true>(S, ws, lane, 0, 0, extw * extw + exth * exth), KBUF);
+        for (int i = lane; i < npts; i += 32) {
+            unsigned long long key = ws.u.keys[i];
+            pts[i] = make_short2((short)((int)(key & 0xFFFF) - 32768), (short)((int)((key >> 16) & 0xFFFF) - 32768));
+        }
+        __syncwarp();
+    }
     for (uint32_t it = 0; it < P.n; ++it) {
         const uint32_t flat = P.item_pixel[it];
         const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
         const uint32_t si = P.stage_base + it;
         ItemOut o;
-        resolve_item<GUIDED>(S, ws, sm.lut, sm.lutg, lane, x, y, R2_INF, P.rand_xy + (size_t)si * S.m, P.rand_map + (size_t)si * S.m, o);
+        resolve_item<GUIDED>(S, ws, sm.lut, sm.lutg, lane, x, y, R2_INF, P.rand_xy + (size_t)si * S.m, P.rand_map + (size_t)si * S.m, o,
+                             use_list ? pts : nullptr, npts);
         if (lane == 0) {
             commit_item(S, P, si, flat, x, y, o);
+            if (use_list && P.is_new && o.kk > 0) {  // same insertions as mask_insert (ms.rs:306-327)
+                int q = npts;
+                pts[q++] = make_short2((short)x, (short)y);
+                if (S.tiling) {
+                    if (x < S.x_l) pts[q++] = make_short2((short)(x + S.W), (short)y);
+                    else if (x > S.x_r) pts[q++] = make_short2((short)(x - S.W), (short)y);
+                    if (y < S.y_b) pts[q++] = make_short2((short)x, (short)(y + S.H));
+                    else if (y > S.y_t) pts[q++] = make_short2((short)x, (short)(y - S.H));
+                }
+            }
             __threadfence();
+        }
+        if (use_list && P.is_new && o.kk > 0) {
+            npts += 1;
+            if (S.tiling) { npts += (x < S.x_l || x > S.x_r) ? 1 : 0; npts += (y < S.y_b || y > S.y_t) ? 1 : 0; }
         }
         __syncwarp();
         fetched += o.fetched; nominal += o.nominal; cands += (unsigned long long)o.ncand;
