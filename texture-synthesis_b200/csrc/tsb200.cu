@@ -57,6 +57,10 @@ template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
     ~DevBuf() { release(); }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
     int ensure(size_t count) {
@@ -264,11 +268,11 @@ struct tsb_generator {
 
     // per-run buffers
     DevBuf<uint32_t> d_item_pixel, d_item_R2, d_pred_cnt, d_preds, d_done, d_pend0, d_pend1, d_ctrl, d_pmap;
-    DevBuf<uint32_t> d_rand_xy, d_pick_idx, d_tmp_u32;
+    DevBuf<uint32_t> d_rand_xy, d_pick_idx, d_tmp_u32, d_read_color, d_read_coord, d_read_id;
     DevBuf<uint8_t> d_rand_map;
     DevBuf<uint32_t> d_npred, d_nsucc, d_succ_off, d_succ_cur, d_succ, d_queue, d_fctl;
     DevBuf<uint8_t> d_cub_temp;
-    int max_ctas_flow = 0;
+    int max_ctas_flow = 0, max_ctas_flow_guided = 0;
     bool use_rounds = false, force_csr = false;
     size_t succ_stride = SUCC_STRIDE;
     uint32_t* h_ctrl = nullptr;  // pinned, 16 words
@@ -341,8 +345,7 @@ int upload_inputs(tsb_generator* g, const tsb_pyramid* examples, uint32_t n_exam
     g->n_ex_all = (int)n_examples;
     g->n_levels = (int)examples[0].n_levels;
     g->ex_w.clear(); g->ex_h.clear(); g->ex_kind.clear(); g->filt.clear();
-    g->d_ex.clear(); g->d_smask.clear();
-    g->d_ex.resize(n_examples); g->d_smask.resize(n_examples);
+    if (g->d_ex.size() != n_examples) { g->d_ex.clear(); g->d_smask.clear(); g->d_ex.resize(n_examples); g->d_smask.resize(n_examples); }
     for (uint32_t e = 0; e < n_examples; ++e) {
         const tsb_pyramid& p = examples[e];
         if (!p.levels || p.width == 0 || p.height == 0 || p.n_levels == 0) return fail(TSB_ERR_INVALID, "example %u is empty", e);
@@ -378,13 +381,14 @@ int upload_inputs(tsb_generator* g, const tsb_pyramid* examples, uint32_t n_exam
         }
     TRY(g->d_exdesc.upload(desc.data(), desc.size(), s));
     g->guided = guides != nullptr;
-    g->d_exg.clear(); g->exg_w.clear(); g->exg_h.clear();
+    g->exg_w.clear(); g->exg_h.clear();
+    if (!guides) g->d_exg.clear();
     if (guides) {
         if (guides->n_examples != n_examples) return fail(TSB_ERR_INVALID, "guides must be given for all examples or none (session.rs:501-524)");
         if ((int)guides->target.n_levels != g->n_levels) return fail(TSB_ERR_INVALID, "target guide pyramid level count mismatch");
         g->tgw = (int)guides->target.width; g->tgh = (int)guides->target.height;
         TRY(upload_pyramid(guides->target, g->d_tguide, s));
-        g->d_exg.resize(n_examples);
+        if (g->d_exg.size() != n_examples) { g->d_exg.clear(); g->d_exg.resize(n_examples); }
         std::vector<DevGuide> gd((size_t)g->n_levels * n_examples);
         for (uint32_t e = 0; e < n_examples; ++e) {
             const tsb_pyramid& p = guides->examples[e];
@@ -615,7 +619,7 @@ int run_phase_flow(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n,
     PhaseClock clk;
     TRY(clk.begin(s));
     const int ga = grid_for(g, n), gl = grid_light(g, n);
-    const int gf = std::max(1, std::min((int)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), g->max_ctas_flow));
+    const int gf = std::max(1, std::min((int)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), g->guided ? g->max_ctas_flow_guided : g->max_ctas_flow));
     uint64_t edges = 0;
     bool use_csr = g->force_csr || (size_t)n * g->succ_stride > g->d_succ.n;
     for (int attempt = 0; attempt < 2; ++attempt) {
@@ -919,6 +923,8 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
     CU(cudaStreamSynchronize(s));
     g->stats.texels_fetched = cnt[ST_FETCHED]; g->stats.texels_nominal = cnt[ST_NOMINAL]; g->stats.candidates = cnt[ST_CANDS];
     if (getenv("TSB_DEBUG_PHASES") && cnt[ST_ITEMS])
+        fprintf(stderr, "[tsb] coop items %.3f, mean unique coherence candidates %.2f\n", (double)cnt[ST_COOP] / cnt[ST_ITEMS], (double)cnt[ST_NUNIQ] / cnt[ST_ITEMS]);
+    if (getenv("TSB_DEBUG_PHASES") && cnt[ST_ITEMS])
         fprintf(stderr, "[tsb] cycles/item: ready %.0f knn %.0f neigh %.0f weight+rand %.0f score %.0f commit %.0f (items %llu)\n",
                 (double)cnt[ST_CYC_READY] / cnt[ST_ITEMS], (double)cnt[ST_CYC_KNN] / cnt[ST_ITEMS], (double)cnt[ST_CYC_NEIGH] / cnt[ST_ITEMS],
                 (double)cnt[ST_CYC_WEIGHT] / cnt[ST_ITEMS], (double)cnt[ST_CYC_SCORE] / cnt[ST_ITEMS], (double)cnt[ST_CYC_COMMIT] / cnt[ST_ITEMS],
@@ -1048,7 +1054,8 @@ int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "cudaGetDeviceProperties failed"));
     g->n_sms = prop.multiProcessorCount;
     g->max_ctas = prop.multiProcessorCount * per_sm;
-    g->max_ctas_flow = prop.multiProcessorCount * std::min(per_sm_flow, per_sm_flow_g);  // persistent grid: co-resident CTAs only
+    g->max_ctas_flow = prop.multiProcessorCount * per_sm_flow;  // persistent grid: co-resident CTAs only
+    g->max_ctas_flow_guided = prop.multiProcessorCount * per_sm_flow_g;
     if ((rc = init_state(g))) return bail(rc);
     if (cudaStreamSynchronize(g->stream) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "generator initialisation failed: %s", cudaGetErrorString(cudaGetLastError())));
     *out = g;
@@ -1132,11 +1139,14 @@ int tsb_generator_resolve(tsb_generator* g, const tsb_params* params, const tsb_
 static int read_unpacked(tsb_generator* g, uint32_t* color, uint32_t* coord, uint32_t* idm) {
     TRY(set_device(g));
     const size_t npix = (size_t)g->W * g->H;
-    DevBuf<uint32_t> dc, dco, di;
+    DevBuf<uint32_t>& dc = g->d_read_color;
+    DevBuf<uint32_t>& dco = g->d_read_coord;
+    DevBuf<uint32_t>& di = g->d_read_id;
     if (color) TRY(dc.ensure(npix));
     if (coord) TRY(dco.ensure(npix * 3));
     if (idm) TRY(di.ensure(npix * 2));
-    k_unpack_state<<<(uint32_t)((npix + 255) / 256), 256, 0, g->stream>>>(g->d_state.p, (uint32_t)npix, dc.p, dco.p, di.p);
+    k_unpack_state<<<(uint32_t)((npix + 255) / 256), 256, 0, g->stream>>>(g->d_state.p, (uint32_t)npix, color ? dc.p : nullptr,
+                                                                           coord ? dco.p : nullptr, idm ? di.p : nullptr);
     CU(cudaGetLastError());
     if (color) CU(cudaMemcpyAsync(color, dc.p, npix * 4, cudaMemcpyDeviceToHost, g->stream));
     if (coord) CU(cudaMemcpyAsync(coord, dco.p, npix * 12, cudaMemcpyDeviceToHost, g->stream));
