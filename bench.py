@@ -25,7 +25,9 @@ sys.path.insert(0, ROOT)
 
 OUT, EX = 2048, 512
 WORKLOAD = f"{OUT}x{OUT} output from synthetic {EX}x{EX} example (synth_texture seed 1), k=50 m=50 cauchy=1.0 backtrack=0.5x5 seed=0"
-CPU_SAMPLE_OUT = 512  # bounded CPU sample: same example and parameters, 512x512 output
+# dram bytes (read+write) of all k_flow launches of one step, from the ncu --set full capture summarised under profiles/
+TRAFFIC_PER_STEP = None
+CPU_SAMPLE_OUT = 1536  # bounded CPU sample: same example and parameters, 1536x1536 output (about 10-20 s on 8-16 cores)
 
 
 def measured_peaks():
@@ -166,15 +168,9 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         t1 = time.perf_counter()
     # device-timed step: CUDA events recorded by the library on its own stream around the whole call
+    from texture_synthesis_b200.parallel import aggregate_throughput
     ms = np.array([s["gpu_ms_total"] for s in stats])
-    t_local = float(ms.sum()) * 1e-3
-    if dist is not None:
-        tt = torch.tensor([t_local], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_max = float(tt.item())
-    else:
-        t_max = t_local
-    value = world * args.steps * OUT * OUT / t_max
+    value, _, t_max = aggregate_throughput(args.steps * OUT * OUT, float(ms.sum()) * 1e-3, dist, "cuda")
 
     # end to end through the public C-ABI call with HOST buffers: H2D of the example pyramid and D2H of the result inside
     e2e_t = []
@@ -186,18 +182,13 @@ def run_ours(args, rank, world, local_rank):
         g.resolve(params, [pyr_pinned])
         capi._check(g.L.tsb_generator_read_color(g.h, out_host.ctypes.data))
         e2e_t.append(time.perf_counter() - a)
-    e2e_local = float(np.sum(e2e_t))
-    if dist is not None:
-        tt = torch.tensor([e2e_local], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_local = float(tt.item())
-    e2e_value = world * len(e2e_t) * OUT * OUT / e2e_local
+    e2e_value, _, _ = aggregate_throughput(len(e2e_t) * OUT * OUT, float(np.sum(e2e_t)), dist, "cuda")
 
     if rank != 0:
         return
     st = stats[-1]
     peaks, peak_src = measured_peaks()
-    # dominant kernel: k_round (K2+K3+K4+K5 fused).  Algorithmic bytes per launch set = texels actually gathered x 4 B
+    # dominant kernel: k_flow (K2+K3+K4+K5 fused, persistent).  Algorithmic bytes per launch set = texels actually gathered x 4 B
     # + per pixel-resolution k*4 B target pattern + k*16 B neighbour state + 16 B written.
     k = 50
     alg_bytes = st["texels_fetched"] * 4 + st["work_items"] * (k * 4 + k * 16 + 16)
@@ -214,19 +205,22 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": float(ms.mean()), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "parallelism": "1 session per GPU (independent sessions, no collective)" if world > 1 else "1 GPU",
-                   "l2": "256 MiB flush buffer written between timed iterations", "schedule": "exact 1-thread order (dependency rounds)",
+                   "l2": "256 MiB flush buffer written between timed iterations", "schedule": "exact 1-thread order: per phase one persistent dataflow kernel (k_flow)",
                    "pixel_resolutions_per_step": int(st["work_items"]), "candidate_evals_per_s": st["candidates"] / (float(ms.mean()) * 1e-3),
                    "host_wall_ms_per_step": (t1 - t0) * 1e3 / args.steps},
         "clocks": clk.summary(),
         "e2e": {"value": e2e_value, "unit": "px/s", "h2d_bytes_per_step": int(pyr.nbytes), "d2h_bytes_per_step": int(out_host.nbytes)},
         "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                     "traffic": None, "peak_source": peak_src, "kernel": "k_round", "kernel_ms_per_step": st["gpu_ms_resolve"],
+                     "traffic": TRAFFIC_PER_STEP, "peak_source": peak_src, "kernel": "k_flow", "kernel_ms_per_step": st["gpu_ms_resolve"],
                      "texels_fetched": int(st["texels_fetched"]), "texels_nominal": int(st["texels_nominal"]),
                      "l2_gather": {"note": "example level is L2 resident: own microbenchmark of random 4-byte gathers over a 1 MiB window",
                                    "peak_gathers_per_s": l2_gps, "peak_useful_gbs": l2_gbs,
                                    "achieved_gathers_per_s": st["texels_fetched"] / kern_s,
-                                   "frac": (st["texels_fetched"] / kern_s / l2_gps) if l2_gps else None}},
+                                   "frac": (st["texels_fetched"] / kern_s / l2_gps) if l2_gps else None,
+                                   "nominal_texel_evals_per_s": st["texels_nominal"] / kern_s,
+                                   "note2": "exact pruning (candidate de-duplication + early-out) removes ~90% of the nominal "
+                                            "(k+m)*k texel comparisons; frac uses texels actually fetched"}},
     }
     if cpu_v is not None:
         line["cpu_baseline"] = {"value": cpu_v, "unit": "px/s", "cores": cores, "kind": "port",

@@ -923,8 +923,6 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
     CU(cudaStreamSynchronize(s));
     g->stats.texels_fetched = cnt[ST_FETCHED]; g->stats.texels_nominal = cnt[ST_NOMINAL]; g->stats.candidates = cnt[ST_CANDS];
     if (getenv("TSB_DEBUG_PHASES") && cnt[ST_ITEMS])
-        fprintf(stderr, "[tsb] coop items %.3f, mean unique coherence candidates %.2f\n", (double)cnt[ST_COOP] / cnt[ST_ITEMS], (double)cnt[ST_NUNIQ] / cnt[ST_ITEMS]);
-    if (getenv("TSB_DEBUG_PHASES") && cnt[ST_ITEMS])
         fprintf(stderr, "[tsb] cycles/item: ready %.0f knn %.0f neigh %.0f weight+rand %.0f score %.0f commit %.0f (items %llu)\n",
                 (double)cnt[ST_CYC_READY] / cnt[ST_ITEMS], (double)cnt[ST_CYC_KNN] / cnt[ST_ITEMS], (double)cnt[ST_CYC_NEIGH] / cnt[ST_ITEMS],
                 (double)cnt[ST_CYC_WEIGHT] / cnt[ST_ITEMS], (double)cnt[ST_CYC_SCORE] / cnt[ST_ITEMS], (double)cnt[ST_CYC_COMMIT] / cnt[ST_ITEMS],
@@ -1053,7 +1051,7 @@ int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "cudaGetDeviceProperties failed"));
     g->n_sms = prop.multiProcessorCount;
-    g->max_ctas = prop.multiProcessorCount * per_sm;
+    g->max_ctas = prop.multiProcessorCount * std::max(per_sm, 4);  // analysis kernels (k_radius: 47 KB smem) fit 4 CTAs per SM
     g->max_ctas_flow = prop.multiProcessorCount * per_sm_flow;  // persistent grid: co-resident CTAs only
     g->max_ctas_flow_guided = prop.multiProcessorCount * per_sm_flow_g;
     if ((rc = init_state(g))) return bail(rc);

@@ -120,12 +120,11 @@ struct __align__(16) WarpScratch {
 
 // statistics accumulated per warp in registers, per CTA in shared memory, flushed once per CTA
 enum { ST_FETCHED = 0, ST_NOMINAL, ST_CANDS, ST_ITEMS, ST_CYC_READY, ST_CYC_KNN, ST_CYC_NEIGH, ST_CYC_WEIGHT,
-       ST_CYC_SCORE, ST_CYC_COMMIT, ST_COOP, ST_NUNIQ, ST_COUNT };
+       ST_CYC_SCORE, ST_CYC_COMMIT, ST_COUNT };
 
 struct ItemOut {
     unsigned long long fetched, nominal;
     long long c_knn, c_neigh, c_weight, c_score;
-    int coop, nuniq;
     int kk, ncand, best;
     int bx, by, bmap;
     uint32_t bpatch;
@@ -252,24 +251,24 @@ __device__ __forceinline__ int knn_search(const StageDev& S, WarpScratch& ws, in
         // unbounded search: do not walk the whole table when the hint says the set is sparse
         if (!bounded && S.r2_hint > (uint32_t)S.RT2) limit = 0;
         int cnt = 0;
-        for (int base = 0; base < limit && cnt < k; base += 256) {
-            short2 o[8];
-            unsigned hits = 0;
+        for (int base = 0; base < limit && cnt < k; base += 128) {
+            short2 o[4];
+            bool hit[4];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {  // 8 x 32 offsets per batch so that the mask loads overlap
+            for (int u = 0; u < 4; ++u) {
                 int idx = base + 32 * u + lane;
+                hit[u] = false;
                 o[u] = make_short2(0, 0);
                 if (idx < limit) {
                     o[u] = __ldg(S.spiral + idx);
-                    hits |= (mask_test(S, x + o[u].x, y + o[u].y) ? 1u : 0u) << u;
+                    hit[u] = mask_test(S, x + o[u].x, y + o[u].y);
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                bool hit = (hits >> u) & 1u;
-                unsigned b = __ballot_sync(FULL, hit);
+            for (int u = 0; u < 4; ++u) {
+                unsigned b = __ballot_sync(FULL, hit[u]);
                 int pos = cnt + __popc(b & lt);
-                if (hit && pos < k) ws.off[pos] = o[u];
+                if (hit[u] && pos < k) ws.off[pos] = o[u];
                 cnt += __popc(b);
             }
         }
@@ -332,27 +331,6 @@ __device__ __forceinline__ int knn_search(const StageDev& S, WarpScratch& ws, in
     return kk;
 }
 
-constexpr int REQ_CAP = 1024;  // per-CTA staging of re-queued items (one global atomic per CTA and round)
-
-constexpr int EX_CACHE = 8;  // example / guide descriptors cached in shared memory (more examples: read from global)
-
-struct __align__(16) CtaSmem {
-    float lut[256];
-    float lutg[256];
-    DevEx ex[EX_CACHE];
-    DevGuide exg[EX_CACHE];
-    WarpScratch ws[WARPS_PER_CTA];
-};
-struct __align__(16) RoundSmem {
-    CtaSmem c;
-    uint32_t req[REQ_CAP];
-    unsigned long long stat[ST_COUNT];
-    uint32_t req_cnt, req_min, req_base, pad;
-};
-
-__device__ __forceinline__ DevEx get_ex(const StageDev& S, const CtaSmem& sm, uint32_t map) { return map < (uint32_t)EX_CACHE ? sm.ex[map] : S.ex[map]; }
-__device__ __forceinline__ DevGuide get_exg(const StageDev& S, const CtaSmem& sm, uint32_t map) { return map < (uint32_t)EX_CACHE ? sm.exg[map] : S.exg[map]; }
-
 // k nearest among an explicit point list held in shared memory (serial start of a synthesis, where the
 // resolved set is tiny and scanning the mask would cost more than looking at every point)
 __device__ __forceinline__ int knn_points(const StageDev& S, WarpScratch& ws, int lane, int x, int y, const short2* pts, int npts, uint32_t* r2_out) {
@@ -379,17 +357,16 @@ __device__ __forceinline__ int knn_points(const StageDev& S, WarpScratch& ws, in
 // One pixel resolution (steps 2-4 of ms.rs:917-986) by one warp.  No commit.
 // ---------------------------------------------------------------------------------------------
 template <bool GUIDED>
-__device__ __forceinline__ void resolve_item(const StageDev& S, const CtaSmem& sm, WarpScratch& ws, int lane, int x, int y, uint32_t R2bound,
+__device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws, const float* __restrict__ s_lut,
+                             const float* __restrict__ s_lutg, int lane, int x, int y, uint32_t R2bound,
                              const uint32_t* __restrict__ rand_xy, const uint8_t* __restrict__ rand_map, ItemOut& out,
                              const short2* pts = nullptr, int npts = 0) {
     const unsigned lt = (1u << lane) - 1u;
-    const float* __restrict__ s_lut = sm.lut;
-    const float* __restrict__ s_lutg = sm.lutg;
     uint32_t r2;
     long long t0 = clock64();
     const int kk = pts ? knn_points(S, ws, lane, x, y, pts, npts, &r2) : knn_search(S, ws, lane, x, y, R2bound, &r2);
     long long t1 = clock64();
-    out.c_knn = t1 - t0; out.c_neigh = out.c_weight = out.c_score = 0; out.fetched = out.nominal = 0; out.coop = 0; out.nuniq = 0;
+    out.c_knn = t1 - t0; out.c_neigh = out.c_weight = out.c_score = 0; out.fetched = out.nominal = 0;
     out.kk = kk;
     out.ncand = 0; out.best = 0; out.bx = out.by = out.bmap = 0; out.bpatch = 0; out.score = 0.f;
     if (kk == 0) return;
@@ -398,62 +375,45 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, const CtaSmem& s
     const double dimx = (double)W, dimy = (double)H;
     const double x2 = __ddiv_rn((double)x, dimx), y2 = __ddiv_rn((double)y, dimy);
     int ncand = 0;
-    for (int base0 = 0; base0 < kk; base0 += 64) {
-        uint4 stv[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {  // both chunks' state loads in flight
-            int j = base0 + 32 * u + lane;
-            stv[u] = make_uint4(0, 0, 0, 0);
-            if (j < kk) {
-                short2 o = ws.off[j];
-                int qx = x + o.x, qy = y + o.y;
-                if (S.tiling) { qx = imod(qx, W); qy = imod(qy, H); }
-                stv[u] = __ldcg(S.state + (size_t)qy * W + qx);
+    for (int base = 0; base < kk; base += 32) {
+        int j = base + lane;
+        bool valid = false;
+        uint32_t cxy = 0, cpatch = 0;
+        uint16_t cmeta = 0;
+        if (j < kk) {
+            short2 o = ws.off[j];
+            int nx = x + o.x, ny = y + o.y;
+            int qx = nx, qy = ny;
+            if (S.tiling) { qx = imod(nx, W); qy = imod(ny, H); }
+            uint4 st = __ldcg(S.state + (size_t)qy * W + qx);
+            ws.tcol[j] = st.x;  // ms.rs:1151-1181 target pattern from the output colour map
+            if (GUIDED) {
+                int gx = nx, gy = ny;
+                if (S.tiling) { gx = imod(nx, S.tgw); gy = imod(ny, S.tgh); }
+                ws.gcol[j] = ((unsigned)gx < (unsigned)S.tgw && (unsigned)gy < (unsigned)S.tgh)
+                                 ? __ldg(S.tguide + (size_t)gy * S.tgw + gx) : OUTSIDE_RGBA;
             }
+            double x1 = __ddiv_rn((double)nx, dimx), y1 = __ddiv_rn((double)ny, dimy);
+            double ddx = __dsub_rn(x1, x2), ddy = __dsub_rn(y1, y2);
+            ws.d[j] = __fma_rn(ddx, ddx, __dmul_rn(ddy, ddy));
+            int sx = (int)(st.y & 0xFFFFu), sy = (int)(st.y >> 16);
+            uint32_t map = st.w & 0xFFFFu;  // id_map's MapId (ms.rs:510-511)
+            int cx = sx - o.x, cy = sy - o.y;  // source of the neighbour + (p - n)
+            if (map < (uint32_t)S.n_ex) {
+                DevEx e = S.ex[map];
+                if ((unsigned)cx < (unsigned)e.w && (unsigned)cy < (unsigned)e.h)
+                    valid = e.smask ? (__ldg(e.smask + (size_t)cy * e.w + cx) != 0) : true;
+            }
+            cxy = (uint32_t)cx | ((uint32_t)cy << 16);
+            cpatch = st.z;
+            cmeta = (uint16_t)map;
         }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int base = base0 + 32 * u;
-            if (base >= kk) break;
-            int j = base + lane;
-            bool valid = false;
-            uint32_t cxy = 0, cpatch = 0;
-            uint16_t cmeta = 0;
-            if (j < kk) {
-                short2 o = ws.off[j];
-                int nx = x + o.x, ny = y + o.y;
-                int qx = nx, qy = ny;
-                if (S.tiling) { qx = imod(nx, W); qy = imod(ny, H); }
-                uint4 st = stv[u];
-                ws.tcol[j] = st.x;  // ms.rs:1151-1181 target pattern from the output colour map
-                if (GUIDED) {
-                    int gx = nx, gy = ny;
-                    if (S.tiling) { gx = imod(nx, S.tgw); gy = imod(ny, S.tgh); }
-                    ws.gcol[j] = ((unsigned)gx < (unsigned)S.tgw && (unsigned)gy < (unsigned)S.tgh)
-                                     ? __ldg(S.tguide + (size_t)gy * S.tgw + gx) : OUTSIDE_RGBA;
-                }
-                double x1 = __ddiv_rn((double)nx, dimx), y1 = __ddiv_rn((double)ny, dimy);
-                double ddx = __dsub_rn(x1, x2), ddy = __dsub_rn(y1, y2);
-                ws.d[j] = __fma_rn(ddx, ddx, __dmul_rn(ddy, ddy));
-                int sx = (int)(st.y & 0xFFFFu), sy = (int)(st.y >> 16);
-                uint32_t map = st.w & 0xFFFFu;  // id_map's MapId (ms.rs:510-511)
-                int cx = sx - o.x, cy = sy - o.y;  // source of the neighbour + (p - n)
-                if (map < (uint32_t)S.n_ex) {
-                    DevEx e = get_ex(S, sm, map);
-                    if ((unsigned)cx < (unsigned)e.w && (unsigned)cy < (unsigned)e.h)
-                        valid = e.smask ? (__ldg(e.smask + (size_t)cy * e.w + cx) != 0) : true;
-                }
-                cxy = (uint32_t)cx | ((uint32_t)cy << 16);
-                cpatch = st.z;
-                cmeta = (uint16_t)map;
-            }
-            unsigned b = __ballot_sync(FULL, valid);
-            if (valid) {
-                int pos = ncand + __popc(b & lt);
-                ws.u.c.cxy[pos] = cxy; ws.u.c.cpatch[pos] = cpatch; ws.cmeta[pos] = cmeta;
-            }
-            ncand += __popc(b);
+        unsigned b = __ballot_sync(FULL, valid);
+        if (valid) {
+            int pos = ncand + __popc(b & lt);
+            ws.u.c.cxy[pos] = cxy; ws.u.c.cpatch[pos] = cpatch; ws.cmeta[pos] = cmeta;
         }
+        ncand += __popc(b);
     }
     __syncwarp();
     long long t2 = clock64();
@@ -509,7 +469,7 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, const CtaSmem& s
         uint32_t map = __ldg(rand_map + r);
         int pos = ncand + r;
         ws.u.c.cxy[pos] = xy;
-        ws.u.c.cpatch[pos] = (xy >> 16) * (uint32_t)get_ex(S, sm, map).w + (xy & 0xFFFFu);  // ms.rs:577
+        ws.u.c.cpatch[pos] = (xy >> 16) * (uint32_t)S.ex[map].w + (xy & 0xFFFFu);  // ms.rs:577
         ws.cmeta[pos] = (uint16_t)(map | 0x8000u);
         ws.corig[pos] = (uint8_t)(ncoh + r);
     }
@@ -521,89 +481,9 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, const CtaSmem& s
     float best = FLT_MAX;
     int besti = 0;
     uint32_t fetched = 0;
-    int first_base = 0;
-    // Few unique coherence candidates (the common case once patches form): 4 lanes share one candidate.  Each
-    // lane gathers a quarter of the neighbours and keeps the products t_j * g_j in registers; the f32 sum is
-    // then accumulated strictly in neighbour order by handing the running sum from lane to lane (ms.rs:1259-1280).
-    if (nuniq_coh > 0 && nuniq_coh <= 8 && kk8 <= 64) {
-        const int c = lane >> 2, sub = lane & 3, per = kk8 >> 2;  // per <= 16
-        const bool act = c < nuniq_coh;
-        float p[16];
-        int cx = 0, cy = 0;
-        DevEx e = get_ex(S, sm, 0);
-        DevGuide ge;
-        if (GUIDED) ge = get_exg(S, sm, 0);
-        if (act) {
-            uint32_t cxy = ws.u.c.cxy[c];
-            uint32_t map = ws.cmeta[c] & 0x7FFFu;
-            cx = (int)(cxy & 0xFFFFu); cy = (int)(cxy >> 16);
-            e = get_ex(S, sm, map);
-            if (GUIDED) ge = get_exg(S, sm, map);
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            uint32_t tex[8], gtex[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int uu = h * 8 + u;
-                tex[u] = OUTSIDE_RGBA; gtex[u] = OUTSIDE_RGBA;
-                if (act && uu < per) {
-                    short2 o = ws.off[sub * per + uu];
-                    int X = cx + o.x, Y = cy + o.y;  // coherence candidates: neighbour pattern c + (n - p), ms.rs:534-540
-                    if ((unsigned)X < (unsigned)e.w && (unsigned)Y < (unsigned)e.h) tex[u] = __ldg(e.px + (size_t)Y * e.w + X);
-                    if (GUIDED) {
-                        if ((unsigned)X < (unsigned)ge.w && (unsigned)Y < (unsigned)ge.h) gtex[u] = __ldg(ge.px + (size_t)Y * ge.w + X);
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int uu = h * 8 + u;
-                p[uu] = 0.f;
-                if (uu < per) {
-                    const int j = sub * per + uu;
-                    uint32_t dd = __vabsdiffu4(ws.tcol[j], tex[u]);
-                    float t = s_lut[dd & 0xFFu];
-                    t = __fadd_rn(t, s_lut[(dd >> 8) & 0xFFu]);
-                    t = __fadd_rn(t, s_lut[(dd >> 16) & 0xFFu]);
-                    t = __fadd_rn(t, s_lut[dd >> 24]);
-                    if (GUIDED) {
-                        uint32_t dg = __vabsdiffu4(ws.gcol[j], gtex[u]);
-                        t = __fadd_rn(t, s_lutg[dg & 0xFFu]);
-                        t = __fadd_rn(t, s_lutg[(dg >> 8) & 0xFFu]);
-                        t = __fadd_rn(t, s_lutg[(dg >> 16) & 0xFFu]);
-                        t = __fadd_rn(t, s_lutg[dg >> 24]);
-                    }
-                    p[uu] = __fmul_rn(t, ws.g[j]);
-                }
-            }
-        }
-        if (act) fetched += (uint32_t)max(0, min(per, kk - sub * per));
-        float s = 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (sub == q) {
-#pragma unroll
-                for (int uu = 0; uu < 16; ++uu)
-                    if (uu < per) s = __fadd_rn(s, p[uu]);
-            }
-            s = __shfl_sync(FULL, s, (lane & ~3) | q);  // hand the running sum to the next quarter
-        }
-        bool win = act && sub == 0 && (s < best);
-        float ms = win ? s : INFINITY;
-        int ma = c;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            float os = __shfl_xor_sync(FULL, ms, o);
-            int oa = __shfl_xor_sync(FULL, ma, o);
-            if (os < ms || (os == ms && oa < ma)) { ms = os; ma = oa; }
-        }
-        if (ms < best) { best = ms; besti = ma; }
-        first_base = nuniq_coh;
-    }
     // coherence candidates get their own round(s) first: they establish `best`, so the random candidates
     // (higher indices, so ties still go to the earlier candidate) early-out after a chunk or two
-    for (int base = first_base; base < ncand; base = (base < nuniq_coh && base + 32 >= nuniq_coh) ? nuniq_coh : base + 32) {
+    for (int base = 0; base < ncand; base = (base < nuniq_coh && base + 32 >= nuniq_coh) ? nuniq_coh : base + 32) {
         const int lim = base < nuniq_coh ? nuniq_coh : ncand;
         int a = base + lane;
         float s = 0.f;
@@ -614,9 +494,9 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, const CtaSmem& s
             int cx = (int)(cxy & 0xFFFFu), cy = (int)(cxy >> 16);
             int sgn = (meta & 0x8000u) ? -1 : 1;
             uint32_t map = meta & 0x7FFFu;
-            DevEx e = get_ex(S, sm, map);
+            DevEx e = S.ex[map];
             DevGuide ge;
-            if (GUIDED) ge = get_exg(S, sm, map);
+            if (GUIDED) ge = S.exg[map];
             ok = true;
             for (int j0 = 0; j0 < kk8; j0 += 8) {
                 uint32_t tex[8], gtex[8];
@@ -672,7 +552,6 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, const CtaSmem& s
     out.fetched = (unsigned long long)fetched * (GUIDED ? 2ull : 1ull);  // neighbour positions evaluated (example + guide texel each)
     out.nominal = (unsigned long long)out.ncand * (unsigned long long)kk * (GUIDED ? 2ull : 1ull);
     out.c_neigh = t2 - t1; out.c_weight = t3 - t2; out.c_score = t4 - t3;
-    out.coop = first_base > 0 ? 1 : 0; out.nuniq = nuniq_coh;
     uint32_t bxy = ws.u.c.cxy[besti];
     out.best = (int)ws.corig[besti];
     out.bx = (int)(bxy & 0xFFFFu);
@@ -683,18 +562,29 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, const CtaSmem& s
     __syncwarp();
 }
 
-__device__ __forceinline__ void load_luts(const StageDev& S, CtaSmem& sm) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) { sm.lut[i] = S.lut_my[i]; sm.lutg[i] = S.lut_guide[i]; }
-    if ((int)threadIdx.x < EX_CACHE && (int)threadIdx.x < S.n_ex) sm.ex[threadIdx.x] = S.ex[threadIdx.x];
-    if ((int)threadIdx.x < EX_CACHE && (int)threadIdx.x < S.n_exg) sm.exg[threadIdx.x] = S.exg[threadIdx.x];
+__device__ __forceinline__ void load_luts(const StageDev& S, float* s_lut, float* s_lutg) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { s_lut[i] = S.lut_my[i]; s_lutg[i] = S.lut_guide[i]; }
     __syncthreads();
 }
 
+constexpr int REQ_CAP = 1024;  // per-CTA staging of re-queued items (one global atomic per CTA and round)
+
+struct __align__(16) CtaSmem {
+    float lut[256];
+    float lutg[256];
+    WarpScratch ws[WARPS_PER_CTA];
+};
+struct __align__(16) RoundSmem {
+    CtaSmem c;
+    uint32_t req[REQ_CAP];
+    unsigned long long stat[ST_COUNT];
+    uint32_t req_cnt, req_min, req_base, pad;
+};
 
 // update(), ms.rs:334-377 (+ flush_resolved's tree insert, ms.rs:296-331); called by lane 0
-__device__ __forceinline__ void commit_item(const StageDev& S, const CtaSmem& sm, const PhaseDev& P, uint32_t si, uint32_t flat, int x, int y, const ItemOut& o) {
+__device__ __forceinline__ void commit_item(const StageDev& S, const PhaseDev& P, uint32_t si, uint32_t flat, int x, int y, const ItemOut& o) {
     if (o.kk > 0) {
-        DevEx e = get_ex(S, sm, (uint32_t)o.bmap);
+        DevEx e = S.ex[o.bmap];
         uint32_t col = __ldg(e.px + (size_t)o.by * e.w + o.bx);
         S.state[flat] = make_uint4(col, (uint32_t)o.bx | ((uint32_t)o.by << 16), o.bpatch, (uint32_t)o.bmap | ((uint32_t)o.bmap << 16));
         if (P.is_new) {
@@ -719,7 +609,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_round(StageDev S, PhaseDev P, u
     CtaSmem& sm = rs.c;
     if (threadIdx.x == 0) { rs.req_cnt = 0; rs.req_min = NONE32; }
     if (threadIdx.x < ST_COUNT) rs.stat[threadIdx.x] = 0ull;
-    load_luts(S, sm);
+    load_luts(S, sm.lut, sm.lutg);
     unsigned long long st_acc[ST_COUNT];
 #pragma unroll
     for (int i = 0; i < ST_COUNT; ++i) st_acc[i] = 0ull;
@@ -761,17 +651,17 @@ __global__ void __launch_bounds__(CTA_THREADS) k_round(StageDev S, PhaseDev P, u
         const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
         const uint32_t si = P.stage_base + it;
         ItemOut o;
-        resolve_item<GUIDED>(S, sm, ws, lane, x, y, P.item_R2[it], P.rand_xy + (size_t)si * S.m,
+        resolve_item<GUIDED>(S, ws, sm.lut, sm.lutg, lane, x, y, P.item_R2[it], P.rand_xy + (size_t)si * S.m,
                              P.rand_map + (size_t)si * S.m, o);
         long long tc0 = clock64();
         if (lane == 0) {
-            commit_item(S, sm, P, si, flat, x, y, o);
+            commit_item(S, P, si, flat, x, y, o);
             __threadfence();  // release
             *((volatile uint32_t*)(P.done + it)) = 1u;
         }
         __syncwarp();
         st_acc[ST_FETCHED] += o.fetched; st_acc[ST_NOMINAL] += o.nominal; st_acc[ST_CANDS] += (unsigned long long)o.ncand;
-        st_acc[ST_ITEMS] += 1ull; st_acc[ST_COOP] += (unsigned long long)o.coop; st_acc[ST_NUNIQ] += (unsigned long long)o.nuniq;
+        st_acc[ST_ITEMS] += 1ull;
         st_acc[ST_CYC_KNN] += (unsigned long long)o.c_knn; st_acc[ST_CYC_NEIGH] += (unsigned long long)o.c_neigh;
         st_acc[ST_CYC_WEIGHT] += (unsigned long long)o.c_weight; st_acc[ST_CYC_SCORE] += (unsigned long long)o.c_score;
         st_acc[ST_CYC_COMMIT] += (unsigned long long)(clock64() - tc0);
@@ -803,7 +693,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_flow(StageDev S, PhaseDev P, Fl
     RoundSmem& rs = *reinterpret_cast<RoundSmem*>(smem_raw);
     CtaSmem& sm = rs.c;
     if (threadIdx.x < ST_COUNT) rs.stat[threadIdx.x] = 0ull;
-    load_luts(S, sm);
+    load_luts(S, sm.lut, sm.lutg);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpScratch& ws = sm.ws[warp];
     unsigned long long st_acc[ST_COUNT];
@@ -823,7 +713,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_flow(StageDev S, PhaseDev P, Fl
             unsigned spins = 0, ns = 32;
             while ((it = vq[slot]) == NONE32) {
                 __nanosleep(ns);
-                if (ns < 2048) ns <<= 1;
+                if (ns < 1024) ns <<= 1;
                 if ((++spins & 1023u) == 0u) {
                     if (vctl[FC_ABORT]) break;
                     if (spins > (1u << 22)) { atomicExch(F.ctl + FC_ABORT, 1u); break; }  // watchdog: never hang the device
@@ -838,11 +728,11 @@ __global__ void __launch_bounds__(CTA_THREADS) k_flow(StageDev S, PhaseDev P, Fl
         const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
         const uint32_t si = P.stage_base + it;
         ItemOut o;
-        resolve_item<GUIDED>(S, sm, ws, lane, x, y, P.item_R2[it], P.rand_xy + (size_t)si * S.m,
+        resolve_item<GUIDED>(S, ws, sm.lut, sm.lutg, lane, x, y, P.item_R2[it], P.rand_xy + (size_t)si * S.m,
                              P.rand_map + (size_t)si * S.m, o);
         long long tc0 = clock64();
         if (lane == 0) {
-            commit_item(S, sm, P, si, flat, x, y, o);
+            commit_item(S, P, si, flat, x, y, o);
             __threadfence();  // release
         }
         __syncwarp();
@@ -858,7 +748,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_flow(StageDev S, PhaseDev P, Fl
             }
         }
         st_acc[ST_FETCHED] += o.fetched; st_acc[ST_NOMINAL] += o.nominal; st_acc[ST_CANDS] += (unsigned long long)o.ncand;
-        st_acc[ST_ITEMS] += 1ull; st_acc[ST_COOP] += (unsigned long long)o.coop; st_acc[ST_NUNIQ] += (unsigned long long)o.nuniq;
+        st_acc[ST_ITEMS] += 1ull;
         st_acc[ST_CYC_KNN] += (unsigned long long)o.c_knn; st_acc[ST_CYC_NEIGH] += (unsigned long long)o.c_neigh;
         st_acc[ST_CYC_WEIGHT] += (unsigned long long)o.c_weight; st_acc[ST_CYC_SCORE] += (unsigned long long)o.c_score;
         st_acc[ST_CYC_COMMIT] += (unsigned long long)(clock64() - tc0);
@@ -878,7 +768,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_serial(StageDev S, PhaseDev P) 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RoundSmem& rs = *reinterpret_cast<RoundSmem*>(smem_raw);
     CtaSmem& sm = rs.c;
-    load_luts(S, sm);
+    load_luts(S, sm.lut, sm.lutg);
     if (threadIdx.x >= 32) return;
     const int lane = threadIdx.x;
     WarpScratch& ws = sm.ws[0];
@@ -904,10 +794,10 @@ __global__ void __launch_bounds__(CTA_THREADS) k_serial(StageDev S, PhaseDev P) 
         const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
         const uint32_t si = P.stage_base + it;
         ItemOut o;
-        resolve_item<GUIDED>(S, sm, ws, lane, x, y, R2_INF, P.rand_xy + (size_t)si * S.m, P.rand_map + (size_t)si * S.m, o,
+        resolve_item<GUIDED>(S, ws, sm.lut, sm.lutg, lane, x, y, R2_INF, P.rand_xy + (size_t)si * S.m, P.rand_map + (size_t)si * S.m, o,
                              use_list ? pts : nullptr, npts);
         if (lane == 0) {
-            commit_item(S, sm, P, si, flat, x, y, o);
+            commit_item(S, P, si, flat, x, y, o);
             if (use_list && P.is_new && o.kk > 0) {  // same insertions as mask_insert (ms.rs:306-327)
                 int q = npts;
                 pts[q++] = make_short2((short)x, (short)y);
@@ -940,7 +830,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_eval_items(StageDev S, uint32_t
                                                              int32_t* neigh, int32_t* res, float* score) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CtaSmem& sm = *reinterpret_cast<CtaSmem*>(smem_raw);
-    load_luts(S, sm);
+    load_luts(S, sm.lut, sm.lutg);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpScratch& ws = sm.ws[warp];
     const uint32_t nwarps = gridDim.x * WARPS_PER_CTA;
@@ -948,7 +838,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_eval_items(StageDev S, uint32_t
         const uint32_t flat = pixel_flat[it];
         const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
         ItemOut o;
-        resolve_item<GUIDED>(S, sm, ws, lane, x, y, R2_INF, rand_xy + (size_t)it * S.m,
+        resolve_item<GUIDED>(S, ws, sm.lut, sm.lutg, lane, x, y, R2_INF, rand_xy + (size_t)it * S.m,
                              rand_map + (size_t)it * S.m, o);
         int32_t* no = neigh + (size_t)it * 2 * S.k;
         for (int j = lane; j < S.k; j += 32) {
