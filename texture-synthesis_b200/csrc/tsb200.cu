@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "tsb_device.cuh"
@@ -271,7 +272,10 @@ struct tsb_generator {
     DevBuf<uint32_t> d_rand_xy, d_pick_idx, d_tmp_u32, d_read_color, d_read_coord, d_read_id;
     DevBuf<uint8_t> d_rand_map;
     DevBuf<uint32_t> d_npred, d_nsucc, d_succ_off, d_succ_cur, d_succ, d_queue, d_fctl;
-    DevBuf<uint8_t> d_cub_temp;
+    DevBuf<uint8_t> d_cub_temp, d_sort_temp;
+    DevBuf<unsigned long long> d_keys, d_keys_sorted;
+    DevBuf<uint32_t> d_v0;
+    cudaStream_t stream2 = nullptr;
     int max_ctas_flow = 0, max_ctas_flow_guided = 0;
     bool use_rounds = false, force_csr = false;
     size_t succ_stride = SUCC_STRIDE;
@@ -294,6 +298,7 @@ struct tsb_generator {
     ~tsb_generator() {
         if (h_ctrl) cudaFreeHost(h_ctrl);
         if (stream) cudaStreamDestroy(stream);
+        if (stream2) cudaStreamDestroy(stream2);
     }
 };
 
@@ -737,11 +742,12 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
     }
     CU(cudaGetLastError());
 
-    // ---- pixel order: pick_random_unresolved (ms.rs:380-389) for every new pixel of every stage.  The index
-    // draws run on the GPU; the swap_remove chain and the per-stage work-item lists are produced by a host
-    // worker thread that runs ahead of the GPU (stage s+1 is planned while stage s executes). ----
-    TRY(g->h_idx.ensure(std::max<size_t>(n_picks, 1)));
-    TRY(g->h_items.ensure(std::max<size_t>(total_items, 1)));
+    // ---- pixel order: pick_random_unresolved (ms.rs:380-389) for every new pixel of every stage, entirely on the
+    // device: index draws (k_pick_indices), then the swap_remove chain resolved in parallel (k_resolve_picks).
+    // Every non-locked resolved pixel is a pick, and redo items follow the resolution order (ms.rs:905-907), so
+    // the work items of every stage are simply a PREFIX of the pick array: item i of a stage = picks[i].
+    TRY(g->h_items.ensure(std::max<size_t>(n_picks, 1)));
+    TRY(g->d_item_pixel.ensure(std::max<size_t>(n_picks, 1)));
     {
         TRY(g->d_pick_idx.ensure(std::max<size_t>(n_picks, 1)));
         size_t un = total;
@@ -754,38 +760,49 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
             }
             un -= sp.n_new;
         }
-        if (n_picks) CU(cudaMemcpyAsync(g->h_idx.p, g->d_pick_idx.p, n_picks * 4, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
-    }
-    std::vector<size_t> stage_item_base(plan.size() + 1, 0);
-    for (size_t i = 0; i < plan.size(); ++i) stage_item_base[i + 1] = stage_item_base[i] + plan[i].n_redo + plan[i].n_new;
-    std::atomic<int> stages_planned{0};
-    std::thread planner([&]() {
-        std::vector<uint32_t>& v = g->unresolved;  // swap_remove chain
-        size_t len = v.size();
-        const uint32_t* idx = g->h_idx.p;
-        for (size_t si = 0; si < plan.size(); ++si) {
-            const StagePlan& sp = plan[si];
-            uint32_t* items = g->h_items.p + stage_item_base[si];
-            for (size_t i = 0; i < sp.n_redo; ++i) items[i] = g->resolved_order[g->locked + i];  // ms.rs:905-907
-            uint32_t* fresh = items + sp.n_redo;
-            for (size_t t = 0; t < sp.n_new; ++t) {
-                uint32_t j = idx[sp.pick_base + t];
-                fresh[t] = v[j];
-                v[j] = v[len - 1];
-                --len;
+        if (n_picks) {
+            const uint32_t T = (uint32_t)n_picks;
+            TRY(g->d_keys.ensure(n_picks)); TRY(g->d_keys_sorted.ensure(n_picks));
+            // v0: the unresolved list as it is now (identity unless inpaint / random_init removed entries)
+            bool identity = g->unresolved.size() == npix;
+            if (identity && (g->inpaint || g->locked)) identity = false;
+            const uint32_t* v0 = nullptr;
+            if (!identity) { TRY(g->d_v0.upload(g->unresolved.data(), g->unresolved.size(), s)); v0 = g->d_v0.p; }
+            k_pick_keys<<<(T + 255) / 256, 256, 0, s>>>(g->d_pick_idx.p, T, g->d_keys.p);
+            int end_bit = 33;
+            while (end_bit < 64 && (total >> (end_bit - 32)) != 0) ++end_bit;
+            size_t tb = 0;
+            CU(cub::DeviceRadixSort::SortKeys(nullptr, tb, g->d_keys.p, g->d_keys_sorted.p, (int)T, 0, end_bit, s));
+            TRY(g->d_sort_temp.ensure(tb + 256));
+            tb = g->d_sort_temp.n;
+            CU(cub::DeviceRadixSort::SortKeys(g->d_sort_temp.p, tb, g->d_keys.p, g->d_keys_sorted.p, (int)T, 0, end_bit, s));
+            k_resolve_picks<<<(T + 255) / 256, 256, 0, s>>>(g->d_keys_sorted.p, T, (uint64_t)total, v0, g->d_pick_idx.p, g->d_item_pixel.p);
+            CU(cudaGetLastError());
+            g->stats.kernel_launches += 4;
+            // host mirrors: the whole order is needed only after the run (resolved list, trace); the first few picks
+            // are needed right away (first random pixel, serial-prefix bookkeeping)
+            const size_t head = std::min<size_t>(n_picks, 4096);
+            CU(cudaMemcpyAsync(g->h_items.p, g->d_item_pixel.p, head * 4, cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));
+            if (n_picks > head) CU(cudaMemcpyAsync(g->h_items.p + head, g->d_item_pixel.p + head, (n_picks - head) * 4, cudaMemcpyDeviceToHost, g->stream2));
+            const size_t left = total - n_picks;
+            if (left) {
+                TRY(g->d_tmp_u32.ensure(left));
+                k_resolve_leftover<<<(uint32_t)((left + 255) / 256), 256, 0, s>>>(g->d_keys_sorted.p, T, (uint64_t)total, v0, (uint32_t)left, g->d_tmp_u32.p);
+                CU(cudaGetLastError());
+                std::vector<uint32_t> rest(left);
+                CU(cudaMemcpyAsync(rest.data(), g->d_tmp_u32.p, left * 4, cudaMemcpyDeviceToHost, s));
+                CU(cudaStreamSynchronize(s));
+                g->unresolved.swap(rest);
+            } else {
+                g->unresolved.clear();
             }
-            // ms.rs:1043-1049: newly resolved pixels join `resolved` in processing order
-            g->resolved_order.insert(g->resolved_order.end(), fresh, fresh + sp.n_new);
-            stages_planned.store((int)si + 1, std::memory_order_release);
         }
-        v.resize(len);
-    });
-    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{planner};
+    }
+    const uint32_t* stage_pixels = g->h_items.p;  // host mirror of the pick array (only its head is valid before the run ends)
     g->stats.host_ms_schedule = now_ms() - t_plan0;
 
     // ---- buffers ----
-    TRY(g->d_item_pixel.ensure(max_stage_items));
     TRY(g->d_item_R2.ensure(max_phase));
     TRY(g->d_pred_cnt.ensure(max_phase));
     if (getenv("TSB_MODE") && !strcmp(getenv("TSB_MODE"), "rounds")) TRY(g->d_preds.ensure(max_phase * (size_t)PRED_CAP));
@@ -838,15 +855,6 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
         }
         const size_t n_items = sp.n_redo + sp.n_new;
         if (n_items == 0) continue;
-        const size_t stage_idx = (size_t)(&sp - &plan[0]);
-        {
-            const double tw = now_ms();
-            while (stages_planned.load(std::memory_order_acquire) <= (int)stage_idx) std::this_thread::yield();
-            g->stats.host_ms_schedule += now_ms() - tw;  // time the GPU had to wait for the planner
-        }
-        const uint32_t* stage_pixels = g->h_items.p + stage_item_base[stage_idx];
-        CU(cudaMemcpyAsync(g->d_item_pixel.p, stage_pixels, n_items * 4, cudaMemcpyHostToDevice, s));
-        if (g->trace) g->tr_pixel.insert(g->tr_pixel.end(), stage_pixels, stage_pixels + n_items);
         // random candidates of every item of the stage: rng seeded with loop_seed + 1 = stage seed + i + 1 (ms.rs:902,945)
         k_rand_candidates<<<(uint32_t)((n_items + 127) / 128), 128, 0, s>>>(S.ex, S.n_ex, m, sp.seed + 1ull, (uint32_t)n_items,
                                                                           g->d_rand_xy.p, g->d_rand_map.p);
@@ -917,6 +925,10 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
         overall_current += sp.pixels_to_resolve;
         trace_base += n_items;
     }
+    // host mirrors of the order: ms.rs:1043-1049 (newly resolved pixels join `resolved` in processing order)
+    CU(cudaStreamSynchronize(g->stream2));
+    g->resolved_order.insert(g->resolved_order.end(), g->h_items.p, g->h_items.p + n_picks);
+    if (g->trace) for (auto& sp : plan) g->tr_pixel.insert(g->tr_pixel.end(), g->h_items.p, g->h_items.p + sp.n_redo + sp.n_new);
     g->trace_n = g->trace ? trace_base : 0;
     unsigned long long cnt[ST_COUNT];
     CU(cudaMemcpyAsync(cnt, g->d_counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, s));
@@ -1006,6 +1018,7 @@ int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
     auto bail = [&](int code) { delete g; return code; };
     if (cudaSetDevice(dev) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "cudaSetDevice(%d) failed", dev));
     if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "stream creation failed"));
+    if (cudaStreamCreateWithFlags(&g->stream2, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "stream creation failed"));
     if (cudaMallocHost((void**)&g->h_ctrl, 64) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "pinned allocation failed"));
     g->W = (int)desc->out_width; g->H = (int)desc->out_height;
     const size_t npix = (size_t)g->W * g->H;

@@ -737,9 +737,9 @@ __global__ void __launch_bounds__(CTA_THREADS) k_flow(StageDev S, PhaseDev P, Fl
         }
         __syncwarp();
         // notify successors; the one that drops a counter to zero publishes the item
-        const uint32_t s0 = F.stride ? it * F.stride : F.succ_off[it];
-        const uint32_t s1 = F.stride ? s0 + F.nsucc[it] : F.succ_off[it + 1];
-        for (uint32_t e = s0 + lane; e < s1; e += 32) {
+        const size_t s0 = F.stride ? (size_t)it * F.stride : (size_t)F.succ_off[it];
+        const size_t s1 = F.stride ? s0 + F.nsucc[it] : (size_t)F.succ_off[it + 1];
+        for (size_t e = s0 + lane; e < s1; e += 32) {
             uint32_t sc = F.succ[e];
             if (atomicSub(F.npred + sc, 1u) == 1u) {
                 __threadfence();
@@ -1072,6 +1072,46 @@ __global__ void k_pick_indices(uint64_t seed_base, uint64_t len0, uint32_t n, ui
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     idx[t] = (uint32_t)Pcg32::seed_from_u64(seed_base + (uint64_t)t).gen_range_usize(len0 - (uint64_t)t);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pixel order on the device.  The reference draws idx_t = gen_range(0..len_t) and does
+// `pixel_t = unresolved.swap_remove(idx_t)` (ms.rs:380-389): out_t = v[idx_t]; v[idx_t] = v[len_t - 1].
+// The value found at position p just before step t is the initial v0[p] unless an earlier step wrote p; the
+// most recent such step ts stored there the value that position (n - ts - 1) held just before ts.  Sorting the
+// keys (idx_t << 32 | t) lets every step resolve its own chain with binary searches, all steps in parallel.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pick_keys(const uint32_t* idx, uint32_t T, unsigned long long* keys) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T) keys[t] = ((unsigned long long)idx[t] << 32) | (unsigned long long)t;
+}
+__device__ __forceinline__ uint32_t chain_value(const unsigned long long* __restrict__ keys, uint32_t T, uint64_t n,
+                                                const uint32_t* __restrict__ v0, uint32_t p, uint32_t tt) {
+    for (;;) {
+        const unsigned long long q = ((unsigned long long)p << 32) | (unsigned long long)tt;
+        uint32_t lo = 0, hi = T;  // lower_bound(q): the entry before it is the last write to p before step tt, if any
+        while (lo < hi) {
+            uint32_t mid = lo + ((hi - lo) >> 1);
+            if (__ldg(keys + mid) < q) lo = mid + 1; else hi = mid;
+        }
+        if (lo == 0) break;
+        const unsigned long long kp = __ldg(keys + lo - 1);
+        if ((uint32_t)(kp >> 32) != p) break;
+        const uint32_t ts = (uint32_t)kp;
+        p = (uint32_t)(n - (uint64_t)ts - 1ull);  // step ts copied the then-last element into position p
+        tt = ts;
+    }
+    return v0 ? __ldg(v0 + p) : p;
+}
+// picks[t] for every step t (time T_query = t, position idx[t])
+__global__ void k_resolve_picks(const unsigned long long* keys, uint32_t T, uint64_t n, const uint32_t* v0, const uint32_t* idx, uint32_t* picks) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T) picks[t] = chain_value(keys, T, n, v0, idx[t], t);
+}
+// the elements left in `unresolved` after all T steps: positions [0, n - T) at time T
+__global__ void k_resolve_leftover(const unsigned long long* keys, uint32_t T, uint64_t n, const uint32_t* v0, uint32_t count, uint32_t* out) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < count) out[p] = chain_value(keys, T, n, v0, p, T);
 }
 
 // ---------------------------------------------------------------------------------------------
