@@ -152,6 +152,22 @@ int tsb_generator_read_uncertainty(tsb_generator* g, uint8_t* rgba);    /* get_u
 int tsb_generator_read_id_maps(tsb_generator* g, uint8_t* patch_rgba, uint8_t* map_rgba); /* get_id_maps, ms.rs:605-633 */
 int tsb_generator_get_stats(tsb_generator* g, tsb_stats* out);
 
+/* ---- band-sharded multi-GPU execution of ONE output (one process per GPU on one node) -------------------------
+ * Every rank creates the same generator, uploads the same inputs and calls tsb_generator_resolve* with the same
+ * parameters.  Before that the ranks link their replicas: prepare (allocates the shared buffers at their final
+ * size) -> export (CUDA IPC handle + offset, 80 bytes per buffer) -> all-gather of the handles by the host application
+ * (torch.distributed / MPI / files) -> attach.  `barrier` must block until every rank has called it (e.g.
+ * torch.distributed.barrier); it is called a few times per dependency phase.  Phases with fewer than 32768 work
+ * items (env TSB_MG_MIN_PHASE) are executed redundantly by every rank; larger ones are sharded by horizontal
+ * band: commits are peer stores into every replica, successor notifications are system-scope atomics on the
+ * owner's counters.  The result is identical to the single-GPU result and ends up on every rank. */
+typedef void (*tsb_barrier_fn)(void* user);
+int tsb_generator_mg_prepare(tsb_generator* g, const tsb_params* params, uint32_t* n_handles);
+int tsb_generator_mg_export(tsb_generator* g, uint8_t* handles /* n_handles * 80 bytes: IPC handle + offset */);
+int tsb_generator_mg_attach(tsb_generator* g, uint32_t rank, uint32_t world, const uint8_t* all_handles /* world * n_handles * 80 */,
+                            tsb_barrier_fn barrier, void* user);
+int tsb_generator_mg_phases(tsb_generator* g, uint64_t* n /* band-sharded phases executed so far */);
+
 const char* tsb_last_error(void);
 int tsb_device_count(void);
 

@@ -12,7 +12,7 @@ OUT = os.path.join(HERE, "libtsb200.so")
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "--fmad=false",                      # the reference's f32/f64 arithmetic is unfused (ms.rs:1259-1280)
-    "-Xcompiler", "-fPIC,-O2,-fno-fast-math,-ffp-contract=off", "-shared", "-Xptxas", "-v",
+    "-Xcompiler", "-fPIC,-O2,-fno-fast-math,-ffp-contract=off", "-shared", "-Xptxas", "-v", "-ldl",
 ]
 
 

@@ -65,6 +65,7 @@ class Stats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+BARRIER_FN = C.CFUNCTYPE(None, C.c_void_p)
 PROGRESS_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64)
 
 # every symbol include/tsb200.h declares
@@ -75,7 +76,8 @@ EXPORTS = [
     "tsb_generator_read_resolved", "tsb_generator_read_uncertainty", "tsb_generator_read_id_maps",
     "tsb_generator_get_stats", "tsb_last_error", "tsb_device_count", "tsb_generator_load_state",
     "tsb_generator_eval_items", "tsb_generator_set_trace", "tsb_generator_trace_count", "tsb_generator_read_trace",
-    "tsb_microbench_gather",
+    "tsb_microbench_gather", "tsb_generator_mg_prepare", "tsb_generator_mg_export", "tsb_generator_mg_attach",
+    "tsb_generator_mg_phases",
 ]
 
 
@@ -117,6 +119,10 @@ def lib():
         L.tsb_generator_trace_count.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.tsb_generator_read_trace.argtypes = [vp, vp, vp, vp, vp, vp]
         L.tsb_microbench_gather.argtypes = [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.tsb_generator_mg_prepare.argtypes = [vp, C.POINTER(Params), C.POINTER(C.c_uint32)]
+        L.tsb_generator_mg_export.argtypes = [vp, vp]
+        L.tsb_generator_mg_attach.argtypes = [vp, C.c_uint32, C.c_uint32, vp, BARRIER_FN, vp]
+        L.tsb_generator_mg_phases.argtypes = [vp, C.POINTER(C.c_uint64)]
         _LIB = L
     return _LIB
 
@@ -317,6 +323,27 @@ class Generator:
         _check(self.L.tsb_generator_eval_items(self.h, C.byref(params), level, adaptive_alpha, p_stage_seed, n,
                                                _p(pixels), _p(loop_seeds), _p(neigh), _p(res), _p(score)))
         return dict(neigh=neigh, res=res, score=score)
+
+    # -- band-sharded multi-GPU ----------------------------------------------------------------
+    def mg_export(self, params):
+        """Allocates the shared buffers and returns this rank's CUDA IPC handles as bytes."""
+        n = C.c_uint32()
+        _check(self.L.tsb_generator_mg_prepare(self.h, C.byref(params), C.byref(n)))
+        buf = np.zeros(n.value * 80, np.uint8)
+        _check(self.L.tsb_generator_mg_export(self.h, _p(buf)))
+        return buf.tobytes()
+
+    def mg_attach(self, rank, world, all_handles, barrier):
+        """all_handles: list (by rank) of the bytes returned by mg_export; barrier: callable blocking until all ranks arrive."""
+        blob = np.frombuffer(b"".join(all_handles), np.uint8).copy()
+        self._barrier_cb = BARRIER_FN(lambda user: barrier())
+        self._keep.append(blob)
+        _check(self.L.tsb_generator_mg_attach(self.h, rank, world, _p(blob), self._barrier_cb, None))
+
+    def mg_phases(self):
+        n = C.c_uint64()
+        _check(self.L.tsb_generator_mg_phases(self.h, C.byref(n)))
+        return n.value
 
     def set_trace(self, on=True):
         _check(self.L.tsb_generator_set_trace(self.h, 1 if on else 0))

@@ -5,6 +5,8 @@
 // Generator::resolve_random_batch (ms.rs:427-445) + Generator::resolve (ms.rs:702-1052).
 #include "../../include/tsb200.h"
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <atomic>
 #include <thread>
@@ -278,6 +280,16 @@ struct tsb_generator {
     cudaStream_t stream2 = nullptr;
     int max_ctas_flow = 0, max_ctas_flow_guided = 0;
     bool use_rounds = false, force_csr = false;
+    // band-sharded multi-GPU execution
+    bool mg_on = false;
+    MgDev h_mg{};
+    DevBuf<MgDev> d_mg;
+    tsb_barrier_fn mg_barrier = nullptr;
+    void* mg_barrier_user = nullptr;
+    std::vector<void*> mg_opened;
+    std::vector<std::pair<cudaIpcMemHandle_t, void*>> mg_blocks;
+    size_t mg_min_phase = 32768;   // smaller phases are executed redundantly by every rank (no communication)
+    uint64_t mg_phases = 0;
     size_t succ_stride = SUCC_STRIDE;
     uint32_t* h_ctrl = nullptr;  // pinned, 16 words
     PinnedBuf<uint32_t> h_idx, h_items;  // pick indices (D2H) and per-stage work-item pixels (H2D)
@@ -562,6 +574,50 @@ int run_phase(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, bool
 }
 
 
+// Stage plan (ms.rs:786-812): levels, seeds and work-item counts of every stage follow from the parameters alone.
+void build_plan(const tsb_generator* g, const tsb_params* prm, std::vector<StagePlan>& plan, size_t& n_picks, size_t& max_stage_items,
+                size_t& max_phase, size_t& total_items) {
+    const size_t total = g->unresolved.size();  // ms.rs:710
+    size_t resolved_n = g->resolved_order.size(), unresolved_n = total;
+    n_picks = 0; max_stage_items = 1; max_phase = 1; total_items = 0;
+    int pyramid_level = 0;
+    for (int p_stage = prm->p_stages; p_stage >= 0; --p_stage) {
+        StagePlan sp;
+        sp.p_stage = p_stage;
+        sp.level = pyramid_level;
+        sp.recolour = pyramid_level > 0;
+        pyramid_level = std::min(pyramid_level + 1, prm->p_stages - 1);
+        sp.seed = (uint64_t)Pcg32::seed_from_u64(prm->seed + (uint64_t)p_stage).next_u32();
+        float fp = powf(prm->p, (float)p_stage) * (float)total;
+        sp.pixels_to_resolve = fp <= 0.0f ? 0 : (size_t)fp;
+        sp.redo_count = resolved_n - g->locked;
+        sp.n_redo = std::min(sp.redo_count, sp.pixels_to_resolve);
+        sp.n_new = std::min(sp.pixels_to_resolve - sp.n_redo, unresolved_n);
+        sp.pick_base = n_picks;
+        sp.resolved_before = resolved_n;
+        sp.adaptive_alpha = 0.0f;
+        if (g->guided && p_stage > 0) {  // ms.rs:846-851
+            float v = prm->alpha * (1.0f - ((float)resolved_n / (float)total));
+            sp.adaptive_alpha = v * (v * v);
+        }
+        n_picks += sp.n_new;
+        unresolved_n -= sp.n_new;
+        resolved_n += sp.n_new;
+        max_stage_items = std::max(max_stage_items, sp.n_redo + sp.n_new);
+        max_phase = std::max(max_phase, std::max(sp.n_redo, sp.n_new));
+        total_items += sp.n_redo + sp.n_new;
+        plan.push_back(sp);
+    }
+}
+
+int ensure_flow_buffers(tsb_generator* g, size_t max_phase) {
+    TRY(g->d_item_R2.ensure(max_phase));
+    TRY(g->d_npred.ensure(max_phase + 1)); TRY(g->d_nsucc.ensure(max_phase + 1)); TRY(g->d_succ_off.ensure(max_phase + 1));
+    TRY(g->d_succ_cur.ensure(max_phase + 1)); TRY(g->d_queue.ensure(max_phase + 1)); TRY(g->d_fctl.ensure(8));
+    TRY(g->d_succ.ensure(max_phase * SUCC_STRIDE + 1024));
+    return 0;
+}
+
 PhaseDev make_phase(tsb_generator* g, uint32_t i0, uint32_t n, bool is_new, uint64_t trace_base) {
     PhaseDev P;
     memset(&P, 0, sizeof(P));
@@ -626,9 +682,115 @@ int run_phase_flow(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n,
     const int ga = grid_for(g, n), gl = grid_light(g, n);
     const int gf = std::max(1, std::min((int)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), g->guided ? g->max_ctas_flow_guided : g->max_ctas_flow));
     uint64_t edges = 0;
+    if (g->mg_on && n >= g->mg_min_phase) {
+        // ---- band-sharded phase: every rank resolves the items of its band; commits go to all replicas ----
+        StageDev Sm = S;
+        Sm.mg = g->d_mg.p;
+        F.stride = (uint32_t)g->succ_stride;
+        auto barrier = [&]() -> int { CU(cudaStreamSynchronize(s)); g->mg_barrier(g->mg_barrier_user); return 0; };
+        TRY(barrier());  // every rank has finished the previous phase before anybody writes into its replica
+        CU(cudaMemsetAsync(F.ctl, 0, 32, s));
+        k_radius<<<ga, CTA_THREADS, sizeof(CtaSmem), s>>>(Sm, P, F);
+        CU(cudaGetLastError());
+        TRY(barrier());  // radii of all items and zeroed counters are visible on every replica
+        if (getenv("TSB_MG_DEBUG")) {
+            std::vector<uint32_t> np(n), ns(n), px(n);
+            cudaMemcpy(np.data(), F.npred, n * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(ns.data(), F.nsucc, n * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(px.data(), P.item_pixel, n * 4, cudaMemcpyDeviceToHost);
+            unsigned long long a = 0, b = 0, nz = 0;
+            for (uint32_t i = 0; i < n; ++i) {
+                int owner = std::min((int)(px[i] / (uint32_t)g->W) / g->h_mg.band_h, g->h_mg.world - 1);
+                if (owner == g->h_mg.rank) { a += np[i]; b += ns[i]; nz += (np[i] || ns[i]) ? 1 : 0; }
+            }
+            fprintf(stderr, "[tsb mg rank %d] after k_radius: own npred sum %llu nsucc sum %llu nonzero items %llu; ptrs local nsucc %p mg nsucc[self] %p\n",
+                    g->h_mg.rank, a, b, nz, (void*)F.nsucc, (void*)g->h_mg.nsucc[g->h_mg.rank]);
+        }
+        k_edges_scan<2><<<gl, CTA_THREADS, 0, s>>>(Sm, P, F);
+        CU(cudaGetLastError());
+        TRY(barrier());  // all edges registered with their owners
+        for (int r = 0; r < g->h_mg.world; ++r) {  // a successor list overflow anywhere invalidates the phase for everybody
+            uint32_t flag = 0;
+            CU(cudaMemcpy(&flag, g->h_mg.ctl[r] + FC_OVERFLOW, 4, cudaMemcpyDeviceToHost));
+            if (flag) return fail(TSB_ERR_UNSUPPORTED, "successor list overflow in a band-sharded phase of %u items (stride %zu)", n, g->succ_stride);
+        }
+        if (getenv("TSB_MG_DEBUG")) {  // invariant: sum of own npred over ranks == sum of own nsucc over ranks == #edges
+            std::vector<uint32_t> np(n), ns(n), px(n);
+            cudaMemcpy(np.data(), F.npred, n * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(ns.data(), F.nsucc, n * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(px.data(), P.item_pixel, n * 4, cudaMemcpyDeviceToHost);
+            unsigned long long a = 0, b = 0, own = 0, a2 = 0, b2 = 0;
+            for (uint32_t i = 0; i < n; ++i) {
+                int owner = std::min((int)(px[i] / (uint32_t)g->W) / g->h_mg.band_h, g->h_mg.world - 1);
+                if (owner == g->h_mg.rank) { a += np[i]; b += ns[i]; ++own; }
+                else { a2 += np[i] < 100000 ? np[i] : 0; b2 += ns[i] < 100000 ? ns[i] : 0; }
+            }
+            fprintf(stderr, "[tsb mg rank %d] phase n=%u own=%llu sum(npred)=%llu sum(nsucc)=%llu | non-own entries: npred %llu nsucc %llu\n",
+                    g->h_mg.rank, n, own, a, b, a2, b2);
+            if (n <= 8192) {  // brute-force expectation from the local view of the radii
+                std::vector<uint32_t> r2(n), enp(n, 0), ens(n, 0);
+                cudaMemcpy(r2.data(), P.item_R2, n * 4, cudaMemcpyDeviceToHost);
+                for (uint32_t i = 0; i < n; ++i) for (uint32_t j = 0; j < i; ++j) {
+                    long dx = (long)(px[i] % (uint32_t)g->W) - (long)(px[j] % (uint32_t)g->W), dy = (long)(px[i] / (uint32_t)g->W) - (long)(px[j] / (uint32_t)g->W);
+                    unsigned long long D = (unsigned long long)(dx * dx + dy * dy);
+                    if (D <= std::max(r2[i], r2[j])) { enp[i]++; ens[j]++; }
+                }
+                unsigned long long te = 0; int shown = 0;
+                for (uint32_t i = 0; i < n; ++i) te += enp[i];
+                fprintf(stderr, "[tsb mg rank %d] expected edges (local radius view) %llu\n", g->h_mg.rank, te);
+                for (uint32_t i = 0; i < n && shown < 10; ++i) {
+                    int owner = std::min((int)(px[i] / (uint32_t)g->W) / g->h_mg.band_h, g->h_mg.world - 1);
+                    if (owner == g->h_mg.rank && (np[i] != enp[i] || ns[i] != ens[i])) {
+                        fprintf(stderr, "[tsb mg rank %d] item %u y=%u R2=%u: npred %u (expected %u) nsucc %u (expected %u)\n", g->h_mg.rank, i,
+                                px[i] / (uint32_t)g->W, r2[i], np[i], enp[i], ns[i], ens[i]);
+                        ++shown;
+                    }
+                }
+            }
+        }
+        k_seed_queue<<<(n + 255) / 256, 256, 0, s>>>(Sm, P, F);
+        CU(cudaGetLastError());
+        TRY(barrier());  // every rank has seeded its queue before any rank starts publishing into it
+        TRY(clk.mid(s));
+        const int gfm = g->guided ? g->max_ctas_flow_guided : g->max_ctas_flow;
+        if (g->guided) k_flow<true, true><<<gfm, CTA_THREADS, sizeof(RoundSmem), s>>>(Sm, P, F);
+        else k_flow<false, true><<<gfm, CTA_THREADS, sizeof(RoundSmem), s>>>(Sm, P, F);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(g->h_ctrl, F.ctl, 32, cudaMemcpyDeviceToHost, s));
+        TRY(barrier());  // every commit of the phase has landed on every replica
+        k_pmap_clear<<<(n + 255) / 256, 256, 0, s>>>(P);
+        CU(cudaGetLastError());
+        g->stats.kernel_launches += 5;
+        g->stats.rounds++;
+        g->mg_phases++;
+        TRY(clk.end(g, s, "flow-mg", i0, n, is_new, g->h_ctrl[FC_NOWN]));
+        if (g->h_ctrl[FC_ABORT] && getenv("TSB_MG_DEBUG")) {
+            std::vector<uint32_t> np(n), px(n), r2(n), ns(n), q(n);
+            cudaMemcpy(np.data(), F.npred, n * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(ns.data(), F.nsucc, n * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(px.data(), P.item_pixel, n * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(r2.data(), P.item_R2, n * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(q.data(), F.queue, n * 4, cudaMemcpyDeviceToHost);
+            std::vector<char> queued(n, 0);
+            for (uint32_t i = 0; i < n; ++i) if (q[i] != NONE32 && q[i] < n) queued[q[i]] = 1;
+            int shown = 0;
+            for (uint32_t i = 0; i < n && shown < 12; ++i) {
+                int y = (int)(px[i] / (uint32_t)g->W), x = (int)(px[i] % (uint32_t)g->W);
+                int owner = std::min(y / g->h_mg.band_h, g->h_mg.world - 1);
+                if (owner == g->h_mg.rank && !queued[i]) {
+                    fprintf(stderr, "[tsb mg rank %d] stuck item %u px (%d,%d) npred %u nsucc %u R2 %u\n", g->h_mg.rank, i, x, y, np[i], ns[i], r2[i]);
+                    ++shown;
+                }
+            }
+        }
+        if (g->h_ctrl[FC_ABORT]) return fail(TSB_ERR_INTERNAL, "band-sharded dataflow phase of %u items stalled on rank %d (head %u tail %u own %u)", n,
+                                             g->h_mg.rank, g->h_ctrl[0], g->h_ctrl[1], g->h_ctrl[FC_NOWN]);
+        return 0;
+    }
     bool use_csr = g->force_csr || (size_t)n * g->succ_stride > g->d_succ.n;
     for (int attempt = 0; attempt < 2; ++attempt) {
         F.stride = use_csr ? 0u : (uint32_t)g->succ_stride;
+        CU(cudaMemsetAsync(F.ctl, 0, 32, s));
         k_radius<<<ga, CTA_THREADS, sizeof(CtaSmem), s>>>(S, P, F);
         CU(cudaGetLastError());
         g->stats.kernel_launches++;
@@ -654,11 +816,11 @@ int run_phase_flow(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n,
             if (n <= PAIR_MAX) k_edges_pairs<2><<<ga, CTA_THREADS, 0, s>>>(S, P, F);
             else k_edges_scan<2><<<gl, CTA_THREADS, 0, s>>>(S, P, F);
         }
-        k_seed_queue<<<(n + 255) / 256, 256, 0, s>>>(P, F);
+        k_seed_queue<<<(n + 255) / 256, 256, 0, s>>>(S, P, F);
         CU(cudaGetLastError());
         if (attempt == 0) TRY(clk.mid(s));
-        if (g->guided) k_flow<true><<<gf, CTA_THREADS, sizeof(RoundSmem), s>>>(S, P, F);
-        else k_flow<false><<<gf, CTA_THREADS, sizeof(RoundSmem), s>>>(S, P, F);
+        if (g->guided) k_flow<true, false><<<gf, CTA_THREADS, sizeof(RoundSmem), s>>>(S, P, F);
+        else k_flow<false, false><<<gf, CTA_THREADS, sizeof(RoundSmem), s>>>(S, P, F);
         k_pmap_clear<<<(n + 255) / 256, 256, 0, s>>>(P);
         CU(cudaGetLastError());
         g->stats.kernel_launches += 4;
@@ -689,41 +851,14 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
     const int m = (int)prm->random_sample_locations;
     const size_t total = g->unresolved.size();  // ms.rs:710
     const size_t npix = (size_t)g->W * g->H;
+    if (g->mg_on && g->trace) return fail(TSB_ERR_UNSUPPORTED, "per-item trace is not available in multi-GPU mode");
+    if (g->mg_on && g->use_rounds) return fail(TSB_ERR_UNSUPPORTED, "TSB_MODE=rounds is single-GPU only");
 
     // ---- stage plan (ms.rs:786-812): everything that defines the pixel order is known up front ----
     const double t_plan0 = now_ms();
     std::vector<StagePlan> plan;
-    size_t resolved_n = g->resolved_order.size(), unresolved_n = total, n_picks = 0, max_stage_items = 1, max_phase = 1, total_items = 0;
-    {
-        int pyramid_level = 0;
-        for (int p_stage = prm->p_stages; p_stage >= 0; --p_stage) {
-            StagePlan sp;
-            sp.p_stage = p_stage;
-            sp.level = pyramid_level;
-            sp.recolour = pyramid_level > 0;
-            pyramid_level = std::min(pyramid_level + 1, prm->p_stages - 1);
-            sp.seed = (uint64_t)Pcg32::seed_from_u64(prm->seed + (uint64_t)p_stage).next_u32();
-            float fp = powf(prm->p, (float)p_stage) * (float)total;
-            sp.pixels_to_resolve = fp <= 0.0f ? 0 : (size_t)fp;
-            sp.redo_count = resolved_n - g->locked;
-            sp.n_redo = std::min(sp.redo_count, sp.pixels_to_resolve);
-            sp.n_new = std::min(sp.pixels_to_resolve - sp.n_redo, unresolved_n);
-            sp.pick_base = n_picks;
-            sp.resolved_before = resolved_n;
-            sp.adaptive_alpha = 0.0f;
-            if (g->guided && p_stage > 0) {  // ms.rs:846-851
-                float v = prm->alpha * (1.0f - ((float)resolved_n / (float)total));
-                sp.adaptive_alpha = v * (v * v);
-            }
-            n_picks += sp.n_new;
-            unresolved_n -= sp.n_new;
-            resolved_n += sp.n_new;
-            max_stage_items = std::max(max_stage_items, sp.n_redo + sp.n_new);
-            max_phase = std::max(max_phase, std::max(sp.n_redo, sp.n_new));
-            total_items += sp.n_redo + sp.n_new;
-            plan.push_back(sp);
-        }
-    }
+    size_t n_picks = 0, max_stage_items = 1, max_phase = 1, total_items = 0;
+    build_plan(g, prm, plan, n_picks, max_stage_items, max_phase, total_items);
     if (max_stage_items > 0xFFFFFFF0ull) return fail(TSB_ERR_UNSUPPORTED, "output too large");
 
     // ---- rebuild the resolved set with tiling mirrors (ms.rs:747-779) ----
@@ -810,9 +945,7 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
     TRY(g->d_pend0.ensure(max_phase));
     TRY(g->d_pend1.ensure(max_phase));
     TRY(g->d_ctrl.ensure(8));
-    TRY(g->d_npred.ensure(max_phase + 1)); TRY(g->d_nsucc.ensure(max_phase + 1)); TRY(g->d_succ_off.ensure(max_phase + 1));
-    TRY(g->d_succ_cur.ensure(max_phase + 1)); TRY(g->d_queue.ensure(max_phase + 1)); TRY(g->d_fctl.ensure(4));
-    TRY(g->d_succ.ensure(max_phase * SUCC_STRIDE + 1024));
+    TRY(ensure_flow_buffers(g, max_phase));
     {
         size_t tb = 0;
         CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, g->d_nsucc.p, g->d_succ_off.p, (int)(max_phase + 1), s));
@@ -1053,14 +1186,16 @@ int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
     cudaFuncSetAttribute(k_eval_items<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
     cudaFuncSetAttribute(k_eval_items<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
     cudaFuncSetAttribute(k_radius, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
-    cudaFuncSetAttribute(k_flow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
-    cudaFuncSetAttribute(k_flow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
+    cudaFuncSetAttribute(k_flow<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
+    cudaFuncSetAttribute(k_flow<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
+    cudaFuncSetAttribute(k_flow<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
+    cudaFuncSetAttribute(k_flow<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
     cudaFuncSetAttribute(k_serial<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
     cudaFuncSetAttribute(k_serial<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_round<false>, CTA_THREADS, sizeof(RoundSmem)) != cudaSuccess || per_sm < 1) per_sm = 1;
     int per_sm_flow = 0, per_sm_flow_g = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_flow, k_flow<false>, CTA_THREADS, sizeof(RoundSmem)) != cudaSuccess || per_sm_flow < 1) per_sm_flow = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_flow_g, k_flow<true>, CTA_THREADS, sizeof(RoundSmem)) != cudaSuccess || per_sm_flow_g < 1) per_sm_flow_g = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_flow, k_flow<false, true>, CTA_THREADS, sizeof(RoundSmem)) != cudaSuccess || per_sm_flow < 1) per_sm_flow = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_flow_g, k_flow<true, true>, CTA_THREADS, sizeof(RoundSmem)) != cudaSuccess || per_sm_flow_g < 1) per_sm_flow_g = 1;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "cudaGetDeviceProperties failed"));
     g->n_sms = prop.multiProcessorCount;
@@ -1076,6 +1211,7 @@ int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
 void tsb_generator_destroy(tsb_generator* g) {
     if (!g) return;
     cudaSetDevice(g->device);
+    for (void* p : g->mg_opened) cudaIpcCloseMemHandle(p);
     delete g;
 }
 
@@ -1331,6 +1467,119 @@ int tsb_generator_eval_items(tsb_generator* g, const tsb_params* prm, int32_t le
             score[t] = 0.f;
         }
     }
+    return 0;
+}
+
+// ---- band-sharded multi-GPU execution: one process per GPU, replicas linked through CUDA IPC ----------------
+enum { MG_STATE = 0, MG_MASK, MG_MASK1, MG_SCORE, MG_R2, MG_NPRED, MG_NSUCC, MG_SUCC, MG_QUEUE, MG_CTL, MG_NBUF };
+enum { MG_ENTRY = 80 };  // bytes per exported buffer: IPC handle (64) + offset inside the allocation block (8) + padding
+
+static void* mg_local_ptr(tsb_generator* g, int which) {
+    switch (which) {
+    case MG_STATE: return g->d_state.p;
+    case MG_MASK: return g->d_mask.p;
+    case MG_MASK1: return g->d_mask1.p;
+    case MG_SCORE: return g->d_score.p;
+    case MG_R2: return g->d_item_R2.p;
+    case MG_NPRED: return g->d_npred.p;
+    case MG_NSUCC: return g->d_nsucc.p;
+    case MG_SUCC: return g->d_succ.p;
+    case MG_QUEUE: return g->d_queue.p;
+    default: return g->d_fctl.p;
+    }
+}
+
+int tsb_generator_mg_prepare(tsb_generator* g, const tsb_params* params, uint32_t* n_handles) {
+    if (!g || !params || !n_handles) return fail(TSB_ERR_INVALID, "null argument");
+    TRY(set_device(g));
+    std::vector<StagePlan> plan;
+    size_t n_picks, max_stage_items, max_phase, total_items;
+    build_plan(g, params, plan, n_picks, max_stage_items, max_phase, total_items);
+    TRY(ensure_flow_buffers(g, max_phase));  // final sizes: the IPC mappings must stay valid for the whole run
+    *n_handles = MG_NBUF;
+    return 0;
+}
+
+// An IPC handle names the whole underlying allocation block and cudaIpcOpenMemHandle returns the BASE of that
+// block; cudaMalloc packs small buffers into shared blocks, so every exported entry carries the buffer's offset
+// inside its block (driver API cuMemGetAddressRange, resolved at run time so that the library has no link-time
+// dependency on libcuda).  Entry layout: 64-byte handle + 8-byte offset + 8 bytes padding = 80 bytes.
+static int ipc_offset_of(void* ptr, uint64_t* off) {
+    typedef int (*fn_t)(unsigned long long*, size_t*, unsigned long long);
+    static fn_t fn = nullptr;
+    if (!fn) {
+        void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return fail(TSB_ERR_CUDA, "libcuda.so.1 not found");
+        fn = (fn_t)dlsym(h, "cuMemGetAddressRange_v2");
+        if (!fn) return fail(TSB_ERR_CUDA, "cuMemGetAddressRange_v2 not found");
+    }
+    unsigned long long base = 0;
+    size_t size = 0;
+    int rc = fn(&base, &size, (unsigned long long)(uintptr_t)ptr);
+    if (rc != 0) return fail(TSB_ERR_CUDA, "cuMemGetAddressRange failed (%d)", rc);
+    *off = (uint64_t)((unsigned long long)(uintptr_t)ptr - base);
+    return 0;
+}
+
+int tsb_generator_mg_export(tsb_generator* g, uint8_t* handles) {
+    if (!g || !handles) return fail(TSB_ERR_INVALID, "null argument");
+    TRY(set_device(g));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    for (int i = 0; i < MG_NBUF; ++i) {
+        uint64_t off = 0;
+        TRY(ipc_offset_of(mg_local_ptr(g, i), &off));
+        memcpy(handles + (size_t)i * MG_ENTRY + 64, &off, 8);
+        cudaIpcMemHandle_t h;
+        cudaError_t e = cudaIpcGetMemHandle(&h, mg_local_ptr(g, i));
+        if (e != cudaSuccess) return fail(TSB_ERR_CUDA, "cudaIpcGetMemHandle failed for shared buffer %d (%p): %s", i, mg_local_ptr(g, i), cudaGetErrorString(e));
+        memcpy(handles + (size_t)i * MG_ENTRY, &h, 64);
+    }
+    return 0;
+}
+
+int tsb_generator_mg_attach(tsb_generator* g, uint32_t rank, uint32_t world, const uint8_t* all_handles, tsb_barrier_fn barrier, void* user) {
+    if (!g || !all_handles || !barrier) return fail(TSB_ERR_INVALID, "null argument");
+    if (world < 2 || world > (uint32_t)MG_MAX || rank >= world) return fail(TSB_ERR_INVALID, "world size must be in [2,%d]", MG_MAX);
+    TRY(set_device(g));
+    MgDev& m = g->h_mg;
+    memset(&m, 0, sizeof(m));
+    m.rank = (int)rank; m.world = (int)world;
+    m.band_h = (g->H + (int)world - 1) / (int)world;
+    for (uint32_t r = 0; r < world; ++r) {
+        void* ptrs[MG_NBUF];
+        for (int i = 0; i < MG_NBUF; ++i) {
+            if (r == rank) { ptrs[i] = mg_local_ptr(g, i); continue; }
+            cudaIpcMemHandle_t h;
+            uint64_t off = 0;
+            const uint8_t* entry = all_handles + ((size_t)r * MG_NBUF + i) * MG_ENTRY;
+            memcpy(&h, entry, 64);
+            memcpy(&off, entry + 64, 8);
+            // several buffers of a peer may live in one allocation block: open every block once
+            void* base = nullptr;
+            for (auto& ob : g->mg_blocks) if (!memcmp(&ob.first, &h, 64)) base = ob.second;
+            if (!base) {
+                CU(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+                g->mg_blocks.push_back({h, base});
+                g->mg_opened.push_back(base);
+            }
+            ptrs[i] = (uint8_t*)base + off;
+        }
+        m.state[r] = (uint4*)ptrs[MG_STATE]; m.mask[r] = (uint32_t*)ptrs[MG_MASK]; m.mask1[r] = (uint32_t*)ptrs[MG_MASK1];
+        m.score[r] = (float*)ptrs[MG_SCORE]; m.item_R2[r] = (uint32_t*)ptrs[MG_R2]; m.npred[r] = (uint32_t*)ptrs[MG_NPRED];
+        m.nsucc[r] = (uint32_t*)ptrs[MG_NSUCC]; m.succ[r] = (uint32_t*)ptrs[MG_SUCC]; m.queue[r] = (uint32_t*)ptrs[MG_QUEUE];
+        m.ctl[r] = (uint32_t*)ptrs[MG_CTL];
+    }
+    TRY(g->d_mg.upload(&m, 1, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    g->mg_barrier = barrier; g->mg_barrier_user = user;
+    if (getenv("TSB_MG_MIN_PHASE")) g->mg_min_phase = (size_t)std::max(1, atoi(getenv("TSB_MG_MIN_PHASE")));
+    g->mg_on = true;
+    return 0;
+}
+
+int tsb_generator_mg_phases(tsb_generator* g, uint64_t* n) {
+    if (!g || !n) return fail(TSB_ERR_INVALID, "null argument");
+    *n = g->mg_phases;
     return 0;
 }
 

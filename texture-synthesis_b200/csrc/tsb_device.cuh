@@ -39,7 +39,27 @@ struct DevGuide {  // one example guide at the current level (NOT filtered, ms.r
     int w, h;
 };
 
+// Band-sharded execution of ONE output over several GPUs of a node.  Every rank keeps a full
+// replica of the synthesis state; work items are owned by the rank whose horizontal band contains their
+// pixel; a commit is written to every replica and successor notifications go to the owner's counters and
+// ready queue -- plain stores and system-scope atomics on peer memory (CUDA IPC mappings, NVLink).
+constexpr int MG_MAX = 8;
+struct MgDev {
+    int rank, world, band_h, pad;
+    uint4* state[MG_MAX];
+    uint32_t* mask[MG_MAX];
+    uint32_t* mask1[MG_MAX];
+    float* score[MG_MAX];
+    uint32_t* item_R2[MG_MAX];
+    uint32_t* npred[MG_MAX];
+    uint32_t* nsucc[MG_MAX];
+    uint32_t* succ[MG_MAX];
+    uint32_t* queue[MG_MAX];
+    uint32_t* ctl[MG_MAX];
+};
+
 struct StageDev {
+    const MgDev* mg;  // nullptr: single GPU, or a phase every rank executes redundantly on its own replica
     // synthesis state
     uint4* state;     // per output pixel {colour RGBA, src x|y<<16, patch id, id_map.map | coord_map.map<<16}
     uint32_t* mask;   // resolved set, bit packed, extended by the tiling margins
@@ -100,7 +120,7 @@ struct FlowDev {
     uint32_t* ctl;       // [0] head  [1] tail  [2] abort flag  [3] successor-list overflow (fixed-stride mode)
     uint32_t stride;     // > 0: successors of item a live in succ[a*stride ..] (single analysis pass); 0: CSR
 };
-enum { FC_HEAD = 0, FC_TAIL = 1, FC_ABORT = 2, FC_OVERFLOW = 3 };
+enum { FC_HEAD = 0, FC_TAIL = 1, FC_ABORT = 2, FC_OVERFLOW = 3, FC_NOWN = 4 };  // FC_NOWN: items owned by this rank (multi-GPU)
 
 struct __align__(16) WarpScratch {
     union {
@@ -140,37 +160,52 @@ __device__ __forceinline__ int isqrt_u32(uint32_t v) {
     return r;
 }
 
+// STABLE = the mask is not being written while this kernel runs (analysis kernels): loads may use L1.
+// Otherwise (resolve kernels, concurrent commits) every load goes to L2.
+template <bool STABLE>
+__device__ __forceinline__ uint32_t mask_word(const uint32_t* p) { return STABLE ? __ldg(p) : __ldcg(p); }
+
+template <bool STABLE = false>
 __device__ __forceinline__ bool mask_test(const StageDev& S, int x, int y) {
     int X = x + S.mx, Y = y + S.my;
     if ((unsigned)X >= (unsigned)(S.wpr * 32) || (unsigned)Y >= (unsigned)S.mrows) return false;
-    return (__ldcg(S.mask + (size_t)Y * S.wpr + (X >> 5)) >> (X & 31)) & 1u;
+    return (mask_word<STABLE>(S.mask + (size_t)Y * S.wpr + (X >> 5)) >> (X & 31)) & 1u;
 }
-__device__ __forceinline__ void mask_set(const StageDev& S, int x, int y) {
+__device__ __forceinline__ int mg_owner_y(const MgDev* mg, int y) { int r = y / mg->band_h; return r < mg->world - 1 ? r : mg->world - 1; }
+
+__device__ __forceinline__ void mask_set_at(const StageDev& S, uint32_t* mask, uint32_t* mask1, bool shared, int x, int y) {
     int X = x + S.mx, Y = y + S.my;
     if ((unsigned)X >= (unsigned)(S.wpr * 32) || (unsigned)Y >= (unsigned)S.mrows) return;
-    atomicOr(S.mask + (size_t)Y * S.wpr + (X >> 5), 1u << (X & 31));
+    uint32_t* s1 = mask1 + (size_t)Y * S.wpr1 + (X >> 10);
+    const uint32_t b1 = 1u << ((X >> 5) & 31);
+    if (shared) {  // replica written by several GPUs: system-scope atomics, summary bit unconditionally
+        atomicOr_system(mask + (size_t)Y * S.wpr + (X >> 5), 1u << (X & 31));
+        atomicOr_system(s1, b1);
+        return;
+    }
+    atomicOr(mask + (size_t)Y * S.wpr + (X >> 5), 1u << (X & 31));
     // the summary bit is published by every writer that does not already SEE it (a plain "first writer
     // sets it" rule would let a reader observe the detail bit before the summary bit)
-    uint32_t* s1 = S.mask1 + (size_t)Y * S.wpr1 + (X >> 10);
-    uint32_t b1 = 1u << ((X >> 5) & 31);
     if (!(__ldcg(s1) & b1)) atomicOr(s1, b1);
 }
+__device__ __forceinline__ void mask_set(const StageDev& S, int x, int y) { mask_set_at(S, S.mask, S.mask1, false, x, y); }
 // flush_resolved, ms.rs:296-331 (tree part): the pixel plus its tiling mirror copies (no diagonal copy)
-__device__ __forceinline__ void mask_insert(const StageDev& S, int x, int y, bool mirrors) {
-    mask_set(S, x, y);
+__device__ __forceinline__ void mask_insert_at(const StageDev& S, uint32_t* mask, uint32_t* mask1, bool shared, int x, int y, bool mirrors) {
+    mask_set_at(S, mask, mask1, shared, x, y);
     if (mirrors) {
-        if (x < S.x_l) mask_set(S, x + S.W, y);
-        else if (x > S.x_r) mask_set(S, x - S.W, y);
-        if (y < S.y_b) mask_set(S, x, y + S.H);
-        else if (y > S.y_t) mask_set(S, x, y - S.H);
+        if (x < S.x_l) mask_set_at(S, mask, mask1, shared, x + S.W, y);
+        else if (x > S.x_r) mask_set_at(S, mask, mask1, shared, x - S.W, y);
+        if (y < S.y_b) mask_set_at(S, mask, mask1, shared, x, y + S.H);
+        else if (y > S.y_t) mask_set_at(S, mask, mask1, shared, x, y - S.H);
     }
 }
+__device__ __forceinline__ void mask_insert(const StageDev& S, int x, int y, bool mirrors) { mask_insert_at(S, S.mask, S.mask1, false, x, y, mirrors); }
 
 // ---------------------------------------------------------------------------------------------
 // General disc scan over the bit mask (any radius).  COLLECT=false: count bits with d^2 <= R2.
 // COLLECT=true: append keys (d^2<<32 | (dy+32768)<<16 | (dx+32768)) to ws.u.keys (ws.cnt).
 // ---------------------------------------------------------------------------------------------
-template <bool COLLECT>
+template <bool COLLECT, bool STABLE = false>
 __device__ __forceinline__ uint32_t scan_disc(const StageDev& S, WarpScratch& ws, int lane, int x, int y, uint32_t R2) {
     int r = isqrt_u32(R2);
     int ylo = max(y - r, -S.my), yhi = min(y + r, S.mrows - 1 - S.my);
@@ -185,13 +220,13 @@ __device__ __forceinline__ uint32_t scan_disc(const StageDev& S, WarpScratch& ws
         const uint32_t* row1 = S.mask1 + (size_t)(yy + S.my) * S.wpr1;
         const int w0 = Xlo >> 5, w1 = Xhi >> 5;
         for (int sw = w0 >> 5; sw <= (w1 >> 5); ++sw) {
-            uint32_t b1 = __ldcg(row1 + sw);
+            uint32_t b1 = mask_word<STABLE>(row1 + sw);
             if (sw == (w0 >> 5)) b1 &= 0xFFFFFFFFu << (w0 & 31);
             if (sw == (w1 >> 5)) b1 &= 0xFFFFFFFFu >> (31 - (w1 & 31));
             while (b1) {
                 int wd = sw * 32 + __ffs(b1) - 1;
                 b1 &= b1 - 1;
-                uint32_t bits = __ldcg(row + wd);
+                uint32_t bits = mask_word<STABLE>(row + wd);
                 if (wd == w0) bits &= 0xFFFFFFFFu << (Xlo & 31);
                 if (wd == w1) bits &= 0xFFFFFFFFu >> (31 - (Xhi & 31));
                 if (!COLLECT) cnt += __popc(bits);
@@ -241,6 +276,7 @@ __device__ __noinline__ void sort_keys(WarpScratch& ws, int lane, int n) {
 // k nearest resolved points of (x,y) in canonical order (d^2, dy, dx) -> ws.off[0..kk).
 // R2bound: if != R2_INF, the caller guarantees that the disc d^2 <= R2bound holds at least k points.
 // Returns kk; *r2_out = d^2 of the k-th neighbour (R2_INF if fewer than k points exist).
+template <bool STABLE = false>
 __device__ __forceinline__ int knn_search(const StageDev& S, WarpScratch& ws, int lane, int x, int y, uint32_t R2bound, uint32_t* r2_out) {
     const int k = S.k;
     const unsigned lt = (1u << lane) - 1u;
@@ -261,7 +297,7 @@ __device__ __forceinline__ int knn_search(const StageDev& S, WarpScratch& ws, in
                 o[u] = make_short2(0, 0);
                 if (idx < limit) {
                     o[u] = __ldg(S.spiral + idx);
-                    hit[u] = mask_test(S, x + o[u].x, y + o[u].y);
+                    hit[u] = mask_test<STABLE>(S, x + o[u].x, y + o[u].y);
                 }
             }
 #pragma unroll
@@ -289,7 +325,7 @@ __device__ __forceinline__ int knn_search(const StageDev& S, WarpScratch& ws, in
     if (R2 != R2_INF) {
         if (lane == 0) ws.cnt = 0;
         __syncwarp();
-        n = (int)scan_disc<true>(S, ws, lane, x, y, R2);
+        n = (int)scan_disc<true, STABLE>(S, ws, lane, x, y, R2);
         if (n > KBUF || (n < k && R2 < R2max)) n = -1;  // overflow (or a stale bound): search below
     }
     if (n < 0) {
@@ -297,7 +333,7 @@ __device__ __forceinline__ int knn_search(const StageDev& S, WarpScratch& ws, in
         R2 = max(S.r2_hint, 4u);
         if (R2 > R2max) R2 = R2max;
         for (;;) {
-            c = scan_disc<false>(S, ws, lane, x, y, R2);
+            c = scan_disc<false, STABLE>(S, ws, lane, x, y, R2);
             if (c >= (uint32_t)k || R2 >= R2max) break;
             lo = R2;
             uint32_t nx = R2 + (R2 >> 1) + 1;
@@ -307,7 +343,7 @@ __device__ __forceinline__ int knn_search(const StageDev& S, WarpScratch& ws, in
             uint32_t hi = R2;
             while (hi - lo > 1) {
                 uint32_t mid = lo + ((hi - lo) >> 1);
-                c = scan_disc<false>(S, ws, lane, x, y, mid);
+                c = scan_disc<false, STABLE>(S, ws, lane, x, y, mid);
                 if (c >= (uint32_t)k) { hi = mid; if (c <= (uint32_t)KBUF) break; }
                 else lo = mid;
             }
@@ -315,7 +351,7 @@ __device__ __forceinline__ int knn_search(const StageDev& S, WarpScratch& ws, in
         }
         if (lane == 0) ws.cnt = 0;
         __syncwarp();
-        n = (int)scan_disc<true>(S, ws, lane, x, y, R2);
+        n = (int)scan_disc<true, STABLE>(S, ws, lane, x, y, R2);
     }
     if (n > KBUF) n = KBUF;  // only reachable with > KBUF exact ties on one circle
     sort_keys(ws, lane, n);
@@ -582,14 +618,27 @@ struct __align__(16) RoundSmem {
 };
 
 // update(), ms.rs:334-377 (+ flush_resolved's tree insert, ms.rs:296-331); called by lane 0
+template <bool MG = false>
 __device__ __forceinline__ void commit_item(const StageDev& S, const PhaseDev& P, uint32_t si, uint32_t flat, int x, int y, const ItemOut& o) {
     if (o.kk > 0) {
         DevEx e = S.ex[o.bmap];
         uint32_t col = __ldg(e.px + (size_t)o.by * e.w + o.bx);
-        S.state[flat] = make_uint4(col, (uint32_t)o.bx | ((uint32_t)o.by << 16), o.bpatch, (uint32_t)o.bmap | ((uint32_t)o.bmap << 16));
-        if (P.is_new) {
-            S.score[flat] = o.score;
-            mask_insert(S, x, y, S.tiling != 0);
+        const uint4 v = make_uint4(col, (uint32_t)o.bx | ((uint32_t)o.by << 16), o.bpatch, (uint32_t)o.bmap | ((uint32_t)o.bmap << 16));
+        if (!MG) {
+            S.state[flat] = v;
+            if (P.is_new) {
+                S.score[flat] = o.score;
+                mask_insert(S, x, y, S.tiling != 0);
+            }
+        } else {  // band-sharded: the commit goes to every replica (peer stores over NVLink)
+            const MgDev* mg = S.mg;
+            for (int r = 0; r < mg->world; ++r) {
+                mg->state[r][flat] = v;
+                if (P.is_new) {
+                    mg->score[r][flat] = o.score;
+                    mask_insert_at(S, mg->mask[r], mg->mask1[r], true, x, y, S.tiling != 0);
+                }
+            }
         }
     }
     if (P.tr_best) {
@@ -687,8 +736,8 @@ __global__ void __launch_bounds__(CTA_THREADS) k_round(StageDev S, PhaseDev P, u
 // Persistent dataflow kernel: one launch per phase.  Warps claim queue slots in order; a slot is
 // published when the last predecessor of an item commits.  Grid = co-resident CTAs only.
 // ---------------------------------------------------------------------------------------------
-template <bool GUIDED>
-__global__ void __launch_bounds__(CTA_THREADS) k_flow(StageDev S, PhaseDev P, FlowDev F) {
+template <bool GUIDED, bool MG>
+__global__ void __launch_bounds__(CTA_THREADS, 3) k_flow(StageDev S, PhaseDev P, FlowDev F) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RoundSmem& rs = *reinterpret_cast<RoundSmem*>(smem_raw);
     CtaSmem& sm = rs.c;
@@ -702,12 +751,13 @@ __global__ void __launch_bounds__(CTA_THREADS) k_flow(StageDev S, PhaseDev P, Fl
     volatile uint32_t* vq = F.queue;
     volatile uint32_t* vctl = F.ctl;
     const bool skip = F.stride && vctl[FC_OVERFLOW];  // incomplete successor lists: do nothing, the host re-plans the phase
+    const uint32_t n_mine = MG ? vctl[FC_NOWN] : P.n;
     for (; !skip;) {
         long long tr0 = clock64();
         uint32_t slot = 0;
         if (lane == 0) slot = atomicAdd(F.ctl + FC_HEAD, 1u);
         slot = __shfl_sync(FULL, slot, 0);
-        if (slot >= P.n) break;
+        if (slot >= n_mine) break;
         uint32_t it = NONE32;
         if (lane == 0) {
             unsigned spins = 0, ns = 32;
@@ -732,19 +782,32 @@ __global__ void __launch_bounds__(CTA_THREADS) k_flow(StageDev S, PhaseDev P, Fl
                              P.rand_map + (size_t)si * S.m, o);
         long long tc0 = clock64();
         if (lane == 0) {
-            commit_item(S, P, si, flat, x, y, o);
-            __threadfence();  // release
+            commit_item<MG>(S, P, si, flat, x, y, o);
+            if (MG) __threadfence_system(); else __threadfence();  // release
         }
         __syncwarp();
         // notify successors; the one that drops a counter to zero publishes the item
         const size_t s0 = F.stride ? (size_t)it * F.stride : (size_t)F.succ_off[it];
         const size_t s1 = F.stride ? s0 + F.nsucc[it] : (size_t)F.succ_off[it + 1];
-        for (size_t e = s0 + lane; e < s1; e += 32) {
-            uint32_t sc = F.succ[e];
-            if (atomicSub(F.npred + sc, 1u) == 1u) {
-                __threadfence();
-                uint32_t pos = atomicAdd(F.ctl + FC_TAIL, 1u);
-                vq[pos] = sc;
+        if (!MG) {
+            for (size_t e = s0 + lane; e < s1; e += 32) {
+                uint32_t sc = F.succ[e];
+                if (atomicSub(F.npred + sc, 1u) == 1u) {
+                    __threadfence();
+                    uint32_t pos = atomicAdd(F.ctl + FC_TAIL, 1u);
+                    vq[pos] = sc;
+                }
+            }
+        } else {
+            const MgDev* mg = S.mg;
+            for (size_t e = s0 + lane; e < s1; e += 32) {
+                uint32_t sc = F.succ[e];
+                const int r = mg_owner_y(mg, (int)(P.item_pixel[sc] / (uint32_t)S.W));  // the successor's owner holds its counter and queue
+                if (atomicSub_system(mg->npred[r] + sc, 1u) == 1u) {
+                    __threadfence_system();
+                    uint32_t pos = atomicAdd_system(mg->ctl[r] + FC_TAIL, 1u);
+                    *((volatile uint32_t*)(mg->queue[r] + pos)) = sc;
+                }
             }
         }
         st_acc[ST_FETCHED] += o.fetched; st_acc[ST_NOMINAL] += o.nominal; st_acc[ST_CANDS] += (unsigned long long)o.ncand;
@@ -868,18 +931,26 @@ __global__ void __launch_bounds__(CTA_THREADS) k_radius(StageDev S, PhaseDev P, 
     for (uint32_t it = blockIdx.x * WARPS_PER_CTA + warp; it < P.n; it += nwarps) {
         const uint32_t flat = P.item_pixel[it];
         const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
+        if (lane == 0) {  // local bookkeeping for EVERY item (the pending-index map and the queue are per replica)
+            P.pmap[flat] = it;
+            if (F.npred) {
+                F.queue[it] = NONE32;
+                if (it == 0) F.nsucc[P.n] = 0;  // F.ctl is zeroed by the host before this kernel
+            }
+        }
+        if (S.mg && mg_owner_y(S.mg, y) != S.mg->rank) continue;  // band-sharded: the owner computes the radius
         uint32_t r2;
-        knn_search(S, ws, lane, x, y, R2_INF, &r2);
+        knn_search<true>(S, ws, lane, x, y, R2_INF, &r2);
         if (lane == 0) {
-            P.item_R2[it] = r2;
+            if (!S.mg) P.item_R2[it] = r2;
+            else {
+                for (int r = 0; r < S.mg->world; ++r) S.mg->item_R2[r][it] = r2;
+                atomicAdd(F.ctl + FC_NOWN, 1u);
+            }
             P.pred_cnt[it] = 0;
             P.done[it] = 0;
             P.pending[0][it] = it;
-            P.pmap[flat] = it;
-            if (F.npred) {
-                F.npred[it] = 0; F.nsucc[it] = 0; F.succ_cur[it] = 0; F.queue[it] = NONE32;
-                if (it == 0) { F.nsucc[P.n] = 0; F.ctl[FC_HEAD] = 0; F.ctl[FC_TAIL] = 0; F.ctl[FC_ABORT] = 0; F.ctl[FC_OVERFLOW] = 0; }
-            }
+            if (F.npred) { F.npred[it] = 0; F.nsucc[it] = 0; F.succ_cur[it] = 0; }
         }
         __syncwarp();
     }
@@ -979,12 +1050,25 @@ __device__ __forceinline__ void edge_emit(const FlowDev& F, uint32_t a, uint32_t
         atomicAdd(F.npred + b, 1u);
     }
 }
+// band-sharded variant: the successor list lives with the owner of a, the counter with the owner of b
+__device__ __forceinline__ void edge_emit_mg(const MgDev* mg, const FlowDev& F, uint32_t a, int ra, uint32_t b, int rb) {
+    uint32_t slot = atomicAdd_system(mg->nsucc[ra] + a, 1u);
+    if (slot < F.stride) mg->succ[ra][(size_t)a * F.stride + slot] = b;
+    else mg->ctl[ra][FC_OVERFLOW] = 1u;
+    atomicAdd_system(mg->npred[rb] + b, 1u);
+}
 template <int PASS>
 __device__ __forceinline__ void edge_visit(const StageDev& S, const PhaseDev& P, const FlowDev& F, uint32_t it, int qx, int qy, uint32_t D) {
     if (S.tiling) { qx = imod(qx, S.W); qy = imod(qy, S.H); }  // conservative: treat the canvas as a torus
     else if ((unsigned)qx >= (unsigned)S.W || (unsigned)qy >= (unsigned)S.H) return;
     uint32_t j = P.pmap[(size_t)qy * S.W + qx];
     if (j == NONE32 || j == it) return;
+    if (S.mg) {  // `it` is owned by this rank; j's owner follows from its row
+        const int rj = mg_owner_y(S.mg, qy), ri = S.mg->rank;
+        if (j < it) edge_emit_mg(S.mg, F, j, rj, it, ri);
+        else if (D > P.item_R2[j]) edge_emit_mg(S.mg, F, it, ri, j, rj);
+        return;
+    }
     if (j < it) edge_emit<PASS>(F, j, it);                       // `it` sees j from its own disc
     else if (D > P.item_R2[j]) edge_emit<PASS>(F, it, j);        // j does not see `it`: registered from this side
 }
@@ -995,12 +1079,16 @@ __global__ void __launch_bounds__(CTA_THREADS) k_edges_scan(StageDev S, PhaseDev
     for (uint32_t it = blockIdx.x * WARPS_PER_CTA + warp; it < P.n; it += nwarps) {
         const uint32_t flat = P.item_pixel[it];
         const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
+        if (S.mg && mg_owner_y(S.mg, y) != S.mg->rank) continue;  // band-sharded: every rank scans its own items
         const uint32_t R2 = P.item_R2[it];
         if (R2 <= (uint32_t)S.RT2) {
-            int limit = (int)__ldg(S.cntLE + R2);
-            for (int idx = lane; idx < limit; idx += 32) {
-                short2 o = __ldg(S.spiral + idx);
-                edge_visit<PASS>(S, P, F, it, x + o.x, y + o.y, (uint32_t)(o.x * o.x + o.y * o.y));
+            // row-major walk over the bounding square of the disc: consecutive lanes read consecutive pixels of
+            // the pending-index map (coalesced), unlike the distance-ordered spiral table
+            const int r = isqrt_u32(R2), side = 2 * r + 1, cells = side * side;
+            for (int c = lane; c < cells; c += 32) {
+                const int dy = c / side - r, dx = c % side - r;
+                const uint32_t D = (uint32_t)(dx * dx + dy * dy);
+                if (D <= R2) edge_visit<PASS>(S, P, F, it, x + dx, y + dy, D);
             }
         } else {
             int rmaxx = S.tiling ? S.W / 2 : S.W, rmaxy = S.tiling ? S.H / 2 : S.H;
@@ -1035,9 +1123,14 @@ __global__ void __launch_bounds__(CTA_THREADS) k_edges_pairs(StageDev S, PhaseDe
         }
     }
 }
-__global__ void k_seed_queue(PhaseDev P, FlowDev F) {
+__global__ void k_seed_queue(StageDev S, PhaseDev P, FlowDev F) {
     uint32_t it = blockIdx.x * blockDim.x + threadIdx.x;
     if (it >= P.n) return;
+    if (S.mg) {  // band-sharded: own items only; the tail counter is also advanced by other GPUs -> system scope
+        if (mg_owner_y(S.mg, (int)(P.item_pixel[it] / (uint32_t)S.W)) != S.mg->rank) return;
+        if (F.npred[it] == 0u) F.queue[atomicAdd_system(F.ctl + FC_TAIL, 1u)] = it;
+        return;
+    }
     if (F.npred[it] == 0u) F.queue[atomicAdd(F.ctl + FC_TAIL, 1u)] = it;
 }
 

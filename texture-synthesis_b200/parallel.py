@@ -37,3 +37,20 @@ def aggregate_throughput(units_this_rank, seconds_this_rank, dist=None, device="
     total = sum_over_ranks(units_this_rank, dist, device)
     t = max_over_ranks(seconds_this_rank, dist, device)
     return total / t, total, t
+
+
+def link_band_sharded(generator, params, dist):
+    """Links the replicas of one output across the ranks of a node (one process per GPU) for band-sharded
+    execution: CUDA IPC handles are exchanged with torch.distributed, the barrier is torch.distributed.barrier."""
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    mine = generator.mg_export(params)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+    generator.mg_attach(rank, world, gathered, barrier)
+    dist.barrier()
+    return rank, world
