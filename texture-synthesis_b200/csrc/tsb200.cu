@@ -757,6 +757,29 @@ int run_phase_flow(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n,
         else k_flow<false, true><<<gfm, CTA_THREADS, sizeof(RoundSmem), s>>>(Sm, P, F);
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(g->h_ctrl, F.ctl, 32, cudaMemcpyDeviceToHost, s));
+        {
+            // bulk push of this rank's band (rows it owns) to every peer replica: state, and for new pixels score and
+            // the resolved mask (plus the tiling mirror rows in the margins, which belong to the first / last band)
+            const MgDev& m = g->h_mg;
+            const int y0 = m.rank * m.band_h, y1 = std::min(g->H, y0 + m.band_h);
+            for (int r = 0; r < m.world && y1 > y0; ++r) {
+                if (r == m.rank) continue;
+                const size_t o = (size_t)y0 * g->W, c = (size_t)(y1 - y0) * g->W;
+                CU(cudaMemcpyAsync(m.state[r] + o, g->d_state.p + o, c * sizeof(uint4), cudaMemcpyDeviceToDevice, s));
+                if (is_new) {
+                    CU(cudaMemcpyAsync(m.score[r] + o, g->d_score.p + o, c * sizeof(float), cudaMemcpyDeviceToDevice, s));
+                    auto push_rows = [&](int ra, int rb) -> int {  // mask rows [ra, rb) in extended coordinates
+                        if (rb <= ra) return 0;
+                        CU(cudaMemcpyAsync(m.mask[r] + (size_t)ra * g->wpr, g->d_mask.p + (size_t)ra * g->wpr, (size_t)(rb - ra) * g->wpr * 4, cudaMemcpyDeviceToDevice, s));
+                        CU(cudaMemcpyAsync(m.mask1[r] + (size_t)ra * g->wpr1, g->d_mask1.p + (size_t)ra * g->wpr1, (size_t)(rb - ra) * g->wpr1 * 4, cudaMemcpyDeviceToDevice, s));
+                        return 0;
+                    };
+                    TRY(push_rows(y0 + g->my, y1 + g->my));
+                    if (S.tiling && m.rank == 0) TRY(push_rows(g->H + g->my, g->mrows));   // mirrors y + H of the top rows
+                    if (S.tiling && m.rank == m.world - 1) TRY(push_rows(0, g->my));          // mirrors y - H of the bottom rows
+                }
+            }
+        }
         TRY(barrier());  // every commit of the phase has landed on every replica
         k_pmap_clear<<<(n + 255) / 256, 256, 0, s>>>(P);
         CU(cudaGetLastError());
@@ -1545,6 +1568,7 @@ int tsb_generator_mg_attach(tsb_generator* g, uint32_t rank, uint32_t world, con
     memset(&m, 0, sizeof(m));
     m.rank = (int)rank; m.world = (int)world;
     m.band_h = (g->H + (int)world - 1) / (int)world;
+    if (m.band_h <= (int)((float)g->H * 0.05f) + 1) return fail(TSB_ERR_UNSUPPORTED, "output too small for %u bands", world);
     for (uint32_t r = 0; r < world; ++r) {
         void* ptrs[MG_NBUF];
         for (int i = 0; i < MG_NBUF; ++i) {

@@ -619,18 +619,22 @@ struct __align__(16) RoundSmem {
 
 // update(), ms.rs:334-377 (+ flush_resolved's tree insert, ms.rs:296-331); called by lane 0
 template <bool MG = false>
-__device__ __forceinline__ void commit_item(const StageDev& S, const PhaseDev& P, uint32_t si, uint32_t flat, int x, int y, const ItemOut& o) {
+__device__ __forceinline__ void commit_item(const StageDev& S, const PhaseDev& P, uint32_t si, uint32_t flat, int x, int y, const ItemOut& o,
+                                            bool to_peers = false) {
     if (o.kk > 0) {
         DevEx e = S.ex[o.bmap];
         uint32_t col = __ldg(e.px + (size_t)o.by * e.w + o.bx);
         const uint4 v = make_uint4(col, (uint32_t)o.bx | ((uint32_t)o.by << 16), o.bpatch, (uint32_t)o.bmap | ((uint32_t)o.bmap << 16));
-        if (!MG) {
+        if (!MG || !to_peers) {
+            // local replica only.  In a band-sharded phase the owner pushes its band rows to the peers in bulk after
+            // the kernel; the local mask is also written by other GPUs (their boundary items), hence system scope.
             S.state[flat] = v;
             if (P.is_new) {
                 S.score[flat] = o.score;
-                mask_insert(S, x, y, S.tiling != 0);
+                if (MG) mask_insert_at(S, S.mask, S.mask1, true, x, y, S.tiling != 0);
+                else mask_insert(S, x, y, S.tiling != 0);
             }
-        } else {  // band-sharded: the commit goes to every replica (peer stores over NVLink)
+        } else {  // an item with a successor on another GPU: the commit goes to every replica right away (peer stores)
             const MgDev* mg = S.mg;
             for (int r = 0; r < mg->world; ++r) {
                 mg->state[r][flat] = v;
@@ -781,14 +785,27 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_flow(StageDev S, PhaseDev P,
         resolve_item<GUIDED>(S, ws, sm.lut, sm.lutg, lane, x, y, P.item_R2[it], P.rand_xy + (size_t)si * S.m,
                              P.rand_map + (size_t)si * S.m, o);
         long long tc0 = clock64();
+        const size_t s0 = F.stride ? (size_t)it * F.stride : (size_t)F.succ_off[it];
+        const size_t s1 = F.stride ? s0 + F.nsucc[it] : (size_t)F.succ_off[it + 1];
+        bool remote_succ = false;
+        if (MG) {
+            // Only an item with a successor on another GPU needs its commit ordered at system scope (that successor is
+            // the only remote reader of this pixel during the phase); everybody else's peer stores just have to land
+            // by the end of the phase.  A system-scope fence costs ~15 us, a device-scope one well under 1 us.
+            const MgDev* mg = S.mg;
+            for (size_t e0 = s0; e0 < s1; e0 += 32) {
+                const size_t e = e0 + lane;
+                bool rem = false;
+                if (e < s1) rem = mg_owner_y(mg, (int)(P.item_pixel[F.succ[e]] / (uint32_t)S.W)) != mg->rank;
+                if (__any_sync(FULL, rem)) { remote_succ = true; break; }
+            }
+        }
         if (lane == 0) {
-            commit_item<MG>(S, P, si, flat, x, y, o);
-            if (MG) __threadfence_system(); else __threadfence();  // release
+            commit_item<MG>(S, P, si, flat, x, y, o, remote_succ);
+            if (MG && remote_succ) __threadfence_system(); else __threadfence();  // release
         }
         __syncwarp();
         // notify successors; the one that drops a counter to zero publishes the item
-        const size_t s0 = F.stride ? (size_t)it * F.stride : (size_t)F.succ_off[it];
-        const size_t s1 = F.stride ? s0 + F.nsucc[it] : (size_t)F.succ_off[it + 1];
         if (!MG) {
             for (size_t e = s0 + lane; e < s1; e += 32) {
                 uint32_t sc = F.succ[e];
