@@ -631,8 +631,7 @@ __device__ __forceinline__ void commit_item(const StageDev& S, const PhaseDev& P
             S.state[flat] = v;
             if (P.is_new) {
                 S.score[flat] = o.score;
-                if (MG) mask_insert_at(S, S.mask, S.mask1, true, x, y, S.tiling != 0);
-                else mask_insert(S, x, y, S.tiling != 0);
+                mask_insert(S, x, y, S.tiling != 0);
             }
         } else {  // an item with a successor on another GPU: the commit goes to every replica right away (peer stores)
             const MgDev* mg = S.mg;
@@ -820,7 +819,13 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_flow(StageDev S, PhaseDev P,
             for (size_t e = s0 + lane; e < s1; e += 32) {
                 uint32_t sc = F.succ[e];
                 const int r = mg_owner_y(mg, (int)(P.item_pixel[sc] / (uint32_t)S.W));  // the successor's owner holds its counter and queue
-                if (atomicSub_system(mg->npred[r] + sc, 1u) == 1u) {
+                if (r == mg->rank) {  // local successor: device-scope operations (all atomics resolve in this GPU's L2)
+                    if (atomicSub(F.npred + sc, 1u) == 1u) {
+                        __threadfence();
+                        uint32_t pos = atomicAdd(F.ctl + FC_TAIL, 1u);
+                        vq[pos] = sc;
+                    }
+                } else if (atomicSub_system(mg->npred[r] + sc, 1u) == 1u) {
                     __threadfence_system();
                     uint32_t pos = atomicAdd_system(mg->ctl[r] + FC_TAIL, 1u);
                     *((volatile uint32_t*)(mg->queue[r] + pos)) = sc;
