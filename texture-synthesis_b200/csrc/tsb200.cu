@@ -1011,17 +1011,25 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
         }
         const size_t n_items = sp.n_redo + sp.n_new;
         if (n_items == 0) continue;
-        // random candidates of every item of the stage: rng seeded with loop_seed + 1 = stage seed + i + 1 (ms.rs:902,945)
-        k_rand_candidates<<<(uint32_t)((n_items + 127) / 128), 128, 0, s>>>(S.ex, S.n_ex, m, sp.seed + 1ull, (uint32_t)n_items,
-                                                                          g->d_rand_xy.p, g->d_rand_map.p);
-        CU(cudaGetLastError());
-        g->stats.kernel_launches++;
+        // random candidates: rng seeded with loop_seed + 1 = stage seed + i + 1 (ms.rs:902,945); generated per phase, and in
+        // band-sharded phases only for the items this rank owns
+        auto gen_rand = [&](size_t i0, size_t n_) -> int {
+            const bool own_only = g->mg_on && n_ >= g->mg_min_phase;
+            k_rand_candidates<<<(uint32_t)((n_ + 127) / 128), 128, 0, s>>>(S.ex, S.n_ex, m, sp.seed + 1ull + (uint64_t)i0, (uint32_t)n_,
+                                                                        g->d_rand_xy.p + i0 * (size_t)m, g->d_rand_map.p + i0 * (size_t)m,
+                                                                        own_only ? g->d_item_pixel.p + i0 : nullptr, g->W, g->h_mg.band_h,
+                                                                        g->h_mg.rank, g->h_mg.world);
+            CU(cudaGetLastError());
+            g->stats.kernel_launches++;
+            return 0;
+        };
 
         size_t resolved_now = sp.resolved_before;
         // ---- redo phase: the resolved set is static, radii are exact ----
         if (sp.n_redo) {
             S.r2_hint = r2_hint_for(g, resolved_now, k);
             S.n_points_max = (uint32_t)std::min<size_t>((tiling ? 3 : 1) * resolved_now, 0xFFFFFFFFull);
+            TRY(gen_rand(0, sp.n_redo));
             if (g->use_rounds) TRY(run_phase(g, S, 0, (uint32_t)sp.n_redo, false, true, trace_base));
             else TRY(run_phase_flow(g, S, 0, (uint32_t)sp.n_redo, false, trace_base));
         }
@@ -1060,6 +1068,7 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
                 }
                 S.n_points_max = (uint32_t)cnt;
             }
+            TRY(gen_rand(cur, n_e));
             if (g->use_rounds) TRY(run_phase(g, S, (uint32_t)cur, (uint32_t)n_e, true, n_e > 1, trace_base));
             else if (serial) TRY(run_serial(g, S, (uint32_t)cur, (uint32_t)n_e, true, trace_base));
             else TRY(run_phase_flow(g, S, (uint32_t)cur, (uint32_t)n_e, true, trace_base));

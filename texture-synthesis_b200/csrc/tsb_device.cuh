@@ -1162,9 +1162,14 @@ __global__ void k_seed_queue(StageDev S, PhaseDev P, FlowDev F) {
 // stream depends only on (stage seed, work-item index) so a whole stage is generated ahead of the rounds.
 // ---------------------------------------------------------------------------------------------
 __global__ void k_rand_candidates(const DevEx* ex, int n_ex, int m, uint64_t seed_base, uint32_t n,
-                                  uint32_t* rand_xy, uint8_t* rand_map) {
+                                  uint32_t* rand_xy, uint8_t* rand_map, const uint32_t* own_pixel = nullptr, int W = 1,
+                                  int band_h = 1, int rank = 0, int world = 1) {
     uint32_t it = blockIdx.x * blockDim.x + threadIdx.x;
     if (it >= n) return;
+    if (own_pixel) {  // band-sharded phase: only the owner of the item needs its candidates
+        int r = (int)(own_pixel[it] / (uint32_t)W) / band_h;
+        if ((r < world - 1 ? r : world - 1) != rank) return;
+    }
     Pcg32 rng = Pcg32::seed_from_u64(seed_base + (uint64_t)it);
     uint32_t* oxy = rand_xy + (size_t)it * m;
     uint8_t* om = rand_map + (size_t)it * m;
