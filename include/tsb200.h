@@ -123,6 +123,11 @@ int tsb_pyramid_build(const uint8_t* rgba, uint32_t w, uint32_t h, uint32_t leve
  * Triangle, utils.rs:67-72 CatmullRom). */
 int tsb_resize(const uint8_t* rgba, uint32_t w, uint32_t h, uint8_t* out, uint32_t nw, uint32_t nh, int filter);
 
+/* Guide preprocessing for style transfer: utils::transform_to_guide_map (utils.rs:101-116: blur(sigma), grayscale,
+ * RGBA (l,l,l,255)) and utils::match_histograms (utils.rs:135-183).  Callers: session.rs:389-393, lib.rs:577-581. */
+int tsb_guide_map(const uint8_t* rgba, uint32_t w, uint32_t h, float sigma, uint8_t* out);
+int tsb_match_histograms(const uint8_t* source, uint32_t sw, uint32_t sh, const uint8_t* target, uint32_t tw, uint32_t th, uint8_t* out);
+
 int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out);
 void tsb_generator_destroy(tsb_generator* g);
 

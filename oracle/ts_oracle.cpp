@@ -124,6 +124,16 @@ struct Pcg32 {
 // ------------------------------------------------------------------------------------
 enum Filter { F_TRIANGLE = 0, F_CATMULLROM = 1, F_GAUSSIAN = 2 };
 
+// image 0.23.12 `blur(sigma)`: the same separable sampler at unchanged size with kernel gaussian(x, sigma)
+// and support 2*sigma (utils.rs:115 calls it with sigma = 2.0)
+static float g_blur_sigma = 2.0f;
+static float blur_kernel(float x) {
+    float r = g_blur_sigma;
+    float norm = 1.0f / (std::sqrt(2.0f * 3.14159265358979323846f) * r);
+    return norm * std::exp(-(x * x) / (2.0f * (r * r)));
+}
+enum { F_BLUR = 3 };
+
 static float kernel_eval(int f, float x) {
     switch (f) {
     case F_TRIANGLE: {
@@ -142,6 +152,7 @@ static float kernel_eval(int f, float x) {
             k = 0.0f;
         return k / 6.0f;
     }
+    case F_BLUR: return blur_kernel(x);
     default: {  // gaussian(x, 0.5)
         const float r = 0.5f;
         float norm = 1.0f / (std::sqrt(2.0f * 3.14159265358979323846f) * r);
@@ -151,12 +162,13 @@ static float kernel_eval(int f, float x) {
 }
 static float kernel_support(int f) { return f == F_TRIANGLE ? 1.0f : (f == F_CATMULLROM ? 2.0f : 3.0f); }
 
+
 struct Taps { int left; std::vector<float> w; float sum; };
 
 static Taps make_taps(int in_sz, int out_sz, int o, int filter) {
     float ratio = (float)in_sz / (float)out_sz;
     float sratio = ratio < 1.0f ? 1.0f : ratio;
-    float support = kernel_support(filter) * sratio;
+    float support = (filter == F_BLUR ? 2.0f * g_blur_sigma : kernel_support(filter)) * sratio;
     float inputx = ((float)o + 0.5f) * ratio;
     int64_t left = (int64_t)std::floor(inputx - support);
     left = std::min<int64_t>(std::max<int64_t>(left, 0), (int64_t)in_sz - 1);
@@ -715,6 +727,46 @@ void orc_resize(const uint8_t* src, int w, int h, uint8_t* dst, int nw, int nh, 
 }
 void orc_pyramid_build(const uint8_t* rgba, int w, int h, uint32_t levels, uint8_t* out) {
     pyramid_build(rgba, w, h, levels == 0 ? 1 : levels, out);
+}
+
+// ---- guide preprocessing (utils.rs:101-183) --------------------------------------------------
+// transform_to_guide_map: blur(sigma) -> grayscale (0.2126 r + 0.7152 g + 0.0722 b in f32, truncated) -> RGBA (l,l,l,255).
+// The resize inside the reference function discards its result (quirk q10).
+void orc_guide_map(const uint8_t* rgba, int w, int h, float sigma, uint8_t* out) {
+    g_blur_sigma = sigma < 0.0f ? 1.0f : sigma;
+    std::vector<uint8_t> blurred((size_t)w * h * 4);
+    resize_rgba(rgba, w, h, blurred.data(), w, h, F_BLUR);
+    for (size_t i = 0; i < (size_t)w * h; ++i) {
+        const uint8_t* p = blurred.data() + i * 4;
+        float l = 0.2126f * (float)p[0] + 0.7152f * (float)p[1] + 0.0722f * (float)p[2];
+        uint8_t v = f32_to_u8_trunc(l);
+        out[i * 4 + 0] = v; out[i * 4 + 1] = v; out[i * 4 + 2] = v; out[i * 4 + 3] = 255;
+    }
+}
+// match_histograms (utils.rs:135-163) with get_histogram / get_cdf (utils.rs:118-133, 165-183); source is modified in place
+void orc_match_histograms(uint8_t* source, int sw, int sh, const uint8_t* target, int tw, int th) {
+    auto cdf = [](const uint8_t* img, size_t n, float* out) {
+        uint32_t hist[256] = {0};
+        for (size_t i = 0; i < n; ++i) hist[img[i * 4]] += 1;
+        for (int i = 0; i < 256; ++i) out[i] = i ? out[i - 1] + (float)hist[i] : (float)hist[i];
+        float mx = out[255];
+        for (int i = 0; i < 256; ++i) out[i] /= mx;
+    };
+    float tc[256], sc[256];
+    cdf(target, (size_t)tw * th, tc);
+    cdf(source, (size_t)sw * sh, sc);
+    uint8_t lut[256];
+    for (int v = 0; v < 256; ++v) {
+        int pos = -1;
+        for (int i = 0; i < 256; ++i) if (tc[i] > sc[v]) { pos = i; break; }
+        // `.position(..).unwrap_or((pixel_value + 1) as usize) as u8 - 1`; u8 arithmetic wraps in release builds
+        unsigned nv = pos >= 0 ? (unsigned)pos : (unsigned)(uint8_t)(v + 1);
+        lut[v] = (uint8_t)((uint8_t)nv - 1);
+    }
+    for (size_t i = 0; i < (size_t)sw * sh; ++i) {
+        uint8_t g = lut[source[i * 4]];
+        source[i * 4 + 0] = g; source[i * 4 + 1] = g; source[i * 4 + 2] = g; source[i * 4 + 3] = 255;
+    }
 }
 
 // ---- generator ------------------------------------------------------------------------

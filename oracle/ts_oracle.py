@@ -76,6 +76,8 @@ def lib():
         L.orc_gen_range_seq.argtypes = [C.c_uint64, C.c_int, C.c_uint64, C.c_uint32, C.c_void_p]
         L.orc_resize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.orc_pyramid_build.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_void_p]
+        L.orc_guide_map.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]
+        L.orc_match_histograms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
         _LIB = L
     return _LIB
 
@@ -99,6 +101,23 @@ def pyramid_build(img, levels):
     out = np.empty((n, h, w, 4), np.uint8)
     lib().orc_pyramid_build(_p(img), w, h, levels, _p(out))
     return out
+
+
+def guide_map(img, sigma=2.0):
+    """transform_to_guide_map (utils.rs:101-116)"""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape[:2]
+    out = np.empty((h, w, 4), np.uint8)
+    lib().orc_guide_map(_p(img), w, h, sigma, _p(out))
+    return out
+
+
+def match_histograms(source, target):
+    """match_histograms (utils.rs:135-163); returns the modified copy of source"""
+    src = np.ascontiguousarray(source, dtype=np.uint8).copy()
+    tgt = np.ascontiguousarray(target, dtype=np.uint8)
+    lib().orc_match_histograms(_p(src), src.shape[1], src.shape[0], _p(tgt), tgt.shape[1], tgt.shape[0])
+    return src
 
 
 class Generator:

@@ -171,3 +171,31 @@ def test_alternative_schedulers_give_the_same_result(env, monkeypatch):
     fa, sa = ref.resolved()
     fb, sb = alt.resolved()
     assert (fa == fb).all() and (sa.view(np.uint32) == sb.view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("shape", [(48, 40), (128, 96), (400, 382)])
+def test_guide_preprocessing_bit_exact(shape):
+    """N2: blur(sigma=2) -> grayscale and histogram matching (utils.rs:101-183) against the oracle."""
+    w, h = shape
+    a, b = synth_texture(w, h, 3), synth_texture(64, 80, 7)
+    g_o, g_g = O.guide_map(a, 2.0), capi().guide_map(a, 2.0)
+    assert (g_o == g_g).all()
+    t_o = O.guide_map(b, 2.0)
+    assert (O.match_histograms(g_o, t_o) == capi().match_histograms(g_g, t_o)).all()
+
+
+def test_style_transfer_session_matches_oracle():
+    """Config 3 (style transfer auto-guides, lib/examples/04_style_transfer.rs) through the Session mirror."""
+    import texture_synthesis_b200 as ts
+    ex, tgt = synth_texture(72, 72, 11), synth_texture(90, 90, 12)
+    gen = ts.Session.builder().add_example(ex).load_target_guide(tgt).output_size(ts.Dims.square(90)).seed(5).build().run(None)
+    img = gen.into_image()
+    # the same pipeline on the oracle
+    tg = O.guide_map(tgt, 2.0)
+    pyr, tpyr = O.pyramid_build(ex, 5), O.pyramid_build(tg, 5)
+    eg = O.pyramid_build(O.match_histograms(O.guide_map(ex, 2.0), tg), 5)
+    go = O.Generator(90, 90)
+    go.set_examples([pyr])
+    go.set_guides(tpyr, [eg])
+    go.resolve(O.make_params(seed=5))
+    assert (go.color() == img).all()

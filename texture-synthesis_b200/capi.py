@@ -77,7 +77,7 @@ EXPORTS = [
     "tsb_generator_get_stats", "tsb_last_error", "tsb_device_count", "tsb_generator_load_state",
     "tsb_generator_eval_items", "tsb_generator_set_trace", "tsb_generator_trace_count", "tsb_generator_read_trace",
     "tsb_microbench_gather", "tsb_generator_mg_prepare", "tsb_generator_mg_export", "tsb_generator_mg_attach",
-    "tsb_generator_mg_phases",
+    "tsb_generator_mg_phases", "tsb_guide_map", "tsb_match_histograms",
 ]
 
 
@@ -98,6 +98,8 @@ def lib():
         L.tsb_pyramid_build.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp]
         L.tsb_resize.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, C.c_uint32, C.c_int]
         L.tsb_generator_create.argtypes = [C.POINTER(GeneratorDesc), C.POINTER(vp)]
+        L.tsb_guide_map.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_float, vp]
+        L.tsb_match_histograms.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, C.c_uint32, vp]
         L.tsb_generator_destroy.argtypes = [vp]
         L.tsb_generator_destroy.restype = None
         L.tsb_generator_random_init.argtypes = [vp, C.c_uint64, C.POINTER(Image), C.c_uint32, C.c_uint64]
@@ -166,6 +168,23 @@ def pyramid_build(img, levels):
     h, w = img.shape[:2]
     out = np.empty((max(1, levels), h, w, 4), np.uint8)
     _check(lib().tsb_pyramid_build(_p(img), w, h, levels, _p(out)))
+    return out
+
+
+def guide_map(img, sigma=2.0):
+    """utils::transform_to_guide_map (reference lib/src/utils.rs:101-116) on the GPU."""
+    img = _rgba(img)
+    h, w = img.shape[:2]
+    out = np.empty((h, w, 4), np.uint8)
+    _check(lib().tsb_guide_map(_p(img), w, h, sigma, _p(out)))
+    return out
+
+
+def match_histograms(source, target):
+    """utils::match_histograms (reference lib/src/utils.rs:135-183) on the GPU; returns the remapped source."""
+    source, target = _rgba(source), _rgba(target)
+    out = np.empty_like(source)
+    _check(lib().tsb_match_histograms(_p(source), source.shape[1], source.shape[0], _p(target), target.shape[1], target.shape[0], _p(out)))
     return out
 
 

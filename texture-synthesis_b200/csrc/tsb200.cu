@@ -98,8 +98,14 @@ struct PinnedBuf {
 // ---------------------------------------------------------------------------------------------
 // image 0.23.12 imageops::resize tap tables (vertical_sample / horizontal_sample share the formula).
 // ---------------------------------------------------------------------------------------------
-float kernel_eval(int f, float x) {
+constexpr int FILTER_BLUR = 3;  // image 0.23.12 `blur(sigma)`: kernel gaussian(x, sigma), support 2*sigma (utils.rs:115)
+
+float kernel_eval(int f, float x, float sigma = 0.5f) {
     switch (f) {
+    case FILTER_BLUR: {
+        float norm = 1.0f / (sqrtf(2.0f * 3.14159265358979323846f) * sigma);
+        return norm * expf(-(x * x) / (2.0f * (sigma * sigma)));
+    }
     case TSB_FILTER_TRIANGLE: {
         float a = fabsf(x);
         return a < 1.0f ? 1.0f - a : 0.0f;
@@ -125,9 +131,9 @@ struct HostTaps {
     std::vector<float> sum, weights;
 };
 
-void build_taps(int in_sz, int out_sz, int filter, HostTaps& t) {
+void build_taps(int in_sz, int out_sz, int filter, HostTaps& t, float sigma = 0.5f) {
     t = HostTaps();
-    const float support0 = filter == TSB_FILTER_TRIANGLE ? 1.0f : (filter == TSB_FILTER_CATMULLROM ? 2.0f : 3.0f);
+    const float support0 = filter == FILTER_BLUR ? 2.0f * sigma : (filter == TSB_FILTER_TRIANGLE ? 1.0f : (filter == TSB_FILTER_CATMULLROM ? 2.0f : 3.0f));
     const float ratio = (float)in_sz / (float)out_sz;
     const float sratio = ratio < 1.0f ? 1.0f : ratio;
     const float support = support0 * sratio;
@@ -143,7 +149,7 @@ void build_taps(int in_sz, int out_sz, int filter, HostTaps& t) {
         t.offset.push_back((int)t.weights.size());
         float sum = 0.0f;
         for (long long i = left; i < right; ++i) {
-            float w = kernel_eval(filter, ((float)i - inputx) / sratio);
+            float w = kernel_eval(filter, ((float)i - inputx) / sratio, sigma);
             t.weights.push_back(w);
             sum += w;
         }
@@ -166,11 +172,11 @@ struct DevTaps {
 };
 
 // resize on device buffers: src (w x h) -> dst (nw x nh); tmp must hold w*nh pixels.
-int device_resize(const uint32_t* src, int w, int h, uint32_t* dst, int nw, int nh, int filter, uint32_t* tmp, cudaStream_t s) {
+int device_resize(const uint32_t* src, int w, int h, uint32_t* dst, int nw, int nh, int filter, uint32_t* tmp, cudaStream_t s, float sigma = 0.5f) {
     if (nw <= 0 || nh <= 0) return 0;
     HostTaps hv, hh;
-    build_taps(h, nh, filter, hv);
-    build_taps(w, nw, filter, hh);
+    build_taps(h, nh, filter, hv, sigma);
+    build_taps(w, nw, filter, hh, sigma);
     DevTaps dv, dh;
     TRY(dv.upload(hv, s));
     TRY(dh.upload(hh, s));
@@ -1143,6 +1149,59 @@ int tsb_resize(const uint8_t* rgba, uint32_t w, uint32_t h, uint8_t* out, uint32
     TRY(dst.ensure((size_t)nw * nh));
     TRY(device_resize(src.p, (int)w, (int)h, dst.p, (int)nw, (int)nh, filter, tmp.p, s));
     CU(cudaMemcpy(out, dst.p, (size_t)nw * nh * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// utils::transform_to_guide_map (utils.rs:101-116): blur(sigma) -> grayscale -> RGBA (l,l,l,255)
+int tsb_guide_map(const uint8_t* rgba, uint32_t w, uint32_t h, float sigma, uint8_t* out) {
+    if (!rgba || !out || w == 0 || h == 0) return fail(TSB_ERR_INVALID, "tsb_guide_map: empty image");
+    if (sigma < 0.0f) sigma = 1.0f;
+    cudaStream_t s = nullptr;
+    const size_t n = (size_t)w * h;
+    DevBuf<uint32_t> src, tmp, dst;
+    TRY(src.upload((const uint32_t*)rgba, n, s));
+    TRY(tmp.ensure(n)); TRY(dst.ensure(n));
+    TRY(device_resize(src.p, (int)w, (int)h, dst.p, (int)w, (int)h, FILTER_BLUR, tmp.p, s, sigma));
+    k_grayscale<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(dst.p, (uint32_t)n);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, dst.p, n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// utils::match_histograms (utils.rs:135-183): `source` is remapped so that its R-channel CDF follows the target's
+int tsb_match_histograms(const uint8_t* source, uint32_t sw, uint32_t sh, const uint8_t* target, uint32_t tw, uint32_t th, uint8_t* out) {
+    if (!source || !target || !out || !sw || !sh || !tw || !th) return fail(TSB_ERR_INVALID, "tsb_match_histograms: empty image");
+    cudaStream_t s = nullptr;
+    const size_t ns = (size_t)sw * sh, nt = (size_t)tw * th;
+    DevBuf<uint32_t> src, tgt, hist, lut;
+    TRY(src.upload((const uint32_t*)source, ns, s));
+    TRY(tgt.upload((const uint32_t*)target, nt, s));
+    TRY(hist.ensure(512)); TRY(lut.ensure(256));
+    CU(cudaMemsetAsync(hist.p, 0, 512 * 4, s));
+    k_histogram_r<<<(uint32_t)((nt + 255) / 256), 256, 0, s>>>(tgt.p, (uint32_t)nt, hist.p);
+    k_histogram_r<<<(uint32_t)((ns + 255) / 256), 256, 0, s>>>(src.p, (uint32_t)ns, hist.p + 256);
+    CU(cudaGetLastError());
+    uint32_t h[512];
+    CU(cudaMemcpy(h, hist.p, sizeof(h), cudaMemcpyDeviceToHost));
+    float tc[256], sc[256];
+    auto cdf = [](const uint32_t* hh, float* o) {  // get_cdf, utils.rs:165-183
+        for (int i = 0; i < 256; ++i) o[i] = i ? o[i - 1] + (float)hh[i] : (float)hh[i];
+        float mx = o[255];
+        for (int i = 0; i < 256; ++i) o[i] /= mx;
+    };
+    cdf(h, tc);
+    cdf(h + 256, sc);
+    uint32_t l[256];
+    for (int v = 0; v < 256; ++v) {
+        int pos = -1;
+        for (int i = 0; i < 256; ++i) if (tc[i] > sc[v]) { pos = i; break; }
+        unsigned nv = pos >= 0 ? (unsigned)pos : (unsigned)(uint8_t)(v + 1);   // unwrap_or((pixel_value + 1) as usize) as u8
+        l[v] = (uint32_t)(uint8_t)((uint8_t)nv - 1);                             // `- 1` in u8 (wraps in release builds)
+    }
+    CU(cudaMemcpy(lut.p, l, sizeof(l), cudaMemcpyHostToDevice));
+    k_apply_lut_r<<<(uint32_t)((ns + 255) / 256), 256, 0, s>>>(src.p, (uint32_t)ns, lut.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, src.p, ns * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -1399,6 +1399,32 @@ __global__ void k_resample_h(const uint32_t* __restrict__ src, int w, int h, uin
     dst[(size_t)y * nw + ox] = resample_finish(a0, a1, a2, a3, t.sum[ox]);
 }
 
+// guide preprocessing (utils.rs:101-183): luma = 0.2126 r + 0.7152 g + 0.0722 b in f32, truncated (image 0.23.12 grayscale)
+__global__ void k_grayscale(uint32_t* img, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t p = img[i];
+    float l = __fadd_rn(__fadd_rn(__fmul_rn(0.2126f, (float)(p & 0xFFu)), __fmul_rn(0.7152f, (float)((p >> 8) & 0xFFu))),
+                        __fmul_rn(0.0722f, (float)((p >> 16) & 0xFFu)));
+    uint32_t v = (uint32_t)(l < 0.f ? 0.f : (l > 255.f ? 255.f : l));
+    img[i] = v | (v << 8) | (v << 16) | 0xFF000000u;
+}
+__global__ void k_histogram_r(const uint32_t* img, uint32_t n, uint32_t* hist) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&h[img[i] & 0xFFu], 1u);
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(hist + threadIdx.x, h[threadIdx.x]);
+}
+__global__ void k_apply_lut_r(uint32_t* img, uint32_t n, const uint32_t* lut) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t v = lut[img[i] & 0xFFu];
+    img[i] = v | (v << 8) | (v << 16) | 0xFF000000u;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Gather microbenchmark: the scoring kernel's access pattern without the arithmetic.  Every lane
 // owns a random window origin and walks `steps` pseudo-neighbour offsets inside a 13x13 window.

@@ -389,53 +389,12 @@ class GeneratedImage:
         return CoordinateTransform(self.inner.coord(), Dims(self.inner.W, self.inner.H), list(self._input_dims))
 
 
-# ---- guide preprocessing (utils.rs:101-183): one-off O(pixels) work outside the hot path ------------
+# ---- guide preprocessing (utils.rs:101-183) runs on the GPU (tsb_guide_map / tsb_match_histograms) ----------
 def transform_to_guide_map(img, blur_sigma):
     """utils.rs:101-116: blur(sigma) -> grayscale -> RGBA (the resize in the reference is a discarded no-op, q10)."""
-    a = img.astype(np.float32)
-    h, w = a.shape[:2]
-    sigma = np.float32(blur_sigma)
-
-    def kern(x):
-        return np.float32(1.0) / (np.sqrt(np.float32(2.0 * np.pi)) * sigma) * np.exp(-(x * x) / (np.float32(2.0) * sigma * sigma))
-
-    def pass_1d(arr, n, axis):
-        out = np.empty_like(arr)
-        support = np.float32(2.0) * sigma
-        for o in range(n):
-            c = np.float32(o) + np.float32(0.5)
-            left = int(min(max(np.floor(c - support), 0), n - 1))
-            right = int(min(max(np.ceil(c + support), left + 1), n))
-            xs = np.arange(left, right, dtype=np.float32) - (c - np.float32(0.5))
-            wts = kern(xs).astype(np.float32)
-            sl = [slice(None)] * 3
-            sl[axis] = slice(left, right)
-            shape = [1, 1, 1]
-            shape[axis] = right - left
-            acc = (arr[tuple(sl)] * wts.reshape(shape)).sum(axis=axis, dtype=np.float32) / wts.sum(dtype=np.float32)
-            so = [slice(None)] * 3
-            so[axis] = o
-            out[tuple(so)] = np.clip(acc, 0, 255).astype(np.uint8).astype(np.float32)
-        return out
-
-    a = pass_1d(a, h, 0)
-    a = pass_1d(a, w, 1)
-    a = a.astype(np.uint8).astype(np.float32)
-    luma = (np.float32(0.2126) * a[..., 0] + np.float32(0.7152) * a[..., 1] + np.float32(0.0722) * a[..., 2]).astype(np.uint8)
-    return np.ascontiguousarray(np.stack([luma, luma, luma, np.full_like(luma, 255)], axis=-1))
+    return capi.guide_map(img, blur_sigma)
 
 
 def match_histograms(source, target):
     """utils.rs:135-183"""
-    def cdf(img):
-        hist = np.bincount(img[..., 0].ravel(), minlength=256).astype(np.float32)
-        c = np.cumsum(hist, dtype=np.float32)
-        return c / c[255]
-    tc, sc = cdf(target), cdf(source)
-    lut = np.empty(256, np.uint8)
-    for v in range(256):
-        pos = np.nonzero(tc > sc[v])[0]
-        nv = int(pos[0]) if len(pos) else (v + 1)
-        lut[v] = np.uint8((nv & 0xFF) - 1 & 0xFF)
-    g = lut[source[..., 0]]
-    return np.ascontiguousarray(np.stack([g, g, g, np.full_like(g, 255)], axis=-1))
+    return capi.match_histograms(source, target)
