@@ -766,7 +766,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_flow(StageDev S, PhaseDev P,
             unsigned spins = 0, ns = 32;
             while ((it = vq[slot]) == NONE32) {
                 __nanosleep(ns);
-                if (ns < 1024) ns <<= 1;
+                if (ns < 256) ns <<= 1;
                 if ((++spins & 1023u) == 0u) {
                     if (vctl[FC_ABORT]) break;
                     if (spins > (1u << 22)) { atomicExch(F.ctl + FC_ABORT, 1u); break; }  // watchdog: never hang the device
@@ -808,11 +808,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_flow(StageDev S, PhaseDev P,
         if (!MG) {
             for (size_t e = s0 + lane; e < s1; e += 32) {
                 uint32_t sc = F.succ[e];
-                if (atomicSub(F.npred + sc, 1u) == 1u) {
-                    __threadfence();
-                    uint32_t pos = atomicAdd(F.ctl + FC_TAIL, 1u);
-                    vq[pos] = sc;
-                }
+                // every predecessor made its commit visible (fence) BEFORE its decrement and consumers read the
+                // mutable state with L2 loads, so the publisher needs no further fence
+                if (atomicSub(F.npred + sc, 1u) == 1u) vq[atomicAdd(F.ctl + FC_TAIL, 1u)] = sc;
             }
         } else {
             const MgDev* mg = S.mg;
