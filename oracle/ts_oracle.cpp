@@ -226,6 +226,7 @@ static void pyramid_build(const uint8_t* src, int w, int h, uint32_t levels, uin
     for (uint32_t i = levels > 0 ? levels - 1 : 0; i >= 1; --i) {
         uint32_t p = 1u << i;
         int sw = (int)((uint32_t)w / p), sh = (int)((uint32_t)h / p);
+        if (sw == 0 || sh == 0) { std::memset(out + n * img, 0, img); ++n; continue; }  // the reference would panic on an empty image
         std::vector<uint8_t> small((size_t)std::max(sw, 0) * std::max(sh, 0) * 4);
         resize_rgba(src, w, h, small.data(), sw, sh, F_GAUSSIAN);
         resize_rgba(small.data(), sw, sh, out + n * img, w, h, F_GAUSSIAN);

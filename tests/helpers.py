@@ -153,3 +153,20 @@ def compare_runs(go, gg, check_scores=True):
         out["score_max_rel"] = float(np.max(np.abs(so - sg) / denom)) if len(so) else 0.0
         out["score_bit_mismatch"] = int((so.view(np.uint32) != sg.view(np.uint32)).sum())
     return out
+
+
+def edge_cases():
+    """Ragged / extreme configurations (tiny outputs, 0 and 1 backtrack stages, k = 1, k + m at the limit, ...)."""
+    return [
+        Case("tiny_16", 16, 16, [(16, 16)], seed=1),
+        Case("stages0", 40, 40, [(24, 24)], seed=2, stages=0),
+        Case("stages1", 40, 40, [(24, 24)], seed=3, stages=1),
+        Case("k5_m3", 48, 32, [(20, 28)], seed=4, k=5, m=3),
+        Case("k1_m1", 24, 24, [(16, 16)], seed=5, k=1, m=1, stages=2),
+        Case("long_37x91", 37, 91, [(30, 17)], seed=6),
+        Case("randinit_many", 20, 20, [(16, 16)], seed=7, random_init=150),
+        Case("p09", 48, 48, [(32, 32)], seed=8, p=0.9, stages=3),
+        Case("k100_m100", 64, 64, [(40, 40)], seed=9, k=100, m=100, stages=3),
+        Case("out_smaller_than_ex", 24, 24, [(96, 96)], seed=10),
+        Case("tiling_tiny", 20, 20, [(16, 16)], seed=11, tiling=True),
+    ]

@@ -199,3 +199,33 @@ def test_style_transfer_session_matches_oracle():
     go.set_guides(tpyr, [eg])
     go.resolve(O.make_params(seed=5))
     assert (go.color() == img).all()
+
+
+from tests.helpers import edge_cases  # noqa: E402
+
+
+@pytest.mark.parametrize("case", edge_cases(), ids=lambda c: c.name)
+def test_edge_cases_identical_to_oracle(case):
+    go, gg = case.run_oracle(), case.run_gpu()
+    r = compare_runs(go, gg, check_scores=False)
+    assert r["color_mismatch"] == 0 and r["coord_mismatch"] == 0 and r["id_mismatch"] == 0 and r["order_equal"], r
+    so, sg = go.resolved()[1], gg.resolved()[1]
+    assert (np.isnan(so) == np.isnan(sg)).all()
+    ok = ~np.isnan(so)
+    assert np.allclose(so[ok], sg[ok], rtol=1e-5, atol=0)
+
+
+def test_unsupported_and_invalid_inputs_fail_loudly():
+    c = capi()
+    case = Case("bad", 32, 32, [(16, 16)], seed=0).build()
+    g = case.gpu_generator()
+    for kw in (dict(k=129), dict(k=100, m=200), dict(cauchy=0.0), dict(cauchy=1.5), dict(m=0), dict(p=-0.1)):
+        with pytest.raises(c.TsbError):
+            g.resolve(c.make_params(**kw), case.pyramids)
+    with pytest.raises(c.TsbError):       # pyramid too shallow for the requested stages
+        g.resolve(c.make_params(stages=5), [case.pyramids[0][:2]])
+    with pytest.raises(c.TsbError):       # image too small for 5 levels (the reference would panic on an empty image)
+        c.pyramid_build(synth_texture(8, 8, 1), 5)
+    all_zero = np.zeros((16, 16, 4), np.uint8)
+    with pytest.raises(c.TsbError):       # a sampling mask that allows nothing would loop forever in the reference
+        g.resolve(c.make_params(), case.pyramids, [c.SAMPLE_IMAGE], [all_zero])

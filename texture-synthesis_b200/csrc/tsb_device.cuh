@@ -454,6 +454,7 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws,
     __syncwarp();
     long long t2 = clock64();
     // ---- weights: mean over the x4-duplicated list, sequential f64 sum (ms.rs:417-423, 1198-1203) ----
+    bool degenerate = false;
     {
         double sum = 0.0;
         for (int j = 0; j < kk; ++j) {
@@ -461,6 +462,7 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws,
             sum = __dadd_rn(sum, d); sum = __dadd_rn(sum, d); sum = __dadd_rn(sum, d); sum = __dadd_rn(sum, d);
         }
         double avg = __ddiv_rn(sum, (double)(kk * 4));
+        degenerate = (avg == 0.0);  // only neighbour = the pixel itself (k = 1 redo): 0/0 -> NaN weights in the reference
         for (int j = lane; j < kk; j += 32) ws.g[j] = (float)exp(-__ddiv_rn(ws.d[j], avg));
     }
     const int kk8 = (kk + 7) & ~7;
@@ -588,6 +590,12 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws,
     out.fetched = (unsigned long long)fetched * (GUIDED ? 2ull : 1ull);  // neighbour positions evaluated (example + guide texel each)
     out.nominal = (unsigned long long)out.ncand * (unsigned long long)kk * (GUIDED ? 2ull : 1ull);
     out.c_neigh = t2 - t1; out.c_weight = t3 - t2; out.c_score = t4 - t3;
+    if (degenerate) {
+        // every score is NaN: `score >= current_best` is never true, so each candidate replaces the previous one and
+        // the LAST candidate wins with a NaN score (ms.rs:1205-1221, 1281)
+        besti = ncand - 1;
+        best = __int_as_float(0x7FC00000);
+    }
     uint32_t bxy = ws.u.c.cxy[besti];
     out.best = (int)ws.corig[besti];
     out.bx = (int)(bxy & 0xFFFFu);
