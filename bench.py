@@ -26,7 +26,7 @@ sys.path.insert(0, ROOT)
 OUT, EX = 2048, 512
 WORKLOAD = f"{OUT}x{OUT} output from synthetic {EX}x{EX} example (synth_texture seed 1), k=50 m=50 cauchy=1.0 backtrack=0.5x5 seed=0"
 # dram bytes (read+write) of all k_flow launches of one step, from the ncu --set full capture summarised under profiles/
-TRAFFIC_PER_STEP = None
+TRAFFIC_PER_STEP = 9.72e9  # 9.33 GB read + 0.39 GB written over the 21 k_flow launches of one step (profiles/r1_kflow_all_launches_2048.txt)
 CPU_SAMPLE_OUT = 1536  # bounded CPU sample: same example and parameters, 1536x1536 output (about 10-20 s on 8-16 cores)
 
 
