@@ -686,6 +686,7 @@ int run_phase_flow(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n,
     PhaseClock clk;
     TRY(clk.begin(s));
     const int ga = grid_for(g, n), gl = grid_light(g, n);
+    // persistent grid: never more than the co-resident CTAs
     const int gf = std::max(1, std::min((int)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), g->guided ? g->max_ctas_flow_guided : g->max_ctas_flow));
     uint64_t edges = 0;
     if (g->mg_on && n >= g->mg_min_phase) {
@@ -1060,8 +1061,11 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
                 continue;
             }
             size_t base = resolved_now - g->inpaint_locked;
-            const bool serial = base < 2 * (size_t)k;  // every item still depends on (almost) all earlier ones
-            size_t n_e = serial ? (g->use_rounds ? 1 : std::min(n_items - cur, 2 * (size_t)k - base)) : std::min(n_items - cur, base);
+            // every item still depends on (almost) all earlier ones: one warp runs them in order, keeping the whole
+            // resolved set as a point list in shared memory while it fits the key buffer
+            const size_t serial_until = std::max<size_t>(2 * (size_t)k, (size_t)KBUF - 32);
+            const bool serial = base < serial_until;
+            size_t n_e = serial ? (g->use_rounds ? 1 : std::min(n_items - cur, serial_until - base)) : std::min(n_items - cur, base);
             S.r2_hint = r2_hint_for(g, resolved_now, k);
             S.n_points_max = (uint32_t)std::min<size_t>((tiling ? 3 : 1) * (resolved_now + n_e), 0xFFFFFFFFull);
             if (serial && tiling && resolved_now + n_e <= (size_t)KBUF) {
