@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -296,6 +297,9 @@ struct tsb_generator {
     std::vector<std::pair<cudaIpcMemHandle_t, void*>> mg_blocks;
     size_t mg_min_phase = 32768;   // smaller phases are executed redundantly by every rank (no communication)
     uint64_t mg_phases = 0;
+    std::function<int(size_t, size_t)> regen_rand;  // regenerates the random candidates of a phase for ALL its items
+    cudaEvent_t ev_rand = nullptr;                   // stage-wide candidate generation on stream2 (single GPU)
+    bool rand_pending = false;
     size_t succ_stride = SUCC_STRIDE;
     uint32_t* h_ctrl = nullptr;  // pinned, 16 words
     PinnedBuf<uint32_t> h_idx, h_items;  // pick indices (D2H) and per-stage work-item pixels (H2D)
@@ -317,6 +321,7 @@ struct tsb_generator {
         if (h_ctrl) cudaFreeHost(h_ctrl);
         if (stream) cudaStreamDestroy(stream);
         if (stream2) cudaStreamDestroy(stream2);
+        if (ev_rand) cudaEventDestroy(ev_rand);
     }
 };
 
@@ -545,6 +550,7 @@ int run_phase(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, bool
         CU(cudaMemsetAsync(g->d_pend0.p, 0, 4, s));
     }
     CU(cudaEventRecord(e1, s));
+    if (g->rand_pending) { CU(cudaStreamWaitEvent(s, g->ev_rand, 0)); g->rand_pending = false; }
     uint32_t known = n, round = 0;
     while (known > 0) {
         int grid = grid_for(g, known);
@@ -667,6 +673,7 @@ int run_serial(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, boo
     PhaseClock clk;
     TRY(clk.begin(s));
     TRY(clk.mid(s));
+    if (g->rand_pending) { CU(cudaStreamWaitEvent(s, g->ev_rand, 0)); g->rand_pending = false; }
     if (g->guided) k_serial<true><<<1, CTA_THREADS, sizeof(RoundSmem), s>>>(S, P);
     else k_serial<false><<<1, CTA_THREADS, sizeof(RoundSmem), s>>>(S, P);
     CU(cudaGetLastError());
@@ -716,10 +723,24 @@ int run_phase_flow(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n,
         k_edges_scan<2><<<gl, CTA_THREADS, 0, s>>>(Sm, P, F);
         CU(cudaGetLastError());
         TRY(barrier());  // all edges registered with their owners
+        bool overflow = false;
         for (int r = 0; r < g->h_mg.world; ++r) {  // a successor list overflow anywhere invalidates the phase for everybody
             uint32_t flag = 0;
             CU(cudaMemcpy(&flag, g->h_mg.ctl[r] + FC_OVERFLOW, 4, cudaMemcpyDeviceToHost));
-            if (flag) return fail(TSB_ERR_UNSUPPORTED, "successor list overflow in a band-sharded phase of %u items (stride %zu)", n, g->succ_stride);
+            overflow |= flag != 0;
+        }
+        TRY(barrier());  // everybody has read the flags before anyone resets its control block
+        if (overflow) {
+            // every rank takes the same decision: execute this phase redundantly on its own replica (single-GPU path with
+            // the CSR fallback); nothing of the phase has been committed yet.  Candidates were generated for own items only.
+            k_pmap_clear<<<(n + 255) / 256, 256, 0, s>>>(P);
+            CU(cudaGetLastError());
+            TRY(g->regen_rand(i0, n));
+            const bool was = g->mg_on;
+            g->mg_on = false;
+            int rc = run_phase_flow(g, S, i0, n, is_new, trace_base);
+            g->mg_on = was;
+            return rc;
         }
         if (getenv("TSB_MG_DEBUG")) {  // invariant: sum of own npred over ranks == sum of own nsucc over ranks == #edges
             std::vector<uint32_t> np(n), ns(n), px(n);
@@ -849,6 +870,7 @@ int run_phase_flow(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n,
         k_seed_queue<<<(n + 255) / 256, 256, 0, s>>>(S, P, F);
         CU(cudaGetLastError());
         if (attempt == 0) TRY(clk.mid(s));
+        if (g->rand_pending) { CU(cudaStreamWaitEvent(s, g->ev_rand, 0)); g->rand_pending = false; }
         if (g->guided) k_flow<true, false><<<gf, CTA_THREADS, sizeof(RoundSmem), s>>>(S, P, F);
         else k_flow<false, false><<<gf, CTA_THREADS, sizeof(RoundSmem), s>>>(S, P, F);
         k_pmap_clear<<<(n + 255) / 256, 256, 0, s>>>(P);
@@ -873,6 +895,7 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
     const double t_start = now_ms();
     cudaStream_t s = g->stream;
     memset(&g->stats, 0, sizeof(g->stats));
+    g->rand_pending = false;
     cudaEvent_t ev_begin, ev_end;
     CU(cudaEventCreate(&ev_begin)); CU(cudaEventCreate(&ev_end));
     CU(cudaEventRecord(ev_begin, s));
@@ -1020,15 +1043,26 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
         if (n_items == 0) continue;
         // random candidates: rng seeded with loop_seed + 1 = stage seed + i + 1 (ms.rs:902,945); generated per phase, and in
         // band-sharded phases only for the items this rank owns
-        auto gen_rand = [&](size_t i0, size_t n_) -> int {
-            const bool own_only = g->mg_on && n_ >= g->mg_min_phase;
-            k_rand_candidates<<<(uint32_t)((n_ + 127) / 128), 128, 0, s>>>(S.ex, S.n_ex, m, sp.seed + 1ull + (uint64_t)i0, (uint32_t)n_,
-                                                                        g->d_rand_xy.p + i0 * (size_t)m, g->d_rand_map.p + i0 * (size_t)m,
-                                                                        own_only ? g->d_item_pixel.p + i0 : nullptr, g->W, g->h_mg.band_h,
-                                                                        g->h_mg.rank, g->h_mg.world);
+        auto launch_rand = [&](size_t i0, size_t n_, bool own_only, cudaStream_t st) -> int {
+            k_rand_candidates<<<(uint32_t)((n_ + 127) / 128), 128, 0, st>>>(S.ex, S.n_ex, m, sp.seed + 1ull + (uint64_t)i0, (uint32_t)n_,
+                                                                         g->d_rand_xy.p + i0 * (size_t)m, g->d_rand_map.p + i0 * (size_t)m,
+                                                                         own_only ? g->d_item_pixel.p + i0 : nullptr, g->W, g->h_mg.band_h,
+                                                                         g->h_mg.rank, g->h_mg.world);
             CU(cudaGetLastError());
             g->stats.kernel_launches++;
             return 0;
+        };
+        g->regen_rand = [&](size_t i0, size_t n_) -> int { return launch_rand(i0, n_, false, s); };
+        if (!g->mg_on) {
+            // single GPU: the whole stage at once on the second stream, overlapped with the dependency analysis of the
+            // first phase; the resolve kernels wait for the event (run_phase_flow / run_serial)
+            TRY(launch_rand(0, n_items, false, g->stream2));
+            CU(cudaEventRecord(g->ev_rand, g->stream2));
+            g->rand_pending = true;
+        }
+        auto gen_rand = [&](size_t i0, size_t n_) -> int {
+            if (!g->mg_on) return 0;
+            return launch_rand(i0, n_, n_ >= g->mg_min_phase, s);
         };
 
         size_t resolved_now = sp.resolved_before;
@@ -1247,6 +1281,7 @@ int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
     if (cudaSetDevice(dev) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "cudaSetDevice(%d) failed", dev));
     if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "stream creation failed"));
     if (cudaStreamCreateWithFlags(&g->stream2, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "stream creation failed"));
+    if (cudaEventCreateWithFlags(&g->ev_rand, cudaEventDisableTiming) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "event creation failed"));
     if (cudaMallocHost((void**)&g->h_ctrl, 64) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "pinned allocation failed"));
     g->W = (int)desc->out_width; g->H = (int)desc->out_height;
     const size_t npix = (size_t)g->W * g->H;
