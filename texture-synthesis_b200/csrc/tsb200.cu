@@ -257,6 +257,7 @@ struct tsb_generator {
     int mx = 0, my = 0, wpr = 0, mrows = 0, wpr1 = 0;
     DevBuf<short2> d_spiral;
     DevBuf<uint32_t> d_cntLE;
+    DevBuf<double> d_divx, d_divy;                  // (double)(i - mx) / W and (double)(i - my) / H over the mask extent
     int spiralN = 0, RT2 = 0;
 
     // inputs (device resident)
@@ -265,6 +266,10 @@ struct tsb_generator {
     std::vector<int> ex_w, ex_h, ex_kind;           // all examples
     std::vector<int> filt;                          // filtered index -> all index
     std::vector<DevBuf<uint32_t>> d_ex;             // per (all) example: levels*w*h
+    std::vector<DevBuf<uint32_t>> d_exf, d_exgf;    // framed copies (EX_PAD texels of the outside colour all round)
+    DevBuf<uint32_t> d_alpha_flag;                  // [0] set when an input texel has alpha != 255, [1] same for the state
+    int pad_pitch = 0;                              // common row pitch of the framed copies, 0 when the sizes differ
+    bool inputs_opaque = false, run_opaque = false, no_fast = false;
     std::vector<DevBuf<uint8_t>> d_smask;           // per (all) example
     DevBuf<DevEx> d_exdesc;                         // [levels][n_ex] filtered
     bool guided = false;
@@ -281,6 +286,12 @@ struct tsb_generator {
     DevBuf<uint32_t> d_rand_xy, d_pick_idx, d_tmp_u32, d_read_color, d_read_coord, d_read_id;
     DevBuf<uint8_t> d_rand_map;
     DevBuf<uint32_t> d_npred, d_nsucc, d_succ_off, d_succ_cur, d_succ, d_queue, d_fctl;
+    DevBuf<short2> d_nb0, d_predl;                  // neighbour lists of the phase analysis (see PhaseDev)
+    DevBuf<uint32_t> d_npredl;
+    size_t list_max_items = 0;                      // phases up to this size use the lists
+    size_t cur_resolved = 0;                        // resolved pixels at the start of the phase being run
+    double list_min_positions = 300.0;              // new phases use the lists when a mask walk would visit at least this many pixels
+    uint32_t predl_stride = 0;
     DevBuf<uint8_t> d_cub_temp, d_sort_temp;
     DevBuf<unsigned long long> d_keys, d_keys_sorted;
     DevBuf<uint32_t> d_v0;
@@ -339,6 +350,7 @@ void fill_stage_geometry(tsb_generator* g, StageDev& S, bool tiling) {
     S.x_l = (int)((float)g->W * 0.05f); S.x_r = g->W - S.x_l;   // ms.rs:308-311
     S.y_b = (int)((float)g->H * 0.05f); S.y_t = g->H - S.y_b;
     S.spiral = g->d_spiral.p; S.cntLE = g->d_cntLE.p; S.spiralN = g->spiralN; S.RT2 = g->RT2;
+    S.divx = g->d_divx.p; S.divy = g->d_divy.p;
     S.k = 1; S.m = 0; S.r2_hint = 16;
     S.counters = nullptr;
 }
@@ -365,6 +377,16 @@ int upload_pyramid(const tsb_pyramid& p, DevBuf<uint32_t>& d, cudaStream_t s) {
     size_t n = (size_t)p.n_levels * p.width * p.height;
     return d.upload((const uint32_t*)p.levels, n, s);
 }
+size_t framed_level_size(int w, int h) { return (size_t)(w + 2 * EX_PAD) * (size_t)(h + 2 * EX_PAD); }
+// framed copy of an uploaded pyramid (all levels); also raises flag[0] when a texel is not fully opaque
+int frame_pyramid(const DevBuf<uint32_t>& src, DevBuf<uint32_t>& dst, int w, int h, int levels, uint32_t* flag, cudaStream_t s) {
+    const size_t n = framed_level_size(w, h) * (size_t)levels;
+    TRY(dst.ensure(n));
+    const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 64);
+    k_frame_levels<<<grid, 256, 0, s>>>(src.p, dst.p, w, h, levels, flag);
+    CU(cudaGetLastError());
+    return 0;
+}
 
 int upload_inputs(tsb_generator* g, const tsb_pyramid* examples, uint32_t n_examples, const tsb_guides* guides, const tsb_sampling* sampling) {
     if (!examples || n_examples == 0) return fail(TSB_ERR_INVALID, "at least one example is required");
@@ -373,7 +395,12 @@ int upload_inputs(tsb_generator* g, const tsb_pyramid* examples, uint32_t n_exam
     g->n_ex_all = (int)n_examples;
     g->n_levels = (int)examples[0].n_levels;
     g->ex_w.clear(); g->ex_h.clear(); g->ex_kind.clear(); g->filt.clear();
-    if (g->d_ex.size() != n_examples) { g->d_ex.clear(); g->d_smask.clear(); g->d_ex.resize(n_examples); g->d_smask.resize(n_examples); }
+    if (g->d_ex.size() != n_examples) {
+        g->d_ex.clear(); g->d_smask.clear(); g->d_exf.clear();
+        g->d_ex.resize(n_examples); g->d_smask.resize(n_examples); g->d_exf.resize(n_examples);
+    }
+    TRY(g->d_alpha_flag.ensure(2));
+    CU(cudaMemsetAsync(g->d_alpha_flag.p, 0, 8, s));
     for (uint32_t e = 0; e < n_examples; ++e) {
         const tsb_pyramid& p = examples[e];
         if (!p.levels || p.width == 0 || p.height == 0 || p.n_levels == 0) return fail(TSB_ERR_INVALID, "example %u is empty", e);
@@ -382,6 +409,7 @@ int upload_inputs(tsb_generator* g, const tsb_pyramid* examples, uint32_t n_exam
         int kind = sampling ? sampling[e].kind : TSB_SAMPLE_ALL;
         g->ex_w.push_back((int)p.width); g->ex_h.push_back((int)p.height); g->ex_kind.push_back(kind);
         TRY(upload_pyramid(p, g->d_ex[e], s));
+        TRY(frame_pyramid(g->d_ex[e], g->d_exf[e], (int)p.width, (int)p.height, g->n_levels, g->d_alpha_flag.p, s));
         if (kind == TSB_SAMPLE_IMAGE) {
             if (!sampling[e].rgba) return fail(TSB_ERR_INVALID, "sampling mask %u is null", e);
             std::vector<uint8_t> r((size_t)p.width * p.height);
@@ -404,10 +432,13 @@ int upload_inputs(tsb_generator* g, const tsb_pyramid* examples, uint32_t n_exam
             DevEx d;
             d.w = g->ex_w[e]; d.h = g->ex_h[e];
             d.px = g->d_ex[e].p + (size_t)l * d.w * d.h;
+            d.pp = g->d_exf[e].p + (size_t)l * framed_level_size(d.w, d.h) + (size_t)EX_PAD * (d.w + 2 * EX_PAD) + EX_PAD;
             d.smask = g->ex_kind[e] == TSB_SAMPLE_IMAGE ? g->d_smask[e].p : nullptr;
             desc[(size_t)l * g->n_ex + f] = d;
         }
     TRY(g->d_exdesc.upload(desc.data(), desc.size(), s));
+    g->pad_pitch = g->ex_w[g->filt[0]] + 2 * EX_PAD;
+    for (int f = 1; f < g->n_ex; ++f) if (g->ex_w[g->filt[f]] + 2 * EX_PAD != g->pad_pitch) g->pad_pitch = 0;
     g->guided = guides != nullptr;
     g->exg_w.clear(); g->exg_h.clear();
     if (!guides) g->d_exg.clear();
@@ -416,24 +447,53 @@ int upload_inputs(tsb_generator* g, const tsb_pyramid* examples, uint32_t n_exam
         if ((int)guides->target.n_levels != g->n_levels) return fail(TSB_ERR_INVALID, "target guide pyramid level count mismatch");
         g->tgw = (int)guides->target.width; g->tgh = (int)guides->target.height;
         TRY(upload_pyramid(guides->target, g->d_tguide, s));
-        if (g->d_exg.size() != n_examples) { g->d_exg.clear(); g->d_exg.resize(n_examples); }
+        {
+            const size_t n = (size_t)g->n_levels * g->tgw * g->tgh;
+            k_alpha_check<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 64), 256, 0, s>>>(g->d_tguide.p, n, g->d_alpha_flag.p);
+        }
+        if (g->d_exg.size() != n_examples) { g->d_exg.clear(); g->d_exgf.clear(); g->d_exg.resize(n_examples); g->d_exgf.resize(n_examples); }
         std::vector<DevGuide> gd((size_t)g->n_levels * n_examples);
         for (uint32_t e = 0; e < n_examples; ++e) {
             const tsb_pyramid& p = guides->examples[e];
             if ((int)p.n_levels != g->n_levels) return fail(TSB_ERR_INVALID, "example guide %u level count mismatch", e);
             TRY(upload_pyramid(p, g->d_exg[e], s));
+            TRY(frame_pyramid(g->d_exg[e], g->d_exgf[e], (int)p.width, (int)p.height, g->n_levels, g->d_alpha_flag.p, s));
             g->exg_w.push_back((int)p.width); g->exg_h.push_back((int)p.height);
+            if ((int)p.width + 2 * EX_PAD != g->pad_pitch) g->pad_pitch = 0;
             for (int l = 0; l < g->n_levels; ++l) {
                 DevGuide d;
                 d.w = (int)p.width; d.h = (int)p.height;
                 d.px = g->d_exg[e].p + (size_t)l * d.w * d.h;
+                d.pp = g->d_exgf[e].p + (size_t)l * framed_level_size(d.w, d.h) + (size_t)EX_PAD * (d.w + 2 * EX_PAD) + EX_PAD;
                 gd[(size_t)l * n_examples + e] = d;
             }
         }
         TRY(g->d_exgdesc.upload(gd.data(), gd.size(), s));
     }
+    uint32_t flag = 1;
+    CU(cudaMemcpyAsync(&flag, g->d_alpha_flag.p, 4, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
+    g->inputs_opaque = flag == 0;
     g->inputs_ready = true;
+    return 0;
+}
+
+// Decides whether this run may drop the alpha term: every input texel and every colour already in the
+// synthesis state (random_init, inpaint, loaded snapshots) must have alpha 255.  Runs on g->stream.
+int decide_opaque(tsb_generator* g) {
+    g->run_opaque = false;
+    g->no_fast = getenv("TSB_NO_FAST") != nullptr;  // debug: general scoring path only (bounds-tested reads, alpha term kept)
+    if (g->no_fast || !g->inputs_opaque) return 0;
+    StageDev S;
+    fill_stage_geometry(g, S, false);
+    CU(cudaMemsetAsync(g->d_alpha_flag.p + 1, 0, 4, g->stream));
+    const size_t n = (size_t)g->W * g->H;
+    k_state_alpha_check<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 64), 256, 0, g->stream>>>(S, g->have_loaded_points ? 1 : 0, g->d_alpha_flag.p + 1);
+    CU(cudaGetLastError());
+    uint32_t flag = 1;
+    CU(cudaMemcpyAsync(&flag, g->d_alpha_flag.p + 1, 4, cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    g->run_opaque = flag == 0;
     return 0;
 }
 
@@ -463,6 +523,8 @@ void stage_inputs(tsb_generator* g, StageDev& S, int level, const tsb_params* p)
     S.tgw = g->tgw; S.tgh = g->tgh;
     S.lut_my = g->d_luts.p; S.lut_guide = g->d_luts.p + 256;
     S.k = (int)p->nearest_neighbors; S.m = (int)p->random_sample_locations;
+    S.pad_pitch = g->no_fast ? 0 : g->pad_pitch;
+    S.opaque = g->run_opaque ? 1 : 0;
 }
 
 // PrerenderedU8Function tables (ms.rs:739-742, 853-858, 1110-1120) reduced to |a-b| (256 entries)
@@ -630,6 +692,21 @@ int ensure_flow_buffers(tsb_generator* g, size_t max_phase) {
     return 0;
 }
 
+// neighbour lists for phases of up to TSB_LIST_MAX items (default 4Mi): k + predl_stride offsets per item
+int ensure_list_buffers(tsb_generator* g, size_t max_phase, uint32_t k) {
+    size_t cap = 4u << 20;
+    if (const char* e = getenv("TSB_LIST_MAX")) cap = (size_t)strtoull(e, nullptr, 10);
+    g->list_max_items = std::min(max_phase, cap);
+    g->predl_stride = std::min<uint32_t>(((2 * k + 31) / 32) * 32, (uint32_t)KBUF - k);
+    if (const char* e = getenv("TSB_LIST_MIN_POS")) g->list_min_positions = atof(e);
+    if (g->mg_on || g->use_rounds || g->force_csr || g->predl_stride == 0) g->list_max_items = 0;
+    if (g->list_max_items == 0) return 0;
+    TRY(g->d_nb0.ensure(g->list_max_items * k));
+    TRY(g->d_predl.ensure(g->list_max_items * g->predl_stride));
+    TRY(g->d_npredl.ensure(g->list_max_items));
+    return 0;
+}
+
 PhaseDev make_phase(tsb_generator* g, uint32_t i0, uint32_t n, bool is_new, uint64_t trace_base) {
     PhaseDev P;
     memset(&P, 0, sizeof(P));
@@ -657,9 +734,20 @@ struct PhaseClock {
         cudaEventElapsedTime(&mr, e1, e2);
         g->stats.gpu_ms_analysis += ma;
         g->stats.gpu_ms_resolve += mr;
-        if (getenv("TSB_DEBUG_PHASES"))
-            fprintf(stderr, "[tsb] %s i0=%u n=%u new=%d extra=%llu analysis_ms=%.3f resolve_ms=%.3f\n", what, i0, n, (int)is_new,
-                    (unsigned long long)extra, ma, mr);
+        if (getenv("TSB_DEBUG_PHASES")) {
+            // per-phase averages of the in-kernel cycle counters (difference to the previous phase)
+            static thread_local unsigned long long prev[ST_COUNT] = {0};
+            unsigned long long cnt[ST_COUNT] = {0};
+            if (g->d_counters.p) cudaMemcpy(cnt, g->d_counters.p, sizeof(cnt), cudaMemcpyDeviceToHost);
+            if (cnt[ST_ITEMS] < prev[ST_ITEMS]) memset(prev, 0, sizeof(prev));  // a new run reset the counters
+            const double it = (double)std::max<unsigned long long>(1, cnt[ST_ITEMS] - prev[ST_ITEMS]);
+            fprintf(stderr, "[tsb] %s i0=%u n=%u new=%d extra=%llu analysis_ms=%.3f resolve_ms=%.3f | cyc/item ready %.0f knn %.0f neigh %.0f "
+                    "weight %.0f score %.0f commit %.0f\n", what, i0, n, (int)is_new, (unsigned long long)extra, ma, mr,
+                    (cnt[ST_CYC_READY] - prev[ST_CYC_READY]) / it, (cnt[ST_CYC_KNN] - prev[ST_CYC_KNN]) / it,
+                    (cnt[ST_CYC_NEIGH] - prev[ST_CYC_NEIGH]) / it, (cnt[ST_CYC_WEIGHT] - prev[ST_CYC_WEIGHT]) / it,
+                    (cnt[ST_CYC_SCORE] - prev[ST_CYC_SCORE]) / it, (cnt[ST_CYC_COMMIT] - prev[ST_CYC_COMMIT]) / it);
+            memcpy(prev, cnt, sizeof(prev));
+        }
         return 0;
     }
     ~PhaseClock() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); if (e2) cudaEventDestroy(e2); }
@@ -841,6 +929,13 @@ int run_phase_flow(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n,
     bool use_csr = g->force_csr || (size_t)n * g->succ_stride > g->d_succ.n;
     for (int attempt = 0; attempt < 2; ++attempt) {
         F.stride = use_csr ? 0u : (uint32_t)g->succ_stride;
+        bool lists = !use_csr && n <= g->list_max_items;  // the lists are built by the fixed-stride edge pass only
+        if (S.tiling && (g->W < 100 || g->H < 100)) lists = false;  // tiny_torus(): one-sided edge registration, no lists
+        // new pixels in an already dense canvas: walking the bit mask (k / density pixels) is cheaper than merging lists
+        if (lists && is_new && (double)S.k * (double)g->W * (double)g->H / (double)std::max<size_t>(1, g->cur_resolved) < g->list_min_positions) lists = false;
+        if (lists) {
+            P.nb0 = g->d_nb0.p; P.predl = g->d_predl.p; P.npredl = g->d_npredl.p; P.predl_stride = g->predl_stride;
+        } else { P.nb0 = nullptr; P.predl = nullptr; P.npredl = nullptr; P.predl_stride = 0; }
         CU(cudaMemsetAsync(F.ctl, 0, 32, s));
         k_radius<<<ga, CTA_THREADS, sizeof(CtaSmem), s>>>(S, P, F);
         CU(cudaGetLastError());
@@ -929,6 +1024,7 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
         k_mask_insert_flat<<<(np + 255) / 256, 256, 0, s>>>(S, g->d_tmp_u32.p, np, tiling ? 1 : 0);
     }
     CU(cudaGetLastError());
+    TRY(decide_opaque(g));
 
     // ---- pixel order: pick_random_unresolved (ms.rs:380-389) for every new pixel of every stage, entirely on the
     // device: index draws (k_pick_indices), then the swap_remove chain resolved in parallel (k_resolve_picks).
@@ -1007,6 +1103,7 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
     g->use_rounds = getenv("TSB_MODE") && !strcmp(getenv("TSB_MODE"), "rounds");
     g->force_csr = getenv("TSB_MODE") && !strcmp(getenv("TSB_MODE"), "csr");
     g->succ_stride = getenv("TSB_SUCC_STRIDE") ? std::max(1, atoi(getenv("TSB_SUCC_STRIDE"))) : SUCC_STRIDE;
+    TRY(ensure_list_buffers(g, max_phase, k));
     TRY(g->d_rand_xy.ensure(max_stage_items * (size_t)m));
     TRY(g->d_rand_map.ensure(max_stage_items * (size_t)m));
     TRY(g->d_luts.ensure(512));
@@ -1044,7 +1141,8 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
         // random candidates: rng seeded with loop_seed + 1 = stage seed + i + 1 (ms.rs:902,945); generated per phase, and in
         // band-sharded phases only for the items this rank owns
         auto launch_rand = [&](size_t i0, size_t n_, bool own_only, cudaStream_t st) -> int {
-            k_rand_candidates<<<(uint32_t)((n_ + 127) / 128), 128, 0, st>>>(S.ex, S.n_ex, m, sp.seed + 1ull + (uint64_t)i0, (uint32_t)n_,
+            const unsigned rb = m <= 64 ? 128u : 32u;  // items per block: the staging area is rb * m * 5 bytes (< 48 KB)
+            k_rand_candidates<<<(uint32_t)((n_ + rb - 1) / rb), rb, (size_t)rb * m * 5 + rb, st>>>(S.ex, S.n_ex, m, sp.seed + 1ull + (uint64_t)i0, (uint32_t)n_,
                                                                          g->d_rand_xy.p + i0 * (size_t)m, g->d_rand_map.p + i0 * (size_t)m,
                                                                          own_only ? g->d_item_pixel.p + i0 : nullptr, g->W, g->h_mg.band_h,
                                                                          g->h_mg.rank, g->h_mg.world);
@@ -1115,7 +1213,7 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
             TRY(gen_rand(cur, n_e));
             if (g->use_rounds) TRY(run_phase(g, S, (uint32_t)cur, (uint32_t)n_e, true, n_e > 1, trace_base));
             else if (serial) TRY(run_serial(g, S, (uint32_t)cur, (uint32_t)n_e, true, trace_base));
-            else TRY(run_phase_flow(g, S, (uint32_t)cur, (uint32_t)n_e, true, trace_base));
+            else { g->cur_resolved = resolved_now; TRY(run_phase_flow(g, S, (uint32_t)cur, (uint32_t)n_e, true, trace_base)); }
             cur += n_e; resolved_now += n_e;
             if (cb) {
                 uint64_t cur_total = overall_current + cur;
@@ -1293,6 +1391,13 @@ int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
     int rc = 0;
     if ((rc = g->d_state.ensure(npix)) || (rc = g->d_score.ensure(npix)) || (rc = g->d_mask.ensure((size_t)g->wpr * g->mrows)) ||
         (rc = g->d_mask1.ensure((size_t)g->wpr1 * g->mrows))) return bail(rc);
+    {   // normalised coordinates of ms.rs:405-415 (an IEEE division each) as tables over every coordinate a point can have
+        std::vector<double> dx((size_t)g->wpr * 32), dy((size_t)g->mrows);
+        for (size_t i = 0; i < dx.size(); ++i) dx[i] = (double)((int)i - g->mx) / (double)g->W;
+        for (size_t i = 0; i < dy.size(); ++i) dy[i] = (double)((int)i - g->my) / (double)g->H;
+        if ((rc = g->d_divx.upload(dx.data(), dx.size(), g->stream)) || (rc = g->d_divy.upload(dy.data(), dy.size(), g->stream))) return bail(rc);
+        if (cudaStreamSynchronize(g->stream) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "table upload failed"));
+    }
     SpiralHost sp = build_spiral(SPIRAL_RT);
     g->spiralN = (int)sp.off.size(); g->RT2 = sp.RT2;
     if ((rc = g->d_spiral.upload(sp.off.data(), sp.off.size(), g->stream)) || (rc = g->d_cntLE.upload(sp.cntLE.data(), sp.cntLE.size(), g->stream))) return bail(rc);
@@ -1556,6 +1661,7 @@ int tsb_generator_eval_items(tsb_generator* g, const tsb_params* prm, int32_t le
     cudaStream_t s = g->stream;
     const int k = (int)prm->nearest_neighbors, m = (int)prm->random_sample_locations;
     TRY(g->d_luts.ensure(512));
+    TRY(decide_opaque(g));
     StageDev S;
     fill_stage_geometry(g, S, prm->tiling_mode != 0);
     stage_inputs(g, S, level, prm);
@@ -1573,7 +1679,8 @@ int tsb_generator_eval_items(tsb_generator* g, const tsb_params* prm, int32_t le
     while (i < n) {
         uint32_t j = i + 1;
         while (j < n && loop_seed[j] == loop_seed[j - 1] + 1) ++j;
-        k_rand_candidates<<<(j - i + 127) / 128, 128, 0, s>>>(S.ex, S.n_ex, m, loop_seed[i] + 1ull, j - i, dxy.p + (size_t)i * m, dmap.p + (size_t)i * m);
+        const unsigned rb = m <= 64 ? 128u : 32u;
+        k_rand_candidates<<<(j - i + rb - 1) / rb, rb, (size_t)rb * m * 5 + rb, s>>>(S.ex, S.n_ex, m, loop_seed[i] + 1ull, j - i, dxy.p + (size_t)i * m, dmap.p + (size_t)i * m);
         CU(cudaGetLastError());
         i = j;
     }

@@ -29,13 +29,19 @@ constexpr uint32_t R2_INF = 0xFFFFFFFFu;
 constexpr uint32_t OUTSIDE_RGBA = 0xFF000000u;  // image::Rgba([0,0,0,255]) little-endian (ms.rs:950)
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
+// Every example / guide level is also kept in a copy framed by EX_PAD texels of the out-of-image colour
+// (ms.rs:950) on each side: a neighbourhood whose offsets are all within EX_PAD of a valid candidate is then
+// read without any bounds test (pp = texel (0,0) inside the framed copy, row pitch = w + 2*EX_PAD).
+constexpr int EX_PAD = 32;
 struct DevEx {  // one (non-ignored) example at the current pyramid level
     const uint32_t* px;
+    const uint32_t* pp;
     const uint8_t* smask;  // R channel of the sampling mask or nullptr (SamplingMethod::All)
     int w, h;
 };
 struct DevGuide {  // one example guide at the current level (NOT filtered, ms.rs:67-81)
     const uint32_t* px;
+    const uint32_t* pp;
     int w, h;
 };
 
@@ -80,10 +86,14 @@ struct StageDev {
     const float* lut_my;     // 256 entries indexed by |a-b|
     const float* lut_guide;  // 256
     // spiral table: offsets sorted by (d^2, dy, dx); cntLE[r2] = #offsets with d^2 <= r2
+    const double* divx;      // [wpr*32]  (double)(i - mx) / W : normalised x of a point (ms.rs:405-415), one IEEE division
+    const double* divy;      // [mrows]   (double)(i - my) / H
     const short2* spiral;
     const uint32_t* cntLE;
     int spiralN, RT2;
     int k, m;
+    int pad_pitch;     // row pitch of the framed copies when every example (and guide) shares it, else 0
+    int opaque;        // 1: every texel this stage can read has alpha 255, so the alpha term is lut[0] = +0 and is skipped
     uint32_t r2_hint;  // starting radius^2 of the general k-NN search
     unsigned long long* counters;  // [ST_COUNT] run statistics (see enum below), flushed once per CTA
 };
@@ -106,7 +116,13 @@ struct PhaseDev {
     // trace (optional, indexed by stage work-item index + trace_base)
     int32_t* tr_best; int32_t* tr_ncand; int32_t* tr_nneigh; float* tr_score;
     uint64_t trace_base;
+    // neighbour lists prepared by the phase analysis (nullptr: every item searches the bit mask instead)
+    short2* nb0;            // [n][k] the k nearest resolved points at phase start, canonical order
+    short2* predl;          // [n][predl_stride] new phases: lower-index items of this phase inside the item's disc (offsets)
+    uint32_t* npredl;       // [n] entries in predl; anything above predl_stride = list unusable, search the mask
+    uint32_t predl_stride;
 };
+constexpr uint32_t PREDL_UNUSABLE = 0xFFFFFFFFu;
 
 // Dataflow execution of one phase: CSR successor lists + a ready queue (every item is enqueued exactly once,
 // so the queue is a plain array of n slots; NONE32 = slot not yet published).
@@ -134,8 +150,11 @@ struct __align__(16) WarpScratch {
     float g[KMAX];
     uint32_t tcol[KMAX];
     uint32_t gcol[KMAX];
+    uint32_t succ_pref[32];   // k_flow: the first 32 successors of the current item, copied in asynchronously
+    uint32_t nsucc_pref;
     int cnt;
-    int pad[3];
+    int pad[2];
+    unsigned long long stat[16];  // per-warp run statistics (ST_*), kept out of the registers
 };
 
 // statistics accumulated per warp in registers, per CTA in shared memory, flushed once per CTA
@@ -149,8 +168,13 @@ struct ItemOut {
     int bx, by, bmap;
     uint32_t bpatch;
     float score;
+    uint32_t bcol;      // colour of the winning candidate (read while scoring)
+    int bcol_valid;
 };
 
+__device__ __forceinline__ void cp_async_u32(uint32_t* smem_dst, const uint32_t* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ int imod(int a, int b) { int r = a % b; return r < 0 ? r + b : r; }
 
 __device__ __forceinline__ int isqrt_u32(uint32_t v) {
@@ -389,6 +413,261 @@ __device__ __forceinline__ int knn_points(const StageDev& S, WarpScratch& ws, in
     return kk;
 }
 
+// Does the resolved set hold a point at the (unwrapped) position (ux, uy) once the pixel at the wrapped
+// position is resolved?  In-canvas: the pixel itself; outside: only the single-axis tiling mirror copies of
+// flush_resolved (ms.rs:308-331), no diagonal ones.
+__device__ __forceinline__ bool point_exists_at(const StageDev& S, int ux, int uy) {
+    const bool xin = (unsigned)ux < (unsigned)S.W, yin = (unsigned)uy < (unsigned)S.H;
+    if (xin && yin) return true;
+    if (!S.tiling || (!xin && !yin)) return false;
+    if (!xin) return ux >= S.W ? (ux - S.W < S.x_l) : (ux + S.W > S.x_r);
+    return uy >= S.H ? (uy - S.H < S.y_b) : (uy + S.H > S.y_t);
+}
+
+// k nearest from the lists the phase analysis prepared: the k nearest at phase start (sorted) merged with the
+// points this phase has added inside the item's disc before it (exactly its in-disc predecessors, all committed
+// by the time the item runs).  No access to the bit mask.
+__device__ __forceinline__ int knn_from_lists(const StageDev& S, WarpScratch& ws, int lane, const short2* __restrict__ nb0,
+                                              const short2* __restrict__ predl, int npl, uint32_t* r2_out) {
+    const int k = S.k;
+    if (npl == 0) {
+        for (int j = lane; j < k; j += 32) ws.off[j] = nb0[j];
+        __syncwarp();
+        const short2 last = ws.off[k - 1];
+        *r2_out = (uint32_t)(last.x * last.x + last.y * last.y);
+        return k;
+    }
+    for (int j = lane; j < k + npl; j += 32) {
+        const short2 o = j < k ? nb0[j] : predl[j - k];
+        ws.u.keys[j] = ((unsigned long long)(uint32_t)(o.x * o.x + o.y * o.y) << 32) | ((unsigned long long)(uint32_t)(o.y + 32768) << 16) |
+                       (unsigned long long)(uint32_t)(o.x + 32768);
+    }
+    __syncwarp();
+    // rank merge: the start list is already sorted and all keys are distinct, so the final position of a key is
+    // its rank in its own list plus the number of smaller keys in the other one; positions >= k drop out.
+    // Three keys per lane share every broadcast read of a phase key.
+    const unsigned long long* keys = ws.u.keys;
+    const int n = k + npl;
+    for (int e0 = 0; e0 < n; e0 += 96) {
+        unsigned long long key[3];
+        int pos[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int e = e0 + 32 * q + lane;
+            key[q] = e < n ? keys[e] : ~0ull;
+            pos[q] = e;
+            if (e >= k) {  // a phase key (or padding): number of start-list keys below it
+                int lo = 0, hi = k;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < key[q]) lo = mid + 1; else hi = mid; }
+                pos[q] = lo;
+            }
+        }
+#pragma unroll 4
+        for (int c = 0; c < npl; ++c) {
+            const unsigned long long kc = keys[k + c];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) pos[q] += kc < key[q] ? 1 : 0;
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            if (key[q] != ~0ull && pos[q] < k)
+                ws.off[pos[q]] = make_short2((short)((int)(key[q] & 0xFFFF) - 32768), (short)((int)((key[q] >> 16) & 0xFFFF) - 32768));
+    }
+    __syncwarp();
+    const short2 last = ws.off[k - 1];
+    *r2_out = (uint32_t)(last.x * last.x + last.y * last.y);
+    return k;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Coherence candidates when at most COOP_CANDS distinct ones remain (the common case: neighbours that agree
+// propose the same source pixel): eight lanes share one candidate.  Lane u of a group gathers and weighs the
+// neighbours [u*B, (u+1)*B), B = kk8/8 <= 8, all at once; the strictly sequential f32 sum of ms.rs:1259-1280
+// is then carried through the group as a chain (lane 0 adds its products in order, hands the running sum to
+// lane 1, ...), so the additions happen in exactly the reference's order.  No early-out is possible in this
+// round (nothing has been scored yet), so nothing is lost by evaluating every neighbour.
+// ---------------------------------------------------------------------------------------------
+constexpr int COOP_CANDS = 4;
+template <bool GUIDED, bool FRAMED, bool OPAQUE>
+__device__ __forceinline__ void score_coherent_shared(const StageDev& S, WarpScratch& ws, const float* __restrict__ s_lut,
+                                                      const float* __restrict__ s_lutg, int lane, int kk, int kk8,
+                                                      int nuniq_coh, float& best, int& besti, uint32_t& fetched, uint32_t& bestcol) {
+    const int* dl = reinterpret_cast<const int*>(ws.d);
+    const int c = lane >> 3, u = lane & 7;
+    const int B = kk8 >> 3, j0 = u * B;
+    uint32_t ccol = 0;
+    float p[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] = 0.f;
+    if (c < nuniq_coh) {
+        const uint32_t cxy = ws.u.c.cxy[c];
+        const int cx = (int)(cxy & 0xFFFFu), cy = (int)(cxy >> 16);
+        const uint32_t map = ws.cmeta[c] & 0x7FFFu;
+        DevEx e = S.ex[map];
+        DevGuide ge;
+        if (GUIDED) ge = S.exg[map];
+        const char* bp = nullptr;
+        const char* gbp = nullptr;
+        if (FRAMED) {
+            const long long c4 = ((long long)cy * S.pad_pitch + cx) * 4;
+            bp = reinterpret_cast<const char*>(e.pp) + c4;
+            if (GUIDED) gbp = reinterpret_cast<const char*>(ge.pp) + c4;
+        }
+        if (u == 0) ccol = FRAMED ? __ldg(reinterpret_cast<const uint32_t*>(bp)) : __ldg(e.px + (size_t)cy * e.w + cx);
+        uint32_t tex[8], gtex[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            tex[i] = OUTSIDE_RGBA;
+            gtex[i] = OUTSIDE_RGBA;
+            if (i < B) {
+                const int j = j0 + i;
+                if (FRAMED) {
+                    const long long o4 = (long long)dl[j];
+                    tex[i] = __ldg(reinterpret_cast<const uint32_t*>(bp + o4));
+                    if (GUIDED) gtex[i] = __ldg(reinterpret_cast<const uint32_t*>(gbp + o4));
+                } else {
+                    short2 o = ws.off[j];
+                    int X = cx + o.x, Y = cy + o.y;
+                    if ((unsigned)X < (unsigned)e.w && (unsigned)Y < (unsigned)e.h) tex[i] = __ldg(e.px + (size_t)Y * e.w + X);
+                    if (GUIDED) {
+                        if ((unsigned)X < (unsigned)ge.w && (unsigned)Y < (unsigned)ge.h) gtex[i] = __ldg(ge.px + (size_t)Y * ge.w + X);
+                    }
+                }
+            }
+        }
+        fetched += (uint32_t)max(0, min(B, kk - j0));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i < B) {
+                const int j = j0 + i;
+                uint32_t dd = __vabsdiffu4(ws.tcol[j], tex[i]);
+                float t = s_lut[dd & 0xFFu];
+                t = __fadd_rn(t, s_lut[(dd >> 8) & 0xFFu]);
+                t = __fadd_rn(t, s_lut[(dd >> 16) & 0xFFu]);
+                if (!OPAQUE) t = __fadd_rn(t, s_lut[dd >> 24]);
+                if (GUIDED) {
+                    uint32_t dg = __vabsdiffu4(ws.gcol[j], gtex[i]);
+                    t = __fadd_rn(t, s_lutg[dg & 0xFFu]);
+                    t = __fadd_rn(t, s_lutg[(dg >> 8) & 0xFFu]);
+                    t = __fadd_rn(t, s_lutg[(dg >> 16) & 0xFFu]);
+                    if (!OPAQUE) t = __fadd_rn(t, s_lutg[dg >> 24]);
+                }
+                p[i] = __fmul_rn(t, ws.g[j]);
+            }
+        }
+    }
+    // the chain: slots beyond B hold +0 and the running sum is never -0, so adding them changes nothing
+    float s = 0.f;
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+        if (u == h) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s = __fadd_rn(s, p[i]);
+        }
+        s = __shfl_sync(FULL, s, (lane & ~7) | h);
+    }
+    // first strict minimum in candidate order (q11); a NaN score (degenerate weights) never wins here
+#pragma unroll
+    for (int cc = 0; cc < COOP_CANDS; ++cc) {
+        const float sc = __shfl_sync(FULL, s, cc * 8);
+        const uint32_t col = __shfl_sync(FULL, ccol, cc * 8);
+        if (cc < nuniq_coh && sc < best) { best = sc; besti = cc; bestcol = col; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// find_best_match / better_match (ms.rs:1184-1288): one lane per candidate, 32 candidates per round.
+// FRAMED: every neighbour offset is within EX_PAD, texels come from the framed copies with no bounds test.
+// OPAQUE: all alphas are 255, the alpha term lut[0] = ln(1 + 0) = +0 is dropped (t + 0 = t for t >= 0).
+// ---------------------------------------------------------------------------------------------
+template <bool GUIDED, bool FRAMED, bool OPAQUE>
+__device__ __forceinline__ void score_candidates(const StageDev& S, WarpScratch& ws, const float* __restrict__ s_lut,
+                                                 const float* __restrict__ s_lutg, int lane, int kk, int kk8, int ncand,
+                                                 int nuniq_coh, int base0, float& best, int& besti, uint32_t& fetched, uint32_t& bestcol) {
+    const int* dl = reinterpret_cast<const int*>(ws.d);
+    // coherence candidates get their own round(s) first: they establish `best`, so the random candidates
+    // (higher indices, so ties still go to the earlier candidate) early-out after a chunk or two
+    for (int base = base0; base < ncand; base = (base < nuniq_coh && base + 32 >= nuniq_coh) ? nuniq_coh : base + 32) {
+        const int lim = base < nuniq_coh ? nuniq_coh : ncand;
+        int a = base + lane;
+        float s = 0.f;
+        bool ok = false;
+        uint32_t ccol = 0;
+        if (a < lim) {
+            uint32_t cxy = ws.u.c.cxy[a];
+            uint32_t meta = ws.cmeta[a];
+            int cx = (int)(cxy & 0xFFFFu), cy = (int)(cxy >> 16);
+            int sgn = (meta & 0x8000u) ? -1 : 1;
+            uint32_t map = meta & 0x7FFFu;
+            DevEx e = S.ex[map];
+            DevGuide ge;
+            if (GUIDED) ge = S.exg[map];
+            const char* bp = nullptr;
+            const char* gbp = nullptr;
+            if (FRAMED) {
+                const long long c4 = ((long long)cy * S.pad_pitch + cx) * 4;
+                bp = reinterpret_cast<const char*>(e.pp) + c4;
+                if (GUIDED) gbp = reinterpret_cast<const char*>(ge.pp) + c4;
+            }
+            ccol = FRAMED ? __ldg(reinterpret_cast<const uint32_t*>(bp)) : __ldg(e.px + (size_t)cy * e.w + cx);
+            ok = true;
+            for (int j0 = 0; j0 < kk8; j0 += 8) {
+                uint32_t tex[8], gtex[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {  // issue the gathers of the chunk first (memory-level parallelism)
+                    const int j = j0 + u;
+                    if (FRAMED) {
+                        const long long o4 = (long long)sgn * (long long)dl[j];
+                        tex[u] = __ldg(reinterpret_cast<const uint32_t*>(bp + o4));
+                        if (GUIDED) gtex[u] = __ldg(reinterpret_cast<const uint32_t*>(gbp + o4));
+                    } else {
+                        short2 o = ws.off[j];
+                        int X = cx + sgn * o.x, Y = cy + sgn * o.y;
+                        tex[u] = OUTSIDE_RGBA;
+                        gtex[u] = OUTSIDE_RGBA;
+                        if ((unsigned)X < (unsigned)e.w && (unsigned)Y < (unsigned)e.h) tex[u] = __ldg(e.px + (size_t)Y * e.w + X);
+                        if (GUIDED) {
+                            if ((unsigned)X < (unsigned)ge.w && (unsigned)Y < (unsigned)ge.h) gtex[u] = __ldg(ge.px + (size_t)Y * ge.w + X);
+                        }
+                    }
+                }
+                fetched += (uint32_t)min(8, kk - j0);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {  // strict left-to-right f32 accumulation (ms.rs:1259-1280)
+                    const int j = j0 + u;
+                    uint32_t dd = __vabsdiffu4(ws.tcol[j], tex[u]);
+                    float t = s_lut[dd & 0xFFu];
+                    t = __fadd_rn(t, s_lut[(dd >> 8) & 0xFFu]);
+                    t = __fadd_rn(t, s_lut[(dd >> 16) & 0xFFu]);
+                    if (!OPAQUE) t = __fadd_rn(t, s_lut[dd >> 24]);
+                    if (GUIDED) {
+                        uint32_t dg = __vabsdiffu4(ws.gcol[j], gtex[u]);
+                        t = __fadd_rn(t, s_lutg[dg & 0xFFu]);
+                        t = __fadd_rn(t, s_lutg[(dg >> 8) & 0xFFu]);
+                        t = __fadd_rn(t, s_lutg[(dg >> 16) & 0xFFu]);
+                        if (!OPAQUE) t = __fadd_rn(t, s_lutg[dg >> 24]);
+                    }
+                    s = __fadd_rn(s, __fmul_rn(t, ws.g[j]));
+                }
+                // early-out vs. the best of earlier rounds (ms.rs:1281); all terms are >= 0, so testing the
+                // prefix only at chunk ends rejects exactly the same candidates
+                if (s >= best) { ok = false; break; }
+            }
+        }
+        bool win = ok && (s < best);
+        float ms = win ? s : INFINITY;
+        int ma = a;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float os = __shfl_xor_sync(FULL, ms, o);
+            int oa = __shfl_xor_sync(FULL, ma, o);
+            if (os < ms || (os == ms && oa < ma)) { ms = os; ma = oa; }
+        }
+        const uint32_t wcol = __shfl_sync(FULL, ccol, (ma - base) & 31);
+        if (ms < best) { best = ms; besti = ma; bestcol = wcol; }  // first strict minimum wins (q11)
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // One pixel resolution (steps 2-4 of ms.rs:917-986) by one warp.  No commit.
 // ---------------------------------------------------------------------------------------------
@@ -396,21 +675,28 @@ template <bool GUIDED>
 __device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws, const float* __restrict__ s_lut,
                              const float* __restrict__ s_lutg, int lane, int x, int y, uint32_t R2bound,
                              const uint32_t* __restrict__ rand_xy, const uint8_t* __restrict__ rand_map, ItemOut& out,
-                             const short2* pts = nullptr, int npts = 0) {
+                             const short2* pts = nullptr, int npts = 0, const short2* nb0 = nullptr,
+                             const short2* predl = nullptr, int npl = 0) {
     const unsigned lt = (1u << lane) - 1u;
     uint32_t r2;
     long long t0 = clock64();
-    const int kk = pts ? knn_points(S, ws, lane, x, y, pts, npts, &r2) : knn_search(S, ws, lane, x, y, R2bound, &r2);
+    const int kk = nb0 ? knn_from_lists(S, ws, lane, nb0, predl, npl, &r2)
+                 : pts ? knn_points(S, ws, lane, x, y, pts, npts, &r2) : knn_search(S, ws, lane, x, y, R2bound, &r2);
     long long t1 = clock64();
     out.c_knn = t1 - t0; out.c_neigh = out.c_weight = out.c_score = 0; out.fetched = out.nominal = 0;
     out.kk = kk;
-    out.ncand = 0; out.best = 0; out.bx = out.by = out.bmap = 0; out.bpatch = 0; out.score = 0.f;
+    out.ncand = 0; out.best = 0; out.bx = out.by = out.bmap = 0; out.bpatch = 0; out.score = 0.f; out.bcol = 0; out.bcol_valid = 0;
     if (kk == 0) return;
+    // the first 64 random candidates of this item: requested now, consumed after the neighbourhood is built
+    uint32_t rxy0 = 0, rxy1 = 0, rmp0 = 0, rmp1 = 0;
+    if (lane < S.m) { rxy0 = __ldg(rand_xy + lane); rmp0 = __ldg(rand_map + lane); }
+    if (lane + 32 < S.m) { rxy1 = __ldg(rand_xy + lane + 32); rmp1 = __ldg(rand_map + lane + 32); }
+    const int ew0 = S.ex[0].w;
     const int W = S.W, H = S.H;
     // ---- neighbour state, distances (ms.rs:405-425), coherence candidates (ms.rs:496-547) ----
-    const double dimx = (double)W, dimy = (double)H;
-    const double x2 = __ddiv_rn((double)x, dimx), y2 = __ddiv_rn((double)y, dimy);
+    const double x2 = __ldg(S.divx + x + S.mx), y2 = __ldg(S.divy + y + S.my);
     int ncand = 0;
+    int reach = 0;  // largest |offset component| of the neighbourhood
     for (int base = 0; base < kk; base += 32) {
         int j = base + lane;
         bool valid = false;
@@ -418,6 +704,7 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws,
         uint16_t cmeta = 0;
         if (j < kk) {
             short2 o = ws.off[j];
+            reach = max(reach, max(abs((int)o.x), abs((int)o.y)));
             int nx = x + o.x, ny = y + o.y;
             int qx = nx, qy = ny;
             if (S.tiling) { qx = imod(nx, W); qy = imod(ny, H); }
@@ -429,7 +716,7 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws,
                 ws.gcol[j] = ((unsigned)gx < (unsigned)S.tgw && (unsigned)gy < (unsigned)S.tgh)
                                  ? __ldg(S.tguide + (size_t)gy * S.tgw + gx) : OUTSIDE_RGBA;
             }
-            double x1 = __ddiv_rn((double)nx, dimx), y1 = __ddiv_rn((double)ny, dimy);
+            double x1 = __ldg(S.divx + nx + S.mx), y1 = __ldg(S.divy + ny + S.my);
             double ddx = __dsub_rn(x1, x2), ddy = __dsub_rn(y1, y2);
             ws.d[j] = __fma_rn(ddx, ddx, __dmul_rn(ddy, ddy));
             int sx = (int)(st.y & 0xFFFFu), sy = (int)(st.y >> 16);
@@ -463,7 +750,15 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws,
         }
         double avg = __ddiv_rn(sum, (double)(kk * 4));
         degenerate = (avg == 0.0);  // only neighbour = the pixel itself (k = 1 redo): 0/0 -> NaN weights in the reference
-        for (int j = lane; j < kk; j += 32) ws.g[j] = (float)exp(-__ddiv_rn(ws.d[j], avg));
+        for (int j = lane; j < kk; j += 64) {  // two independent evaluations per lane in flight
+            const int j1 = j + 32;
+            const bool two = j1 < kk;
+            const double q0 = -__ddiv_rn(ws.d[j], avg);
+            const double q1 = two ? -__ddiv_rn(ws.d[j1], avg) : 0.0;
+            const double e0 = exp(q0), e1 = exp(q1);
+            ws.g[j] = (float)e0;
+            if (two) ws.g[j1] = (float)e1;
+        }
     }
     const int kk8 = (kk + 7) & ~7;
     // pad to a multiple of 8 with zero-weight neighbours: t * 0 = +0 and s + 0 = s, so the sum is unchanged
@@ -503,11 +798,13 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws,
     const int nuniq_coh = ncand;
     // ---- random candidates (ms.rs:549-599), pre-generated by k_rand_candidates ----
     for (int r = lane; r < S.m; r += 32) {
-        uint32_t xy = __ldg(rand_xy + r);
-        uint32_t map = __ldg(rand_map + r);
+        uint32_t xy, map;
+        if (r < 32) { xy = rxy0; map = rmp0; }
+        else if (r < 64) { xy = rxy1; map = rmp1; }
+        else { xy = __ldg(rand_xy + r); map = __ldg(rand_map + r); }
         int pos = ncand + r;
         ws.u.c.cxy[pos] = xy;
-        ws.u.c.cpatch[pos] = (xy >> 16) * (uint32_t)S.ex[map].w + (xy & 0xFFFFu);  // ms.rs:577
+        ws.u.c.cpatch[pos] = (xy >> 16) * (uint32_t)(S.n_ex == 1 ? ew0 : S.ex[map].w) + (xy & 0xFFFFu);  // ms.rs:577
         ws.cmeta[pos] = (uint16_t)(map | 0x8000u);
         ws.corig[pos] = (uint8_t)(ncoh + r);
     }
@@ -518,72 +815,25 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws,
     // ---- find_best_match / better_match (ms.rs:1184-1288): one lane per candidate ----
     float best = FLT_MAX;
     int besti = 0;
-    uint32_t fetched = 0;
-    // coherence candidates get their own round(s) first: they establish `best`, so the random candidates
-    // (higher indices, so ties still go to the earlier candidate) early-out after a chunk or two
-    for (int base = 0; base < ncand; base = (base < nuniq_coh && base + 32 >= nuniq_coh) ? nuniq_coh : base + 32) {
-        const int lim = base < nuniq_coh ? nuniq_coh : ncand;
-        int a = base + lane;
-        float s = 0.f;
-        bool ok = false;
-        if (a < lim) {
-            uint32_t cxy = ws.u.c.cxy[a];
-            uint32_t meta = ws.cmeta[a];
-            int cx = (int)(cxy & 0xFFFFu), cy = (int)(cxy >> 16);
-            int sgn = (meta & 0x8000u) ? -1 : 1;
-            uint32_t map = meta & 0x7FFFu;
-            DevEx e = S.ex[map];
-            DevGuide ge;
-            if (GUIDED) ge = S.exg[map];
-            ok = true;
-            for (int j0 = 0; j0 < kk8; j0 += 8) {
-                uint32_t tex[8], gtex[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {  // issue the gathers of the chunk first (memory-level parallelism)
-                    const int j = j0 + u;
-                    short2 o = ws.off[j];
-                    int X = cx + sgn * o.x, Y = cy + sgn * o.y;
-                    tex[u] = OUTSIDE_RGBA;
-                    gtex[u] = OUTSIDE_RGBA;
-                    if ((unsigned)X < (unsigned)e.w && (unsigned)Y < (unsigned)e.h) tex[u] = __ldg(e.px + (size_t)Y * e.w + X);
-                    if (GUIDED) {
-                        if ((unsigned)X < (unsigned)ge.w && (unsigned)Y < (unsigned)ge.h) gtex[u] = __ldg(ge.px + (size_t)Y * ge.w + X);
-                    }
-                }
-                fetched += (uint32_t)min(8, kk - j0);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {  // strict left-to-right f32 accumulation (ms.rs:1259-1280)
-                    const int j = j0 + u;
-                    uint32_t dd = __vabsdiffu4(ws.tcol[j], tex[u]);
-                    float t = s_lut[dd & 0xFFu];
-                    t = __fadd_rn(t, s_lut[(dd >> 8) & 0xFFu]);
-                    t = __fadd_rn(t, s_lut[(dd >> 16) & 0xFFu]);
-                    t = __fadd_rn(t, s_lut[dd >> 24]);
-                    if (GUIDED) {
-                        uint32_t dg = __vabsdiffu4(ws.gcol[j], gtex[u]);
-                        t = __fadd_rn(t, s_lutg[dg & 0xFFu]);
-                        t = __fadd_rn(t, s_lutg[(dg >> 8) & 0xFFu]);
-                        t = __fadd_rn(t, s_lutg[(dg >> 16) & 0xFFu]);
-                        t = __fadd_rn(t, s_lutg[dg >> 24]);
-                    }
-                    s = __fadd_rn(s, __fmul_rn(t, ws.g[j]));
-                }
-                // early-out vs. the best of earlier rounds (ms.rs:1281); all terms are >= 0, so testing the
-                // prefix only at chunk ends rejects exactly the same candidates
-                if (s >= best) { ok = false; break; }
-            }
-        }
-        bool win = ok && (s < best);
-        float ms = win ? s : INFINITY;
-        int ma = a;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            float os = __shfl_xor_sync(FULL, ms, o);
-            int oa = __shfl_xor_sync(FULL, ma, o);
-            if (os < ms || (os == ms && oa < ma)) { ms = os; ma = oa; }
-        }
-        if (ms < best) { best = ms; besti = ma; }  // first strict minimum wins (q11)
+    uint32_t fetched = 0, bestcol = 0;
+    reach = __reduce_max_sync(FULL, reach);
+    const bool framed = S.pad_pitch != 0 && reach <= EX_PAD;
+    if (framed) {
+        // linear texel offsets (bytes) of the neighbourhood in the framed copies; the distances are dead by now
+        int* dl = reinterpret_cast<int*>(ws.d);
+        for (int j = lane; j < kk8; j += 32) { short2 o = ws.off[j]; dl[j] = ((int)o.y * S.pad_pitch + (int)o.x) * 4; }
+        __syncwarp();
     }
+    const bool shared_round = nuniq_coh >= 1 && nuniq_coh <= COOP_CANDS && kk8 <= 64;
+    const int base0 = shared_round ? nuniq_coh : 0;
+#define TSB_SCORE(FR, OP)                                                                                              \
+    do {                                                                                                               \
+        if (shared_round) score_coherent_shared<GUIDED, FR, OP>(S, ws, s_lut, s_lutg, lane, kk, kk8, nuniq_coh, best, besti, fetched, bestcol); \
+        score_candidates<GUIDED, FR, OP>(S, ws, s_lut, s_lutg, lane, kk, kk8, ncand, nuniq_coh, base0, best, besti, fetched, bestcol); \
+    } while (0)
+    if (framed) { if (S.opaque) TSB_SCORE(true, true); else TSB_SCORE(true, false); }
+    else { if (S.opaque) TSB_SCORE(false, true); else TSB_SCORE(false, false); }
+#undef TSB_SCORE
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) fetched += __shfl_xor_sync(FULL, fetched, o);
     long long t4 = clock64();
@@ -602,6 +852,8 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws,
     out.by = (int)(bxy >> 16);
     out.bmap = (int)(ws.cmeta[besti] & 0x7FFFu);
     out.bpatch = ws.u.c.cpatch[besti];
+    out.bcol = bestcol;
+    out.bcol_valid = (!degenerate && best != FLT_MAX) ? 1 : 0;
     out.score = best;
     __syncwarp();
 }
@@ -631,7 +883,7 @@ __device__ __forceinline__ void commit_item(const StageDev& S, const PhaseDev& P
                                             bool to_peers = false) {
     if (o.kk > 0) {
         DevEx e = S.ex[o.bmap];
-        uint32_t col = __ldg(e.px + (size_t)o.by * e.w + o.bx);
+        const uint32_t col = o.bcol_valid ? o.bcol : __ldg(e.px + (size_t)o.by * e.w + o.bx);
         const uint4 v = make_uint4(col, (uint32_t)o.bx | ((uint32_t)o.by << 16), o.bpatch, (uint32_t)o.bmap | ((uint32_t)o.bmap << 16));
         if (!MG || !to_peers) {
             // local replica only.  In a band-sharded phase the owner pushes its band rows to the peers in bulk after
@@ -756,9 +1008,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_flow(StageDev S, PhaseDev P,
     load_luts(S, sm.lut, sm.lutg);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpScratch& ws = sm.ws[warp];
-    unsigned long long st_acc[ST_COUNT];
-#pragma unroll
-    for (int i = 0; i < ST_COUNT; ++i) st_acc[i] = 0ull;
+    if (lane < 16) ws.stat[lane] = 0ull;  // statistics live in shared memory, updated by lane 0
+    __syncwarp();
+    const bool pref = !MG && F.stride != 0u;  // fixed-stride successor lists are complete before this kernel starts
     volatile uint32_t* vq = F.queue;
     volatile uint32_t* vctl = F.ctl;
     const bool skip = F.stride && vctl[FC_OVERFLOW];  // incomplete successor lists: do nothing, the host re-plans the phase
@@ -784,16 +1036,35 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_flow(StageDev S, PhaseDev P,
         it = __shfl_sync(FULL, it, 0);
         if (it == NONE32) break;
         __threadfence();  // acquire: commits of all predecessors are visible below
-        st_acc[ST_CYC_READY] += (unsigned long long)(clock64() - tr0);
+        if (lane == 0) ws.stat[ST_CYC_READY] += (unsigned long long)(clock64() - tr0);
+        if (pref) {
+            // the item's successor list is needed only after its commit: start copying it to shared memory now
+            cp_async_u32(&ws.succ_pref[lane], F.succ + (size_t)it * F.stride + lane);
+            if (lane == 0) cp_async_u32(&ws.nsucc_pref, F.nsucc + it);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
         const uint32_t flat = P.item_pixel[it];
         const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
         const uint32_t si = P.stage_base + it;
+        {   // the random candidates are read late (after the neighbourhood is built) and usually come from HBM: pull them in now
+            const char* rx = reinterpret_cast<const char*>(P.rand_xy + (size_t)si * S.m);
+            for (int b = lane * 128; b < S.m * 4; b += 32 * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(rx + b));
+            if (lane == 31) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.rand_map + (size_t)si * S.m));
+        }
         ItemOut o;
+        const short2* nb0 = nullptr;
+        const short2* predl = nullptr;
+        int npl = 0;
+        if (P.nb0) {  // neighbour lists from the phase analysis
+            const uint32_t c = P.npredl[it];
+            if (c <= P.predl_stride) { nb0 = P.nb0 + (size_t)it * S.k; predl = P.predl + (size_t)it * P.predl_stride; npl = (int)c; }
+        }
         resolve_item<GUIDED>(S, ws, sm.lut, sm.lutg, lane, x, y, P.item_R2[it], P.rand_xy + (size_t)si * S.m,
-                             P.rand_map + (size_t)si * S.m, o);
+                             P.rand_map + (size_t)si * S.m, o, nullptr, 0, nb0, predl, npl);
         long long tc0 = clock64();
+        if (pref) { asm volatile("cp.async.wait_all;" ::: "memory"); __syncwarp(); }
         const size_t s0 = F.stride ? (size_t)it * F.stride : (size_t)F.succ_off[it];
-        const size_t s1 = F.stride ? s0 + F.nsucc[it] : (size_t)F.succ_off[it + 1];
+        const size_t s1 = F.stride ? s0 + (pref ? ws.nsucc_pref : F.nsucc[it]) : (size_t)F.succ_off[it + 1];
         bool remote_succ = false;
         if (MG) {
             // Only an item with a successor on another GPU needs its commit ordered at system scope (that successor is
@@ -815,7 +1086,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_flow(StageDev S, PhaseDev P,
         // notify successors; the one that drops a counter to zero publishes the item
         if (!MG) {
             for (size_t e = s0 + lane; e < s1; e += 32) {
-                uint32_t sc = F.succ[e];
+                uint32_t sc = (pref && e < s0 + 32) ? ws.succ_pref[lane] : F.succ[e];
                 // every predecessor made its commit visible (fence) BEFORE its decrement and consumers read the
                 // mutable state with L2 loads, so the publisher needs no further fence
                 if (atomicSub(F.npred + sc, 1u) == 1u) vq[atomicAdd(F.ctl + FC_TAIL, 1u)] = sc;
@@ -838,15 +1109,17 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_flow(StageDev S, PhaseDev P,
                 }
             }
         }
-        st_acc[ST_FETCHED] += o.fetched; st_acc[ST_NOMINAL] += o.nominal; st_acc[ST_CANDS] += (unsigned long long)o.ncand;
-        st_acc[ST_ITEMS] += 1ull;
-        st_acc[ST_CYC_KNN] += (unsigned long long)o.c_knn; st_acc[ST_CYC_NEIGH] += (unsigned long long)o.c_neigh;
-        st_acc[ST_CYC_WEIGHT] += (unsigned long long)o.c_weight; st_acc[ST_CYC_SCORE] += (unsigned long long)o.c_score;
-        st_acc[ST_CYC_COMMIT] += (unsigned long long)(clock64() - tc0);
+        if (lane == 0) {
+            ws.stat[ST_FETCHED] += o.fetched; ws.stat[ST_NOMINAL] += o.nominal; ws.stat[ST_CANDS] += (unsigned long long)o.ncand;
+            ws.stat[ST_ITEMS] += 1ull;
+            ws.stat[ST_CYC_KNN] += (unsigned long long)o.c_knn; ws.stat[ST_CYC_NEIGH] += (unsigned long long)o.c_neigh;
+            ws.stat[ST_CYC_WEIGHT] += (unsigned long long)o.c_weight; ws.stat[ST_CYC_SCORE] += (unsigned long long)o.c_score;
+            ws.stat[ST_CYC_COMMIT] += (unsigned long long)(clock64() - tc0);
+        }
+        __syncwarp();
     }
     if (lane == 0 && S.counters) {
-#pragma unroll
-        for (int i = 0; i < ST_COUNT; ++i) if (st_acc[i]) atomicAdd(&rs.stat[i], st_acc[i]);
+        for (int i = 0; i < ST_COUNT; ++i) if (ws.stat[i]) atomicAdd(&rs.stat[i], ws.stat[i]);
     }
     __syncthreads();
     if (S.counters && threadIdx.x < ST_COUNT && rs.stat[threadIdx.x]) atomicAdd(S.counters + threadIdx.x, rs.stat[threadIdx.x]);
@@ -969,6 +1242,10 @@ __global__ void __launch_bounds__(CTA_THREADS) k_radius(StageDev S, PhaseDev P, 
         if (S.mg && mg_owner_y(S.mg, y) != S.mg->rank) continue;  // band-sharded: the owner computes the radius
         uint32_t r2;
         knn_search<true>(S, ws, lane, x, y, R2_INF, &r2);
+        if (P.nb0) {
+            if (r2 != R2_INF) for (int j = lane; j < S.k; j += 32) P.nb0[(size_t)it * S.k + j] = ws.off[j];
+            if (lane == 0) P.npredl[it] = r2 != R2_INF ? 0u : PREDL_UNUSABLE;
+        }
         if (lane == 0) {
             if (!S.mg) P.item_R2[it] = r2;
             else {
@@ -1100,6 +1377,31 @@ __device__ __forceinline__ void edge_visit(const StageDev& S, const PhaseDev& P,
     if (j < it) edge_emit<PASS>(F, j, it);                       // `it` sees j from its own disc
     else if (D > P.item_R2[j]) edge_emit<PASS>(F, it, j);        // j does not see `it`: registered from this side
 }
+// A tiling canvas so small that one disc of the dense walk can meet the same pixel through two wrapped offsets while
+// the (clipped) large-radius walk meets it once: the split bookkeeping below needs both sides to agree, so such
+// canvases keep the one-sided registration (and no neighbour lists, see run_phase_flow).
+__device__ __forceinline__ bool tiny_torus(const StageDev& S) { return S.tiling && (S.W < 100 || S.H < 100); }
+// the bookkeeping scheme of the single-GPU fixed-stride pass (see k_edges_scan) for one visited pixel, plain atomics
+__device__ __forceinline__ void edge_visit_own(const StageDev& S, const PhaseDev& P, const FlowDev& F, uint32_t it, int qx, int qy, uint32_t D) {
+    if (S.tiling) { qx = imod(qx, S.W); qy = imod(qy, S.H); }
+    else if ((unsigned)qx >= (unsigned)S.W || (unsigned)qy >= (unsigned)S.H) return;
+    const uint32_t j = P.pmap[(size_t)qy * S.W + qx];
+    if (j == NONE32 || j == it) return;
+    const bool blind = D > P.item_R2[j];
+    if (j < it) {
+        atomicAdd(F.npred + it, 1u);
+        if (blind) {
+            const uint32_t slot = atomicAdd(F.nsucc + j, 1u);
+            if (slot < F.stride) F.succ[(size_t)j * F.stride + slot] = it;
+            else F.ctl[FC_OVERFLOW] = 1u;
+        }
+    } else {
+        const uint32_t slot = atomicAdd(F.nsucc + it, 1u);
+        if (slot < F.stride) F.succ[(size_t)it * F.stride + slot] = j;
+        else F.ctl[FC_OVERFLOW] = 1u;
+        if (blind) atomicAdd(F.npred + j, 1u);
+    }
+}
 template <int PASS>
 __global__ void __launch_bounds__(CTA_THREADS) k_edges_scan(StageDev S, PhaseDev P, FlowDev F) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1113,6 +1415,73 @@ __global__ void __launch_bounds__(CTA_THREADS) k_edges_scan(StageDev S, PhaseDev
             // row-major walk over the bounding square of the disc: consecutive lanes read consecutive pixels of
             // the pending-index map (coalesced), unlike the distance-ordered spiral table
             const int r = isqrt_u32(R2), side = 2 * r + 1, cells = side * side;
+            if (PASS == 2 && !S.mg && !tiny_torus(S)) {
+                // Single-GPU fixed-stride build.  Whoever SEES the other end of an edge does its own half of the
+                // bookkeeping: the lower item appends the higher one to its own successor list, the higher item
+                // counts the lower one in its own predecessor counter.  Both are the same address for the whole
+                // warp, so they are aggregated (one atomic per chunk / per item); only the half that belongs to an
+                // item which does NOT see this one (its radius is smaller than the distance) needs a remote atomic.
+                uint32_t n_in = 0, n_pl = 0;
+                const bool want_pl = P.nb0 != nullptr && P.is_new != 0u;
+                for (int c0 = 0; c0 < cells; c0 += 32) {
+                    const int c = c0 + lane;
+                    int kind = 0; uint32_t j = NONE32;  // kind 1: lower item in the disc, 2: higher item in the disc
+                    bool blind = false;                 // the other item does not see this one
+                    bool pl = false; short2 plo = make_short2(0, 0);
+                    if (c < cells) {
+                        const int dy = c / side - r, dx = c % side - r;
+                        const uint32_t D = (uint32_t)(dx * dx + dy * dy);
+                        if (D <= R2) {
+                            int qx = x + dx, qy = y + dy;
+                            bool in = true;
+                            if (S.tiling) { qx = imod(qx, S.W); qy = imod(qy, S.H); }
+                            else in = (unsigned)qx < (unsigned)S.W && (unsigned)qy < (unsigned)S.H;
+                            if (in) {
+                                j = P.pmap[(size_t)qy * S.W + qx];
+                                if (j != NONE32 && j != it) {
+                                    kind = j < it ? 1 : 2;
+                                    blind = D > P.item_R2[j];
+                                    // a lower item whose pixel (or mirror copy) will be a point inside this disc
+                                    if (want_pl && kind == 1 && point_exists_at(S, x + dx, y + dy)) { pl = true; plo = make_short2((short)dx, (short)dy); }
+                                }
+                            }
+                        }
+                    }
+                    if (kind == 1) {
+                        ++n_in;
+                        if (blind) {  // j cannot know about this successor: put it on j's list from here
+                            const uint32_t slot = atomicAdd(F.nsucc + j, 1u);
+                            if (slot < F.stride) F.succ[(size_t)j * F.stride + slot] = it;
+                            else F.ctl[FC_OVERFLOW] = 1u;
+                        }
+                    }
+                    if (want_pl) {
+                        const uint32_t bpl = __ballot_sync(FULL, pl);
+                        if (pl) {
+                            const uint32_t slot = n_pl + __popc(bpl & ((1u << lane) - 1u));
+                            if (slot < P.predl_stride) P.predl[(size_t)it * P.predl_stride + slot] = plo;
+                        }
+                        n_pl += __popc(bpl);
+                    }
+                    const uint32_t bout = __ballot_sync(FULL, kind == 2);
+                    if (bout) {
+                        const int leader = __ffs(bout) - 1;
+                        uint32_t base = 0;
+                        if (lane == leader) base = atomicAdd(F.nsucc + it, (uint32_t)__popc(bout));
+                        base = __shfl_sync(FULL, base, leader);
+                        if (kind == 2) {
+                            const uint32_t slot = base + __popc(bout & ((1u << lane) - 1u));
+                            if (slot < F.stride) F.succ[(size_t)it * F.stride + slot] = j;
+                            else F.ctl[FC_OVERFLOW] = 1u;
+                            if (blind) atomicAdd(F.npred + j, 1u);  // j does not count this predecessor itself
+                        }
+                    }
+                }
+                n_in = __reduce_add_sync(FULL, n_in);
+                if (lane == 0 && n_in) atomicAdd(F.npred + it, n_in);
+                if (want_pl && lane == 0) P.npredl[it] = n_pl;
+                continue;
+            }
             for (int c = lane; c < cells; c += 32) {
                 const int dy = c / side - r, dx = c % side - r;
                 const uint32_t D = (uint32_t)(dx * dx + dy * dy);
@@ -1122,10 +1491,26 @@ __global__ void __launch_bounds__(CTA_THREADS) k_edges_scan(StageDev S, PhaseDev
             int rmaxx = S.tiling ? S.W / 2 : S.W, rmaxy = S.tiling ? S.H / 2 : S.H;
             int r = isqrt_u32(R2);
             int ry = min(r, rmaxy);
+            // in-disc predecessor list: not for the torus walk (it does not enumerate the mirror copies) and not for R2_INF
+            const bool want_pl = PASS == 2 && !S.mg && P.nb0 != nullptr && P.is_new != 0u;
+            const bool can_pl = want_pl && !S.tiling && R2 != R2_INF;
+            if (want_pl && !can_pl && lane == 0) P.npredl[it] = PREDL_UNUSABLE;
             for (int dy = -ry; dy <= ry; ++dy) {
                 int w = min(isqrt_u32(R2 - (uint32_t)(dy * dy)), rmaxx);
-                for (int dx = -w + lane; dx <= w; dx += 32)
-                    edge_visit<PASS>(S, P, F, it, x + dx, y + dy, (uint32_t)(dx * dx + dy * dy));
+                for (int dx = -w + lane; dx <= w; dx += 32) {
+                    if (PASS == 2 && !S.mg && !tiny_torus(S)) edge_visit_own(S, P, F, it, x + dx, y + dy, (uint32_t)(dx * dx + dy * dy));
+                    else edge_visit<PASS>(S, P, F, it, x + dx, y + dy, (uint32_t)(dx * dx + dy * dy));
+                    if (can_pl) {
+                        const int qx = x + dx, qy = y + dy;
+                        if ((unsigned)qx < (unsigned)S.W && (unsigned)qy < (unsigned)S.H) {
+                            const uint32_t j = P.pmap[(size_t)qy * S.W + qx];
+                            if (j < it) {  // NONE32 is never below an item index
+                                const uint32_t slot = atomicAdd(P.npredl + it, 1u);
+                                if (slot < P.predl_stride) P.predl[(size_t)it * P.predl_stride + slot] = make_short2((short)dx, (short)dy);
+                            }
+                        }
+                    }
+                }
             }
         }
     }
@@ -1138,17 +1523,32 @@ __global__ void __launch_bounds__(CTA_THREADS) k_edges_pairs(StageDev S, PhaseDe
         const uint32_t flat = P.item_pixel[it];
         const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
         const uint32_t R2 = P.item_R2[it];
+        const bool want_pl = PASS == 2 && !S.mg && P.nb0 != nullptr && P.is_new != 0u;
+        const bool can_pl = want_pl && !S.tiling && R2 != R2_INF;
+        uint32_t n_pl = 0;
         for (uint32_t base = 0; base < it; base += 32) {
             uint32_t j = base + lane;
+            bool pl = false; short2 plo = make_short2(0, 0);
             if (j < it) {
                 uint32_t fj = P.item_pixel[j];
-                int dx = abs((int)(fj % (uint32_t)S.W) - x), dy = abs((int)(fj / (uint32_t)S.W) - y);
+                const int sdx = (int)(fj % (uint32_t)S.W) - x, sdy = (int)(fj / (uint32_t)S.W) - y;
+                int dx = abs(sdx), dy = abs(sdy);
                 if (S.tiling) { dx = min(dx, S.W - dx); dy = min(dy, S.H - dy); }
                 unsigned long long D = (unsigned long long)dx * dx + (unsigned long long)dy * dy;
                 uint32_t Rm = max(R2, P.item_R2[j]);
                 if ((Rm == R2_INF) || (D <= (unsigned long long)Rm)) edge_emit<PASS>(F, j, it);
+                if (can_pl && D <= (unsigned long long)R2) { pl = true; plo = make_short2((short)sdx, (short)sdy); }
+            }
+            if (can_pl) {
+                const uint32_t bpl = __ballot_sync(FULL, pl);
+                if (pl) {
+                    const uint32_t slot = n_pl + __popc(bpl & ((1u << lane) - 1u));
+                    if (slot < P.predl_stride) P.predl[(size_t)it * P.predl_stride + slot] = plo;
+                }
+                n_pl += __popc(bpl);
             }
         }
+        if (want_pl && lane == 0) P.npredl[it] = can_pl ? n_pl : PREDL_UNUSABLE;
     }
 }
 __global__ void k_seed_queue(StageDev S, PhaseDev P, FlowDev F) {
@@ -1170,26 +1570,44 @@ __global__ void k_seed_queue(StageDev S, PhaseDev P, FlowDev F) {
 __global__ void k_rand_candidates(const DevEx* ex, int n_ex, int m, uint64_t seed_base, uint32_t n,
                                   uint32_t* rand_xy, uint8_t* rand_map, const uint32_t* own_pixel = nullptr, int W = 1,
                                   int band_h = 1, int rank = 0, int world = 1) {
-    uint32_t it = blockIdx.x * blockDim.x + threadIdx.x;
-    if (it >= n) return;
-    if (own_pixel) {  // band-sharded phase: only the owner of the item needs its candidates
+    // each thread draws the m candidates of one item into shared memory; the block then writes its (contiguous)
+    // slice of the two arrays with coalesced stores
+    extern __shared__ __align__(16) unsigned char rc_smem[];
+    uint32_t* sxy = reinterpret_cast<uint32_t*>(rc_smem);                    // [blockDim.x][m]
+    uint8_t* smap = rc_smem + (size_t)blockDim.x * m * 4;                    // [blockDim.x][m]
+    uint8_t* sown = smap + (size_t)blockDim.x * m;                           // [blockDim.x]
+    const uint32_t it0 = blockIdx.x * blockDim.x;
+    const uint32_t it = it0 + threadIdx.x;
+    bool mine = it < n;
+    if (mine && own_pixel) {  // band-sharded phase: only the owner of the item needs its candidates
         int r = (int)(own_pixel[it] / (uint32_t)W) / band_h;
-        if ((r < world - 1 ? r : world - 1) != rank) return;
+        mine = (r < world - 1 ? r : world - 1) == rank;
     }
-    Pcg32 rng = Pcg32::seed_from_u64(seed_base + (uint64_t)it);
-    uint32_t* oxy = rand_xy + (size_t)it * m;
-    uint8_t* om = rand_map + (size_t)it * m;
-    for (int r = 0; r < m; ++r) {
-        uint32_t map = (uint32_t)rng.gen_range_usize((uint64_t)n_ex);
-        DevEx e = ex[map];
-        uint32_t rx, ry;
-        for (;;) {
-            rx = rng.gen_range_u32((uint32_t)e.w);
-            ry = rng.gen_range_u32((uint32_t)e.h);
-            if (!e.smask || e.smask[(size_t)ry * e.w + rx] != 0) break;
+    sown[threadIdx.x] = mine ? 1 : 0;
+    if (mine) {
+        Pcg32 rng = Pcg32::seed_from_u64(seed_base + (uint64_t)it);
+        uint32_t* oxy = sxy + (size_t)threadIdx.x * m;
+        uint8_t* om = smap + (size_t)threadIdx.x * m;
+        for (int r = 0; r < m; ++r) {
+            uint32_t map = (uint32_t)rng.gen_range_usize((uint64_t)n_ex);
+            DevEx e = ex[map];
+            uint32_t rx, ry;
+            for (;;) {
+                rx = rng.gen_range_u32((uint32_t)e.w);
+                ry = rng.gen_range_u32((uint32_t)e.h);
+                if (!e.smask || e.smask[(size_t)ry * e.w + rx] != 0) break;
+            }
+            oxy[r] = rx | (ry << 16);
+            om[r] = (uint8_t)map;
         }
-        oxy[r] = rx | (ry << 16);
-        om[r] = (uint8_t)map;
+    }
+    __syncthreads();
+    const uint32_t rows = min((uint32_t)blockDim.x, n > it0 ? n - it0 : 0u);
+    const uint32_t total = rows * (uint32_t)m;
+    uint32_t* gxy = rand_xy + (size_t)it0 * m;
+    uint8_t* gmap = rand_map + (size_t)it0 * m;
+    for (uint32_t f = threadIdx.x; f < total; f += blockDim.x) {
+        if (sown[f / (uint32_t)m]) { gxy[f] = sxy[f]; gmap[f] = smap[f]; }
     }
 }
 
@@ -1258,6 +1676,44 @@ __global__ void k_recolour(StageDev S) {
 }
 
 // (re)insert resolved pixels into the mask with their tiling mirrors (ms.rs:764-778)
+// framed copies of all levels of one pyramid (see EX_PAD); flag[0] is raised when a source texel has alpha != 255
+__global__ void k_frame_levels(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int w, int h, int levels, uint32_t* flag) {
+    const int pw = w + 2 * EX_PAD, ph = h + 2 * EX_PAD;
+    const size_t per = (size_t)pw * ph, n = per * (size_t)levels;
+    bool bad = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int l = (int)(i / per);
+        const size_t r = i - (size_t)l * per;
+        const int Y = (int)(r / pw) - EX_PAD, X = (int)(r % pw) - EX_PAD;
+        uint32_t v = OUTSIDE_RGBA;
+        if ((unsigned)X < (unsigned)w && (unsigned)Y < (unsigned)h) {
+            v = src[(size_t)l * w * h + (size_t)Y * w + X];
+            bad |= (v >> 24) != 0xFFu;
+        }
+        dst[i] = v;
+    }
+    if (bad) *flag = 1u;
+}
+__global__ void k_alpha_check(const uint32_t* __restrict__ src, size_t n, uint32_t* flag) {
+    bool bad = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) bad |= (src[i] >> 24) != 0xFFu;
+    if (bad) *flag = 1u;
+}
+// colours already in the synthesis state: resolved pixels only, or every pixel for a loaded snapshot
+__global__ void k_state_alpha_check(StageDev S, int all_pixels, uint32_t* flag) {
+    const size_t n = (size_t)S.W * S.H;
+    bool bad = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        bool look = all_pixels != 0;
+        if (!look) {
+            const int X = (int)(i % (size_t)S.W) + S.mx, Y = (int)(i / (size_t)S.W) + S.my;
+            look = (S.mask[(size_t)Y * S.wpr + (X >> 5)] >> (X & 31)) & 1u;
+        }
+        if (look) bad |= (S.state[i].x >> 24) != 0xFFu;
+    }
+    if (bad) *flag = 1u;
+}
+
 __global__ void k_mask_insert_flat(StageDev S, const uint32_t* flat, uint32_t n, int mirrors) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
