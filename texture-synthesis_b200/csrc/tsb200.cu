@@ -1195,7 +1195,10 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
             size_t base = resolved_now - g->inpaint_locked;
             // every item still depends on (almost) all earlier ones: one warp runs them in order, keeping the whole
             // resolved set as a point list in shared memory while it fits the key buffer
-            const size_t serial_until = std::max<size_t>(2 * (size_t)k, (size_t)KBUF - 32);
+            // (the dataflow kernel overlaps the independent parts of consecutive items, so it takes over as soon as
+            // every item can find its k neighbours, i.e. the radii are finite)
+            size_t serial_until = std::max<size_t>((size_t)k + 14, 64);
+            if (const char* e = getenv("TSB_SERIAL_UNTIL")) serial_until = std::max<size_t>((size_t)k + 1, (size_t)atoi(e));
             const bool serial = base < serial_until;
             size_t n_e = serial ? (g->use_rounds ? 1 : std::min(n_items - cur, serial_until - base)) : std::min(n_items - cur, base);
             S.r2_hint = r2_hint_for(g, resolved_now, k);

@@ -151,9 +151,9 @@ struct __align__(16) WarpScratch {
     uint32_t tcol[KMAX];
     uint32_t gcol[KMAX];
     uint32_t succ_pref[32];   // k_flow: the first 32 successors of the current item, copied in asynchronously
-    uint32_t nsucc_pref;
+    uint32_t nsucc_pref, nrem_pref;
     int cnt;
-    int pad[2];
+    int pad[1];
     unsigned long long stat[16];  // per-warp run statistics (ST_*), kept out of the registers
 };
 
@@ -1041,6 +1041,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_flow(StageDev S, PhaseDev P,
             // the item's successor list is needed only after its commit: start copying it to shared memory now
             cp_async_u32(&ws.succ_pref[lane], F.succ + (size_t)it * F.stride + lane);
             if (lane == 0) cp_async_u32(&ws.nsucc_pref, F.nsucc + it);
+            if (lane == 1) cp_async_u32(&ws.nrem_pref, F.succ_cur + it);
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
         const uint32_t flat = P.item_pixel[it];
@@ -1085,8 +1086,13 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_flow(StageDev S, PhaseDev P,
         __syncwarp();
         // notify successors; the one that drops a counter to zero publishes the item
         if (!MG) {
-            for (size_t e = s0 + lane; e < s1; e += 32) {
-                uint32_t sc = (pref && e < s0 + 32) ? ws.succ_pref[lane] : F.succ[e];
+            // fixed-stride lists: own entries from the front, entries registered by other items from the back
+            const uint32_t n_back = F.stride ? (pref ? ws.nrem_pref : F.succ_cur[it]) : 0u;
+            const size_t n_all = (s1 - s0) + n_back;
+            for (size_t e = lane; e < n_all; e += 32) {
+                uint32_t sc;
+                if (e < s1 - s0) sc = (pref && e < 32) ? ws.succ_pref[lane] : F.succ[s0 + e];
+                else sc = F.succ[s0 + F.stride - 1u - (e - (s1 - s0))];
                 // every predecessor made its commit visible (fence) BEFORE its decrement and consumers read the
                 // mutable state with L2 loads, so the publisher needs no further fence
                 if (atomicSub(F.npred + sc, 1u) == 1u) vq[atomicAdd(F.ctl + FC_TAIL, 1u)] = sc;
@@ -1390,9 +1396,9 @@ __device__ __forceinline__ void edge_visit_own(const StageDev& S, const PhaseDev
     const bool blind = D > P.item_R2[j];
     if (j < it) {
         atomicAdd(F.npred + it, 1u);
-        if (blind) {
-            const uint32_t slot = atomicAdd(F.nsucc + j, 1u);
-            if (slot < F.stride) F.succ[(size_t)j * F.stride + slot] = it;
+        if (blind) {  // remote entries fill j's list from the back
+            const uint32_t back = atomicAdd(F.succ_cur + j, 1u);
+            if (back < F.stride) F.succ[(size_t)j * F.stride + (F.stride - 1u - back)] = it;
             else F.ctl[FC_OVERFLOW] = 1u;
         }
     } else {
@@ -1417,66 +1423,76 @@ __global__ void __launch_bounds__(CTA_THREADS) k_edges_scan(StageDev S, PhaseDev
             const int r = isqrt_u32(R2), side = 2 * r + 1, cells = side * side;
             if (PASS == 2 && !S.mg && !tiny_torus(S)) {
                 // Single-GPU fixed-stride build.  Whoever SEES the other end of an edge does its own half of the
-                // bookkeeping: the lower item appends the higher one to its own successor list, the higher item
-                // counts the lower one in its own predecessor counter.  Both are the same address for the whole
-                // warp, so they are aggregated (one atomic per chunk / per item); only the half that belongs to an
-                // item which does NOT see this one (its radius is smaller than the distance) needs a remote atomic.
-                uint32_t n_in = 0, n_pl = 0;
+                // bookkeeping: the lower item appends the higher one to the FRONT of its own successor list (no
+                // atomics: only this warp writes there), the higher item counts the lower one in its own predecessor
+                // counter (one atomic per item).  Only the half that belongs to an item which does NOT see this one
+                // (its radius is smaller than the distance) needs a remote atomic; remote successor entries fill the
+                // list from the BACK (counter succ_cur), k_seed_queue flags a list whose two ends met.
+                uint32_t n_in = 0, n_pl = 0, n_own = 0;
                 const bool want_pl = P.nb0 != nullptr && P.is_new != 0u;
-                for (int c0 = 0; c0 < cells; c0 += 32) {
-                    const int c = c0 + lane;
-                    int kind = 0; uint32_t j = NONE32;  // kind 1: lower item in the disc, 2: higher item in the disc
-                    bool blind = false;                 // the other item does not see this one
-                    bool pl = false; short2 plo = make_short2(0, 0);
-                    if (c < cells) {
-                        const int dy = c / side - r, dx = c % side - r;
-                        const uint32_t D = (uint32_t)(dx * dx + dy * dy);
-                        if (D <= R2) {
-                            int qx = x + dx, qy = y + dy;
-                            bool in = true;
-                            if (S.tiling) { qx = imod(qx, S.W); qy = imod(qy, S.H); }
-                            else in = (unsigned)qx < (unsigned)S.W && (unsigned)qy < (unsigned)S.H;
-                            if (in) {
-                                j = P.pmap[(size_t)qy * S.W + qx];
-                                if (j != NONE32 && j != it) {
-                                    kind = j < it ? 1 : 2;
-                                    blind = D > P.item_R2[j];
-                                    // a lower item whose pixel (or mirror copy) will be a point inside this disc
-                                    if (want_pl && kind == 1 && point_exists_at(S, x + dx, y + dy)) { pl = true; plo = make_short2((short)dx, (short)dy); }
-                                }
+                const uint32_t inv = 0xFFFFFFFFu / (uint32_t)side + 1u;  // c / side == __umulhi(c, inv) while c * side < 2^32
+                const unsigned lt = (1u << lane) - 1u;
+                uint32_t* my_succ = F.succ + (size_t)it * F.stride;
+                for (int c0 = 0; c0 < cells; c0 += 64) {  // two chunks per turn: their loads overlap
+                    uint32_t j[2], D[2], r2j[2];
+                    int dxs[2], dys[2];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int c = c0 + 32 * q + lane;
+                        j[q] = NONE32; D[q] = 0; r2j[q] = 0; dxs[q] = 0; dys[q] = 0;
+                        if (c < cells) {
+                            const int row = (int)__umulhi((uint32_t)c, inv);
+                            const int dy = row - r, dx = c - row * side - r;
+                            D[q] = (uint32_t)(dx * dx + dy * dy);
+                            dxs[q] = dx; dys[q] = dy;
+                            if (D[q] <= R2) {
+                                int qx = x + dx, qy = y + dy;
+                                bool in = true;
+                                if (S.tiling) { qx = imod(qx, S.W); qy = imod(qy, S.H); }
+                                else in = (unsigned)qx < (unsigned)S.W && (unsigned)qy < (unsigned)S.H;
+                                if (in) j[q] = P.pmap[(size_t)qy * S.W + qx];
                             }
                         }
                     }
-                    if (kind == 1) {
-                        ++n_in;
-                        if (blind) {  // j cannot know about this successor: put it on j's list from here
-                            const uint32_t slot = atomicAdd(F.nsucc + j, 1u);
-                            if (slot < F.stride) F.succ[(size_t)j * F.stride + slot] = it;
-                            else F.ctl[FC_OVERFLOW] = 1u;
-                        }
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        if (j[q] == it) j[q] = NONE32;
+                        if (j[q] != NONE32) r2j[q] = P.item_R2[j[q]];
                     }
-                    if (want_pl) {
-                        const uint32_t bpl = __ballot_sync(FULL, pl);
-                        if (pl) {
-                            const uint32_t slot = n_pl + __popc(bpl & ((1u << lane) - 1u));
-                            if (slot < P.predl_stride) P.predl[(size_t)it * P.predl_stride + slot] = plo;
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const bool found = j[q] != NONE32;
+                        const bool lower = found && j[q] < it, higher = found && !lower;
+                        const bool blind = found && D[q] > r2j[q];  // the other item does not see this one
+                        if (lower) {
+                            ++n_in;
+                            if (blind) {  // j cannot know about this successor: put it on j's list from here
+                                const uint32_t back = atomicAdd(F.succ_cur + j[q], 1u);
+                                if (back < F.stride) F.succ[(size_t)j[q] * F.stride + (F.stride - 1u - back)] = it;
+                                else F.ctl[FC_OVERFLOW] = 1u;
+                            }
                         }
-                        n_pl += __popc(bpl);
-                    }
-                    const uint32_t bout = __ballot_sync(FULL, kind == 2);
-                    if (bout) {
-                        const int leader = __ffs(bout) - 1;
-                        uint32_t base = 0;
-                        if (lane == leader) base = atomicAdd(F.nsucc + it, (uint32_t)__popc(bout));
-                        base = __shfl_sync(FULL, base, leader);
-                        if (kind == 2) {
-                            const uint32_t slot = base + __popc(bout & ((1u << lane) - 1u));
-                            if (slot < F.stride) F.succ[(size_t)it * F.stride + slot] = j;
+                        if (want_pl) {
+                            // a lower item whose pixel (or mirror copy) will be a point inside this disc
+                            const bool pl = lower && point_exists_at(S, x + dxs[q], y + dys[q]);
+                            const uint32_t bpl = __ballot_sync(FULL, pl);
+                            if (pl) {
+                                const uint32_t slot = n_pl + __popc(bpl & lt);
+                                if (slot < P.predl_stride) P.predl[(size_t)it * P.predl_stride + slot] = make_short2((short)dxs[q], (short)dys[q]);
+                            }
+                            n_pl += __popc(bpl);
+                        }
+                        const uint32_t bout = __ballot_sync(FULL, higher);
+                        if (higher) {
+                            const uint32_t slot = n_own + __popc(bout & lt);
+                            if (slot < F.stride) my_succ[slot] = j[q];
                             else F.ctl[FC_OVERFLOW] = 1u;
-                            if (blind) atomicAdd(F.npred + j, 1u);  // j does not count this predecessor itself
+                            if (blind) atomicAdd(F.npred + j[q], 1u);  // j does not count this predecessor itself
                         }
+                        n_own += __popc(bout);
                     }
                 }
+                if (lane == 0) F.nsucc[it] = n_own;
                 n_in = __reduce_add_sync(FULL, n_in);
                 if (lane == 0 && n_in) atomicAdd(F.npred + it, n_in);
                 if (want_pl && lane == 0) P.npredl[it] = n_pl;
@@ -1559,6 +1575,7 @@ __global__ void k_seed_queue(StageDev S, PhaseDev P, FlowDev F) {
         if (F.npred[it] == 0u) F.queue[atomicAdd_system(F.ctl + FC_TAIL, 1u)] = it;
         return;
     }
+    if (F.stride && F.nsucc[it] + F.succ_cur[it] > F.stride) F.ctl[FC_OVERFLOW] = 1u;  // the two ends of the successor list met
     if (F.npred[it] == 0u) F.queue[atomicAdd(F.ctl + FC_TAIL, 1u)] = it;
 }
 
