@@ -687,7 +687,7 @@ void build_plan(const tsb_generator* g, const tsb_params* prm, std::vector<Stage
 int ensure_flow_buffers(tsb_generator* g, size_t max_phase) {
     TRY(g->d_item_R2.ensure(max_phase));
     TRY(g->d_npred.ensure(max_phase + 1)); TRY(g->d_nsucc.ensure(max_phase + 1)); TRY(g->d_succ_off.ensure(max_phase + 1));
-    TRY(g->d_succ_cur.ensure(max_phase + 1)); TRY(g->d_queue.ensure(max_phase + 1)); TRY(g->d_fctl.ensure(8));
+    TRY(g->d_succ_cur.ensure(max_phase + 1)); TRY(g->d_queue.ensure(max_phase + 1)); TRY(g->d_fctl.ensure(64));  // [0..8) control words, [32..64) targets of the release stores
     TRY(g->d_succ.ensure(max_phase * SUCC_STRIDE + 1024));
     return 0;
 }

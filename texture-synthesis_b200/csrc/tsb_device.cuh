@@ -1035,7 +1035,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_flow(StageDev S, PhaseDev P,
         }
         it = __shfl_sync(FULL, it, 0);
         if (it == NONE32) break;
-        __threadfence();  // acquire: commits of all predecessors are visible below
+        // Acquire.  Every read of mutable data below (state, resolved-set mask) is an L2 load (ld.cg) whose address
+        // depends on `it`, and every predecessor made its commit visible in L2 before it decremented this item's
+        // counter, so single-GPU phases need no fence here -- in particular not __threadfence(), which also
+        // invalidates the SM's whole L1 (CCTL.IVALL) and with it the cached example texels of all resident warps.
+        if (MG) __threadfence();
+        else asm volatile("" ::: "memory");
         if (lane == 0) ws.stat[ST_CYC_READY] += (unsigned long long)(clock64() - tr0);
         if (pref) {
             // the item's successor list is needed only after its commit: start copying it to shared memory now
@@ -1081,7 +1086,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_flow(StageDev S, PhaseDev P,
         }
         if (lane == 0) {
             commit_item<MG>(S, P, si, flat, x, y, o, remote_succ);
-            if (MG && remote_succ) __threadfence_system(); else __threadfence();  // release
+            // release: the commit is visible device-wide before any successor counter is touched.  A release store
+            // (MEMBAR.ALL.GPU + store) instead of __threadfence() (MEMBAR.SC.GPU + L1 invalidation, see above).
+            if (MG) { if (remote_succ) __threadfence_system(); else __threadfence(); }
+            else asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(F.ctl + 32 + (blockIdx.x & 31)), "r"(it) : "memory");
         }
         __syncwarp();
         // notify successors; the one that drops a counter to zero publishes the item
