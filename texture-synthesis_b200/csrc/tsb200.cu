@@ -699,7 +699,7 @@ int ensure_list_buffers(tsb_generator* g, size_t max_phase, uint32_t k) {
     g->list_max_items = std::min(max_phase, cap);
     g->predl_stride = std::min<uint32_t>(((2 * k + 31) / 32) * 32, (uint32_t)KBUF - k);
     if (const char* e = getenv("TSB_LIST_MIN_POS")) g->list_min_positions = atof(e);
-    if (g->mg_on || g->use_rounds || g->force_csr || g->predl_stride == 0) g->list_max_items = 0;
+    if (g->use_rounds || g->force_csr || g->predl_stride == 0) g->list_max_items = 0;
     if (g->list_max_items == 0) return 0;
     TRY(g->d_nb0.ensure(g->list_max_items * k));
     TRY(g->d_predl.ensure(g->list_max_items * g->predl_stride));
@@ -770,6 +770,15 @@ int run_serial(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, boo
     return clk.end(g, s, "serial", i0, n, is_new, 0);
 }
 
+// Does this phase use the neighbour lists of the analysis (PhaseDev::nb0 / predl) instead of walking the bit mask?
+bool use_lists(const tsb_generator* g, const StageDev& S, uint32_t n, bool is_new) {
+    if (n > g->list_max_items) return false;
+    if (S.tiling && (g->W < 100 || g->H < 100)) return false;  // tiny_torus(): one-sided edge registration, no lists
+    // new pixels in an already dense canvas: walking the bit mask (k / density pixels) is cheaper than merging lists
+    if (is_new && (double)S.k * (double)g->W * (double)g->H / (double)std::max<size_t>(1, g->cur_resolved) < g->list_min_positions) return false;
+    return true;
+}
+
 // Items [i0, i0+n) in dataflow order: radius -> CSR dependency graph -> persistent kernel.
 int run_phase_flow(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, bool is_new, uint64_t trace_base) {
     cudaStream_t s = g->stream;
@@ -789,6 +798,7 @@ int run_phase_flow(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n,
         StageDev Sm = S;
         Sm.mg = g->d_mg.p;
         F.stride = (uint32_t)g->succ_stride;
+        if (use_lists(g, S, n, is_new)) { P.nb0 = g->d_nb0.p; P.predl = g->d_predl.p; P.npredl = g->d_npredl.p; P.predl_stride = g->predl_stride; }
         auto barrier = [&]() -> int { CU(cudaStreamSynchronize(s)); g->mg_barrier(g->mg_barrier_user); return 0; };
         TRY(barrier());  // every rank has finished the previous phase before anybody writes into its replica
         CU(cudaMemsetAsync(F.ctl, 0, 32, s));
@@ -929,11 +939,7 @@ int run_phase_flow(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n,
     bool use_csr = g->force_csr || (size_t)n * g->succ_stride > g->d_succ.n;
     for (int attempt = 0; attempt < 2; ++attempt) {
         F.stride = use_csr ? 0u : (uint32_t)g->succ_stride;
-        bool lists = !use_csr && n <= g->list_max_items;  // the lists are built by the fixed-stride edge pass only
-        if (S.tiling && (g->W < 100 || g->H < 100)) lists = false;  // tiny_torus(): one-sided edge registration, no lists
-        // new pixels in an already dense canvas: walking the bit mask (k / density pixels) is cheaper than merging lists
-        if (lists && is_new && (double)S.k * (double)g->W * (double)g->H / (double)std::max<size_t>(1, g->cur_resolved) < g->list_min_positions) lists = false;
-        if (lists) {
+        if (!use_csr && use_lists(g, S, n, is_new)) {  // the lists are built by the fixed-stride edge pass only
             P.nb0 = g->d_nb0.p; P.predl = g->d_predl.p; P.npredl = g->d_npredl.p; P.predl_stride = g->predl_stride;
         } else { P.nb0 = nullptr; P.predl = nullptr; P.npredl = nullptr; P.predl_stride = 0; }
         CU(cudaMemsetAsync(F.ctl, 0, 32, s));

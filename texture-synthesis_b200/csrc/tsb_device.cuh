@@ -1506,17 +1506,30 @@ __global__ void __launch_bounds__(CTA_THREADS) k_edges_scan(StageDev S, PhaseDev
                 if (want_pl && lane == 0) P.npredl[it] = n_pl;
                 continue;
             }
+            const bool want_pl_mg = PASS == 2 && S.mg != nullptr && P.nb0 != nullptr && P.is_new != 0u;
             for (int c = lane; c < cells; c += 32) {
                 const int dy = c / side - r, dx = c % side - r;
                 const uint32_t D = (uint32_t)(dx * dx + dy * dy);
-                if (D <= R2) edge_visit<PASS>(S, P, F, it, x + dx, y + dy, D);
+                if (D <= R2) {
+                    edge_visit<PASS>(S, P, F, it, x + dx, y + dy, D);
+                    if (want_pl_mg) {  // band-sharded phase: in-disc predecessor list of this (owned) item
+                        int qx = x + dx, qy = y + dy;
+                        bool in = true;
+                        if (S.tiling) { qx = imod(qx, S.W); qy = imod(qy, S.H); }
+                        else in = (unsigned)qx < (unsigned)S.W && (unsigned)qy < (unsigned)S.H;
+                        if (in && P.pmap[(size_t)qy * S.W + qx] < it && point_exists_at(S, x + dx, y + dy)) {  // NONE32 is never below an index
+                            const uint32_t slot = atomicAdd(P.npredl + it, 1u);
+                            if (slot < P.predl_stride) P.predl[(size_t)it * P.predl_stride + slot] = make_short2((short)dx, (short)dy);
+                        }
+                    }
+                }
             }
         } else {
             int rmaxx = S.tiling ? S.W / 2 : S.W, rmaxy = S.tiling ? S.H / 2 : S.H;
             int r = isqrt_u32(R2);
             int ry = min(r, rmaxy);
             // in-disc predecessor list: not for the torus walk (it does not enumerate the mirror copies) and not for R2_INF
-            const bool want_pl = PASS == 2 && !S.mg && P.nb0 != nullptr && P.is_new != 0u;
+            const bool want_pl = PASS == 2 && P.nb0 != nullptr && P.is_new != 0u;
             const bool can_pl = want_pl && !S.tiling && R2 != R2_INF;
             if (want_pl && !can_pl && lane == 0) P.npredl[it] = PREDL_UNUSABLE;
             for (int dy = -ry; dy <= ry; ++dy) {
