@@ -296,7 +296,7 @@ struct tsb_generator {
     DevBuf<unsigned long long> d_keys, d_keys_sorted;
     DevBuf<uint32_t> d_v0;
     cudaStream_t stream2 = nullptr;
-    int max_ctas_flow = 0, max_ctas_flow_guided = 0;
+    int max_ctas_flow = 0, max_ctas_flow_guided = 0, max_ctas_radius = 0;
     bool use_rounds = false, force_csr = false;
     // band-sharded multi-GPU execution
     bool mg_on = false;
@@ -598,7 +598,7 @@ int run_phase(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, bool
     if (analyze) {
         FlowDev F0;
         memset(&F0, 0, sizeof(F0));
-        TRY(launch_resolve_kernel(g, k_radius, grid_for(g, n), sizeof(CtaSmem), S, P, F0));
+        TRY(launch_resolve_kernel(g, k_radius, grid_for(g, n), sizeof(KnnScratch) * WARPS_PER_CTA, S, P, F0));
         if (n <= PAIR_MAX) k_preds_pairs<<<grid_for(g, n), CTA_THREADS, 0, s>>>(S, P);
         else k_preds_scan<<<grid_for(g, n), CTA_THREADS, 0, s>>>(S, P);
         CU(cudaGetLastError());
@@ -790,6 +790,7 @@ int run_phase_flow(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n,
     PhaseClock clk;
     TRY(clk.begin(s));
     const int ga = grid_for(g, n), gl = grid_light(g, n);
+    const int gr = std::max(1, std::min((int)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), g->max_ctas_radius));
     // persistent grid: never more than the co-resident CTAs
     const int gf = std::max(1, std::min((int)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), g->guided ? g->max_ctas_flow_guided : g->max_ctas_flow));
     uint64_t edges = 0;
@@ -802,7 +803,7 @@ int run_phase_flow(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n,
         auto barrier = [&]() -> int { CU(cudaStreamSynchronize(s)); g->mg_barrier(g->mg_barrier_user); return 0; };
         TRY(barrier());  // every rank has finished the previous phase before anybody writes into its replica
         CU(cudaMemsetAsync(F.ctl, 0, 32, s));
-        k_radius<<<ga, CTA_THREADS, sizeof(CtaSmem), s>>>(Sm, P, F);
+        k_radius<<<gr, CTA_THREADS, sizeof(KnnScratch) * WARPS_PER_CTA, s>>>(Sm, P, F);
         CU(cudaGetLastError());
         TRY(barrier());  // radii of all items and zeroed counters are visible on every replica
         if (getenv("TSB_MG_DEBUG")) {
@@ -943,7 +944,7 @@ int run_phase_flow(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n,
             P.nb0 = g->d_nb0.p; P.predl = g->d_predl.p; P.npredl = g->d_npredl.p; P.predl_stride = g->predl_stride;
         } else { P.nb0 = nullptr; P.predl = nullptr; P.npredl = nullptr; P.predl_stride = 0; }
         CU(cudaMemsetAsync(F.ctl, 0, 32, s));
-        k_radius<<<ga, CTA_THREADS, sizeof(CtaSmem), s>>>(S, P, F);
+        k_radius<<<gr, CTA_THREADS, sizeof(KnnScratch) * WARPS_PER_CTA, s>>>(S, P, F);
         CU(cudaGetLastError());
         g->stats.kernel_launches++;
         if (use_csr) {
@@ -1429,7 +1430,7 @@ int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
     cudaFuncSetAttribute(k_round<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
     cudaFuncSetAttribute(k_eval_items<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
     cudaFuncSetAttribute(k_eval_items<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
-    cudaFuncSetAttribute(k_radius, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
+    cudaFuncSetAttribute(k_radius, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(KnnScratch) * WARPS_PER_CTA));
     cudaFuncSetAttribute(k_flow<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
     cudaFuncSetAttribute(k_flow<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
     cudaFuncSetAttribute(k_flow<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
@@ -1446,6 +1447,9 @@ int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
     g->max_ctas = prop.multiProcessorCount * std::max(per_sm, 4);  // analysis kernels (k_radius: 47 KB smem) fit 4 CTAs per SM
     g->max_ctas_flow = prop.multiProcessorCount * per_sm_flow;  // persistent grid: co-resident CTAs only
     g->max_ctas_flow_guided = prop.multiProcessorCount * per_sm_flow_g;
+    int per_sm_radius = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_radius, k_radius, CTA_THREADS, sizeof(KnnScratch) * WARPS_PER_CTA) != cudaSuccess || per_sm_radius < 1) per_sm_radius = 4;
+    g->max_ctas_radius = prop.multiProcessorCount * per_sm_radius;  // one wave of co-resident CTAs, grid-stride over the items
     if ((rc = init_state(g))) return bail(rc);
     if (cudaStreamSynchronize(g->stream) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "generator initialisation failed: %s", cudaGetErrorString(cudaGetLastError())));
     *out = g;

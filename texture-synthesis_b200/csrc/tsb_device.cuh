@@ -157,6 +157,14 @@ struct __align__(16) WarpScratch {
     unsigned long long stat[16];  // per-warp run statistics (ST_*), kept out of the registers
 };
 
+// What the k-NN search alone needs (the phase analysis runs with this, at a higher occupancy than the resolve kernels)
+struct __align__(16) KnnScratch {
+    union { unsigned long long keys[KBUF]; } u;
+    short2 off[KMAX];
+    int cnt;
+    int pad[3];
+};
+
 // statistics accumulated per warp in registers, per CTA in shared memory, flushed once per CTA
 enum { ST_FETCHED = 0, ST_NOMINAL, ST_CANDS, ST_ITEMS, ST_CYC_READY, ST_CYC_KNN, ST_CYC_NEIGH, ST_CYC_WEIGHT,
        ST_CYC_SCORE, ST_CYC_COMMIT, ST_COUNT };
@@ -229,8 +237,8 @@ __device__ __forceinline__ void mask_insert(const StageDev& S, int x, int y, boo
 // General disc scan over the bit mask (any radius).  COLLECT=false: count bits with d^2 <= R2.
 // COLLECT=true: append keys (d^2<<32 | (dy+32768)<<16 | (dx+32768)) to ws.u.keys (ws.cnt).
 // ---------------------------------------------------------------------------------------------
-template <bool COLLECT, bool STABLE = false>
-__device__ __forceinline__ uint32_t scan_disc(const StageDev& S, WarpScratch& ws, int lane, int x, int y, uint32_t R2) {
+template <bool COLLECT, bool STABLE = false, class WS = WarpScratch>
+__device__ __forceinline__ uint32_t scan_disc(const StageDev& S, WS& ws, int lane, int x, int y, uint32_t R2) {
     int r = isqrt_u32(R2);
     int ylo = max(y - r, -S.my), yhi = min(y + r, S.mrows - 1 - S.my);
     uint32_t cnt = 0;
@@ -278,7 +286,8 @@ __device__ __forceinline__ uint32_t scan_disc(const StageDev& S, WarpScratch& ws
     return (uint32_t)ws.cnt;
 }
 
-__device__ __noinline__ void sort_keys(WarpScratch& ws, int lane, int n) {
+template <class WS>
+__device__ __noinline__ void sort_keys(WS& ws, int lane, int n) {
     int n2 = 32;
     while (n2 < n) n2 <<= 1;
     for (int i = n + lane; i < n2; i += 32) ws.u.keys[i] = ~0ull;
@@ -300,8 +309,8 @@ __device__ __noinline__ void sort_keys(WarpScratch& ws, int lane, int n) {
 // k nearest resolved points of (x,y) in canonical order (d^2, dy, dx) -> ws.off[0..kk).
 // R2bound: if != R2_INF, the caller guarantees that the disc d^2 <= R2bound holds at least k points.
 // Returns kk; *r2_out = d^2 of the k-th neighbour (R2_INF if fewer than k points exist).
-template <bool STABLE = false>
-__device__ __forceinline__ int knn_search(const StageDev& S, WarpScratch& ws, int lane, int x, int y, uint32_t R2bound, uint32_t* r2_out) {
+template <bool STABLE = false, class WS = WarpScratch>
+__device__ __forceinline__ int knn_search(const StageDev& S, WS& ws, int lane, int x, int y, uint32_t R2bound, uint32_t* r2_out) {
     const int k = S.k;
     const unsigned lt = (1u << lane) - 1u;
     // ---- path A: spiral walk over the fixed-offset table ----
@@ -1239,9 +1248,9 @@ __global__ void __launch_bounds__(CTA_THREADS) k_eval_items(StageDev S, uint32_t
 // Conflict radius of every item: distance^2 of its k-th nearest resolved point at phase start.
 __global__ void __launch_bounds__(CTA_THREADS) k_radius(StageDev S, PhaseDev P, FlowDev F) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    CtaSmem& sm = *reinterpret_cast<CtaSmem*>(smem_raw);
+    KnnScratch* all_ws = reinterpret_cast<KnnScratch*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpScratch& ws = sm.ws[warp];
+    KnnScratch& ws = all_ws[warp];
     const uint32_t nwarps = gridDim.x * WARPS_PER_CTA;
     for (uint32_t it = blockIdx.x * WARPS_PER_CTA + warp; it < P.n; it += nwarps) {
         const uint32_t flat = P.item_pixel[it];
