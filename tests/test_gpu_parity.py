@@ -158,19 +158,26 @@ def test_session_mirror_runs_like_reference_example_01():
     assert (go.color() == img).all()
 
 
-@pytest.mark.parametrize("env", [{"TSB_MODE": "csr"}, {"TSB_MODE": "rounds"}, {"TSB_SUCC_STRIDE": "6"}], ids=["csr", "rounds", "stride_overflow"])
+@pytest.mark.parametrize("env", [{"TSB_MODE": "csr"}, {"TSB_MODE": "rounds"}, {"TSB_MODE": "epochs"}, {"TSB_MODE": "epochs", "TSB_SUCC_STRIDE": "6"},
+                                 {"TSB_MODE": "epochs", "TSB_LIST_MAX": "0"}, {"TSB_NO_FAST": "1"}],
+                         ids=["csr", "rounds", "epochs", "epochs_stride_overflow", "epochs_mask_search", "general_scoring"])
 def test_alternative_schedulers_give_the_same_result(env, monkeypatch):
-    """The dependency scheduler has three interchangeable implementations (fixed-stride successor lists, CSR
-    fallback on overflow, host-visible rounds): all must reproduce the serial order exactly."""
-    case = Case("sched", 96, 80, [(64, 48)], seed=17, tiling=True).build()
-    ref = case.run_gpu()
+    """The dependency scheduler has interchangeable implementations (default: whole stages with exact timed
+    neighbour lists; doubling epochs with fixed-stride successor lists, with the CSR fallback on overflow, with or
+    without the analysis neighbour lists; host-visible rounds) and two scoring paths: all must reproduce the serial
+    order exactly."""
+    cases = [Case("sched", 96, 80, [(64, 48)], seed=17, tiling=True).build(),
+             Case("sched_big_tiling", 208, 176, [(64, 48)], seed=18, tiling=True).build(),
+             Case("sched_big", 200, 168, [(72, 56)], seed=19).build()]
+    refs = [c.run_gpu() for c in cases]
     for k_, v in env.items():
         monkeypatch.setenv(k_, v)
-    alt = case.run_gpu()
-    assert (ref.coord() == alt.coord()).all() and (ref.color() == alt.color()).all()
-    fa, sa = ref.resolved()
-    fb, sb = alt.resolved()
-    assert (fa == fb).all() and (sa.view(np.uint32) == sb.view(np.uint32)).all()
+    for case, ref in zip(cases, refs):
+        alt = case.run_gpu()
+        assert (ref.coord() == alt.coord()).all() and (ref.color() == alt.color()).all(), case.name
+        fa, sa = ref.resolved()
+        fb, sb = alt.resolved()
+        assert (fa == fb).all() and (sa.view(np.uint32) == sb.view(np.uint32)).all(), case.name
 
 
 @pytest.mark.parametrize("shape", [(48, 40), (128, 96), (400, 382)])

@@ -253,6 +253,8 @@ struct tsb_generator {
     DevBuf<uint4> d_state;
     DevBuf<float> d_score;
     DevBuf<uint32_t> d_mask, d_mask1;
+    DevBuf<uint32_t> d_pmask, d_pmask1;            // the current stage's new pixels (+ mirror copies), geometry of d_mask
+    bool stage_lists = false;                       // new pixels of a stage as ONE dataflow phase with exact timed lists
     DevBuf<uint32_t> d_inp_mask, d_inp_color;
     int mx = 0, my = 0, wpr = 0, mrows = 0, wpr1 = 0;
     DevBuf<short2> d_spiral;
@@ -770,6 +772,55 @@ int run_serial(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, boo
     return clk.end(g, s, "serial", i0, n, is_new, 0);
 }
 
+// All remaining new pixels [i0, i0+n) of a stage as ONE dataflow phase (single GPU): exact neighbour lists "as of" every
+// item's serial time (k_lists_timed), read-after-write edges from those lists (CSR), persistent kernel.
+int run_stage_new(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, size_t resolved_before, uint64_t trace_base) {
+    cudaStream_t s = g->stream;
+    PhaseDev P = make_phase(g, i0, n, true, trace_base);
+    P.nb0 = g->d_nb0.p; P.npredl = g->d_npredl.p; P.predl = nullptr; P.predl_stride = 0;
+    FlowDev F;
+    F.npred = g->d_npred.p; F.nsucc = g->d_nsucc.p; F.succ_off = g->d_succ_off.p; F.succ_cur = g->d_succ_cur.p;
+    F.succ = g->d_succ.p; F.queue = g->d_queue.p; F.ctl = g->d_fctl.p; F.stride = 0;
+    g->stats.phases++;
+    PhaseClock clk;
+    TRY(clk.begin(s));
+    const int gl = grid_light(g, n);
+    const int gr = std::max(1, std::min((int)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), g->max_ctas_radius));
+    const int gf = std::max(1, std::min((int)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), g->guided ? g->max_ctas_flow_guided : g->max_ctas_flow));
+    const unsigned nb = (n + 255) / 256;
+    CU(cudaMemsetAsync(F.ctl, 0, 32, s));
+    CU(cudaMemsetAsync(g->d_pmask.p, 0, (size_t)g->wpr * g->mrows * 4, s));
+    CU(cudaMemsetAsync(g->d_pmask1.p, 0, (size_t)g->wpr1 * g->mrows * 4, s));
+    k_mask_insert_flat_at<<<nb, 256, 0, s>>>(S, g->d_pmask.p, g->d_pmask1.p, P.item_pixel, n, S.tiling);
+    k_pmap_fill<<<nb, 256, 0, s>>>(P);
+    TimeFilter T;
+    T.pend = g->d_pmask.p; T.pend1 = g->d_pmask1.p; T.pmap = g->d_pmap.p; T.idx = 0; T.hint = 0; T.n_points_max = 0;
+    k_lists_timed<<<gr, CTA_THREADS, sizeof(KnnScratch) * WARPS_PER_CTA, s>>>(S, P, F, T, (uint32_t)std::min<size_t>(resolved_before, 0xFFFFFFFFull));
+    k_edges_lists<0><<<gl, CTA_THREADS, 0, s>>>(S, P, F);
+    CU(cudaGetLastError());
+    size_t temp_bytes = g->d_cub_temp.n;
+    CU(cub::DeviceScan::ExclusiveSum(g->d_cub_temp.p, temp_bytes, F.nsucc, F.succ_off, (int)(n + 1), s));
+    CU(cudaMemcpyAsync(g->h_ctrl, F.succ_off + n, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    const uint64_t edges = g->h_ctrl[0];
+    if (edges > g->d_succ.n) { TRY(g->d_succ.ensure(edges + edges / 4 + 1024)); F.succ = g->d_succ.p; }
+    k_edges_lists<1><<<gl, CTA_THREADS, 0, s>>>(S, P, F);
+    k_seed_queue<<<nb, 256, 0, s>>>(S, P, F);
+    CU(cudaGetLastError());
+    TRY(clk.mid(s));
+    if (g->rand_pending) { CU(cudaStreamWaitEvent(s, g->ev_rand, 0)); g->rand_pending = false; }
+    if (g->guided) k_flow<true, false><<<gf, CTA_THREADS, sizeof(RoundSmem), s>>>(S, P, F);
+    else k_flow<false, false><<<gf, CTA_THREADS, sizeof(RoundSmem), s>>>(S, P, F);
+    k_pmap_clear<<<nb, 256, 0, s>>>(P);
+    CU(cudaGetLastError());
+    g->stats.kernel_launches += 11;
+    g->stats.rounds++;
+    CU(cudaMemcpyAsync(g->h_ctrl, F.ctl, 12, cudaMemcpyDeviceToHost, s));
+    TRY(clk.end(g, s, "stage-new", i0, n, true, edges));
+    if (g->h_ctrl[FC_ABORT]) return fail(TSB_ERR_INTERNAL, "stage-wide dataflow phase of %u items stalled (head %u tail %u)", n, g->h_ctrl[0], g->h_ctrl[1]);
+    return 0;
+}
+
 // Does this phase use the neighbour lists of the analysis (PhaseDev::nb0 / predl) instead of walking the bit mask?
 bool use_lists(const tsb_generator* g, const StageDev& S, uint32_t n, bool is_new) {
     if (n > g->list_max_items) return false;
@@ -1110,6 +1161,18 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
     g->use_rounds = getenv("TSB_MODE") && !strcmp(getenv("TSB_MODE"), "rounds");
     g->force_csr = getenv("TSB_MODE") && !strcmp(getenv("TSB_MODE"), "csr");
     g->succ_stride = getenv("TSB_SUCC_STRIDE") ? std::max(1, atoi(getenv("TSB_SUCC_STRIDE"))) : SUCC_STRIDE;
+    g->stage_lists = !g->mg_on && !g->use_rounds && !g->force_csr && !(getenv("TSB_MODE") && !strcmp(getenv("TSB_MODE"), "epochs"));
+    if (g->stage_lists) {  // whole stages as one phase: the per-phase buffers must hold a stage's new pixels
+        size_t max_new = 1;
+        for (auto& sp : plan) max_new = std::max(max_new, sp.n_new);
+        max_phase = std::max(max_phase, max_new);
+        TRY(ensure_flow_buffers(g, max_phase));
+        size_t tb = 0;
+        CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, g->d_nsucc.p, g->d_succ_off.p, (int)(max_phase + 1), s));
+        TRY(g->d_cub_temp.ensure(tb + 256));
+        TRY(g->d_pmask.ensure((size_t)g->wpr * g->mrows));
+        TRY(g->d_pmask1.ensure((size_t)g->wpr1 * g->mrows));
+    }
     TRY(ensure_list_buffers(g, max_phase, k));
     TRY(g->d_rand_xy.ensure(max_stage_items * (size_t)m));
     TRY(g->d_rand_map.ensure(max_stage_items * (size_t)m));
@@ -1200,6 +1263,18 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
                 continue;
             }
             size_t base = resolved_now - g->inpaint_locked;
+            bool whole_stage = false;
+            if (g->stage_lists && base >= std::max<size_t>((size_t)k + 14, 64) && n_items - cur <= g->list_max_items) {
+                // the rest of the stage as one dataflow phase (exact timed neighbour lists, run_stage_new)
+                const size_t n_e = n_items - cur;
+                S.r2_hint = r2_hint_for(g, resolved_now, k);
+                S.n_points_max = (uint32_t)std::min<size_t>((tiling ? 3 : 1) * (resolved_now + n_e), 0xFFFFFFFFull);
+                TRY(gen_rand(cur, n_e));
+                TRY(run_stage_new(g, S, (uint32_t)cur, (uint32_t)n_e, resolved_now, trace_base));
+                cur += n_e; resolved_now += n_e;
+                whole_stage = true;
+            }
+            if (!whole_stage) {
             // every item still depends on (almost) all earlier ones: one warp runs them in order, keeping the whole
             // resolved set as a point list in shared memory while it fits the key buffer
             // (the dataflow kernel overlaps the independent parts of consecutive items, so it takes over as soon as
@@ -1225,6 +1300,7 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
             else if (serial) TRY(run_serial(g, S, (uint32_t)cur, (uint32_t)n_e, true, trace_base));
             else { g->cur_resolved = resolved_now; TRY(run_phase_flow(g, S, (uint32_t)cur, (uint32_t)n_e, true, trace_base)); }
             cur += n_e; resolved_now += n_e;
+            }
             if (cb) {
                 uint64_t cur_total = overall_current + cur;
                 uint32_t pcnt = (uint32_t)lroundf((float)cur_total / (float)overall_total * 100.0f);

@@ -197,6 +197,26 @@ __device__ __forceinline__ int isqrt_u32(uint32_t v) {
 template <bool STABLE>
 __device__ __forceinline__ uint32_t mask_word(const uint32_t* p) { return STABLE ? __ldg(p) : __ldcg(p); }
 
+// k-NN "as of" a serial time inside a stage: the resolved set plus the stage's own new pixels with a lower index.
+struct TimeFilter {
+    const uint32_t* pend;    // bit mask (geometry of S.mask) of ALL new pixels of the stage, tiling mirror copies included
+    const uint32_t* pend1;   // its summary (geometry of S.mask1)
+    const uint32_t* pmap;    // W*H: stage index of the new pixel at a canvas position, NONE32 elsewhere
+    uint32_t idx;            // only items with a stage index below this one count
+    uint32_t hint;           // starting radius^2 of the search
+    uint32_t n_points_max;   // upper bound of the number of points at that time
+};
+template <bool STABLE = false>
+__device__ __forceinline__ bool mask_test_at(const StageDev& S, const uint32_t* mask, int x, int y) {
+    int X = x + S.mx, Y = y + S.my;
+    if ((unsigned)X >= (unsigned)(S.wpr * 32) || (unsigned)Y >= (unsigned)S.mrows) return false;
+    return (mask_word<STABLE>(mask + (size_t)Y * S.wpr + (X >> 5)) >> (X & 31)) & 1u;
+}
+// the new pixel (or mirror copy) at the unwrapped position (x, y) belongs to an item below T.idx
+__device__ __forceinline__ bool time_passes(const StageDev& S, const TimeFilter& T, int x, int y) {
+    if (S.tiling) { x = imod(x, S.W); y = imod(y, S.H); }
+    return __ldg(T.pmap + (size_t)y * S.W + x) < T.idx;
+}
 template <bool STABLE = false>
 __device__ __forceinline__ bool mask_test(const StageDev& S, int x, int y) {
     int X = x + S.mx, Y = y + S.my;
@@ -237,8 +257,9 @@ __device__ __forceinline__ void mask_insert(const StageDev& S, int x, int y, boo
 // General disc scan over the bit mask (any radius).  COLLECT=false: count bits with d^2 <= R2.
 // COLLECT=true: append keys (d^2<<32 | (dy+32768)<<16 | (dx+32768)) to ws.u.keys (ws.cnt).
 // ---------------------------------------------------------------------------------------------
-template <bool COLLECT, bool STABLE = false, class WS = WarpScratch>
-__device__ __forceinline__ uint32_t scan_disc(const StageDev& S, WS& ws, int lane, int x, int y, uint32_t R2) {
+template <bool COLLECT, bool STABLE, bool FILTER, class WS>
+__device__ __forceinline__ uint32_t scan_rows(const StageDev& S, WS& ws, int lane, int x, int y, uint32_t R2, const uint32_t* mask,
+                                              const uint32_t* mask1, const TimeFilter* T) {
     int r = isqrt_u32(R2);
     int ylo = max(y - r, -S.my), yhi = min(y + r, S.mrows - 1 - S.my);
     uint32_t cnt = 0;
@@ -248,8 +269,8 @@ __device__ __forceinline__ uint32_t scan_disc(const StageDev& S, WS& ws, int lan
         int xlo = max(x - w, -S.mx), xhi = min(x + w, S.wpr * 32 - 1 - S.mx);
         if (xlo > xhi) continue;
         int Xlo = xlo + S.mx, Xhi = xhi + S.mx;
-        const uint32_t* row = S.mask + (size_t)(yy + S.my) * S.wpr;
-        const uint32_t* row1 = S.mask1 + (size_t)(yy + S.my) * S.wpr1;
+        const uint32_t* row = mask + (size_t)(yy + S.my) * S.wpr;
+        const uint32_t* row1 = mask1 + (size_t)(yy + S.my) * S.wpr1;
         const int w0 = Xlo >> 5, w1 = Xhi >> 5;
         for (int sw = w0 >> 5; sw <= (w1 >> 5); ++sw) {
             uint32_t b1 = mask_word<STABLE>(row1 + sw);
@@ -261,12 +282,15 @@ __device__ __forceinline__ uint32_t scan_disc(const StageDev& S, WS& ws, int lan
                 uint32_t bits = mask_word<STABLE>(row + wd);
                 if (wd == w0) bits &= 0xFFFFFFFFu << (Xlo & 31);
                 if (wd == w1) bits &= 0xFFFFFFFFu >> (31 - (Xhi & 31));
-                if (!COLLECT) cnt += __popc(bits);
+                if (!COLLECT && !FILTER) cnt += __popc(bits);
                 else {
                     while (bits) {
                         int b = __ffs(bits) - 1;
                         bits &= bits - 1;
-                        int dx = (wd * 32 + b - S.mx) - x;
+                        const int px = wd * 32 + b - S.mx;
+                        if (FILTER && !time_passes(S, *T, px, yy)) continue;
+                        if (!COLLECT) { ++cnt; continue; }
+                        int dx = px - x;
                         unsigned long long key = ((unsigned long long)(uint32_t)(dx * dx + dy * dy) << 32) |
                                                  ((unsigned long long)(uint32_t)(dy + 32768) << 16) |
                                                  (unsigned long long)(uint32_t)(dx + 32768);
@@ -277,6 +301,13 @@ __device__ __forceinline__ uint32_t scan_disc(const StageDev& S, WS& ws, int lan
             }
         }
     }
+    return cnt;
+}
+// T != nullptr: the stage's new pixels below T->idx count as points too (second pass over their own mask)
+template <bool COLLECT, bool STABLE = false, class WS = WarpScratch>
+__device__ __forceinline__ uint32_t scan_disc(const StageDev& S, WS& ws, int lane, int x, int y, uint32_t R2, const TimeFilter* T = nullptr) {
+    uint32_t cnt = scan_rows<COLLECT, STABLE, false>(S, ws, lane, x, y, R2, S.mask, S.mask1, nullptr);
+    if (T) cnt += scan_rows<COLLECT, true, true>(S, ws, lane, x, y, R2, T->pend, T->pend1, T);
     if (!COLLECT) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
@@ -310,15 +341,18 @@ __device__ __noinline__ void sort_keys(WS& ws, int lane, int n) {
 // R2bound: if != R2_INF, the caller guarantees that the disc d^2 <= R2bound holds at least k points.
 // Returns kk; *r2_out = d^2 of the k-th neighbour (R2_INF if fewer than k points exist).
 template <bool STABLE = false, class WS = WarpScratch>
-__device__ __forceinline__ int knn_search(const StageDev& S, WS& ws, int lane, int x, int y, uint32_t R2bound, uint32_t* r2_out) {
+__device__ __forceinline__ int knn_search(const StageDev& S, WS& ws, int lane, int x, int y, uint32_t R2bound, uint32_t* r2_out,
+                                          const TimeFilter* T = nullptr) {
     const int k = S.k;
+    const uint32_t hint = T ? T->hint : S.r2_hint;
+    const uint32_t npmax = T ? T->n_points_max : S.n_points_max;
     const unsigned lt = (1u << lane) - 1u;
     // ---- path A: spiral walk over the fixed-offset table ----
     bool bounded = (R2bound != R2_INF) && (R2bound <= (uint32_t)S.RT2);
     if (bounded || R2bound == R2_INF) {
         int limit = bounded ? (int)__ldg(S.cntLE + R2bound) : S.spiralN;
         // unbounded search: do not walk the whole table when the hint says the set is sparse
-        if (!bounded && S.r2_hint > (uint32_t)S.RT2) limit = 0;
+        if (!bounded && hint > (uint32_t)S.RT2) limit = 0;
         int cnt = 0;
         for (int base = 0; base < limit && cnt < k; base += 128) {
             short2 o[4];
@@ -331,6 +365,7 @@ __device__ __forceinline__ int knn_search(const StageDev& S, WS& ws, int lane, i
                 if (idx < limit) {
                     o[u] = __ldg(S.spiral + idx);
                     hit[u] = mask_test<STABLE>(S, x + o[u].x, y + o[u].y);
+                    if (T && !hit[u] && mask_test_at<true>(S, T->pend, x + o[u].x, y + o[u].y)) hit[u] = time_passes(S, *T, x + o[u].x, y + o[u].y);
                 }
             }
 #pragma unroll
@@ -354,19 +389,19 @@ __device__ __forceinline__ int knn_search(const StageDev& S, WS& ws, int lane, i
     uint32_t R2 = R2bound;
     uint32_t c = 0;
     int n = -1;
-    if (S.n_points_max <= (uint32_t)KBUF) R2 = R2max;  // the whole set fits the key buffer: take everything
+    if (npmax <= (uint32_t)KBUF) R2 = R2max;  // the whole set fits the key buffer: take everything
     if (R2 != R2_INF) {
         if (lane == 0) ws.cnt = 0;
         __syncwarp();
-        n = (int)scan_disc<true, STABLE>(S, ws, lane, x, y, R2);
+        n = (int)scan_disc<true, STABLE>(S, ws, lane, x, y, R2, T);
         if (n > KBUF || (n < k && R2 < R2max)) n = -1;  // overflow (or a stale bound): search below
     }
     if (n < 0) {
         uint32_t lo = 0;
-        R2 = max(S.r2_hint, 4u);
+        R2 = max(hint, 4u);
         if (R2 > R2max) R2 = R2max;
         for (;;) {
-            c = scan_disc<false, STABLE>(S, ws, lane, x, y, R2);
+            c = scan_disc<false, STABLE>(S, ws, lane, x, y, R2, T);
             if (c >= (uint32_t)k || R2 >= R2max) break;
             lo = R2;
             uint32_t nx = R2 + (R2 >> 1) + 1;
@@ -376,7 +411,7 @@ __device__ __forceinline__ int knn_search(const StageDev& S, WS& ws, int lane, i
             uint32_t hi = R2;
             while (hi - lo > 1) {
                 uint32_t mid = lo + ((hi - lo) >> 1);
-                c = scan_disc<false, STABLE>(S, ws, lane, x, y, mid);
+                c = scan_disc<false, STABLE>(S, ws, lane, x, y, mid, T);
                 if (c >= (uint32_t)k) { hi = mid; if (c <= (uint32_t)KBUF) break; }
                 else lo = mid;
             }
@@ -384,7 +419,7 @@ __device__ __forceinline__ int knn_search(const StageDev& S, WS& ws, int lane, i
         }
         if (lane == 0) ws.cnt = 0;
         __syncwarp();
-        n = (int)scan_disc<true, STABLE>(S, ws, lane, x, y, R2);
+        n = (int)scan_disc<true, STABLE>(S, ws, lane, x, y, R2, T);
     }
     if (n > KBUF) n = KBUF;  // only reachable with > KBUF exact ties on one circle
     sort_keys(ws, lane, n);
@@ -437,13 +472,15 @@ __device__ __forceinline__ bool point_exists_at(const StageDev& S, int ux, int u
 // points this phase has added inside the item's disc before it (exactly its in-disc predecessors, all committed
 // by the time the item runs).  No access to the bit mask.
 __device__ __forceinline__ int knn_from_lists(const StageDev& S, WarpScratch& ws, int lane, const short2* __restrict__ nb0,
-                                              const short2* __restrict__ predl, int npl, uint32_t* r2_out) {
-    const int k = S.k;
+                                              const short2* __restrict__ predl, int npl, uint32_t* r2_out, int nbk = -1) {
+    const int k = nbk >= 0 ? nbk : S.k;  // nbk: the list is the final neighbourhood and may be shorter than k (early pixels)
     if (npl == 0) {
+        *r2_out = R2_INF;
+        if (k == 0) return 0;
         for (int j = lane; j < k; j += 32) ws.off[j] = nb0[j];
         __syncwarp();
         const short2 last = ws.off[k - 1];
-        *r2_out = (uint32_t)(last.x * last.x + last.y * last.y);
+        if (k == S.k) *r2_out = (uint32_t)(last.x * last.x + last.y * last.y);
         return k;
     }
     for (int j = lane; j < k + npl; j += 32) {
@@ -685,11 +722,11 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws,
                              const float* __restrict__ s_lutg, int lane, int x, int y, uint32_t R2bound,
                              const uint32_t* __restrict__ rand_xy, const uint8_t* __restrict__ rand_map, ItemOut& out,
                              const short2* pts = nullptr, int npts = 0, const short2* nb0 = nullptr,
-                             const short2* predl = nullptr, int npl = 0) {
+                             const short2* predl = nullptr, int npl = 0, int nbk = -1) {
     const unsigned lt = (1u << lane) - 1u;
     uint32_t r2;
     long long t0 = clock64();
-    const int kk = nb0 ? knn_from_lists(S, ws, lane, nb0, predl, npl, &r2)
+    const int kk = nb0 ? knn_from_lists(S, ws, lane, nb0, predl, npl, &r2, nbk)
                  : pts ? knn_points(S, ws, lane, x, y, pts, npts, &r2) : knn_search(S, ws, lane, x, y, R2bound, &r2);
     long long t1 = clock64();
     out.c_knn = t1 - t0; out.c_neigh = out.c_weight = out.c_score = 0; out.fetched = out.nominal = 0;
@@ -1070,12 +1107,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_flow(StageDev S, PhaseDev P,
         const short2* nb0 = nullptr;
         const short2* predl = nullptr;
         int npl = 0;
+        int nbk = -1;
         if (P.nb0) {  // neighbour lists from the phase analysis
             const uint32_t c = P.npredl[it];
-            if (c <= P.predl_stride) { nb0 = P.nb0 + (size_t)it * S.k; predl = P.predl + (size_t)it * P.predl_stride; npl = (int)c; }
+            if (!P.predl) { nb0 = P.nb0 + (size_t)it * S.k; nbk = (int)c; }  // exact lists "as of" the item's serial time
+            else if (c <= P.predl_stride) { nb0 = P.nb0 + (size_t)it * S.k; predl = P.predl + (size_t)it * P.predl_stride; npl = (int)c; }
         }
         resolve_item<GUIDED>(S, ws, sm.lut, sm.lutg, lane, x, y, P.item_R2[it], P.rand_xy + (size_t)si * S.m,
-                             P.rand_map + (size_t)si * S.m, o, nullptr, 0, nb0, predl, npl);
+                             P.rand_map + (size_t)si * S.m, o, nullptr, 0, nb0, predl, npl, nbk);
         long long tc0 = clock64();
         if (pref) { asm volatile("cp.async.wait_all;" ::: "memory"); __syncwarp(); }
         const size_t s0 = F.stride ? (size_t)it * F.stride : (size_t)F.succ_off[it];
@@ -1281,6 +1320,76 @@ __global__ void __launch_bounds__(CTA_THREADS) k_radius(StageDev S, PhaseDev P, 
             if (F.npred) { F.npred[it] = 0; F.nsucc[it] = 0; F.succ_cur[it] = 0; }
         }
         __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage-wide analysis of the NEW pixels (single GPU).  Every item's neighbourhood is computed exactly "as of" its
+// own serial time -- the resolved set plus the stage's new pixels with a lower index -- so the resolve kernel needs
+// no search, and the dependency graph is the plain read-after-write relation (an item waits for the new pixels in
+// its own list): the whole stage is one dataflow phase, no epochs.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pmap_fill(PhaseDev P) {
+    uint32_t it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it < P.n) P.pmap[P.item_pixel[it]] = it;
+}
+__global__ void k_mask_insert_flat_at(StageDev S, uint32_t* mask, uint32_t* mask1, const uint32_t* flat, uint32_t n, int mirrors) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    mask_insert_at(S, mask, mask1, false, (int)(flat[i] % (uint32_t)S.W), (int)(flat[i] / (uint32_t)S.W), mirrors != 0);
+}
+__global__ void __launch_bounds__(CTA_THREADS) k_lists_timed(StageDev S, PhaseDev P, FlowDev F, TimeFilter T0, uint32_t n_before) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    KnnScratch* all_ws = reinterpret_cast<KnnScratch*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    KnnScratch& ws = all_ws[warp];
+    const uint32_t nwarps = gridDim.x * WARPS_PER_CTA;
+    const double area = (double)S.W * (double)S.H;
+    for (uint32_t it = blockIdx.x * WARPS_PER_CTA + warp; it < P.n; it += nwarps) {
+        const uint32_t flat = P.item_pixel[it];
+        const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
+        TimeFilter T = T0;
+        T.idx = it;
+        const double npts = (double)n_before + (double)it;
+        T.hint = (uint32_t)fmin(fmax(1.5 * (double)S.k * area / (3.14159265358979 * fmax(npts, 1.0)), 8.0), 4.0e9);
+        T.n_points_max = (uint32_t)fmin((S.tiling ? 3.0 : 1.0) * npts, 4.0e9);
+        uint32_t r2;
+        const int kk = knn_search<true>(S, ws, lane, x, y, R2_INF, &r2, &T);
+        for (int j = lane; j < kk; j += 32) P.nb0[(size_t)it * S.k + j] = ws.off[j];
+        if (lane == 0) {
+            P.npredl[it] = (uint32_t)kk;
+            P.item_R2[it] = r2;
+            F.queue[it] = NONE32;
+            F.npred[it] = 0; F.nsucc[it] = 0; F.succ_cur[it] = 0;
+            if (it == 0) F.nsucc[P.n] = 0;
+        }
+        __syncwarp();
+    }
+}
+// edges j -> it for every new pixel j (of this stage, lower index) in the list of `it`.  PASS 0 counts, PASS 1 fills the CSR lists.
+template <int PASS>
+__global__ void __launch_bounds__(CTA_THREADS) k_edges_lists(StageDev S, PhaseDev P, FlowDev F) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nwarps = gridDim.x * WARPS_PER_CTA;
+    for (uint32_t it = blockIdx.x * WARPS_PER_CTA + warp; it < P.n; it += nwarps) {
+        const uint32_t flat = P.item_pixel[it];
+        const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
+        const int kk = (int)P.npredl[it];
+        uint32_t cnt = 0;
+        for (int e = lane; e < kk; e += 32) {
+            const short2 o = P.nb0[(size_t)it * S.k + e];
+            int qx = x + o.x, qy = y + o.y;
+            if (S.tiling) { qx = imod(qx, S.W); qy = imod(qy, S.H); }
+            const uint32_t j = P.pmap[(size_t)qy * S.W + qx];
+            if (j < it) {  // NONE32 (a pixel resolved before this stage) is never below an index
+                if (PASS == 0) { atomicAdd(F.nsucc + j, 1u); ++cnt; }
+                else { const uint32_t slot = atomicAdd(F.succ_cur + j, 1u); F.succ[(size_t)F.succ_off[j] + slot] = it; }
+            }
+        }
+        if (PASS == 0) {
+            cnt = __reduce_add_sync(FULL, cnt);
+            if (lane == 0) F.npred[it] = cnt;
+        }
     }
 }
 
