@@ -795,6 +795,11 @@ int run_stage_new(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, 
     k_pmap_fill<<<nb, 256, 0, s>>>(P);
     TimeFilter T;
     T.pend = g->d_pmask.p; T.pend1 = g->d_pmask1.p; T.pmap = g->d_pmap.p; T.idx = 0; T.hint = 0; T.n_points_max = 0;
+    T.item_pixel = P.item_pixel;
+    // early items: the disc is large and the pixel mask inside it holds ~n*k/N later pixels; walking the <= idx earlier
+    // items is cheaper while idx^2 < n*k
+    T.brute_below = (uint32_t)std::min<double>(sqrt((double)n * (double)S.k), 65536.0);
+    if (const char* e = getenv("TSB_BRUTE_BELOW")) T.brute_below = (uint32_t)atoi(e);
     k_lists_timed<<<gr, CTA_THREADS, sizeof(KnnScratch) * WARPS_PER_CTA, s>>>(S, P, F, T, (uint32_t)std::min<size_t>(resolved_before, 0xFFFFFFFFull));
     k_edges_lists<0><<<gl, CTA_THREADS, 0, s>>>(S, P, F);
     CU(cudaGetLastError());

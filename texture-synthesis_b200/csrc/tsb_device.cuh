@@ -205,6 +205,8 @@ struct TimeFilter {
     uint32_t idx;            // only items with a stage index below this one count
     uint32_t hint;           // starting radius^2 of the search
     uint32_t n_points_max;   // upper bound of the number of points at that time
+    const uint32_t* item_pixel;  // the stage's new pixels in serial order (flat canvas positions)
+    uint32_t brute_below;    // items with an index below this look at the item list itself instead of the pixel mask
 };
 template <bool STABLE = false>
 __device__ __forceinline__ bool mask_test_at(const StageDev& S, const uint32_t* mask, int x, int y) {
@@ -303,11 +305,41 @@ __device__ __forceinline__ uint32_t scan_rows(const StageDev& S, WS& ws, int lan
     }
     return cnt;
 }
+// The same for the stage's own new pixels when only few of them precede the item: walk the item list [0, T.idx)
+// (coalesced) instead of the pixel mask, whose disc at that time is large and full of LATER pixels.
+template <bool COLLECT, class WS>
+__device__ __forceinline__ uint32_t scan_items(const StageDev& S, WS& ws, int lane, int x, int y, uint32_t R2, const TimeFilter& T) {
+    uint32_t cnt = 0;
+    for (uint32_t j = lane; j < T.idx; j += 32) {
+        const uint32_t f = __ldg(T.item_pixel + j);
+        const int xj = (int)(f % (uint32_t)S.W), yj = (int)(f / (uint32_t)S.W);
+        // the pixel and, with tiling, its mirror copies (flush_resolved, ms.rs:306-327)
+        int px[3], py[3], np = 1;
+        px[0] = xj; py[0] = yj;
+        if (S.tiling) {
+            if (xj < S.x_l) { px[np] = xj + S.W; py[np] = yj; ++np; } else if (xj > S.x_r) { px[np] = xj - S.W; py[np] = yj; ++np; }
+            if (yj < S.y_b) { px[np] = xj; py[np] = yj + S.H; ++np; } else if (yj > S.y_t) { px[np] = xj; py[np] = yj - S.H; ++np; }
+        }
+        for (int q = 0; q < np; ++q) {
+            const long long dx = px[q] - x, dy = py[q] - y;
+            const unsigned long long D = (unsigned long long)(dx * dx + dy * dy);
+            if (D > (unsigned long long)R2) continue;
+            if (!COLLECT) { ++cnt; continue; }
+            unsigned long long key = (D << 32) | ((unsigned long long)(uint32_t)((int)dy + 32768) << 16) | (unsigned long long)(uint32_t)((int)dx + 32768);
+            int slot = atomicAdd(&ws.cnt, 1);
+            if (slot < KBUF) ws.u.keys[slot] = key;
+        }
+    }
+    return cnt;
+}
 // T != nullptr: the stage's new pixels below T->idx count as points too (second pass over their own mask)
 template <bool COLLECT, bool STABLE = false, class WS = WarpScratch>
 __device__ __forceinline__ uint32_t scan_disc(const StageDev& S, WS& ws, int lane, int x, int y, uint32_t R2, const TimeFilter* T = nullptr) {
     uint32_t cnt = scan_rows<COLLECT, STABLE, false>(S, ws, lane, x, y, R2, S.mask, S.mask1, nullptr);
-    if (T) cnt += scan_rows<COLLECT, true, true>(S, ws, lane, x, y, R2, T->pend, T->pend1, T);
+    if (T) {
+        if (T->idx < T->brute_below) cnt += scan_items<COLLECT>(S, ws, lane, x, y, R2, *T);
+        else cnt += scan_rows<COLLECT, true, true>(S, ws, lane, x, y, R2, T->pend, T->pend1, T);
+    }
     if (!COLLECT) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
