@@ -26,7 +26,7 @@ sys.path.insert(0, ROOT)
 OUT, EX = 2048, 512
 WORKLOAD = f"{OUT}x{OUT} output from synthetic {EX}x{EX} example (synth_texture seed 1), k=50 m=50 cauchy=1.0 backtrack=0.5x5 seed=0"
 # dram bytes (read+write) of all k_flow launches of one step, from the ncu --set full capture summarised under profiles/
-TRAFFIC_PER_STEP = 9.72e9  # 9.33 GB read + 0.39 GB written over the 21 k_flow launches of one step (profiles/r1_kflow_all_launches_2048.txt)
+TRAFFIC_PER_STEP = 14.85e9  # 14.42 GB read + 0.43 GB written over the 11 k_flow launches of one step (profiles/r1_kflow_all_launches_2048.txt)
 CPU_SAMPLE_OUT = 2048  # CPU sample = the full workload (2048x2048 output, about 9 s on 16 host cores)
 
 
@@ -189,9 +189,9 @@ def run_ours(args, rank, world, local_rank):
     st = stats[-1]
     peaks, peak_src = measured_peaks()
     # dominant kernel: k_flow (K2+K3+K4+K5 fused, persistent).  Algorithmic bytes per launch set = texels actually gathered x 4 B
-    # + per pixel-resolution k*4 B target pattern + k*16 B neighbour state + 16 B written.
+    # + per pixel-resolution k*4 B target pattern + k*16 B neighbour state + k*4 B neighbour list + 16 B written.
     k = 50
-    alg_bytes = st["texels_fetched"] * 4 + st["work_items"] * (k * 4 + k * 16 + 16)
+    alg_bytes = st["texels_fetched"] * 4 + st["work_items"] * (k * 4 + k * 16 + k * 4 + 16)  # + k*4: prepared neighbour list
     kern_s = st["gpu_ms_resolve"] * 1e-3
     achieved = alg_bytes / kern_s / 1e9
     try:

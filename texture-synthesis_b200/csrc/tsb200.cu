@@ -290,7 +290,8 @@ struct tsb_generator {
     DevBuf<uint32_t> d_npred, d_nsucc, d_succ_off, d_succ_cur, d_succ, d_queue, d_fctl;
     DevBuf<short2> d_nb0, d_predl;                  // neighbour lists of the phase analysis (see PhaseDev)
     DevBuf<uint32_t> d_npredl;
-    size_t list_max_items = 0;                      // phases up to this size use the lists
+    size_t list_max_items = 0, predl_max_items = 0; // phases up to this size use the lists (nb0 / predl)
+    size_t stage_list_max = 4u << 20;               // larger (dense, throughput-bound) stages keep the epoch scheduler: its analysis is cheaper
     size_t cur_resolved = 0;                        // resolved pixels at the start of the phase being run
     double list_min_positions = 300.0;              // new phases use the lists when a mask walk would visit at least this many pixels
     uint32_t predl_stride = 0;
@@ -695,16 +696,20 @@ int ensure_flow_buffers(tsb_generator* g, size_t max_phase) {
 }
 
 // neighbour lists for phases of up to TSB_LIST_MAX items (default 4Mi): k + predl_stride offsets per item
+// Neighbour lists: k offsets per item (nb0) for phases of up to TSB_LIST_MAX items (default 64 Mi: 13 GB at k = 50), and
+// predl_stride in-disc predecessors per item (predl) for the new-pixel phases of the epoch scheduler (up to 4 Mi items).
 int ensure_list_buffers(tsb_generator* g, size_t max_phase, uint32_t k) {
-    size_t cap = 4u << 20;
-    if (const char* e = getenv("TSB_LIST_MAX")) cap = (size_t)strtoull(e, nullptr, 10);
+    size_t cap = 64u << 20, cap_predl = 4u << 20;
+    if (const char* e = getenv("TSB_LIST_MAX")) cap = cap_predl = (size_t)strtoull(e, nullptr, 10);
     g->list_max_items = std::min(max_phase, cap);
+    g->predl_max_items = std::min(max_phase, cap_predl);
     g->predl_stride = std::min<uint32_t>(((2 * k + 31) / 32) * 32, (uint32_t)KBUF - k);
     if (const char* e = getenv("TSB_LIST_MIN_POS")) g->list_min_positions = atof(e);
-    if (g->use_rounds || g->force_csr || g->predl_stride == 0) g->list_max_items = 0;
+    if (const char* e = getenv("TSB_STAGE_LIST_MAX")) g->stage_list_max = (size_t)strtoull(e, nullptr, 10);
+    if (g->use_rounds || g->force_csr || g->predl_stride == 0) g->list_max_items = g->predl_max_items = 0;
     if (g->list_max_items == 0) return 0;
     TRY(g->d_nb0.ensure(g->list_max_items * k));
-    TRY(g->d_predl.ensure(g->list_max_items * g->predl_stride));
+    TRY(g->d_predl.ensure(std::max<size_t>(g->predl_max_items, 1) * g->predl_stride));  // never null: a null predl means "exact lists" to the kernels
     TRY(g->d_npredl.ensure(g->list_max_items));
     return 0;
 }
@@ -828,7 +833,7 @@ int run_stage_new(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, 
 
 // Does this phase use the neighbour lists of the analysis (PhaseDev::nb0 / predl) instead of walking the bit mask?
 bool use_lists(const tsb_generator* g, const StageDev& S, uint32_t n, bool is_new) {
-    if (n > g->list_max_items) return false;
+    if (n > (is_new ? g->predl_max_items : g->list_max_items)) return false;
     if (S.tiling && (g->W < 100 || g->H < 100)) return false;  // tiny_torus(): one-sided edge registration, no lists
     // new pixels in an already dense canvas: walking the bit mask (k / density pixels) is cheaper than merging lists
     if (is_new && (double)S.k * (double)g->W * (double)g->H / (double)std::max<size_t>(1, g->cur_resolved) < g->list_min_positions) return false;
@@ -1269,7 +1274,7 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
             }
             size_t base = resolved_now - g->inpaint_locked;
             bool whole_stage = false;
-            if (g->stage_lists && base >= std::max<size_t>((size_t)k + 14, 64) && n_items - cur <= g->list_max_items) {
+            if (g->stage_lists && base >= std::max<size_t>((size_t)k + 14, 64) && n_items - cur <= std::min(g->list_max_items, g->stage_list_max)) {
                 // the rest of the stage as one dataflow phase (exact timed neighbour lists, run_stage_new)
                 const size_t n_e = n_items - cur;
                 S.r2_hint = r2_hint_for(g, resolved_now, k);
