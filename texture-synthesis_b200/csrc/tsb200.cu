@@ -1171,7 +1171,7 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
     g->use_rounds = getenv("TSB_MODE") && !strcmp(getenv("TSB_MODE"), "rounds");
     g->force_csr = getenv("TSB_MODE") && !strcmp(getenv("TSB_MODE"), "csr");
     g->succ_stride = getenv("TSB_SUCC_STRIDE") ? std::max(1, atoi(getenv("TSB_SUCC_STRIDE"))) : SUCC_STRIDE;
-    g->stage_lists = !g->mg_on && !g->use_rounds && !g->force_csr && !(getenv("TSB_MODE") && !strcmp(getenv("TSB_MODE"), "epochs"));
+    g->stage_lists = !g->use_rounds && !g->force_csr && !(getenv("TSB_MODE") && !strcmp(getenv("TSB_MODE"), "epochs"));
     if (g->stage_lists) {  // whole stages as one phase: the per-phase buffers must hold a stage's new pixels
         size_t max_new = 1;
         for (auto& sp : plan) max_new = std::max(max_new, sp.n_new);
@@ -1274,12 +1274,15 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
             }
             size_t base = resolved_now - g->inpaint_locked;
             bool whole_stage = false;
-            if (g->stage_lists && base >= std::max<size_t>((size_t)k + 14, 64) && n_items - cur <= std::min(g->list_max_items, g->stage_list_max)) {
+            // band-sharded runs: only stages that are dependency bound (small, or growing the resolved set at least 4x) take
+            // this route -- every rank then executes the stage redundantly on its own replica, with no communication
+            const bool mg_ok = !g->mg_on || n_items - cur <= 2 * g->mg_min_phase || resolved_now * 4 <= n_items - cur;
+            if (g->stage_lists && mg_ok && base >= std::max<size_t>((size_t)k + 14, 64) && n_items - cur <= std::min(g->list_max_items, g->stage_list_max)) {
                 // the rest of the stage as one dataflow phase (exact timed neighbour lists, run_stage_new)
                 const size_t n_e = n_items - cur;
                 S.r2_hint = r2_hint_for(g, resolved_now, k);
                 S.n_points_max = (uint32_t)std::min<size_t>((tiling ? 3 : 1) * (resolved_now + n_e), 0xFFFFFFFFull);
-                TRY(gen_rand(cur, n_e));
+                if (g->mg_on) TRY(launch_rand(cur, n_e, false, s));  // executed redundantly by every rank: candidates for ALL items
                 TRY(run_stage_new(g, S, (uint32_t)cur, (uint32_t)n_e, resolved_now, trace_base));
                 cur += n_e; resolved_now += n_e;
                 whole_stage = true;
