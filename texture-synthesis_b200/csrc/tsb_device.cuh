@@ -653,6 +653,51 @@ __device__ __forceinline__ void score_coherent_shared(const StageDev& S, WarpScr
     }
 }
 
+// N consecutive neighbours [j0, j0+N) of one candidate: the gathers first (memory-level parallelism), then the strict
+// left-to-right f32 accumulation of ms.rs:1259-1280
+template <bool GUIDED, bool FRAMED, bool OPAQUE, int N>
+__device__ __forceinline__ float score_chunk(const WarpScratch& ws, const float* __restrict__ s_lut, const float* __restrict__ s_lutg,
+                                             const int* __restrict__ dl, const char* bp, const char* gbp, const DevEx& e,
+                                             const DevGuide& ge, int cx, int cy, int sgn, int j0, float s) {
+    uint32_t tex[N], gtex[N];
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+        const int j = j0 + u;
+        if (FRAMED) {
+            const long long o4 = (long long)sgn * (long long)dl[j];
+            tex[u] = __ldg(reinterpret_cast<const uint32_t*>(bp + o4));
+            if (GUIDED) gtex[u] = __ldg(reinterpret_cast<const uint32_t*>(gbp + o4));
+        } else {
+            short2 o = ws.off[j];
+            int X = cx + sgn * o.x, Y = cy + sgn * o.y;
+            tex[u] = OUTSIDE_RGBA;
+            gtex[u] = OUTSIDE_RGBA;
+            if ((unsigned)X < (unsigned)e.w && (unsigned)Y < (unsigned)e.h) tex[u] = __ldg(e.px + (size_t)Y * e.w + X);
+            if (GUIDED) {
+                if ((unsigned)X < (unsigned)ge.w && (unsigned)Y < (unsigned)ge.h) gtex[u] = __ldg(ge.px + (size_t)Y * ge.w + X);
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+        const int j = j0 + u;
+        uint32_t dd = __vabsdiffu4(ws.tcol[j], tex[u]);
+        float t = s_lut[dd & 0xFFu];
+        t = __fadd_rn(t, s_lut[(dd >> 8) & 0xFFu]);
+        t = __fadd_rn(t, s_lut[(dd >> 16) & 0xFFu]);
+        if (!OPAQUE) t = __fadd_rn(t, s_lut[dd >> 24]);
+        if (GUIDED) {
+            uint32_t dg = __vabsdiffu4(ws.gcol[j], gtex[u]);
+            t = __fadd_rn(t, s_lutg[dg & 0xFFu]);
+            t = __fadd_rn(t, s_lutg[(dg >> 8) & 0xFFu]);
+            t = __fadd_rn(t, s_lutg[(dg >> 16) & 0xFFu]);
+            if (!OPAQUE) t = __fadd_rn(t, s_lutg[dg >> 24]);
+        }
+        s = __fadd_rn(s, __fmul_rn(t, ws.g[j]));
+    }
+    return s;
+}
+
 // ---------------------------------------------------------------------------------------------
 // find_best_match / better_match (ms.rs:1184-1288): one lane per candidate, 32 candidates per round.
 // FRAMED: every neighbour offset is within EX_PAD, texels come from the framed copies with no bounds test.
@@ -689,47 +734,25 @@ __device__ __forceinline__ void score_candidates(const StageDev& S, WarpScratch&
             }
             ccol = FRAMED ? __ldg(reinterpret_cast<const uint32_t*>(bp)) : __ldg(e.px + (size_t)cy * e.w + cx);
             ok = true;
-            for (int j0 = 0; j0 < kk8; j0 += 8) {
-                uint32_t tex[8], gtex[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {  // issue the gathers of the chunk first (memory-level parallelism)
-                    const int j = j0 + u;
-                    if (FRAMED) {
-                        const long long o4 = (long long)sgn * (long long)dl[j];
-                        tex[u] = __ldg(reinterpret_cast<const uint32_t*>(bp + o4));
-                        if (GUIDED) gtex[u] = __ldg(reinterpret_cast<const uint32_t*>(gbp + o4));
-                    } else {
-                        short2 o = ws.off[j];
-                        int X = cx + sgn * o.x, Y = cy + sgn * o.y;
-                        tex[u] = OUTSIDE_RGBA;
-                        gtex[u] = OUTSIDE_RGBA;
-                        if ((unsigned)X < (unsigned)e.w && (unsigned)Y < (unsigned)e.h) tex[u] = __ldg(e.px + (size_t)Y * e.w + X);
-                        if (GUIDED) {
-                            if ((unsigned)X < (unsigned)ge.w && (unsigned)Y < (unsigned)ge.h) gtex[u] = __ldg(ge.px + (size_t)Y * ge.w + X);
-                        }
-                    }
+            // Early-out vs. the best of earlier rounds (ms.rs:1281): all terms are >= 0, so testing the prefix only at
+            // chunk ends rejects exactly the same candidates.  Once a best exists most candidates fall within the
+            // first few (nearest, heaviest) neighbours, so the first eight are taken as two chunks of four.
+            int j0 = 0;
+            if (best != FLT_MAX) {
+                s = score_chunk<GUIDED, FRAMED, OPAQUE, 4>(ws, s_lut, s_lutg, dl, bp, gbp, e, ge, cx, cy, sgn, 0, s);
+                fetched += (uint32_t)min(4, kk);
+                if (s >= best) ok = false;
+                else {
+                    s = score_chunk<GUIDED, FRAMED, OPAQUE, 4>(ws, s_lut, s_lutg, dl, bp, gbp, e, ge, cx, cy, sgn, 4, s);
+                    fetched += (uint32_t)max(0, min(4, kk - 4));
+                    if (s >= best) ok = false;
                 }
+                j0 = 8;
+            }
+            for (; ok && j0 < kk8; j0 += 8) {
+                s = score_chunk<GUIDED, FRAMED, OPAQUE, 8>(ws, s_lut, s_lutg, dl, bp, gbp, e, ge, cx, cy, sgn, j0, s);
                 fetched += (uint32_t)min(8, kk - j0);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {  // strict left-to-right f32 accumulation (ms.rs:1259-1280)
-                    const int j = j0 + u;
-                    uint32_t dd = __vabsdiffu4(ws.tcol[j], tex[u]);
-                    float t = s_lut[dd & 0xFFu];
-                    t = __fadd_rn(t, s_lut[(dd >> 8) & 0xFFu]);
-                    t = __fadd_rn(t, s_lut[(dd >> 16) & 0xFFu]);
-                    if (!OPAQUE) t = __fadd_rn(t, s_lut[dd >> 24]);
-                    if (GUIDED) {
-                        uint32_t dg = __vabsdiffu4(ws.gcol[j], gtex[u]);
-                        t = __fadd_rn(t, s_lutg[dg & 0xFFu]);
-                        t = __fadd_rn(t, s_lutg[(dg >> 8) & 0xFFu]);
-                        t = __fadd_rn(t, s_lutg[(dg >> 16) & 0xFFu]);
-                        if (!OPAQUE) t = __fadd_rn(t, s_lutg[dg >> 24]);
-                    }
-                    s = __fadd_rn(s, __fmul_rn(t, ws.g[j]));
-                }
-                // early-out vs. the best of earlier rounds (ms.rs:1281); all terms are >= 0, so testing the
-                // prefix only at chunk ends rejects exactly the same candidates
-                if (s >= best) { ok = false; break; }
+                if (s >= best) ok = false;
             }
         }
         bool win = ok && (s < best);
@@ -1776,17 +1799,40 @@ __global__ void k_rand_candidates(const DevEx* ex, int n_ex, int m, uint64_t see
         Pcg32 rng = Pcg32::seed_from_u64(seed_base + (uint64_t)it);
         uint32_t* oxy = sxy + (size_t)threadIdx.x * m;
         uint8_t* om = smap + (size_t)threadIdx.x * m;
-        for (int r = 0; r < m; ++r) {
-            uint32_t map = (uint32_t)rng.gen_range_usize((uint64_t)n_ex);
-            DevEx e = ex[map];
-            uint32_t rx, ry;
-            for (;;) {
-                rx = rng.gen_range_u32((uint32_t)e.w);
-                ry = rng.gen_range_u32((uint32_t)e.h);
-                if (!e.smask || e.smask[(size_t)ry * e.w + rx] != 0) break;
+        if (n_ex == 1) {
+            // One example (the common case): gen_range(0..1) still consumes 64-bit draws until v <= 2^63 - 1, i.e. until
+            // the top bit of the high word is clear, and always yields 0; the zones of the coordinate draws are fixed.
+            const DevEx e = ex[0];
+            const uint32_t w = (uint32_t)e.w, h = (uint32_t)e.h;
+            const uint32_t zw = (w << Pcg32::clz32(w)) - 1u, zh = (h << Pcg32::clz32(h)) - 1u;
+            for (int r = 0; r < m; ++r) {
+                uint32_t hi;
+                do { rng.step(); hi = rng.next_u32(); } while (hi >> 31);  // low word drawn and dropped, high word tested
+                uint32_t rx, ry;
+                for (;;) {
+                    uint64_t mm;
+                    do { mm = (uint64_t)rng.next_u32() * (uint64_t)w; } while ((uint32_t)mm > zw);
+                    rx = (uint32_t)(mm >> 32);
+                    do { mm = (uint64_t)rng.next_u32() * (uint64_t)h; } while ((uint32_t)mm > zh);
+                    ry = (uint32_t)(mm >> 32);
+                    if (!e.smask || e.smask[(size_t)ry * e.w + rx] != 0) break;
+                }
+                oxy[r] = rx | (ry << 16);
+                om[r] = 0;
             }
-            oxy[r] = rx | (ry << 16);
-            om[r] = (uint8_t)map;
+        } else {
+            for (int r = 0; r < m; ++r) {
+                uint32_t map = (uint32_t)rng.gen_range_usize((uint64_t)n_ex);
+                DevEx e = ex[map];
+                uint32_t rx, ry;
+                for (;;) {
+                    rx = rng.gen_range_u32((uint32_t)e.w);
+                    ry = rng.gen_range_u32((uint32_t)e.h);
+                    if (!e.smask || e.smask[(size_t)ry * e.w + rx] != 0) break;
+                }
+                oxy[r] = rx | (ry << 16);
+                om[r] = (uint8_t)map;
+            }
         }
     }
     __syncthreads();
