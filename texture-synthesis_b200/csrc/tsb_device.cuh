@@ -397,7 +397,10 @@ __device__ __forceinline__ int knn_search(const StageDev& S, WS& ws, int lane, i
                 if (idx < limit) {
                     o[u] = __ldg(S.spiral + idx);
                     hit[u] = mask_test<STABLE>(S, x + o[u].x, y + o[u].y);
-                    if (T && !hit[u] && mask_test_at<true>(S, T->pend, x + o[u].x, y + o[u].y)) hit[u] = time_passes(S, *T, x + o[u].x, y + o[u].y);
+                    if (T) {  // both masks are requested before either is looked at
+                        const bool pend = mask_test_at<true>(S, T->pend, x + o[u].x, y + o[u].y);
+                        if (!hit[u] && pend) hit[u] = time_passes(S, *T, x + o[u].x, y + o[u].y);
+                    }
                 }
             }
 #pragma unroll
