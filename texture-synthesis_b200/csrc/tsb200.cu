@@ -293,6 +293,7 @@ struct tsb_generator {
     size_t list_max_items = 0, predl_max_items = 0; // phases up to this size use the lists (nb0 / predl)
     size_t stage_list_max = 4u << 20;               // larger (dense, throughput-bound) stages keep the epoch scheduler: its analysis is cheaper
     size_t cur_resolved = 0;                        // resolved pixels at the start of the phase being run
+    bool cur_resolved_redo_ok = false;              // the redo phase being run has more than k resolved points (finite radii everywhere)
     double list_min_positions = 300.0;              // new phases use the lists when a mask walk would visit at least this many pixels
     uint32_t predl_stride = 0;
     DevBuf<uint8_t> d_cub_temp, d_sort_temp;
@@ -777,6 +778,24 @@ int run_serial(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, boo
     return clk.end(g, s, "serial", i0, n, is_new, 0);
 }
 
+// k_flow instantiations: <guided, band-sharded, all-alpha-255, lists-only>
+template <bool MG>
+int launch_flow(tsb_generator* g, int grid, const StageDev& S, const PhaseDev& P, const FlowDev& F, bool lists_only) {
+    cudaStream_t s = g->stream;
+    const bool op = S.opaque != 0;
+#define TSB_FLOW(G, O, L) k_flow<G, MG, O, L><<<grid, CTA_THREADS, sizeof(RoundSmem), s>>>(S, P, F)
+    if (MG || !lists_only) {
+        if (g->guided) { if (op) TSB_FLOW(true, true, false); else TSB_FLOW(true, false, false); }
+        else { if (op) TSB_FLOW(false, true, false); else TSB_FLOW(false, false, false); }
+    } else {
+        if (g->guided) { if (op) TSB_FLOW(true, true, (!MG)); else TSB_FLOW(true, false, (!MG)); }
+        else { if (op) TSB_FLOW(false, true, (!MG)); else TSB_FLOW(false, false, (!MG)); }
+    }
+#undef TSB_FLOW
+    CU(cudaGetLastError());
+    return 0;
+}
+
 // All remaining new pixels [i0, i0+n) of a stage as ONE dataflow phase (single GPU): exact neighbour lists "as of" every
 // item's serial time (k_lists_timed), read-after-write edges from those lists (CSR), persistent kernel.
 int run_stage_new(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, size_t resolved_before, uint64_t trace_base) {
@@ -819,8 +838,7 @@ int run_stage_new(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, 
     CU(cudaGetLastError());
     TRY(clk.mid(s));
     if (g->rand_pending) { CU(cudaStreamWaitEvent(s, g->ev_rand, 0)); g->rand_pending = false; }
-    if (g->guided) k_flow<true, false><<<gf, CTA_THREADS, sizeof(RoundSmem), s>>>(S, P, F);
-    else k_flow<false, false><<<gf, CTA_THREADS, sizeof(RoundSmem), s>>>(S, P, F);
+    TRY(launch_flow<false>(g, gf, S, P, F, true));  // every item has its exact list
     k_pmap_clear<<<nb, 256, 0, s>>>(P);
     CU(cudaGetLastError());
     g->stats.kernel_launches += 11;
@@ -941,8 +959,7 @@ int run_phase_flow(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n,
         TRY(barrier());  // every rank has seeded its queue before any rank starts publishing into it
         TRY(clk.mid(s));
         const int gfm = g->guided ? g->max_ctas_flow_guided : g->max_ctas_flow;
-        if (g->guided) k_flow<true, true><<<gfm, CTA_THREADS, sizeof(RoundSmem), s>>>(Sm, P, F);
-        else k_flow<false, true><<<gfm, CTA_THREADS, sizeof(RoundSmem), s>>>(Sm, P, F);
+        TRY(launch_flow<true>(g, gfm, Sm, P, F, false));
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(g->h_ctrl, F.ctl, 32, cudaMemcpyDeviceToHost, s));
         {
@@ -1034,8 +1051,9 @@ int run_phase_flow(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n,
         CU(cudaGetLastError());
         if (attempt == 0) TRY(clk.mid(s));
         if (g->rand_pending) { CU(cudaStreamWaitEvent(s, g->ev_rand, 0)); g->rand_pending = false; }
-        if (g->guided) k_flow<true, false><<<gf, CTA_THREADS, sizeof(RoundSmem), s>>>(S, P, F);
-        else k_flow<false, false><<<gf, CTA_THREADS, sizeof(RoundSmem), s>>>(S, P, F);
+        // a redo phase with lists never needs the mask search (every item has k neighbours when this path is taken with
+        // more than k resolved points); new-pixel epochs may (a predecessor list can overflow)
+        TRY(launch_flow<false>(g, gf, S, P, F, P.nb0 != nullptr && !is_new && g->cur_resolved_redo_ok));
         k_pmap_clear<<<(n + 255) / 256, 256, 0, s>>>(P);
         CU(cudaGetLastError());
         g->stats.kernel_launches += 4;
@@ -1250,7 +1268,7 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
             S.n_points_max = (uint32_t)std::min<size_t>((tiling ? 3 : 1) * resolved_now, 0xFFFFFFFFull);
             TRY(gen_rand(0, sp.n_redo));
             if (g->use_rounds) TRY(run_phase(g, S, 0, (uint32_t)sp.n_redo, false, true, trace_base));
-            else TRY(run_phase_flow(g, S, 0, (uint32_t)sp.n_redo, false, trace_base));
+            else { g->cur_resolved_redo_ok = resolved_now > (size_t)k; TRY(run_phase_flow(g, S, 0, (uint32_t)sp.n_redo, false, trace_base)); }
         }
         // ---- new pixels, in epochs over which the resolved count at most doubles ----
         size_t cur = sp.n_redo;
@@ -1520,16 +1538,17 @@ int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
     cudaFuncSetAttribute(k_eval_items<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
     cudaFuncSetAttribute(k_eval_items<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
     cudaFuncSetAttribute(k_radius, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(KnnScratch) * WARPS_PER_CTA));
-    cudaFuncSetAttribute(k_flow<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
-    cudaFuncSetAttribute(k_flow<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
-    cudaFuncSetAttribute(k_flow<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
-    cudaFuncSetAttribute(k_flow<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
+#define TSB_FLOW_ATTR(G, M, O, L) cudaFuncSetAttribute(k_flow<G, M, O, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem))
+    TSB_FLOW_ATTR(false, false, false, false); TSB_FLOW_ATTR(false, false, true, false); TSB_FLOW_ATTR(false, false, false, true); TSB_FLOW_ATTR(false, false, true, true);
+    TSB_FLOW_ATTR(true, false, false, false); TSB_FLOW_ATTR(true, false, true, false); TSB_FLOW_ATTR(true, false, false, true); TSB_FLOW_ATTR(true, false, true, true);
+    TSB_FLOW_ATTR(false, true, false, false); TSB_FLOW_ATTR(false, true, true, false); TSB_FLOW_ATTR(true, true, false, false); TSB_FLOW_ATTR(true, true, true, false);
+#undef TSB_FLOW_ATTR
     cudaFuncSetAttribute(k_serial<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
     cudaFuncSetAttribute(k_serial<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_round<false>, CTA_THREADS, sizeof(RoundSmem)) != cudaSuccess || per_sm < 1) per_sm = 1;
     int per_sm_flow = 0, per_sm_flow_g = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_flow, k_flow<false, true>, CTA_THREADS, sizeof(RoundSmem)) != cudaSuccess || per_sm_flow < 1) per_sm_flow = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_flow_g, k_flow<true, true>, CTA_THREADS, sizeof(RoundSmem)) != cudaSuccess || per_sm_flow_g < 1) per_sm_flow_g = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_flow, k_flow<false, true, false, false>, CTA_THREADS, sizeof(RoundSmem)) != cudaSuccess || per_sm_flow < 1) per_sm_flow = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_flow_g, k_flow<true, true, false, false>, CTA_THREADS, sizeof(RoundSmem)) != cudaSuccess || per_sm_flow_g < 1) per_sm_flow_g = 1;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "cudaGetDeviceProperties failed"));
     g->n_sms = prop.multiProcessorCount;

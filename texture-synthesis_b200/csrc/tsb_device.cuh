@@ -775,7 +775,10 @@ __device__ __forceinline__ void score_candidates(const StageDev& S, WarpScratch&
 // ---------------------------------------------------------------------------------------------
 // One pixel resolution (steps 2-4 of ms.rs:917-986) by one warp.  No commit.
 // ---------------------------------------------------------------------------------------------
-template <bool GUIDED>
+// OPQ: 1 / 0 = the alpha term is known at compile time to be skipped / kept, -1 = decided at run time (S.opaque).
+// LISTS: the neighbourhood always comes from the analysis lists (nb0 != nullptr), the mask search is not compiled in.
+// Both only shrink the code of the persistent kernel (instruction fetch is a measurable share of its stalls).
+template <bool GUIDED, int OPQ = -1, bool LISTS = false>
 __device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws, const float* __restrict__ s_lut,
                              const float* __restrict__ s_lutg, int lane, int x, int y, uint32_t R2bound,
                              const uint32_t* __restrict__ rand_xy, const uint8_t* __restrict__ rand_map, ItemOut& out,
@@ -784,7 +787,7 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws,
     const unsigned lt = (1u << lane) - 1u;
     uint32_t r2;
     long long t0 = clock64();
-    const int kk = nb0 ? knn_from_lists(S, ws, lane, nb0, predl, npl, &r2, nbk)
+    const int kk = (LISTS || nb0) ? knn_from_lists(S, ws, lane, nb0, predl, npl, &r2, nbk)
                  : pts ? knn_points(S, ws, lane, x, y, pts, npts, &r2) : knn_search(S, ws, lane, x, y, R2bound, &r2);
     long long t1 = clock64();
     out.c_knn = t1 - t0; out.c_neigh = out.c_weight = out.c_score = 0; out.fetched = out.nominal = 0;
@@ -935,7 +938,9 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws,
         if (shared_round) score_coherent_shared<GUIDED, FR, OP>(S, ws, s_lut, s_lutg, lane, kk, kk8, nuniq_coh, best, besti, fetched, bestcol); \
         score_candidates<GUIDED, FR, OP>(S, ws, s_lut, s_lutg, lane, kk, kk8, ncand, nuniq_coh, base0, best, besti, fetched, bestcol); \
     } while (0)
-    if (framed) { if (S.opaque) TSB_SCORE(true, true); else TSB_SCORE(true, false); }
+    if (OPQ == 1) { if (framed) TSB_SCORE(true, true); else TSB_SCORE(false, true); }
+    else if (OPQ == 0) { if (framed) TSB_SCORE(true, false); else TSB_SCORE(false, false); }
+    else if (framed) { if (S.opaque) TSB_SCORE(true, true); else TSB_SCORE(true, false); }
     else { if (S.opaque) TSB_SCORE(false, true); else TSB_SCORE(false, false); }
 #undef TSB_SCORE
 #pragma unroll
@@ -1103,7 +1108,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_round(StageDev S, PhaseDev P, u
 // Persistent dataflow kernel: one launch per phase.  Warps claim queue slots in order; a slot is
 // published when the last predecessor of an item commits.  Grid = co-resident CTAs only.
 // ---------------------------------------------------------------------------------------------
-template <bool GUIDED, bool MG>
+template <bool GUIDED, bool MG, bool OPAQUE, bool LISTS>
 __global__ void __launch_bounds__(CTA_THREADS, 3) k_flow(StageDev S, PhaseDev P, FlowDev F) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RoundSmem& rs = *reinterpret_cast<RoundSmem*>(smem_raw);
@@ -1171,8 +1176,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_flow(StageDev S, PhaseDev P,
             if (!P.predl) { nb0 = P.nb0 + (size_t)it * S.k; nbk = (int)c; }  // exact lists "as of" the item's serial time
             else if (c <= P.predl_stride) { nb0 = P.nb0 + (size_t)it * S.k; predl = P.predl + (size_t)it * P.predl_stride; npl = (int)c; }
         }
-        resolve_item<GUIDED>(S, ws, sm.lut, sm.lutg, lane, x, y, P.item_R2[it], P.rand_xy + (size_t)si * S.m,
-                             P.rand_map + (size_t)si * S.m, o, nullptr, 0, nb0, predl, npl, nbk);
+        if (LISTS && !nb0) {  // the host promised a usable list for every item of this phase
+            if (lane == 0) atomicExch(F.ctl + FC_ABORT, 1u);
+            break;
+        }
+        resolve_item<GUIDED, OPAQUE ? 1 : 0, LISTS>(S, ws, sm.lut, sm.lutg, lane, x, y, P.item_R2[it], P.rand_xy + (size_t)si * S.m,
+                                                    P.rand_map + (size_t)si * S.m, o, nullptr, 0, nb0, predl, npl, nbk);
         long long tc0 = clock64();
         if (pref) { asm volatile("cp.async.wait_all;" ::: "memory"); __syncwarp(); }
         const size_t s0 = F.stride ? (size_t)it * F.stride : (size_t)F.succ_off[it];
