@@ -772,6 +772,18 @@ __device__ __forceinline__ void score_candidates(const StageDev& S, WarpScratch&
     }
 }
 
+struct ScoreOut { float best; int besti; uint32_t fetched, bestcol; };
+// the bounds-tested scoring path as a real function (see resolve_item)
+template <bool GUIDED, bool OPAQUE>
+__device__ __noinline__ ScoreOut score_unframed(const StageDev& S, WarpScratch& ws, const float* __restrict__ s_lut, const float* __restrict__ s_lutg,
+                                                int lane, int kk, int kk8, int ncand, int nuniq_coh, bool shared_round) {
+    ScoreOut r;
+    r.best = FLT_MAX; r.besti = 0; r.fetched = 0; r.bestcol = 0;
+    if (shared_round) score_coherent_shared<GUIDED, false, OPAQUE>(S, ws, s_lut, s_lutg, lane, kk, kk8, nuniq_coh, r.best, r.besti, r.fetched, r.bestcol);
+    score_candidates<GUIDED, false, OPAQUE>(S, ws, s_lut, s_lutg, lane, kk, kk8, ncand, nuniq_coh, shared_round ? nuniq_coh : 0, r.best, r.besti, r.fetched, r.bestcol);
+    return r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // One pixel resolution (steps 2-4 of ms.rs:917-986) by one warp.  No commit.
 // ---------------------------------------------------------------------------------------------
@@ -938,8 +950,15 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws,
         if (shared_round) score_coherent_shared<GUIDED, FR, OP>(S, ws, s_lut, s_lutg, lane, kk, kk8, nuniq_coh, best, besti, fetched, bestcol); \
         score_candidates<GUIDED, FR, OP>(S, ws, s_lut, s_lutg, lane, kk, kk8, ncand, nuniq_coh, base0, best, besti, fetched, bestcol); \
     } while (0)
-    if (OPQ == 1) { if (framed) TSB_SCORE(true, true); else TSB_SCORE(false, true); }
-    else if (OPQ == 0) { if (framed) TSB_SCORE(true, false); else TSB_SCORE(false, false); }
+    if (OPQ == 1 || OPQ == 0) {
+        // persistent kernel: the framed path is the hot one (fine stages); the bounds-tested one is kept out of line so
+        // that it does not dilute the instruction cache
+        if (framed) TSB_SCORE(true, (OPQ == 1));
+        else {
+            const ScoreOut r = score_unframed<GUIDED, (OPQ == 1)>(S, ws, s_lut, s_lutg, lane, kk, kk8, ncand, nuniq_coh, shared_round);
+            best = r.best; besti = r.besti; fetched = r.fetched; bestcol = r.bestcol;
+        }
+    }
     else if (framed) { if (S.opaque) TSB_SCORE(true, true); else TSB_SCORE(true, false); }
     else { if (S.opaque) TSB_SCORE(false, true); else TSB_SCORE(false, false); }
 #undef TSB_SCORE
