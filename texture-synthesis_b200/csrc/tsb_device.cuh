@@ -1,15 +1,19 @@
 // tsb_device.cuh -- sm_100a kernels of the texture-synthesis hot path.
 //
 // One warp performs one "pixel resolution" (reference lib/src/ms.rs:887-1011):
-//   K2  k nearest resolved neighbours  : spiral walk / disc scan over a bit-packed resolved mask
-//                                         (replaces TreeGrid + rstar, ms.rs:1313-1531)
-//   K3  candidates                      : coherence candidates from the neighbours' source coordinates
-//                                         (ms.rs:496-547) + pre-generated PCG-exact random ones (ms.rs:549-599)
-//   K4  cost + argmin                   : one lane per candidate, strict f32 order (ms.rs:1184-1288)
+//   K2  k nearest resolved neighbours  : (replaces TreeGrid + rstar, ms.rs:1313-1531) prepared by the phase analysis as
+//                                         a per-item list -- spiral walk / disc scan over a bit-packed resolved mask,
+//                                         for new pixels "as of" the item's serial time (k_lists_timed) -- and only
+//                                         loaded by the resolve kernel (knn_from_lists); knn_search is the fallback
+//   K3  candidates                      : coherence candidates from the neighbours' source coordinates, exactly
+//                                         de-duplicated (ms.rs:496-547) + pre-generated PCG-exact random ones (549-599)
+//   K4  cost + argmin                   : eight lanes per candidate with the f32 sum carried as a chain when few
+//                                         coherence candidates remain, else one lane per candidate; strict f32 order
+//                                         (ms.rs:1184-1288)
 //   K5  commit                          : ms.rs:334-377 / 296-331
-// Rounds of mutually independent work items are executed in the exact serial order semantics of
-// the single-threaded reference: an item runs once every lower-index item inside its conflict
-// radius has committed (see DESIGN.md "Exact wave schedule").
+// Work items are executed in the exact serial-order semantics of the single-threaded reference by a persistent
+// dataflow kernel (k_flow): an item runs once every lower-index item it reads from (or that reads what it
+// overwrites) has committed.
 #pragma once
 #include <cuda_runtime.h>
 #include <cfloat>
