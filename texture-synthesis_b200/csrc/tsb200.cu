@@ -512,6 +512,7 @@ int check_params(const tsb_generator* g, const tsb_params* p) {
     if (p->nearest_neighbors == 0 || p->nearest_neighbors > (uint32_t)KMAX) return fail(TSB_ERR_UNSUPPORTED, "nearest_neighbors must be in [1,%d]", KMAX);
     if (p->nearest_neighbors + p->random_sample_locations > (uint64_t)CANDMAX)
         return fail(TSB_ERR_UNSUPPORTED, "nearest_neighbors + random_sample_locations must be <= %d", CANDMAX);
+    if (p->random_sample_locations == 0) return fail(TSB_ERR_INVALID, "random_sample_locations must be at least 1 (session.rs:489-496; without random candidates a pixel can be left with no candidate at all)");
     if (p->cauchy_dispersion == 0.0f) return fail(TSB_ERR_UNSUPPORTED, "cauchy_dispersion == 0 yields NaN costs in the reference (quirk q14); not supported");
     int need_levels = p->p_stages == 0 ? 1 : p->p_stages;
     if (g->n_levels < need_levels) return fail(TSB_ERR_INVALID, "example pyramids have %d levels, %d needed", g->n_levels, need_levels);
