@@ -269,9 +269,10 @@ struct tsb_generator {
     std::vector<int> filt;                          // filtered index -> all index
     std::vector<DevBuf<uint32_t>> d_ex;             // per (all) example: levels*w*h
     std::vector<DevBuf<uint32_t>> d_exf, d_exgf;    // framed copies (EX_PAD texels of the outside colour all round)
-    DevBuf<uint32_t> d_alpha_flag;                  // [0] set when an input texel has alpha != 255, [1] same for the state
+    DevBuf<uint32_t> d_alpha_flag;                  // [level] set when an input texel of that pyramid level has alpha != 255, [64] same for the state
+    std::vector<uint8_t> level_opaque;              // per pyramid level: every input texel has alpha 255
     int pad_pitch = 0;                              // common row pitch of the framed copies, 0 when the sizes differ
-    bool inputs_opaque = false, run_opaque = false, no_fast = false;
+    bool run_opaque = false, no_fast = false;
     std::vector<DevBuf<uint8_t>> d_smask;           // per (all) example
     DevBuf<DevEx> d_exdesc;                         // [levels][n_ex] filtered
     bool guided = false;
@@ -403,8 +404,9 @@ int upload_inputs(tsb_generator* g, const tsb_pyramid* examples, uint32_t n_exam
         g->d_ex.clear(); g->d_smask.clear(); g->d_exf.clear();
         g->d_ex.resize(n_examples); g->d_smask.resize(n_examples); g->d_exf.resize(n_examples);
     }
-    TRY(g->d_alpha_flag.ensure(2));
-    CU(cudaMemsetAsync(g->d_alpha_flag.p, 0, 8, s));
+    if (g->n_levels > 64) return fail(TSB_ERR_UNSUPPORTED, "more than 64 pyramid levels");
+    TRY(g->d_alpha_flag.ensure(65));
+    CU(cudaMemsetAsync(g->d_alpha_flag.p, 0, 65 * 4, s));
     for (uint32_t e = 0; e < n_examples; ++e) {
         const tsb_pyramid& p = examples[e];
         if (!p.levels || p.width == 0 || p.height == 0 || p.n_levels == 0) return fail(TSB_ERR_INVALID, "example %u is empty", e);
@@ -453,7 +455,7 @@ int upload_inputs(tsb_generator* g, const tsb_pyramid* examples, uint32_t n_exam
         TRY(upload_pyramid(guides->target, g->d_tguide, s));
         {
             const size_t n = (size_t)g->n_levels * g->tgw * g->tgh;
-            k_alpha_check<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 64), 256, 0, s>>>(g->d_tguide.p, n, g->d_alpha_flag.p);
+            k_alpha_check<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 64), 256, 0, s>>>(g->d_tguide.p, n, (size_t)g->tgw * g->tgh, g->d_alpha_flag.p);
         }
         if (g->d_exg.size() != n_examples) { g->d_exg.clear(); g->d_exgf.clear(); g->d_exg.resize(n_examples); g->d_exgf.resize(n_examples); }
         std::vector<DevGuide> gd((size_t)g->n_levels * n_examples);
@@ -474,28 +476,32 @@ int upload_inputs(tsb_generator* g, const tsb_pyramid* examples, uint32_t n_exam
         }
         TRY(g->d_exgdesc.upload(gd.data(), gd.size(), s));
     }
-    uint32_t flag = 1;
-    CU(cudaMemcpyAsync(&flag, g->d_alpha_flag.p, 4, cudaMemcpyDeviceToHost, s));
+    uint32_t flags[64];
+    CU(cudaMemcpyAsync(flags, g->d_alpha_flag.p, (size_t)g->n_levels * 4, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    g->inputs_opaque = flag == 0;
+    g->level_opaque.assign((size_t)g->n_levels, 0);
+    for (int l = 0; l < g->n_levels; ++l) g->level_opaque[l] = flags[l] == 0 ? 1 : 0;
     g->inputs_ready = true;
     return 0;
 }
 
-// Decides whether this run may drop the alpha term: every input texel and every colour already in the
-// synthesis state (random_init, inpaint, loaded snapshots) must have alpha 255.  Runs on g->stream.
-int decide_opaque(tsb_generator* g) {
+// Decides whether the stage working on pyramid level `level` may drop the alpha term: every input texel of that level
+// and every colour currently in the synthesis state (re-coloured from that level at the start of the stage,
+// ms.rs:687-700; random_init, inpaint, loaded snapshots) must have alpha 255.  (Blurred levels usually hold a few 254s --
+// the truncating resize -- so in practice this is the last two stages, which work on the unblurred level: 3/4 of the
+// work.)  Runs on g->stream.
+int decide_opaque(tsb_generator* g, int level) {
     g->run_opaque = false;
     g->no_fast = getenv("TSB_NO_FAST") != nullptr;  // debug: general scoring path only (bounds-tested reads, alpha term kept)
-    if (g->no_fast || !g->inputs_opaque) return 0;
+    if (g->no_fast || level < 0 || level >= (int)g->level_opaque.size() || !g->level_opaque[level]) return 0;
     StageDev S;
     fill_stage_geometry(g, S, false);
-    CU(cudaMemsetAsync(g->d_alpha_flag.p + 1, 0, 4, g->stream));
+    CU(cudaMemsetAsync(g->d_alpha_flag.p + 64, 0, 4, g->stream));
     const size_t n = (size_t)g->W * g->H;
-    k_state_alpha_check<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 64), 256, 0, g->stream>>>(S, g->have_loaded_points ? 1 : 0, g->d_alpha_flag.p + 1);
+    k_state_alpha_check<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 64), 256, 0, g->stream>>>(S, g->have_loaded_points ? 1 : 0, g->d_alpha_flag.p + 64);
     CU(cudaGetLastError());
     uint32_t flag = 1;
-    CU(cudaMemcpyAsync(&flag, g->d_alpha_flag.p + 1, 4, cudaMemcpyDeviceToHost, g->stream));
+    CU(cudaMemcpyAsync(&flag, g->d_alpha_flag.p + 64, 4, cudaMemcpyDeviceToHost, g->stream));
     CU(cudaStreamSynchronize(g->stream));
     g->run_opaque = flag == 0;
     return 0;
@@ -1111,7 +1117,6 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
         k_mask_insert_flat<<<(np + 255) / 256, 256, 0, s>>>(S, g->d_tmp_u32.p, np, tiling ? 1 : 0);
     }
     CU(cudaGetLastError());
-    TRY(decide_opaque(g));
 
     // ---- pixel order: pick_random_unresolved (ms.rs:380-389) for every new pixel of every stage, entirely on the
     // device: index draws (k_pick_indices), then the swap_remove chain resolved in parallel (k_resolve_picks).
@@ -1235,6 +1240,8 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
             CU(cudaGetLastError());
             g->stats.kernel_launches++;
         }
+        TRY(decide_opaque(g, sp.level));
+        S.opaque = g->run_opaque ? 1 : 0;
         const size_t n_items = sp.n_redo + sp.n_new;
         if (n_items == 0) continue;
         // random candidates: rng seeded with loop_seed + 1 = stage seed + i + 1 (ms.rs:902,945); generated per phase, and in
@@ -1783,7 +1790,7 @@ int tsb_generator_eval_items(tsb_generator* g, const tsb_params* prm, int32_t le
     cudaStream_t s = g->stream;
     const int k = (int)prm->nearest_neighbors, m = (int)prm->random_sample_locations;
     TRY(g->d_luts.ensure(512));
-    TRY(decide_opaque(g));
+    TRY(decide_opaque(g, level));
     StageDev S;
     fill_stage_geometry(g, S, prm->tiling_mode != 0);
     stage_inputs(g, S, level, prm);

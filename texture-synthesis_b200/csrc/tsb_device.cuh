@@ -1945,7 +1945,7 @@ __global__ void k_recolour(StageDev S) {
 }
 
 // (re)insert resolved pixels into the mask with their tiling mirrors (ms.rs:764-778)
-// framed copies of all levels of one pyramid (see EX_PAD); flag[0] is raised when a source texel has alpha != 255
+// framed copies of all levels of one pyramid (see EX_PAD); flag[level] is raised when a source texel of that level has alpha != 255
 __global__ void k_frame_levels(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int w, int h, int levels, uint32_t* flag) {
     const int pw = w + 2 * EX_PAD, ph = h + 2 * EX_PAD;
     const size_t per = (size_t)pw * ph, n = per * (size_t)levels;
@@ -1957,16 +1957,15 @@ __global__ void k_frame_levels(const uint32_t* __restrict__ src, uint32_t* __res
         uint32_t v = OUTSIDE_RGBA;
         if ((unsigned)X < (unsigned)w && (unsigned)Y < (unsigned)h) {
             v = src[(size_t)l * w * h + (size_t)Y * w + X];
-            bad |= (v >> 24) != 0xFFu;
+            if ((v >> 24) != 0xFFu) flag[l] = 1u;  // per pyramid level
         }
         dst[i] = v;
     }
-    if (bad) *flag = 1u;
+    (void)bad;
 }
-__global__ void k_alpha_check(const uint32_t* __restrict__ src, size_t n, uint32_t* flag) {
-    bool bad = false;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) bad |= (src[i] >> 24) != 0xFFu;
-    if (bad) *flag = 1u;
+__global__ void k_alpha_check(const uint32_t* __restrict__ src, size_t n, size_t per_level, uint32_t* flag) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        if ((src[i] >> 24) != 0xFFu) flag[i / per_level] = 1u;
 }
 // colours already in the synthesis state: resolved pixels only, or every pixel for a loaded snapshot
 __global__ void k_state_alpha_check(StageDev S, int all_pixels, uint32_t* flag) {
