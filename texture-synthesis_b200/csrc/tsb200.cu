@@ -698,7 +698,7 @@ void build_plan(const tsb_generator* g, const tsb_params* prm, std::vector<Stage
 int ensure_flow_buffers(tsb_generator* g, size_t max_phase) {
     TRY(g->d_item_R2.ensure(max_phase));
     TRY(g->d_npred.ensure(max_phase + 1)); TRY(g->d_nsucc.ensure(max_phase + 1)); TRY(g->d_succ_off.ensure(max_phase + 1));
-    TRY(g->d_succ_cur.ensure(max_phase + 1)); TRY(g->d_queue.ensure(max_phase + 1)); TRY(g->d_fctl.ensure(64));  // [0..8) control words, [32..64) targets of the release stores
+    TRY(g->d_succ_cur.ensure(max_phase + 1)); TRY(g->d_queue.ensure(max_phase + 1)); TRY(g->d_fctl.ensure(FC_WORDS));
     TRY(g->d_succ.ensure(max_phase * SUCC_STRIDE + 1024));
     return 0;
 }
@@ -819,7 +819,7 @@ int run_stage_new(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, 
     const int gr = std::max(1, std::min((int)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), g->max_ctas_radius));
     const int gf = std::max(1, std::min((int)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), g->guided ? g->max_ctas_flow_guided : g->max_ctas_flow));
     const unsigned nb = (n + 255) / 256;
-    CU(cudaMemsetAsync(F.ctl, 0, 32, s));
+    CU(cudaMemsetAsync(F.ctl, 0, FC_RELEASE * 4, s));
     CU(cudaMemsetAsync(g->d_pmask.p, 0, (size_t)g->wpr * g->mrows * 4, s));
     CU(cudaMemsetAsync(g->d_pmask1.p, 0, (size_t)g->wpr1 * g->mrows * 4, s));
     k_mask_insert_flat_at<<<nb, 256, 0, s>>>(S, g->d_pmask.p, g->d_pmask1.p, P.item_pixel, n, S.tiling);
@@ -852,7 +852,7 @@ int run_stage_new(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, 
     g->stats.rounds++;
     CU(cudaMemcpyAsync(g->h_ctrl, F.ctl, 12, cudaMemcpyDeviceToHost, s));
     TRY(clk.end(g, s, "stage-new", i0, n, true, edges));
-    if (g->h_ctrl[FC_ABORT]) return fail(TSB_ERR_INTERNAL, "stage-wide dataflow phase of %u items stalled (head %u tail %u)", n, g->h_ctrl[0], g->h_ctrl[1]);
+    if (g->h_ctrl[FC_ABORT]) return fail(TSB_ERR_INTERNAL, "stage-wide dataflow phase of %u items stalled", n);
     return 0;
 }
 
@@ -888,7 +888,7 @@ int run_phase_flow(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n,
         if (use_lists(g, S, n, is_new)) { P.nb0 = g->d_nb0.p; P.predl = g->d_predl.p; P.npredl = g->d_npredl.p; P.predl_stride = g->predl_stride; }
         auto barrier = [&]() -> int { CU(cudaStreamSynchronize(s)); g->mg_barrier(g->mg_barrier_user); return 0; };
         TRY(barrier());  // every rank has finished the previous phase before anybody writes into its replica
-        CU(cudaMemsetAsync(F.ctl, 0, 32, s));
+        CU(cudaMemsetAsync(F.ctl, 0, FC_RELEASE * 4, s));
         k_radius<<<gr, CTA_THREADS, sizeof(KnnScratch) * WARPS_PER_CTA, s>>>(Sm, P, F);
         CU(cudaGetLastError());
         TRY(barrier());  // radii of all items and zeroed counters are visible on every replica
@@ -1018,8 +1018,8 @@ int run_phase_flow(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n,
                 }
             }
         }
-        if (g->h_ctrl[FC_ABORT]) return fail(TSB_ERR_INTERNAL, "band-sharded dataflow phase of %u items stalled on rank %d (head %u tail %u own %u)", n,
-                                             g->h_mg.rank, g->h_ctrl[0], g->h_ctrl[1], g->h_ctrl[FC_NOWN]);
+        if (g->h_ctrl[FC_ABORT]) return fail(TSB_ERR_INTERNAL, "band-sharded dataflow phase of %u items stalled on rank %d (head %u own %u)", n,
+                                             g->h_mg.rank, g->h_ctrl[FC_HEAD], g->h_ctrl[FC_NOWN]);
         return 0;
     }
     bool use_csr = g->force_csr || (size_t)n * g->succ_stride > g->d_succ.n;
@@ -1028,7 +1028,7 @@ int run_phase_flow(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n,
         if (!use_csr && use_lists(g, S, n, is_new)) {  // the lists are built by the fixed-stride edge pass only
             P.nb0 = g->d_nb0.p; P.predl = g->d_predl.p; P.npredl = g->d_npredl.p; P.predl_stride = g->predl_stride;
         } else { P.nb0 = nullptr; P.predl = nullptr; P.npredl = nullptr; P.predl_stride = 0; }
-        CU(cudaMemsetAsync(F.ctl, 0, 32, s));
+        CU(cudaMemsetAsync(F.ctl, 0, FC_RELEASE * 4, s));
         k_radius<<<gr, CTA_THREADS, sizeof(KnnScratch) * WARPS_PER_CTA, s>>>(S, P, F);
         CU(cudaGetLastError());
         g->stats.kernel_launches++;
@@ -1072,7 +1072,7 @@ int run_phase_flow(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n,
     }
     CU(cudaMemcpyAsync(g->h_ctrl, F.ctl, 12, cudaMemcpyDeviceToHost, s));
     TRY(clk.end(g, s, "flow", i0, n, is_new, edges));
-    if (g->h_ctrl[FC_ABORT]) return fail(TSB_ERR_INTERNAL, "dataflow phase of %u items stalled (head %u tail %u)", n, g->h_ctrl[0], g->h_ctrl[1]);
+    if (g->h_ctrl[FC_ABORT]) return fail(TSB_ERR_INTERNAL, "dataflow phase of %u items stalled", n);
     return 0;
 }
 

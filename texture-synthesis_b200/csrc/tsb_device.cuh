@@ -137,10 +137,13 @@ struct FlowDev {
     uint32_t* succ_cur;  // [n]   fill cursors
     uint32_t* succ;      // [edges]
     uint32_t* queue;     // [n]
-    uint32_t* ctl;       // [0] head  [1] tail  [2] abort flag  [3] successor-list overflow (fixed-stride mode)
+    uint32_t* ctl;       // control block, see FC_*
     uint32_t stride;     // > 0: successors of item a live in succ[a*stride ..] (single analysis pass); 0: CSR
 };
-enum { FC_HEAD = 0, FC_TAIL = 1, FC_ABORT = 2, FC_OVERFLOW = 3, FC_NOWN = 4 };  // FC_NOWN: items owned by this rank (multi-GPU)
+// Control block (32-bit words).  Queue head, queue tail and the targets of the release stores are the hottest addresses of
+// the whole run (every work item touches each once), so each has a 128-byte line of its own; sharing one line cost 2 %.
+enum { FC_HEAD = 0, FC_ABORT = 2, FC_OVERFLOW = 3, FC_NOWN = 4,  // FC_NOWN: items owned by this rank (multi-GPU)
+       FC_TAIL = 64, FC_RELEASE = 128, FC_WORDS = FC_RELEASE + 32 * 32 };
 
 struct __align__(16) WarpScratch {
     union {
@@ -1227,7 +1230,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_flow(StageDev S, PhaseDev P,
             // release: the commit is visible device-wide before any successor counter is touched.  A release store
             // (MEMBAR.ALL.GPU + store) instead of __threadfence() (MEMBAR.SC.GPU + L1 invalidation, see above).
             if (MG) { if (remote_succ) __threadfence_system(); else __threadfence(); }
-            else asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(F.ctl + 32 + (blockIdx.x & 31)), "r"(it) : "memory");
+            else asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(F.ctl + FC_RELEASE + 32 * (blockIdx.x & 31)), "r"(it) : "memory");
         }
         __syncwarp();
         // notify successors; the one that drops a counter to zero publishes the item
