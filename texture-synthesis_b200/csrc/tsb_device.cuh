@@ -1652,19 +1652,35 @@ __global__ void __launch_bounds__(CTA_THREADS) k_edges_scan(StageDev S, PhaseDev
                 const uint32_t inv = 0xFFFFFFFFu / (uint32_t)side + 1u;  // c / side == __umulhi(c, inv) while c * side < 2^32
                 const unsigned lt = (1u << lane) - 1u;
                 uint32_t* my_succ = F.succ + (size_t)it * F.stride;
-                for (int c0 = 0; c0 < cells; c0 += 64) {  // two chunks per turn: their loads overlap
+                // Redo phase without tiling: every resolved point is a pixel of the canvas, so the items inside the disc
+                // are found among the k nearest stored by k_radius (those closer than the k-th) plus the pixels at exactly
+                // the k-th distance (a short run of the spiral table) -- k + a few lookups instead of (2r+1)^2.
+                const bool from_list = P.nb0 != nullptr && P.is_new == 0u && !S.tiling;
+                const int ring0 = from_list ? (R2 ? (int)__ldg(S.cntLE + R2 - 1u) : 0) : 0;
+                const int n_visit = from_list ? S.k + ((int)__ldg(S.cntLE + R2) - ring0) : cells;
+                for (int c0 = 0; c0 < n_visit; c0 += 64) {  // two chunks per turn: their loads overlap
                     uint32_t j[2], D[2], r2j[2];
                     int dxs[2], dys[2];
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         const int c = c0 + 32 * q + lane;
                         j[q] = NONE32; D[q] = 0; r2j[q] = 0; dxs[q] = 0; dys[q] = 0;
-                        if (c < cells) {
-                            const int row = (int)__umulhi((uint32_t)c, inv);
-                            const int dy = row - r, dx = c - row * side - r;
-                            D[q] = (uint32_t)(dx * dx + dy * dy);
+                        if (c < n_visit) {
+                            int dx, dy;
+                            bool take;
+                            if (from_list) {
+                                const short2 o = c < S.k ? P.nb0[(size_t)it * S.k + c] : __ldg(S.spiral + ring0 + (c - S.k));
+                                dx = o.x; dy = o.y;
+                                D[q] = (uint32_t)(dx * dx + dy * dy);
+                                take = c < S.k ? D[q] < R2 : true;  // list entries at exactly R2 are covered by the ring
+                            } else {
+                                const int row = (int)__umulhi((uint32_t)c, inv);
+                                dy = row - r; dx = c - row * side - r;
+                                D[q] = (uint32_t)(dx * dx + dy * dy);
+                                take = D[q] <= R2;
+                            }
                             dxs[q] = dx; dys[q] = dy;
-                            if (D[q] <= R2) {
+                            if (take) {
                                 int qx = x + dx, qy = y + dy;
                                 bool in = true;
                                 if (S.tiling) { qx = imod(qx, S.W); qy = imod(qy, S.H); }
