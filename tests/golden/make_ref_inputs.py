@@ -40,6 +40,16 @@ def main():
     path = os.path.join(HERE, "ref_imgs.npz")
     np.savez_compressed(path, **out)
     print(os.path.getsize(path) // 1024, "KiB")
+    # full-size decodes (no rescale, masks untouched: the reference thresholds the decoded bytes itself, ms.rs:272,1546),
+    # consumed by tests/fullsize_cases.py for the BASELINE configs and lib/tests/diff.rs at the reference's real sizes.
+    # RGB only where alpha is 255 everywhere (smaller file).
+    full = {}
+    for key, rel in FILES.items():
+        a = np.asarray(Image.open(os.path.join(REF, rel)).convert("RGBA")).copy()
+        full[key] = a[..., :3].copy() if (a[..., 3] == 255).all() else a
+    path = os.path.join(HERE, "ref_imgs_full.npz")
+    np.savez_compressed(path, **full)
+    print(os.path.getsize(path) // 1024, "KiB (full size)")
 
 
 if __name__ == "__main__":

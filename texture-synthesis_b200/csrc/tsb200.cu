@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <functional>
 #include <string>
 #include <vector>
@@ -24,6 +25,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "tsb_device.cuh"
+#include "tsb_stream.cuh"
 
 using namespace tsb;
 
@@ -301,7 +303,7 @@ struct tsb_generator {
     DevBuf<unsigned long long> d_keys, d_keys_sorted;
     DevBuf<uint32_t> d_v0;
     cudaStream_t stream2 = nullptr;
-    int max_ctas_flow = 0, max_ctas_flow_guided = 0, max_ctas_radius = 0;
+    int max_ctas_flow = 0, max_ctas_flow_guided = 0, max_ctas_radius = 0, max_ctas_stream = 0, max_ctas_stream_guided = 0;
     bool use_rounds = false, force_csr = false;
     // band-sharded multi-GPU execution
     bool mg_on = false;
@@ -321,6 +323,23 @@ struct tsb_generator {
     PinnedBuf<uint32_t> h_idx, h_items;  // pick indices (D2H) and per-stage work-item pixels (H2D)
     bool pmap_ready = false;
 
+    // in-order streaming scheduler (tsb_stream.cuh)
+    DevBuf<uint4> d_state2;                         // second state buffer (redo phases write here, then the two swap)
+    DevBuf<uint32_t> d_tmap;                        // pixel -> position in the pick array
+    DevBuf<uint8_t> r_nbk, r_rand_map;              // ring of per-item lists written by the analysis stream
+    DevBuf<short2> r_nb;
+    DevBuf<float> r_g;
+    DevBuf<uint4> r_low;
+    DevBuf<uint32_t> r_rand_xy;
+    DevBuf<float> d_luts_all;                       // [stage][512]
+    PinnedBuf<float> h_luts_all;
+    DevBuf<uint32_t> d_sctl;                        // [chunk][SC_WORDS] + abort flag
+    cudaStream_t stream3 = nullptr;                 // host copies that must not delay the analysis stream
+    uint32_t* h_progress = nullptr;                 // mapped pinned word: work items claimed so far
+    uint32_t* d_progress = nullptr;                 // its device alias
+    bool state_init_opaque = true;                  // every colour in the state before the run has alpha 255
+    bool inpaint_opaque = true;                     // the same for the locked inpaint pixels as created
+
     // trace
     bool trace = false;
     DevBuf<int32_t> d_tr_best, d_tr_ncand, d_tr_nneigh;
@@ -337,6 +356,8 @@ struct tsb_generator {
         if (h_ctrl) cudaFreeHost(h_ctrl);
         if (stream) cudaStreamDestroy(stream);
         if (stream2) cudaStreamDestroy(stream2);
+        if (stream3) cudaStreamDestroy(stream3);
+        if (h_progress) cudaFreeHost(h_progress);
         if (ev_rand) cudaEventDestroy(ev_rand);
     }
 };
@@ -374,6 +395,7 @@ int init_state(tsb_generator* g) {
     g->resolved_order = g->resolved0;
     g->locked = g->inpaint_locked = g->resolved0.size();
     g->have_loaded_points = false;
+    g->state_init_opaque = g->inpaint_opaque;
     return 0;
 }
 
@@ -465,7 +487,9 @@ int upload_inputs(tsb_generator* g, const tsb_pyramid* examples, uint32_t n_exam
             TRY(upload_pyramid(p, g->d_exg[e], s));
             TRY(frame_pyramid(g->d_exg[e], g->d_exgf[e], (int)p.width, (int)p.height, g->n_levels, g->d_alpha_flag.p, s));
             g->exg_w.push_back((int)p.width); g->exg_h.push_back((int)p.height);
-            if ((int)p.width + 2 * EX_PAD != g->pad_pitch) g->pad_pitch = 0;
+            // the framed (bounds-test-free) scoring path addresses example and guide with ONE offset: both must have the
+            // same dimensions (a guide of another size keeps its own bounds, ms.rs:1265-1273)
+            if ((int)p.width != g->ex_w[e] || (int)p.height != g->ex_h[e] || (int)p.width + 2 * EX_PAD != g->pad_pitch) g->pad_pitch = 0;
             for (int l = 0; l < g->n_levels; ++l) {
                 DevGuide d;
                 d.w = (int)p.width; d.h = (int)p.height;
@@ -539,8 +563,7 @@ void stage_inputs(tsb_generator* g, StageDev& S, int level, const tsb_params* p)
 }
 
 // PrerenderedU8Function tables (ms.rs:739-742, 853-858, 1110-1120) reduced to |a-b| (256 entries)
-int upload_luts(tsb_generator* g, const tsb_params* p, float adaptive_alpha) {
-    float h[512];
+void fill_luts(const tsb_generator* g, const tsb_params* p, float adaptive_alpha, float* h) {
     float sig2 = p->cauchy_dispersion * p->cauchy_dispersion;
     for (int d = 0; d < 256; ++d) {
         float x = (float)d / 255.0f;
@@ -549,6 +572,10 @@ int upload_luts(tsb_generator* g, const tsb_params* p, float adaptive_alpha) {
         if (g->guided) { h[d] = (1.0f - adaptive_alpha) * cauchy; h[256 + d] = adaptive_alpha * x2; }
         else { h[d] = cauchy; h[256 + d] = 0.0f; }
     }
+}
+int upload_luts(tsb_generator* g, const tsb_params* p, float adaptive_alpha) {
+    float h[512];
+    fill_luts(g, p, adaptive_alpha, h);
     CU(cudaMemcpyAsync(g->d_luts.p, h, sizeof(h), cudaMemcpyHostToDevice, g->stream));
     CU(cudaStreamSynchronize(g->stream));
     return 0;
@@ -693,6 +720,70 @@ void build_plan(const tsb_generator* g, const tsb_params* prm, std::vector<Stage
         total_items += sp.n_redo + sp.n_new;
         plan.push_back(sp);
     }
+}
+
+// ---- pixel order: pick_random_unresolved (ms.rs:380-389) for every new pixel of every stage, entirely on the
+// device: index draws (k_pick_indices), then the swap_remove chain resolved in parallel (k_resolve_picks).
+// Every non-locked resolved pixel is a pick, and redo items follow the resolution order (ms.rs:905-907), so
+// the work items of every stage are simply a PREFIX of the pick array: item i of a stage = picks[i].
+// Leaves the picks in g->d_item_pixel (device), their first 4096 in g->h_items (host; the rest arrives on stream2) and
+// the pixels never picked in g->unresolved.
+int plan_pixel_order(tsb_generator* g, const std::vector<StagePlan>& plan, size_t n_picks, size_t total, size_t npix) {
+    cudaStream_t s = g->stream;
+    TRY(g->h_items.ensure(std::max<size_t>(n_picks, 1)));
+    TRY(g->d_item_pixel.ensure(std::max<size_t>(n_picks, 1)));
+    {
+        TRY(g->d_pick_idx.ensure(std::max<size_t>(n_picks, 1)));
+        size_t un = total;
+        for (auto& sp : plan) {
+            if (sp.n_new) {
+                uint32_t nn = (uint32_t)sp.n_new;
+                k_pick_indices<<<(nn + 255) / 256, 256, 0, s>>>(sp.seed + (uint64_t)sp.redo_count, (uint64_t)un, nn, g->d_pick_idx.p + sp.pick_base);
+                CU(cudaGetLastError());
+                g->stats.kernel_launches++;
+            }
+            un -= sp.n_new;
+        }
+        if (n_picks) {
+            const uint32_t T = (uint32_t)n_picks;
+            TRY(g->d_keys.ensure(n_picks)); TRY(g->d_keys_sorted.ensure(n_picks));
+            // v0: the unresolved list as it is now (identity unless inpaint / random_init removed entries)
+            bool identity = g->unresolved.size() == npix;
+            if (identity && (g->inpaint || g->locked)) identity = false;
+            const uint32_t* v0 = nullptr;
+            if (!identity) { TRY(g->d_v0.upload(g->unresolved.data(), g->unresolved.size(), s)); v0 = g->d_v0.p; }
+            k_pick_keys<<<(T + 255) / 256, 256, 0, s>>>(g->d_pick_idx.p, T, g->d_keys.p);
+            int end_bit = 33;
+            while (end_bit < 64 && (total >> (end_bit - 32)) != 0) ++end_bit;
+            size_t tb = 0;
+            CU(cub::DeviceRadixSort::SortKeys(nullptr, tb, g->d_keys.p, g->d_keys_sorted.p, (int)T, 0, end_bit, s));
+            TRY(g->d_sort_temp.ensure(tb + 256));
+            tb = g->d_sort_temp.n;
+            CU(cub::DeviceRadixSort::SortKeys(g->d_sort_temp.p, tb, g->d_keys.p, g->d_keys_sorted.p, (int)T, 0, end_bit, s));
+            k_resolve_picks<<<(T + 255) / 256, 256, 0, s>>>(g->d_keys_sorted.p, T, (uint64_t)total, v0, g->d_pick_idx.p, g->d_item_pixel.p);
+            CU(cudaGetLastError());
+            g->stats.kernel_launches += 4;
+            // host mirrors: the whole order is needed only after the run (resolved list, trace); the first few picks
+            // are needed right away (first random pixel, serial-prefix bookkeeping)
+            const size_t head = std::min<size_t>(n_picks, 4096);
+            CU(cudaMemcpyAsync(g->h_items.p, g->d_item_pixel.p, head * 4, cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));
+            if (n_picks > head) CU(cudaMemcpyAsync(g->h_items.p + head, g->d_item_pixel.p + head, (n_picks - head) * 4, cudaMemcpyDeviceToHost, g->stream3));
+            const size_t left = total - n_picks;
+            if (left) {
+                TRY(g->d_tmp_u32.ensure(left));
+                k_resolve_leftover<<<(uint32_t)((left + 255) / 256), 256, 0, s>>>(g->d_keys_sorted.p, T, (uint64_t)total, v0, (uint32_t)left, g->d_tmp_u32.p);
+                CU(cudaGetLastError());
+                std::vector<uint32_t> rest(left);
+                CU(cudaMemcpyAsync(rest.data(), g->d_tmp_u32.p, left * 4, cudaMemcpyDeviceToHost, s));
+                CU(cudaStreamSynchronize(s));
+                g->unresolved.swap(rest);
+            } else {
+                g->unresolved.clear();
+            }
+        }
+    }
+    return 0;
 }
 
 int ensure_flow_buffers(tsb_generator* g, size_t max_phase) {
@@ -1118,63 +1209,7 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
     }
     CU(cudaGetLastError());
 
-    // ---- pixel order: pick_random_unresolved (ms.rs:380-389) for every new pixel of every stage, entirely on the
-    // device: index draws (k_pick_indices), then the swap_remove chain resolved in parallel (k_resolve_picks).
-    // Every non-locked resolved pixel is a pick, and redo items follow the resolution order (ms.rs:905-907), so
-    // the work items of every stage are simply a PREFIX of the pick array: item i of a stage = picks[i].
-    TRY(g->h_items.ensure(std::max<size_t>(n_picks, 1)));
-    TRY(g->d_item_pixel.ensure(std::max<size_t>(n_picks, 1)));
-    {
-        TRY(g->d_pick_idx.ensure(std::max<size_t>(n_picks, 1)));
-        size_t un = total;
-        for (auto& sp : plan) {
-            if (sp.n_new) {
-                uint32_t nn = (uint32_t)sp.n_new;
-                k_pick_indices<<<(nn + 255) / 256, 256, 0, s>>>(sp.seed + (uint64_t)sp.redo_count, (uint64_t)un, nn, g->d_pick_idx.p + sp.pick_base);
-                CU(cudaGetLastError());
-                g->stats.kernel_launches++;
-            }
-            un -= sp.n_new;
-        }
-        if (n_picks) {
-            const uint32_t T = (uint32_t)n_picks;
-            TRY(g->d_keys.ensure(n_picks)); TRY(g->d_keys_sorted.ensure(n_picks));
-            // v0: the unresolved list as it is now (identity unless inpaint / random_init removed entries)
-            bool identity = g->unresolved.size() == npix;
-            if (identity && (g->inpaint || g->locked)) identity = false;
-            const uint32_t* v0 = nullptr;
-            if (!identity) { TRY(g->d_v0.upload(g->unresolved.data(), g->unresolved.size(), s)); v0 = g->d_v0.p; }
-            k_pick_keys<<<(T + 255) / 256, 256, 0, s>>>(g->d_pick_idx.p, T, g->d_keys.p);
-            int end_bit = 33;
-            while (end_bit < 64 && (total >> (end_bit - 32)) != 0) ++end_bit;
-            size_t tb = 0;
-            CU(cub::DeviceRadixSort::SortKeys(nullptr, tb, g->d_keys.p, g->d_keys_sorted.p, (int)T, 0, end_bit, s));
-            TRY(g->d_sort_temp.ensure(tb + 256));
-            tb = g->d_sort_temp.n;
-            CU(cub::DeviceRadixSort::SortKeys(g->d_sort_temp.p, tb, g->d_keys.p, g->d_keys_sorted.p, (int)T, 0, end_bit, s));
-            k_resolve_picks<<<(T + 255) / 256, 256, 0, s>>>(g->d_keys_sorted.p, T, (uint64_t)total, v0, g->d_pick_idx.p, g->d_item_pixel.p);
-            CU(cudaGetLastError());
-            g->stats.kernel_launches += 4;
-            // host mirrors: the whole order is needed only after the run (resolved list, trace); the first few picks
-            // are needed right away (first random pixel, serial-prefix bookkeeping)
-            const size_t head = std::min<size_t>(n_picks, 4096);
-            CU(cudaMemcpyAsync(g->h_items.p, g->d_item_pixel.p, head * 4, cudaMemcpyDeviceToHost, s));
-            CU(cudaStreamSynchronize(s));
-            if (n_picks > head) CU(cudaMemcpyAsync(g->h_items.p + head, g->d_item_pixel.p + head, (n_picks - head) * 4, cudaMemcpyDeviceToHost, g->stream2));
-            const size_t left = total - n_picks;
-            if (left) {
-                TRY(g->d_tmp_u32.ensure(left));
-                k_resolve_leftover<<<(uint32_t)((left + 255) / 256), 256, 0, s>>>(g->d_keys_sorted.p, T, (uint64_t)total, v0, (uint32_t)left, g->d_tmp_u32.p);
-                CU(cudaGetLastError());
-                std::vector<uint32_t> rest(left);
-                CU(cudaMemcpyAsync(rest.data(), g->d_tmp_u32.p, left * 4, cudaMemcpyDeviceToHost, s));
-                CU(cudaStreamSynchronize(s));
-                g->unresolved.swap(rest);
-            } else {
-                g->unresolved.clear();
-            }
-        }
-    }
+    TRY(plan_pixel_order(g, plan, n_picks, total, npix));
     const uint32_t* stage_pixels = g->h_items.p;  // host mirror of the pick array (only its head is valid before the run ends)
     g->stats.host_ms_schedule = now_ms() - t_plan0;
 
@@ -1359,6 +1394,7 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
     }
     // host mirrors of the order: ms.rs:1043-1049 (newly resolved pixels join `resolved` in processing order)
     CU(cudaStreamSynchronize(g->stream2));
+    CU(cudaStreamSynchronize(g->stream3));
     g->resolved_order.insert(g->resolved_order.end(), g->h_items.p, g->h_items.p + n_picks);
     if (g->trace) for (auto& sp : plan) g->tr_pixel.insert(g->tr_pixel.end(), g->h_items.p, g->h_items.p + sp.n_redo + sp.n_new);
     g->trace_n = g->trace ? trace_base : 0;
@@ -1381,6 +1417,429 @@ int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, vo
     g->stats.wall_ms_total = now_ms() - t_start;
     g->stats.gpu_ms_other = ms_total - g->stats.gpu_ms_resolve - g->stats.gpu_ms_analysis;
     g->have_loaded_points = false;
+    return 0;
+}
+
+// =============================================================================================
+// In-order streaming scheduler (default).  See tsb_stream.cuh for the device side.
+// Host: ONE pass that enqueues everything -- the analysis of every chunk on stream2 (it depends on (seed, size, parameters)
+// only and therefore runs ahead of the synthesis, limited by the size of the list ring), the resolve kernels on the main
+// stream, linked by events -- and a single synchronisation at the end (plus the progress poll when a callback is given).
+// =============================================================================================
+struct ChunkPlan {
+    int stage;              // index into the stage plan
+    bool redo;
+    size_t first, n;        // stage work-item range
+    size_t slot;            // first item slot in the list ring
+    bool phase_first, phase_last;
+    cudaEvent_t ev_ready = nullptr, ev_done = nullptr, ev_t0 = nullptr;
+};
+
+struct EventPool {
+    std::vector<cudaEvent_t> all;
+    ~EventPool() { for (auto e : all) cudaEventDestroy(e); }
+    int get(cudaEvent_t* out, bool timing) {
+        CU(cudaEventCreateWithFlags(out, timing ? cudaEventDefault : cudaEventDisableTiming));
+        all.push_back(*out);
+        return 0;
+    }
+};
+
+template <bool REDO>
+int launch_stream(tsb_generator* g, int grid, const StageDev& S, const ChunkDev& C, const StreamDev& D) {
+    cudaStream_t s = g->stream;
+    const bool op = S.opaque != 0;
+    if (g->guided) { if (op) k_stream<true, true, REDO><<<grid, CTA_THREADS, sizeof(RoundSmem), s>>>(S, C, D); else k_stream<true, false, REDO><<<grid, CTA_THREADS, sizeof(RoundSmem), s>>>(S, C, D); }
+    else { if (op) k_stream<false, true, REDO><<<grid, CTA_THREADS, sizeof(RoundSmem), s>>>(S, C, D); else k_stream<false, false, REDO><<<grid, CTA_THREADS, sizeof(RoundSmem), s>>>(S, C, D); }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, void* user) {
+    if (!g->inputs_ready) return fail(TSB_ERR_INVALID, "inputs have not been uploaded");
+    TRY(check_params(g, prm));
+    TRY(set_device(g));
+    const double t_start = now_ms();
+    cudaStream_t s = g->stream, s2 = g->stream2;
+    memset(&g->stats, 0, sizeof(g->stats));
+    EventPool events;
+    cudaEvent_t ev_begin, ev_end, ev_a0, ev_a1, ev_picks;
+    TRY(events.get(&ev_begin, true)); TRY(events.get(&ev_end, true)); TRY(events.get(&ev_a0, true)); TRY(events.get(&ev_a1, true));
+    TRY(events.get(&ev_picks, false));
+    CU(cudaEventRecord(ev_begin, s));
+    const bool tiling = prm->tiling_mode != 0;
+    const uint32_t k = prm->nearest_neighbors;
+    const int m = (int)prm->random_sample_locations;
+    const size_t total = g->unresolved.size();  // ms.rs:710
+    const size_t npix = (size_t)g->W * g->H;
+
+    // ---- stage plan (ms.rs:786-812) and pixel order ----
+    const double t_plan0 = now_ms();
+    std::vector<StagePlan> plan;
+    size_t n_picks = 0, max_stage_items = 1, max_phase = 1, total_items = 0;
+    build_plan(g, prm, plan, n_picks, max_stage_items, max_phase, total_items);
+    if (max_stage_items > 0xFFFFFFF0ull) return fail(TSB_ERR_UNSUPPORTED, "output too large");
+    if (plan.size() > 120) return fail(TSB_ERR_UNSUPPORTED, "more than 119 backtrack stages");
+    TRY(plan_pixel_order(g, plan, n_picks, total, npix));
+    const uint32_t* stage_pixels = g->h_items.p;  // host mirror (only its head is valid before the run ends)
+    TRY(g->d_tmap.ensure(npix));
+    CU(cudaMemsetAsync(g->d_tmap.p, 0xFF, npix * 4, s));
+    if (n_picks) k_tmap_fill<<<(uint32_t)((n_picks + 255) / 256), 256, 0, s>>>(g->d_item_pixel.p, (uint32_t)n_picks, g->d_tmap.p);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ev_picks, s));
+    g->stats.host_ms_schedule = now_ms() - t_plan0;
+
+    // ---- cost tables of every stage (ms.rs:739-742, 853-858), one upload ----
+    const size_t n_stages = plan.size();
+    TRY(g->h_luts_all.ensure(n_stages * 512)); TRY(g->d_luts_all.ensure(n_stages * 512));
+    for (size_t si = 0; si < n_stages; ++si) fill_luts(g, prm, plan[si].adaptive_alpha, g->h_luts_all.p + si * 512);
+    CU(cudaMemcpyAsync(g->d_luts_all.p, g->h_luts_all.p, n_stages * 512 * sizeof(float), cudaMemcpyHostToDevice, s));
+
+    // ---- chunks: runs of consecutive work items of one phase ----
+    size_t chunk_max = 2u << 20;
+    if (const char* e = getenv("TSB_CHUNK")) chunk_max = std::max<size_t>(1024, (size_t)strtoull(e, nullptr, 10));
+    std::vector<ChunkPlan> chunks;
+    bool first_pixel_fixed = false;  // the very first pixel of a fresh run has no neighbour: resolve_at_random (ms.rs:1002-1009)
+    for (size_t si = 0; si < n_stages; ++si) {
+        const StagePlan& sp = plan[si];
+        auto add_phase = [&](bool redo, size_t a, size_t b) {
+            for (size_t c0 = a; c0 < b; c0 += chunk_max) {
+                ChunkPlan c;
+                c.stage = (int)si; c.redo = redo; c.first = c0; c.n = std::min(chunk_max, b - c0); c.slot = 0;
+                c.phase_first = c0 == a; c.phase_last = c0 + c.n == b;
+                chunks.push_back(c);
+            }
+        };
+        if (sp.n_redo) add_phase(true, 0, sp.n_redo);
+        size_t a = sp.n_redo;
+        if (sp.n_new && sp.resolved_before == 0) { first_pixel_fixed = true; a += 1; }
+        if (sp.n_redo + sp.n_new > a) add_phase(false, a, sp.n_redo + sp.n_new);
+    }
+    // ---- list ring ----
+    const size_t bytes_per_item = 1 + (size_t)k * 8 + 16 + (size_t)m * 5;
+    size_t ring_mb = 24576;
+    if (const char* e = getenv("TSB_RING_MB")) ring_mb = std::max<size_t>(64, (size_t)strtoull(e, nullptr, 10));
+    size_t ring_items = std::min(std::max<size_t>(total_items, 1), ring_mb * (1u << 20) / bytes_per_item);
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            size_t have = g->r_nb.n * sizeof(short2) + g->r_g.n * 4 + g->r_low.n * 16 + g->r_rand_xy.n * 4 + g->r_rand_map.n + g->r_nbk.n;
+            size_t cap = (free_b + have) / 2 / bytes_per_item;  // never take more than half of what is free
+            ring_items = std::min(ring_items, std::max<size_t>(cap, 1));
+        }
+    }
+    size_t largest = 1;
+    for (auto& c : chunks) largest = std::max(largest, c.n);
+    if (ring_items < 2 * largest) {  // smaller chunks so that two of them fit the ring
+        const size_t cm = std::max<size_t>(1024, ring_items / 3);
+        std::vector<ChunkPlan> split;
+        for (auto& c : chunks)
+            for (size_t o = 0; o < c.n; o += cm) {
+                ChunkPlan d = c;
+                d.first = c.first + o; d.n = std::min(cm, c.n - o);
+                d.phase_first = c.phase_first && o == 0; d.phase_last = c.phase_last && o + d.n == c.n;
+                split.push_back(d);
+            }
+        chunks.swap(split);
+        largest = std::min(largest, cm);
+        ring_items = std::max(ring_items, 2 * largest);
+    }
+    TRY(g->r_nbk.ensure(ring_items)); TRY(g->r_nb.ensure(ring_items * k)); TRY(g->r_g.ensure(ring_items * k)); TRY(g->r_low.ensure(ring_items));
+    TRY(g->r_rand_xy.ensure(ring_items * (size_t)m)); TRY(g->r_rand_map.ensure(ring_items * (size_t)m));
+    TRY(g->d_sctl.ensure((chunks.size() + 1) * SC_WORDS));
+    CU(cudaMemsetAsync(g->d_sctl.p, 0, (chunks.size() + 1) * SC_WORDS * 4, s));
+    uint32_t* abort_flag = g->d_sctl.p + chunks.size() * SC_WORDS;
+    TRY(g->d_counters.ensure(ST_COUNT));
+    CU(cudaMemsetAsync(g->d_counters.p, 0, ST_COUNT * sizeof(unsigned long long), s));
+    TRY(g->d_pmask.ensure((size_t)g->wpr * g->mrows));
+    TRY(g->d_pmask1.ensure((size_t)g->wpr1 * g->mrows));
+    TRY(g->d_state2.ensure(npix));
+    g->trace_n = 0;
+    g->tr_pixel.clear(); g->tr_fix_idx.clear();
+    if (g->trace) {
+        TRY(g->d_tr_best.ensure(total_items)); TRY(g->d_tr_ncand.ensure(total_items));
+        TRY(g->d_tr_nneigh.ensure(total_items)); TRY(g->d_tr_score.ensure(total_items));
+    }
+    for (auto& c : chunks) { TRY(events.get(&c.ev_ready, false)); TRY(events.get(&c.ev_done, true)); TRY(events.get(&c.ev_t0, true)); }
+    uint32_t watchdog_ms = 20000;
+    if (const char* e = getenv("TSB_WATCHDOG_MS")) watchdog_ms = (uint32_t)std::max(1, atoi(e));
+    *g->h_progress = 0;
+
+    // ---- analysis stream: resolved-set mask with the tiling mirrors (ms.rs:747-779), then chunk after chunk ----
+    CU(cudaStreamWaitEvent(s2, ev_picks, 0));
+    CU(cudaEventRecord(ev_a0, s2));
+    StageDev A;  // geometry + analysis-owned mask
+    fill_stage_geometry(g, A, tiling);
+    A.k = (int)k; A.m = m;
+    CU(cudaMemsetAsync(g->d_mask.p, 0, (size_t)g->wpr * g->mrows * 4, s2));
+    CU(cudaMemsetAsync(g->d_mask1.p, 0, (size_t)g->wpr1 * g->mrows * 4, s2));
+    DevBuf<uint32_t> d_init_points;
+    if (g->have_loaded_points) {
+        TRY(d_init_points.upload((const uint32_t*)g->loaded_points.data(), g->loaded_points.size(), s2));
+        uint32_t np = (uint32_t)(g->loaded_points.size() / 2);
+        if (np) k_mask_insert_points<<<(np + 255) / 256, 256, 0, s2>>>(A, (const int32_t*)d_init_points.p, np);
+    } else if (!g->resolved_order.empty()) {
+        TRY(d_init_points.upload(g->resolved_order.data(), g->resolved_order.size(), s2));
+        uint32_t np = (uint32_t)g->resolved_order.size();
+        k_mask_insert_flat<<<(np + 255) / 256, 256, 0, s2>>>(A, d_init_points.p, np, tiling ? 1 : 0);
+    }
+    CU(cudaGetLastError());
+
+    std::deque<size_t> live;       // chunks whose lists occupy the ring (analysis enqueued, slots not yet reclaimed)
+    size_t ring_head = 0;
+    size_t a_next = 0, r_next = 0;  // next chunk to analyse / to resolve
+    auto chunk_dev = [&](const ChunkPlan& c) {
+        ChunkDev C;
+        C.pixel = g->d_item_pixel.p + c.first;
+        C.nbk = g->r_nbk.p + c.slot; C.nb = g->r_nb.p + c.slot * k; C.g = g->r_g.p + c.slot * k; C.low = g->r_low.p + c.slot;
+        C.rand_xy = g->r_rand_xy.p + c.slot * (size_t)m; C.rand_map = g->r_rand_map.p + c.slot * (size_t)m;
+        C.n = (uint32_t)c.n; C.first = (uint32_t)c.first;
+        return C;
+    };
+    // returns 1 when the ring has no room until more resolve kernels have been enqueued
+    auto enqueue_analysis = [&](ChunkPlan& c) -> int {
+        size_t off = ring_head;
+        if (off + c.n > ring_items) off = 0;
+        while (!live.empty()) {
+            const ChunkPlan& f = chunks[live.front()];
+            const bool overlap = off < f.slot + f.n && f.slot < off + c.n;
+            if (!overlap) break;
+            if (live.front() >= r_next) return 1;  // its resolve kernel is not enqueued yet: no event to wait for
+            CU(cudaStreamWaitEvent(s2, f.ev_done, 0));
+            live.pop_front();
+        }
+        c.slot = off;
+        ring_head = off + c.n;
+        const StagePlan& sp = plan[c.stage];
+        StageDev S = A;
+        S.ex = g->d_exdesc.p + (size_t)sp.level * g->n_ex; S.n_ex = g->n_ex;
+        const ChunkDev C = chunk_dev(c);
+        const uint32_t n = (uint32_t)c.n;
+        const int gr = std::max(1, std::min((int)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), g->max_ctas_radius));
+        const size_t first_new = sp.n_redo + ((sp.n_new && sp.resolved_before == 0) ? 1 : 0);
+        const size_t n_new_phase = sp.n_redo + sp.n_new - first_new;
+        TimeFilter T;
+        memset(&T, 0, sizeof(T));
+        if (c.redo) {
+            S.r2_hint = r2_hint_for(g, sp.resolved_before, k);
+            S.n_points_max = (uint32_t)std::min<size_t>((tiling ? 3 : 1) * sp.resolved_before, 0xFFFFFFFFull);
+            k_lists_chunk<true><<<gr, CTA_THREADS, sizeof(KnnScratch) * WARPS_PER_CTA, s2>>>(S, C, T, g->d_tmap.p, 0u, 0u);
+        } else {
+            const size_t resolved_now = sp.resolved_before + (first_new - sp.n_redo);
+            if (c.phase_first) {
+                if (first_new > sp.n_redo) {  // the randomly resolved first pixel joins the set WITHOUT mirror copies (ms.rs:473)
+                    k_mask_insert_flat<<<1, 32, 0, s2>>>(A, g->d_item_pixel.p + sp.n_redo, 1u, 0);
+                }
+                CU(cudaMemsetAsync(g->d_pmask.p, 0, (size_t)g->wpr * g->mrows * 4, s2));
+                CU(cudaMemsetAsync(g->d_pmask1.p, 0, (size_t)g->wpr1 * g->mrows * 4, s2));
+                const uint32_t nn = (uint32_t)n_new_phase;
+                k_mask_insert_flat_at<<<(nn + 255) / 256, 256, 0, s2>>>(A, g->d_pmask.p, g->d_pmask1.p, g->d_item_pixel.p + first_new, nn, tiling ? 1 : 0);
+            }
+            S.r2_hint = r2_hint_for(g, resolved_now, k);
+            S.n_points_max = (uint32_t)std::min<size_t>((tiling ? 3 : 1) * (resolved_now + n_new_phase), 0xFFFFFFFFull);
+            T.pend = g->d_pmask.p; T.pend1 = g->d_pmask1.p; T.pmap = g->d_tmap.p;
+            T.item_pixel = g->d_item_pixel.p + first_new;
+            T.brute_below = (uint32_t)std::min<double>(sqrt((double)n_new_phase * (double)k), 65536.0);
+            if (const char* e = getenv("TSB_BRUTE_BELOW")) T.brute_below = (uint32_t)atoi(e);
+            k_lists_chunk<false><<<gr, CTA_THREADS, sizeof(KnnScratch) * WARPS_PER_CTA, s2>>>(S, C, T, g->d_tmap.p, (uint32_t)first_new,
+                                                                                               (uint32_t)std::min<size_t>(resolved_now, 0xFFFFFFFFull));
+        }
+        CU(cudaGetLastError());
+        {
+            const unsigned wb = k <= 96 ? 128u : 64u;
+            k_weights<<<(n + wb - 1) / wb, wb, (size_t)wb * k * 4, s2>>>(S, C);
+            const unsigned rb = m <= 64 ? 128u : 32u;  // items per block: the staging area is rb * m * 5 bytes (< 48 KB)
+            k_rand_candidates<<<(n + rb - 1) / rb, rb, (size_t)rb * m * 5 + rb, s2>>>(S.ex, S.n_ex, m, sp.seed + 1ull + (uint64_t)c.first, n, C.rand_xy, C.rand_map);
+            CU(cudaGetLastError());
+        }
+        if (!c.redo && c.phase_last) {  // the stage's new pixels join the resolved set of the next stage's analysis
+            const uint32_t nn = (uint32_t)n_new_phase;
+            k_mask_insert_flat<<<(nn + 255) / 256, 256, 0, s2>>>(A, g->d_item_pixel.p + first_new, nn, tiling ? 1 : 0);
+            CU(cudaGetLastError());
+        }
+        CU(cudaEventRecord(c.ev_ready, s2));
+        g->stats.kernel_launches += 3;
+        return 0;
+    };
+
+    // ---- resolve stream ----
+    StageDev S;
+    fill_stage_geometry(g, S, tiling);
+    S.counters = g->d_counters.p;
+    bool state_opaque = g->state_init_opaque;  // every resolved colour in the state has alpha 255
+    int cur_stage = -1;
+    size_t progress_base = 0;
+    uint64_t trace_base = 0;
+    std::vector<uint64_t> stage_trace_base(n_stages, 0), stage_progress_base(n_stages, 0);
+    {
+        uint64_t tb = 0, pb = 0;
+        for (size_t si = 0; si < n_stages; ++si) { stage_trace_base[si] = tb; stage_progress_base[si] = pb; tb += plan[si].n_redo + plan[si].n_new; pb += plan[si].pixels_to_resolve; }
+    }
+    (void)progress_base; (void)trace_base;
+    const int grid_full = g->guided ? g->max_ctas_stream_guided : g->max_ctas_stream;
+    auto begin_stage = [&](int si) -> int {
+        const StagePlan& sp = plan[si];
+        stage_inputs(g, S, sp.level, prm);
+        S.state = g->d_state.p;
+        S.lut_my = g->d_luts_all.p + (size_t)si * 512; S.lut_guide = S.lut_my + 256;
+        if (sp.recolour) {  // next_pyramid_level, ms.rs:687-700
+            k_recolour<<<(uint32_t)((npix + 255) / 256), 256, 0, s>>>(S);
+            CU(cudaGetLastError());
+            g->stats.kernel_launches++;
+            // recoloured pixels take the level's alphas; a pixel whose source is out of range keeps its colour
+            const bool may_keep = g->inpaint || g->locked > 0 || g->have_loaded_points;
+            state_opaque = (may_keep ? state_opaque : true) && g->level_opaque[sp.level];
+        }
+        g->no_fast = getenv("TSB_NO_FAST") != nullptr;
+        g->run_opaque = !g->no_fast && state_opaque && sp.level < (int)g->level_opaque.size() && g->level_opaque[sp.level];
+        S.opaque = g->run_opaque ? 1 : 0;
+        S.pad_pitch = g->no_fast ? 0 : g->pad_pitch;
+        state_opaque = state_opaque && g->level_opaque[sp.level];  // this stage commits texels of this level
+        if (sp.n_new && sp.resolved_before == 0) {
+            // no resolved neighbour at all: resolve_at_random(seed = p_stage_seed), ms.rs:1002-1009 -> 447-475
+            uint32_t flat = stage_pixels[sp.n_redo];
+            uint32_t rmap = (uint32_t)Pcg32::seed_from_u64(sp.seed).gen_range_usize((uint64_t)g->n_ex);
+            int e = g->filt[rmap];
+            uint32_t rx = Pcg32::seed_from_u64(sp.seed).gen_range_u32((uint32_t)g->ex_w[e]);
+            uint32_t ry = Pcg32::seed_from_u64(sp.seed).gen_range_u32((uint32_t)g->ex_h[e]);
+            uint32_t* item = g->h_ctrl;  // pinned
+            item[0] = flat; item[1] = rx; item[2] = ry; item[3] = rmap;
+            TRY(g->d_tmp_u32.ensure(4));
+            CU(cudaMemcpyAsync(g->d_tmp_u32.p, item, 16, cudaMemcpyHostToDevice, s));
+            k_commit_fixed<<<1, 32, 0, s>>>(S, S.ex, g->d_tmp_u32.p, 1, 0);
+            CU(cudaGetLastError());
+            g->stats.kernel_launches++;
+            if (g->trace) g->tr_fix_idx.push_back(stage_trace_base[si] + sp.n_redo);
+        }
+        return 0;
+    };
+    auto enqueue_resolve = [&](ChunkPlan& c) -> int {
+        const StagePlan& sp = plan[c.stage];
+        if (c.stage != cur_stage) {
+            for (int si = cur_stage + 1; si <= c.stage; ++si) TRY(begin_stage(si));  // stages without work items still recolour
+            cur_stage = c.stage;
+        }
+        StreamDev D;
+        memset(&D, 0, sizeof(D));
+        if (c.redo && c.phase_first) {
+            // redo results go to the other buffer: pixels that are not re-resolved must be there too
+            CU(cudaMemcpyAsync(g->d_state2.p, g->d_state.p, npix * sizeof(uint4), cudaMemcpyDeviceToDevice, s));
+        }
+        if (c.redo) { D.prev = g->d_state.p; D.cur = g->d_state2.p; }
+        else { D.prev = nullptr; D.cur = g->d_state.p; }
+        const size_t ci = (size_t)(&c - chunks.data());
+        D.ctl = g->d_sctl.p + ci * SC_WORDS;
+        D.abort_flag = abort_flag;
+        D.progress = cb ? g->d_progress : nullptr;
+        D.progress_base = (uint32_t)std::min<uint64_t>(stage_progress_base[c.stage] + c.first, 0xFFFFFFFFull);
+        D.tag = (uint32_t)(2 * c.stage + (c.redo ? 1 : 2));
+        D.watchdog_ms = watchdog_ms;
+        if (g->trace) { D.tr_best = g->d_tr_best.p; D.tr_ncand = g->d_tr_ncand.p; D.tr_nneigh = g->d_tr_nneigh.p; D.tr_score = g->d_tr_score.p; }
+        D.trace_base = stage_trace_base[c.stage];
+        StageDev Sc = S;
+        Sc.state = D.cur;
+        const ChunkDev C = chunk_dev(c);
+        int grid = std::max(1, std::min((int)((c.n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), grid_full));
+        // a phase that multiplies the resolved set is bound by its dependency depth, not by throughput: one CTA per SM
+        // leaves the rest of the machine to the analysis stream
+        const size_t before = sp.resolved_before + (c.redo ? 0 : (c.first - sp.n_redo));
+        if (!c.redo && before * 4 < c.n) grid = std::min(grid, g->n_sms);
+        CU(cudaStreamWaitEvent(s, c.ev_ready, 0));
+        CU(cudaEventRecord(c.ev_t0, s));
+        if (c.redo) TRY(launch_stream<true>(g, grid, Sc, C, D)); else TRY(launch_stream<false>(g, grid, Sc, C, D));
+        CU(cudaEventRecord(c.ev_done, s));
+        g->stats.kernel_launches++;
+        g->stats.phases += c.phase_first ? 1 : 0;
+        g->stats.rounds++;
+        if (c.redo && c.phase_last) std::swap(g->d_state.p, g->d_state2.p);  // both hold npix entries
+        return 0;
+    };
+
+    while (r_next < chunks.size()) {
+        while (a_next < chunks.size()) {
+            int rc = enqueue_analysis(chunks[a_next]);
+            if (rc == 1) break;
+            if (rc != 0) return rc;
+            live.push_back(a_next);
+            ++a_next;
+        }
+        if (a_next <= r_next) return fail(TSB_ERR_INTERNAL, "list ring too small for chunk %zu", r_next);
+        TRY(enqueue_resolve(chunks[r_next]));
+        ++r_next;
+    }
+    for (int si = cur_stage + 1; si < (int)n_stages; ++si) TRY(begin_stage(si));
+    CU(cudaEventRecord(ev_a1, s2));
+    CU(cudaStreamWaitEvent(s, ev_a1, 0));
+    CU(cudaMemcpyAsync(g->h_ctrl + 8, abort_flag, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(ev_end, s));
+
+    // ---- progress (ProgressNotifier, ms.rs:1054-1107): the calling thread polls the claim counter, as the reference's main
+    // thread does (ms.rs:1026-1034), and reports every change of the integer percentage with a snapshot of the colours ----
+    if (cb) {
+        uint64_t overall_total = 0;
+        for (auto& sp : plan) overall_total += sp.pixels_to_resolve;
+        std::vector<uint8_t> img(npix * 4);
+        DevBuf<uint32_t> snap;
+        TRY(snap.ensure(npix));
+        uint32_t last_pcnt = 0;
+        auto report = [&](uint64_t cur_total) -> int {
+            if (overall_total == 0) return 0;
+            const uint32_t pcnt = (uint32_t)lroundf((float)cur_total / (float)overall_total * 100.0f);
+            if (pcnt == last_pcnt) return 0;
+            last_pcnt = pcnt;
+            // snapshot on the copy stream: racy by design, like the reference's read of the shared colour map
+            k_unpack_state<<<(uint32_t)((npix + 255) / 256), 256, 0, g->stream3>>>(g->d_state.p, (uint32_t)npix, snap.p, nullptr, nullptr);
+            CU(cudaMemcpyAsync(img.data(), snap.p, npix * 4, cudaMemcpyDeviceToHost, g->stream3));
+            CU(cudaStreamSynchronize(g->stream3));
+            size_t si = 0;
+            while (si + 1 < n_stages && cur_total >= stage_progress_base[si + 1]) ++si;
+            cb(user, img.data(), (uint32_t)g->W, (uint32_t)g->H, cur_total, overall_total, cur_total - stage_progress_base[si], plan[si].pixels_to_resolve);
+            return 0;
+        };
+        while (cudaEventQuery(ev_end) == cudaErrorNotReady) {
+            TRY(report(*(volatile uint32_t*)g->h_progress));
+            std::this_thread::sleep_for(std::chrono::microseconds(200));
+        }
+        TRY(report(overall_total));
+    }
+    CU(cudaEventSynchronize(ev_end));
+    CU(cudaStreamSynchronize(s2));
+    if (g->h_ctrl[8]) return fail(TSB_ERR_INTERNAL, "resolve stalled: a work item waited more than %u ms for a neighbour (TSB_WATCHDOG_MS)", watchdog_ms);
+
+    // host mirrors of the order: ms.rs:1043-1049 (newly resolved pixels join `resolved` in processing order)
+    CU(cudaStreamSynchronize(g->stream3));
+    g->resolved_order.insert(g->resolved_order.end(), g->h_items.p, g->h_items.p + n_picks);
+    if (g->trace) for (auto& sp : plan) g->tr_pixel.insert(g->tr_pixel.end(), g->h_items.p, g->h_items.p + sp.n_redo + sp.n_new);
+    g->trace_n = g->trace ? total_items : 0;
+    unsigned long long cnt[ST_COUNT];
+    CU(cudaMemcpy(cnt, g->d_counters.p, sizeof(cnt), cudaMemcpyDeviceToHost));
+    g->stats.texels_fetched = cnt[ST_FETCHED]; g->stats.texels_nominal = cnt[ST_NOMINAL]; g->stats.candidates = cnt[ST_CANDS];
+    const bool dbg = getenv("TSB_DEBUG_PHASES") != nullptr;
+    for (auto& c : chunks) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c.ev_t0, c.ev_done);
+        g->stats.gpu_ms_resolve += ms;
+        if (dbg) {
+            float t0 = 0.f;
+            cudaEventElapsedTime(&t0, ev_begin, c.ev_t0);
+            fprintf(stderr, "[tsb] chunk stage %d %s first=%zu n=%zu start=%.3f ms resolve_ms=%.3f\n", c.stage, c.redo ? "redo" : "new", c.first, c.n, t0, ms);
+        }
+    }
+    float ms_a = 0.f, ms_total = 0.f;
+    cudaEventElapsedTime(&ms_a, ev_a0, ev_a1);
+    cudaEventElapsedTime(&ms_total, ev_begin, ev_end);
+    g->stats.gpu_ms_analysis = ms_a;  // overlapped with the resolve kernels
+    if (dbg && cnt[ST_ITEMS])
+        fprintf(stderr, "[tsb] analysis stream %.3f ms (overlapped), total %.3f ms | cycles/item: wait %.0f lists %.0f neigh %.0f rand %.0f score %.0f commit %.0f (items %llu)\n",
+                ms_a, ms_total, (double)cnt[ST_CYC_READY] / cnt[ST_ITEMS], (double)cnt[ST_CYC_KNN] / cnt[ST_ITEMS], (double)cnt[ST_CYC_NEIGH] / cnt[ST_ITEMS],
+                (double)cnt[ST_CYC_WEIGHT] / cnt[ST_ITEMS], (double)cnt[ST_CYC_SCORE] / cnt[ST_ITEMS], (double)cnt[ST_CYC_COMMIT] / cnt[ST_ITEMS], cnt[ST_ITEMS]);
+    g->stats.work_items = total_items;
+    g->stats.gpu_ms_total = ms_total;
+    g->stats.wall_ms_total = now_ms() - t_start;
+    g->stats.gpu_ms_other = ms_total - g->stats.gpu_ms_resolve;
+    g->have_loaded_points = false;
+    g->state_init_opaque = state_opaque;
+    (void)first_pixel_fixed;
     return 0;
 }
 
@@ -1504,6 +1963,9 @@ int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
     if (cudaSetDevice(dev) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "cudaSetDevice(%d) failed", dev));
     if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "stream creation failed"));
     if (cudaStreamCreateWithFlags(&g->stream2, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "stream creation failed"));
+    if (cudaStreamCreateWithFlags(&g->stream3, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "stream creation failed"));
+    if (cudaHostAlloc((void**)&g->h_progress, 64, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&g->d_progress, g->h_progress, 0) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "mapped allocation failed"));
     if (cudaEventCreateWithFlags(&g->ev_rand, cudaEventDisableTiming) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "event creation failed"));
     if (cudaMallocHost((void**)&g->h_ctrl, 64) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "pinned allocation failed"));
     g->W = (int)desc->out_width; g->H = (int)desc->out_height;
@@ -1534,7 +1996,7 @@ int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
             (rc = g->d_inp_color.upload((const uint32_t*)desc->inpaint_color, npix, g->stream))) return bail(rc);
         for (size_t i = 0; i < npix; ++i) {  // ms.rs:271-279
             if (desc->inpaint_mask[i * 4] < 255) g->unresolved0.push_back((uint32_t)i);
-            else g->resolved0.push_back((uint32_t)i);
+            else { g->resolved0.push_back((uint32_t)i); if (desc->inpaint_color[i * 4 + 3] != 255) g->inpaint_opaque = false; }
         }
     } else {
         g->unresolved0.resize(npix);
@@ -1551,6 +2013,13 @@ int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
     TSB_FLOW_ATTR(true, false, false, false); TSB_FLOW_ATTR(true, false, true, false); TSB_FLOW_ATTR(true, false, false, true); TSB_FLOW_ATTR(true, false, true, true);
     TSB_FLOW_ATTR(false, true, false, false); TSB_FLOW_ATTR(false, true, true, false); TSB_FLOW_ATTR(true, true, false, false); TSB_FLOW_ATTR(true, true, true, false);
 #undef TSB_FLOW_ATTR
+#define TSB_STREAM_ATTR(G, O, R) cudaFuncSetAttribute(k_stream<G, O, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem))
+    TSB_STREAM_ATTR(false, false, false); TSB_STREAM_ATTR(false, true, false); TSB_STREAM_ATTR(false, false, true); TSB_STREAM_ATTR(false, true, true);
+    TSB_STREAM_ATTR(true, false, false); TSB_STREAM_ATTR(true, true, false); TSB_STREAM_ATTR(true, false, true); TSB_STREAM_ATTR(true, true, true);
+#undef TSB_STREAM_ATTR
+    cudaFuncSetAttribute(k_lists_chunk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(KnnScratch) * WARPS_PER_CTA));
+    cudaFuncSetAttribute(k_lists_chunk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(KnnScratch) * WARPS_PER_CTA));
+    cudaFuncSetAttribute(k_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(k_serial<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
     cudaFuncSetAttribute(k_serial<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_round<false>, CTA_THREADS, sizeof(RoundSmem)) != cudaSuccess || per_sm < 1) per_sm = 1;
@@ -1563,6 +2032,13 @@ int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
     g->max_ctas = prop.multiProcessorCount * std::max(per_sm, 4);  // analysis kernels (k_radius: 47 KB smem) fit 4 CTAs per SM
     g->max_ctas_flow = prop.multiProcessorCount * per_sm_flow;  // persistent grid: co-resident CTAs only
     g->max_ctas_flow_guided = prop.multiProcessorCount * per_sm_flow_g;
+    {
+        int ps = 0, psg = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, k_stream<false, false, true>, CTA_THREADS, sizeof(RoundSmem)) != cudaSuccess || ps < 1) ps = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&psg, k_stream<true, false, true>, CTA_THREADS, sizeof(RoundSmem)) != cudaSuccess || psg < 1) psg = 1;
+        g->max_ctas_stream = prop.multiProcessorCount * ps;
+        g->max_ctas_stream_guided = prop.multiProcessorCount * psg;
+    }
     int per_sm_radius = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_radius, k_radius, CTA_THREADS, sizeof(KnnScratch) * WARPS_PER_CTA) != cudaSuccess || per_sm_radius < 1) per_sm_radius = 4;
     g->max_ctas_radius = prop.multiProcessorCount * per_sm_radius;  // one wave of co-resident CTAs, grid-stride over the items
@@ -1612,6 +2088,7 @@ int tsb_generator_random_init(tsb_generator* g, uint64_t count, const tsb_image*
         uint32_t rx = Pcg32::seed_from_u64(s2).gen_range_u32(top[rmap].width);
         uint32_t ry = Pcg32::seed_from_u64(s2).gen_range_u32(top[rmap].height);
         items.push_back(flat); items.push_back(rx); items.push_back(ry); items.push_back(rmap);
+        if (top[rmap].rgba[((size_t)ry * top[rmap].width + rx) * 4 + 3] != 255) g->state_init_opaque = false;
         g->resolved_order.push_back(flat);
     }
     g->locked += (size_t)count;  // ms.rs:444
@@ -1634,9 +2111,16 @@ int tsb_generator_upload_inputs(tsb_generator* g, const tsb_pyramid* examples, u
     return upload_inputs(g, examples, n_examples, guides, sampling);
 }
 
+static int resolve_dispatch(tsb_generator* g, const tsb_params* params, tsb_progress_fn cb, void* user) {
+    // default: the in-order streaming scheduler; TSB_MODE selects the older schedulers (cross-checks), which the band-sharded
+    // multi-GPU path still uses
+    if (g->mg_on || getenv("TSB_MODE")) return resolve_impl(g, params, cb, user);
+    return resolve_stream(g, params, cb, user);
+}
+
 int tsb_generator_resolve_resident(tsb_generator* g, const tsb_params* params, tsb_progress_fn cb, void* user) {
     if (!g || !params) return fail(TSB_ERR_INVALID, "null argument");
-    return resolve_impl(g, params, cb, user);
+    return resolve_dispatch(g, params, cb, user);
 }
 
 int tsb_generator_resolve(tsb_generator* g, const tsb_params* params, const tsb_pyramid* examples, uint32_t n_examples,
@@ -1644,7 +2128,7 @@ int tsb_generator_resolve(tsb_generator* g, const tsb_params* params, const tsb_
     if (!g || !params) return fail(TSB_ERR_INVALID, "null argument");
     TRY(set_device(g));
     TRY(upload_inputs(g, examples, n_examples, guides, sampling));
-    return resolve_impl(g, params, cb, user);
+    return resolve_dispatch(g, params, cb, user);
 }
 
 static int read_unpacked(tsb_generator* g, uint32_t* color, uint32_t* coord, uint32_t* idm) {
@@ -1772,7 +2256,15 @@ int tsb_generator_load_state(tsb_generator* g, const uint8_t* color, const uint3
     }
     // unresolved = every pixel not in the resolved list, in ascending order (order only matters for later picks)
     std::vector<uint8_t> isres(npix, 0);
-    for (uint64_t i = 0; i < n_resolved; ++i) isres[resolved_flat[i]] = 1;
+    g->state_init_opaque = true;
+    for (uint64_t i = 0; i < n_resolved; ++i) { isres[resolved_flat[i]] = 1; if (color[(size_t)resolved_flat[i] * 4 + 3] != 255) g->state_init_opaque = false; }
+    if (n_resolved) {
+        DevBuf<uint32_t> df;
+        TRY(df.upload(resolved_flat, n_resolved, s));
+        k_tag_locked<<<(uint32_t)((n_resolved + 255) / 256), 256, 0, s>>>(g->d_state.p, df.p, (uint32_t)n_resolved);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(s));
+    }
     g->unresolved.clear();
     for (size_t i = 0; i < npix; ++i) if (!isres[i]) g->unresolved.push_back((uint32_t)i);
     CU(cudaStreamSynchronize(s));

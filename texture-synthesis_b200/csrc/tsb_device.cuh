@@ -33,6 +33,18 @@ constexpr uint32_t R2_INF = 0xFFFFFFFFu;
 constexpr uint32_t OUTSIDE_RGBA = 0xFF000000u;  // image::Rgba([0,0,0,255]) little-endian (ms.rs:950)
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
+// state[p].w = id_map's MapId (bits 0-11) | coord_map's MapId (bits 12-23) | tag (bits 24-31).  The tag says when the
+// pixel was last written: 0 = never resolved, TAG_LOCKED = present before the run (inpaint, random_init, loaded
+// snapshot), otherwise the id of the phase that committed it (stage s, counted from the first stage: redo phase 2s+1,
+// new-pixel phase 2s+2).  The in-order resolve kernel (k_stream) waits on these tags instead of a ready queue.
+constexpr uint32_t MAP_MASK = 0xFFFu, TAG_LOCKED = 255u, TAG_LEGACY = 254u;
+__host__ __device__ __forceinline__ uint32_t st_idmap(uint32_t w) { return w & MAP_MASK; }
+__host__ __device__ __forceinline__ uint32_t st_coordmap(uint32_t w) { return (w >> 12) & MAP_MASK; }
+__host__ __device__ __forceinline__ uint32_t st_tag(uint32_t w) { return w >> 24; }
+__host__ __device__ __forceinline__ uint32_t st_pack_w(uint32_t idmap, uint32_t coordmap, uint32_t tag) {
+    return (idmap & MAP_MASK) | ((coordmap & MAP_MASK) << 12) | (tag << 24);
+}
+
 // Every example / guide level is also kept in a copy framed by EX_PAD texels of the out-of-image colour
 // (ms.rs:950) on each side: a neighbourhood whose offsets are all within EX_PAD of a valid candidate is then
 // read without any bounds test (pp = texel (0,0) inside the framed copy, row pitch = w + 2*EX_PAD).
@@ -209,7 +221,8 @@ struct TimeFilter {
     const uint32_t* pend;    // bit mask (geometry of S.mask) of ALL new pixels of the stage, tiling mirror copies included
     const uint32_t* pend1;   // its summary (geometry of S.mask1)
     const uint32_t* pmap;    // W*H: stage index of the new pixel at a canvas position, NONE32 elsewhere
-    uint32_t idx;            // only items with a stage index below this one count
+    uint32_t idx;            // only items with a phase index below this one count (position in item_pixel)
+    uint32_t idx_cmp;        // the same bound in the units of pmap (phase-local index, or global pick index for a time map)
     uint32_t hint;           // starting radius^2 of the search
     uint32_t n_points_max;   // upper bound of the number of points at that time
     const uint32_t* item_pixel;  // the stage's new pixels in serial order (flat canvas positions)
@@ -224,7 +237,7 @@ __device__ __forceinline__ bool mask_test_at(const StageDev& S, const uint32_t* 
 // the new pixel (or mirror copy) at the unwrapped position (x, y) belongs to an item below T.idx
 __device__ __forceinline__ bool time_passes(const StageDev& S, const TimeFilter& T, int x, int y) {
     if (S.tiling) { x = imod(x, S.W); y = imod(y, S.H); }
-    return __ldg(T.pmap + (size_t)y * S.W + x) < T.idx;
+    return __ldg(T.pmap + (size_t)y * S.W + x) < T.idx_cmp;
 }
 template <bool STABLE = false>
 __device__ __forceinline__ bool mask_test(const StageDev& S, int x, int y) {
@@ -791,6 +804,13 @@ __device__ __noinline__ ScoreOut score_unframed(const StageDev& S, WarpScratch& 
     return r;
 }
 
+template <bool GUIDED, int OPQ>
+__device__ __forceinline__ void resolve_tail(const StageDev& S, WarpScratch& ws, const float* __restrict__ s_lut,
+                                             const float* __restrict__ s_lutg, int lane, int kk, int ncand, int reach, bool degenerate,
+                                             const uint32_t* __restrict__ rand_xy, const uint8_t* __restrict__ rand_map,
+                                             uint32_t rxy0, uint32_t rxy1, uint32_t rmp0, uint32_t rmp1, long long t1, long long t2,
+                                             ItemOut& out);
+
 // ---------------------------------------------------------------------------------------------
 // One pixel resolution (steps 2-4 of ms.rs:917-986) by one warp.  No commit.
 // ---------------------------------------------------------------------------------------------
@@ -817,7 +837,6 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws,
     uint32_t rxy0 = 0, rxy1 = 0, rmp0 = 0, rmp1 = 0;
     if (lane < S.m) { rxy0 = __ldg(rand_xy + lane); rmp0 = __ldg(rand_map + lane); }
     if (lane + 32 < S.m) { rxy1 = __ldg(rand_xy + lane + 32); rmp1 = __ldg(rand_map + lane + 32); }
-    const int ew0 = S.ex[0].w;
     const int W = S.W, H = S.H;
     // ---- neighbour state, distances (ms.rs:405-425), coherence candidates (ms.rs:496-547) ----
     const double x2 = __ldg(S.divx + x + S.mx), y2 = __ldg(S.divy + y + S.my);
@@ -846,7 +865,7 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws,
             double ddx = __dsub_rn(x1, x2), ddy = __dsub_rn(y1, y2);
             ws.d[j] = __fma_rn(ddx, ddx, __dmul_rn(ddy, ddy));
             int sx = (int)(st.y & 0xFFFFu), sy = (int)(st.y >> 16);
-            uint32_t map = st.w & 0xFFFFu;  // id_map's MapId (ms.rs:510-511)
+            uint32_t map = st_idmap(st.w);  // id_map's MapId (ms.rs:510-511)
             int cx = sx - o.x, cy = sy - o.y;  // source of the neighbour + (p - n)
             if (map < (uint32_t)S.n_ex) {
                 DevEx e = S.ex[map];
@@ -886,6 +905,20 @@ __device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws,
             if (two) ws.g[j1] = (float)e1;
         }
     }
+    resolve_tail<GUIDED, OPQ>(S, ws, s_lut, s_lutg, lane, kk, ncand, reach, degenerate, rand_xy, rand_map, rxy0, rxy1, rmp0, rmp1, t1, t2, out);
+}
+
+// Second half of a pixel resolution, shared by every resolve kernel: exact de-duplication of the coherence candidates
+// already in ws.u.c (ncoh of them), the pre-generated random candidates, scoring and argmin.  Expects ws.off / ws.g /
+// ws.tcol (/ ws.gcol) for kk neighbours; `degenerate` = NaN weights (see resolve_item).
+template <bool GUIDED, int OPQ>
+__device__ __forceinline__ void resolve_tail(const StageDev& S, WarpScratch& ws, const float* __restrict__ s_lut,
+                                             const float* __restrict__ s_lutg, int lane, int kk, int ncand, int reach, bool degenerate,
+                                             const uint32_t* __restrict__ rand_xy, const uint8_t* __restrict__ rand_map,
+                                             uint32_t rxy0, uint32_t rxy1, uint32_t rmp0, uint32_t rmp1, long long t1, long long t2,
+                                             ItemOut& out) {
+    const unsigned lt = (1u << lane) - 1u;
+    const int ew0 = S.ex[0].w;
     const int kk8 = (kk + 7) & ~7;
     // pad to a multiple of 8 with zero-weight neighbours: t * 0 = +0 and s + 0 = s, so the sum is unchanged
     if (lane < kk8 - kk) { int j = kk + lane; ws.off[j] = make_short2(0, 0); ws.g[j] = 0.f; ws.tcol[j] = 0u; ws.gcol[j] = 0u; }
@@ -1019,7 +1052,7 @@ __device__ __forceinline__ void commit_item(const StageDev& S, const PhaseDev& P
     if (o.kk > 0) {
         DevEx e = S.ex[o.bmap];
         const uint32_t col = o.bcol_valid ? o.bcol : __ldg(e.px + (size_t)o.by * e.w + o.bx);
-        const uint4 v = make_uint4(col, (uint32_t)o.bx | ((uint32_t)o.by << 16), o.bpatch, (uint32_t)o.bmap | ((uint32_t)o.bmap << 16));
+        const uint4 v = make_uint4(col, (uint32_t)o.bx | ((uint32_t)o.by << 16), o.bpatch, st_pack_w((uint32_t)o.bmap, (uint32_t)o.bmap, TAG_LEGACY));
         if (!MG || !to_peers) {
             // local replica only.  In a band-sharded phase the owner pushes its band rows to the peers in bulk after
             // the kernel; the local mask is also written by other GPUs (their boundary items), hence system scope.
@@ -1442,7 +1475,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_lists_timed(StageDev S, PhaseDe
         const uint32_t flat = P.item_pixel[it];
         const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
         TimeFilter T = T0;
-        T.idx = it;
+        T.idx = it; T.idx_cmp = it;
         const double npts = (double)n_before + (double)it;
         T.hint = (uint32_t)fmin(fmax(1.5 * (double)S.k * area / (3.14159265358979 * fmax(npts, 1.0)), 8.0), 4.0e9);
         T.n_points_max = (uint32_t)fmin((S.tiling ? 3.0 : 1.0) * npts, 4.0e9);
@@ -1953,10 +1986,9 @@ __global__ void k_resolve_leftover(const unsigned long long* keys, uint32_t T, u
 __global__ void k_recolour(StageDev S) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= (uint32_t)(S.W * S.H)) return;
-    int x = (int)(p % (uint32_t)S.W), y = (int)(p / (uint32_t)S.W);
-    if (!mask_test(S, x, y)) return;
     uint4 st = S.state[p];
-    uint32_t map = st.w >> 16;  // coord_map's MapId
+    if (st_tag(st.w) == 0u) return;  // not resolved
+    uint32_t map = st_coordmap(st.w);  // coord_map's MapId
     if (map >= (uint32_t)S.n_ex) return;
     DevEx e = S.ex[map];
     int sx = (int)(st.y & 0xFFFFu), sy = (int)(st.y >> 16);
@@ -1991,12 +2023,8 @@ __global__ void k_state_alpha_check(StageDev S, int all_pixels, uint32_t* flag) 
     const size_t n = (size_t)S.W * S.H;
     bool bad = false;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        bool look = all_pixels != 0;
-        if (!look) {
-            const int X = (int)(i % (size_t)S.W) + S.mx, Y = (int)(i / (size_t)S.W) + S.my;
-            look = (S.mask[(size_t)Y * S.wpr + (X >> 5)] >> (X & 31)) & 1u;
-        }
-        if (look) bad |= (S.state[i].x >> 24) != 0xFFu;
+        const uint4 st = S.state[i];
+        if (all_pixels != 0 || st_tag(st.w) != 0u) bad |= (st.x >> 24) != 0xFFu;
     }
     if (bad) *flag = 1u;
 }
@@ -2018,7 +2046,7 @@ __global__ void k_commit_fixed(StageDev S, const DevEx* imgs, const uint32_t* it
     if (i >= n) return;
     uint32_t flat = items[4 * i], sx = items[4 * i + 1], sy = items[4 * i + 2], map = items[4 * i + 3];
     DevEx e = imgs[map];
-    S.state[flat] = make_uint4(e.px[(size_t)sy * e.w + sx], sx | (sy << 16), flat, map | (map << 16));
+    S.state[flat] = make_uint4(e.px[(size_t)sy * e.w + sx], sx | (sy << 16), flat, st_pack_w(map, map, TAG_LOCKED));
     S.score[flat] = 0.f;
     if (insert) mask_set(S, (int)(flat % (uint32_t)S.W), (int)(flat / (uint32_t)S.W));  // is_tiling_mode = false (ms.rs:473)
 }
@@ -2036,7 +2064,7 @@ __global__ void k_state_init_inpaint(uint4* state, float* score, const uint32_t*
     if (p >= n) return;
     bool locked = (mask_rgba[p] & 0xFFu) == 255u;
     uint32_t x = p % (uint32_t)W, y = p / (uint32_t)W;
-    state[p] = locked ? make_uint4(color[p], x | (y << 16), 0u, example_index << 16) : make_uint4(color[p], 0, 0, 0);
+    state[p] = locked ? make_uint4(color[p], x | (y << 16), 0u, st_pack_w(0u, example_index, TAG_LOCKED)) : make_uint4(color[p], 0, 0, 0);
     score[p] = 0.f;
 }
 __global__ void k_unpack_state(const uint4* state, uint32_t n, uint32_t* color, uint32_t* coord, uint32_t* idm) {
@@ -2044,13 +2072,18 @@ __global__ void k_unpack_state(const uint4* state, uint32_t n, uint32_t* color, 
     if (p >= n) return;
     uint4 st = state[p];
     if (color) color[p] = st.x;
-    if (coord) { coord[3 * p] = st.y & 0xFFFFu; coord[3 * p + 1] = st.y >> 16; coord[3 * p + 2] = st.w >> 16; }
-    if (idm) { idm[2 * p] = st.z; idm[2 * p + 1] = st.w & 0xFFFFu; }
+    if (coord) { coord[3 * p] = st.y & 0xFFFFu; coord[3 * p + 1] = st.y >> 16; coord[3 * p + 2] = st_coordmap(st.w); }
+    if (idm) { idm[2 * p] = st.z; idm[2 * p + 1] = st_idmap(st.w); }
 }
 __global__ void k_pack_state(uint4* state, uint32_t n, const uint32_t* color, const uint32_t* coord, const uint32_t* idm) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    state[p] = make_uint4(color[p], coord[3 * p] | (coord[3 * p + 1] << 16), idm[2 * p], idm[2 * p + 1] | (coord[3 * p + 2] << 16));
+    state[p] = make_uint4(color[p], coord[3 * p] | (coord[3 * p + 1] << 16), idm[2 * p], st_pack_w(idm[2 * p + 1], coord[3 * p + 2], 0u));
+}
+// marks the listed pixels as resolved before the run (loaded snapshot)
+__global__ void k_tag_locked(uint4* state, const uint32_t* flat, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) state[flat[i]].w |= TAG_LOCKED << 24;
 }
 __global__ void k_gather_scores(const float* score, const uint32_t* flat, uint32_t n, float* out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2066,7 +2099,7 @@ __global__ void k_uncertainty(StageDev S, uint32_t* out) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= (uint32_t)(S.W * S.H)) return;
     uint32_t v = 0;
-    if (mask_test(S, (int)(p % (uint32_t)S.W), (int)(p / (uint32_t)S.W))) {
+    if (st_tag(S.state[p].w) != 0u) {
         float f = __fmul_rn(fminf(S.score[p], 1.0f), 255.0f);
         uint32_t s = (uint32_t)(f < 0.f ? 0.f : (f > 255.f ? 255.f : f));  // `as u8` saturates, NaN -> 0
         if (!(f == f)) s = 0;
@@ -2078,7 +2111,7 @@ __global__ void k_id_maps(const uint4* state, uint32_t n, uint32_t* patch_rgba, 
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     uint4 st = state[p];
-    uint32_t pid = st.z, mid = st.w & 0xFFFFu;
+    uint32_t pid = st.z, mid = st_idmap(st.w);
     uint32_t a0 = Pcg32::seed_from_u64((uint64_t)pid).gen_range_u8(255);
     uint32_t a1 = Pcg32::seed_from_u64((uint64_t)(uint32_t)(pid * 5u + 21u)).gen_range_u8(255);
     uint32_t a2 = Pcg32::seed_from_u64((uint64_t)(pid / 4u + 12u)).gen_range_u8(255);
