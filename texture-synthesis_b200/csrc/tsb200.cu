@@ -23,6 +23,8 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 
 #include "tsb_device.cuh"
 #include "tsb_stream.cuh"
@@ -337,6 +339,20 @@ struct tsb_generator {
     cudaStream_t stream3 = nullptr;                 // host copies that must not delay the analysis stream
     uint32_t* h_progress = nullptr;                 // mapped pinned word: work items claimed so far
     uint32_t* d_progress = nullptr;                 // its device alias
+    // band-sharded execution on the streaming scheduler: one process per GPU, replicas linked through CUDA IPC
+    bool mgs_on = false;
+    int mgs_rank = 0, mgs_world = 1, mgs_band_h = 0;
+    uint4* mgs_A[MG_MAX] = {nullptr};               // every rank's first / second state buffer (peer-mapped)
+    uint4* mgs_B[MG_MAX] = {nullptr};
+    float* mgs_score[MG_MAX] = {nullptr};
+    uint32_t* mgs_sync[MG_MAX] = {nullptr};         // every rank's barrier flag block
+    DevBuf<uint32_t> d_mgs_sync;                    // [MG_MAX] flags written by the peers
+    DevBuf<uint32_t*> d_mgs_sync_ptrs;
+    uint32_t mgs_seq = 0;                           // barrier sequence number (identical on all ranks)
+    size_t mgs_shard_min = 32768;                   // smaller phases are executed redundantly by every rank
+    DevBuf<uint8_t> d_own_flag;
+    DevBuf<uint32_t> d_own_pos, d_own_t, d_own_pix, d_own_cnt;
+    uint64_t mgs_sharded_chunks = 0;
     bool state_init_opaque = true;                  // every colour in the state before the run has alpha 255
     bool inpaint_opaque = true;                     // the same for the locked inpaint pixels as created
 
@@ -1432,7 +1448,10 @@ struct ChunkPlan {
     size_t first, n;        // stage work-item range
     size_t slot;            // first item slot in the list ring
     bool phase_first, phase_last;
-    cudaEvent_t ev_ready = nullptr, ev_done = nullptr, ev_t0 = nullptr;
+    bool sharded = false;   // band-sharded run: this rank resolves only the items of its band, [own_lo, own_lo + own_n) of its own list
+    size_t own_lo = 0, own_n = 0;
+    size_t items() const { return sharded ? own_n : n; }
+    cudaEvent_t ev_ready = nullptr, ev_done = nullptr, ev_t0 = nullptr, ev_a0 = nullptr;
 };
 
 struct EventPool {
@@ -1445,12 +1464,12 @@ struct EventPool {
     }
 };
 
-template <bool REDO>
+template <bool REDO, bool MG>
 int launch_stream(tsb_generator* g, int grid, const StageDev& S, const ChunkDev& C, const StreamDev& D) {
     cudaStream_t s = g->stream;
     const bool op = S.opaque != 0;
-    if (g->guided) { if (op) k_stream<true, true, REDO><<<grid, CTA_THREADS, sizeof(RoundSmem), s>>>(S, C, D); else k_stream<true, false, REDO><<<grid, CTA_THREADS, sizeof(RoundSmem), s>>>(S, C, D); }
-    else { if (op) k_stream<false, true, REDO><<<grid, CTA_THREADS, sizeof(RoundSmem), s>>>(S, C, D); else k_stream<false, false, REDO><<<grid, CTA_THREADS, sizeof(RoundSmem), s>>>(S, C, D); }
+    if (g->guided) { if (op) k_stream<true, true, REDO, MG><<<grid, CTA_THREADS, sizeof(RoundSmem), s>>>(S, C, D); else k_stream<true, false, REDO, MG><<<grid, CTA_THREADS, sizeof(RoundSmem), s>>>(S, C, D); }
+    else { if (op) k_stream<false, true, REDO, MG><<<grid, CTA_THREADS, sizeof(RoundSmem), s>>>(S, C, D); else k_stream<false, false, REDO, MG><<<grid, CTA_THREADS, sizeof(RoundSmem), s>>>(S, C, D); }
     CU(cudaGetLastError());
     return 0;
 }
@@ -1515,6 +1534,54 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         if (sp.n_new && sp.resolved_before == 0) { first_pixel_fixed = true; a += 1; }
         if (sp.n_redo + sp.n_new > a) add_phase(false, a, sp.n_redo + sp.n_new);
     }
+    // ---- band-sharded run: which phases are sharded, and this rank's items of every sharded chunk ----
+    if (g->mgs_on && g->trace) return fail(TSB_ERR_UNSUPPORTED, "per-item trace is not available in multi-GPU mode");
+    if (g->mgs_on && n_picks) {
+        // A phase is sharded once its k-NN discs are small against the band height (the estimate r^2 = k * area / (pi *
+        // resolved) shrinks monotonically) and it has enough items; from then on every phase is (a replica only keeps its
+        // own band up to date).  Sparse phases are dependency bound anyway: every rank executes them on its own replica.
+        bool latched = false;
+        const double area = (double)g->W * (double)g->H;
+        for (auto& c : chunks) {
+            const StagePlan& sp = plan[c.stage];
+            if (!latched && c.phase_first) {
+                const size_t phase_n = c.redo ? sp.n_redo : sp.n_new;
+                const double r = sqrt((double)k * area / (3.14159265358979 * (double)std::max<size_t>(sp.resolved_before, 1)));
+                if (phase_n >= g->mgs_shard_min && r * 8.0 <= (double)g->mgs_band_h) latched = true;
+            }
+            c.sharded = latched;
+        }
+        const uint32_t T = (uint32_t)n_picks;
+        TRY(g->d_own_flag.ensure(n_picks + 1)); TRY(g->d_own_pos.ensure(n_picks + 1)); TRY(g->d_own_t.ensure(n_picks)); TRY(g->d_own_pix.ensure(n_picks));
+        TRY(g->d_own_cnt.ensure(4));
+        CU(cudaMemsetAsync(g->d_own_flag.p + n_picks, 0, 1, s));
+        k_own_flags<<<(T + 255) / 256, 256, 0, s>>>(g->d_item_pixel.p, T, g->W, g->mgs_band_h, g->mgs_world, g->mgs_rank, g->d_own_flag.p);
+        CU(cudaGetLastError());
+        size_t tb1 = 0, tb2 = 0;
+        CU(cub::DeviceScan::ExclusiveSum(nullptr, tb1, g->d_own_flag.p, g->d_own_pos.p, (int)(n_picks + 1), s));
+        cub::CountingInputIterator<uint32_t> counting(0u);
+        CU(cub::DeviceSelect::Flagged(nullptr, tb2, counting, g->d_own_flag.p, g->d_own_t.p, g->d_own_cnt.p, (int)n_picks, s));
+        TRY(g->d_cub_temp.ensure(std::max(tb1, tb2) + 256));
+        tb1 = tb2 = g->d_cub_temp.n;
+        CU(cub::DeviceScan::ExclusiveSum(g->d_cub_temp.p, tb1, g->d_own_flag.p, g->d_own_pos.p, (int)(n_picks + 1), s));
+        CU(cub::DeviceSelect::Flagged(g->d_cub_temp.p, tb2, counting, g->d_own_flag.p, g->d_own_t.p, g->d_own_cnt.p, (int)n_picks, s));
+        // own counts at the chunk boundaries
+        std::vector<uint32_t> bidx;
+        for (auto& c : chunks) { bidx.push_back((uint32_t)c.first); bidx.push_back((uint32_t)(c.first + c.n)); }
+        DevBuf<uint32_t> d_bidx, d_bpos;
+        std::vector<uint32_t> bpos(bidx.size());
+        TRY(d_bidx.upload(bidx.data(), bidx.size(), s)); TRY(d_bpos.ensure(bidx.size()));
+        k_gather_u32<<<(uint32_t)((bidx.size() + 255) / 256), 256, 0, s>>>(g->d_own_pos.p, d_bidx.p, (uint32_t)bidx.size(), d_bpos.p);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(bpos.data(), d_bpos.p, bidx.size() * 4, cudaMemcpyDeviceToHost, s));
+        uint32_t n_own_total = 0;
+        CU(cudaMemcpyAsync(&n_own_total, g->d_own_cnt.p, 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        if (n_own_total) k_gather_u32<<<(n_own_total + 255) / 256, 256, 0, s>>>(g->d_item_pixel.p, g->d_own_t.p, n_own_total, g->d_own_pix.p);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ev_picks, s));  // the analysis stream also needs the own-item lists
+        for (size_t i = 0; i < chunks.size(); ++i) { chunks[i].own_lo = bpos[2 * i]; chunks[i].own_n = bpos[2 * i + 1] - bpos[2 * i]; }
+    }
     // ---- list ring ----
     const size_t bytes_per_item = 1 + (size_t)k * 8 + 16 + (size_t)m * 5;
     size_t ring_mb = 24576;
@@ -1529,7 +1596,8 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         }
     }
     size_t largest = 1;
-    for (auto& c : chunks) largest = std::max(largest, c.n);
+    for (auto& c : chunks) largest = std::max(largest, c.items());
+    if (g->mgs_on) ring_items = std::max(ring_items, 2 * largest);  // (own-item ranges are per chunk: no re-splitting)
     if (ring_items < 2 * largest) {  // smaller chunks so that two of them fit the ring
         const size_t cm = std::max<size_t>(1024, ring_items / 3);
         std::vector<ChunkPlan> split;
@@ -1560,7 +1628,7 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         TRY(g->d_tr_best.ensure(total_items)); TRY(g->d_tr_ncand.ensure(total_items));
         TRY(g->d_tr_nneigh.ensure(total_items)); TRY(g->d_tr_score.ensure(total_items));
     }
-    for (auto& c : chunks) { TRY(events.get(&c.ev_ready, false)); TRY(events.get(&c.ev_done, true)); TRY(events.get(&c.ev_t0, true)); }
+    for (auto& c : chunks) { TRY(events.get(&c.ev_ready, true)); TRY(events.get(&c.ev_done, true)); TRY(events.get(&c.ev_t0, true)); TRY(events.get(&c.ev_a0, true)); }
     uint32_t watchdog_ms = 20000;
     if (const char* e = getenv("TSB_WATCHDOG_MS")) watchdog_ms = (uint32_t)std::max(1, atoi(e));
     *g->h_progress = 0;
@@ -1593,28 +1661,30 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         C.pixel = g->d_item_pixel.p + c.first;
         C.nbk = g->r_nbk.p + c.slot; C.nb = g->r_nb.p + c.slot * k; C.g = g->r_g.p + c.slot * k; C.low = g->r_low.p + c.slot;
         C.rand_xy = g->r_rand_xy.p + c.slot * (size_t)m; C.rand_map = g->r_rand_map.p + c.slot * (size_t)m;
-        C.n = (uint32_t)c.n; C.first = (uint32_t)c.first;
+        C.n = (uint32_t)c.n; C.first = (uint32_t)c.first; C.tidx = nullptr;
+        if (c.sharded) { C.pixel = g->d_own_pix.p + c.own_lo; C.tidx = g->d_own_t.p + c.own_lo; C.n = (uint32_t)c.own_n; }
         return C;
     };
     // returns 1 when the ring has no room until more resolve kernels have been enqueued
     auto enqueue_analysis = [&](ChunkPlan& c) -> int {
         size_t off = ring_head;
-        if (off + c.n > ring_items) off = 0;
+        if (off + c.items() > ring_items) off = 0;
         while (!live.empty()) {
             const ChunkPlan& f = chunks[live.front()];
-            const bool overlap = off < f.slot + f.n && f.slot < off + c.n;
+            const bool overlap = off < f.slot + f.items() && f.slot < off + c.items();
             if (!overlap) break;
             if (live.front() >= r_next) return 1;  // its resolve kernel is not enqueued yet: no event to wait for
             CU(cudaStreamWaitEvent(s2, f.ev_done, 0));
             live.pop_front();
         }
         c.slot = off;
-        ring_head = off + c.n;
+        ring_head = off + c.items();
+        CU(cudaEventRecord(c.ev_a0, s2));
         const StagePlan& sp = plan[c.stage];
         StageDev S = A;
         S.ex = g->d_exdesc.p + (size_t)sp.level * g->n_ex; S.n_ex = g->n_ex;
         const ChunkDev C = chunk_dev(c);
-        const uint32_t n = (uint32_t)c.n;
+        const uint32_t n = C.n;  // this rank's items of the chunk
         const int gr = std::max(1, std::min((int)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), g->max_ctas_radius));
         const size_t first_new = sp.n_redo + ((sp.n_new && sp.resolved_before == 0) ? 1 : 0);
         const size_t n_new_phase = sp.n_redo + sp.n_new - first_new;
@@ -1623,7 +1693,7 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         if (c.redo) {
             S.r2_hint = r2_hint_for(g, sp.resolved_before, k);
             S.n_points_max = (uint32_t)std::min<size_t>((tiling ? 3 : 1) * sp.resolved_before, 0xFFFFFFFFull);
-            k_lists_chunk<true><<<gr, CTA_THREADS, sizeof(KnnScratch) * WARPS_PER_CTA, s2>>>(S, C, T, g->d_tmap.p, 0u, 0u);
+            if (n) k_lists_chunk<true><<<gr, CTA_THREADS, sizeof(KnnScratch) * WARPS_PER_CTA, s2>>>(S, C, T, g->d_tmap.p, 0u, 0u);
         } else {
             const size_t resolved_now = sp.resolved_before + (first_new - sp.n_redo);
             if (c.phase_first) {
@@ -1641,15 +1711,16 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
             T.item_pixel = g->d_item_pixel.p + first_new;
             T.brute_below = (uint32_t)std::min<double>(sqrt((double)n_new_phase * (double)k), 65536.0);
             if (const char* e = getenv("TSB_BRUTE_BELOW")) T.brute_below = (uint32_t)atoi(e);
-            k_lists_chunk<false><<<gr, CTA_THREADS, sizeof(KnnScratch) * WARPS_PER_CTA, s2>>>(S, C, T, g->d_tmap.p, (uint32_t)first_new,
-                                                                                               (uint32_t)std::min<size_t>(resolved_now, 0xFFFFFFFFull));
+            if (n) k_lists_chunk<false><<<gr, CTA_THREADS, sizeof(KnnScratch) * WARPS_PER_CTA, s2>>>(S, C, T, g->d_tmap.p, (uint32_t)first_new,
+                                                                                                      (uint32_t)std::min<size_t>(resolved_now, 0xFFFFFFFFull));
         }
         CU(cudaGetLastError());
-        {
-            const unsigned wb = k <= 96 ? 128u : 64u;
-            k_weights<<<(n + wb - 1) / wb, wb, (size_t)wb * k * 4, s2>>>(S, C);
+        if (n) {
+            const unsigned wgroups = (n + 31u) / 32u;
+            k_weights<<<std::max(1u, std::min((wgroups + KW_WARPS - 1) / KW_WARPS, (unsigned)g->n_sms * 8u)), KW_WARPS * 32, (size_t)KW_WARPS * k * 33 * sizeof(double), s2>>>(S, C);
             const unsigned rb = m <= 64 ? 128u : 32u;  // items per block: the staging area is rb * m * 5 bytes (< 48 KB)
-            k_rand_candidates<<<(n + rb - 1) / rb, rb, (size_t)rb * m * 5 + rb, s2>>>(S.ex, S.n_ex, m, sp.seed + 1ull + (uint64_t)c.first, n, C.rand_xy, C.rand_map);
+            k_rand_candidates<<<(n + rb - 1) / rb, rb, (size_t)rb * m * 5 + rb, s2>>>(S.ex, S.n_ex, m, sp.seed + 1ull + (c.sharded ? 0ull : (uint64_t)c.first), n,
+                                                                                   C.rand_xy, C.rand_map, nullptr, 1, 1, 0, 1, C.tidx);
             CU(cudaGetLastError());
         }
         if (!c.redo && c.phase_last) {  // the stage's new pixels join the resolved set of the next stage's analysis
@@ -1677,8 +1748,17 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
     }
     (void)progress_base; (void)trace_base;
     const int grid_full = g->guided ? g->max_ctas_stream_guided : g->max_ctas_stream;
+    bool stage_prologue_pending = false;  // a recolour happened since the last kernel of this rank
+    auto mg_barrier = [&]() -> int {
+        const uint32_t seq = ++g->mgs_seq;
+        k_mg_signal<<<1, 32, 0, s>>>(g->d_mgs_sync_ptrs.p, g->mgs_world, g->mgs_rank, seq);
+        k_mg_wait<<<1, 32, 0, s>>>(g->d_mgs_sync.p, g->mgs_world, seq, watchdog_ms, abort_flag);
+        CU(cudaGetLastError());
+        return 0;
+    };
     auto begin_stage = [&](int si) -> int {
         const StagePlan& sp = plan[si];
+        stage_prologue_pending = stage_prologue_pending || sp.recolour;
         stage_inputs(g, S, sp.level, prm);
         S.state = g->d_state.p;
         S.lut_my = g->d_luts_all.p + (size_t)si * 512; S.lut_guide = S.lut_my + 256;
@@ -1715,6 +1795,7 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
     };
     auto enqueue_resolve = [&](ChunkPlan& c) -> int {
         const StagePlan& sp = plan[c.stage];
+        if (c.sharded && c.phase_first) TRY(mg_barrier());  // every rank has finished the previous phase: nobody reads what the prologue changes
         if (c.stage != cur_stage) {
             for (int si = cur_stage + 1; si <= c.stage; ++si) TRY(begin_stage(si));  // stages without work items still recolour
             cur_stage = c.stage;
@@ -1739,14 +1820,31 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         StageDev Sc = S;
         Sc.state = D.cur;
         const ChunkDev C = chunk_dev(c);
-        int grid = std::max(1, std::min((int)((c.n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), grid_full));
+        int grid = std::max(1, std::min((int)((C.n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), grid_full));
         // a phase that multiplies the resolved set is bound by its dependency depth, not by throughput: one CTA per SM
         // leaves the rest of the machine to the analysis stream
         const size_t before = sp.resolved_before + (c.redo ? 0 : (c.first - sp.n_redo));
         if (!c.redo && before * 4 < c.n) grid = std::min(grid, g->n_sms);
+        if (c.sharded) {
+            if (c.phase_first && (c.redo || stage_prologue_pending)) TRY(mg_barrier());  // ... and every replica is through its own prologue
+            D.world = g->mgs_world; D.rank = g->mgs_rank; D.band_h = g->mgs_band_h;
+            D.y0 = g->mgs_rank * g->mgs_band_h; D.y1 = g->mgs_rank == g->mgs_world - 1 ? g->H : std::min(g->H, D.y0 + g->mgs_band_h);
+            const bool flip = g->d_state.p != g->mgs_A[g->mgs_rank];  // the same on every rank
+            for (int r = 0; r < g->mgs_world; ++r) {
+                const uint4* a = flip ? g->mgs_B[r] : g->mgs_A[r];  // what every rank calls d_state right now
+                const uint4* b = flip ? g->mgs_A[r] : g->mgs_B[r];
+                D.prev_r[r] = c.redo ? a : nullptr;
+                D.cur_r[r] = c.redo ? b : a;
+            }
+            g->mgs_sharded_chunks++;
+        }
+        stage_prologue_pending = false;
         CU(cudaStreamWaitEvent(s, c.ev_ready, 0));
         CU(cudaEventRecord(c.ev_t0, s));
-        if (c.redo) TRY(launch_stream<true>(g, grid, Sc, C, D)); else TRY(launch_stream<false>(g, grid, Sc, C, D));
+        if (C.n) {
+            if (c.sharded) { if (c.redo) TRY((launch_stream<true, true>(g, grid, Sc, C, D))); else TRY((launch_stream<false, true>(g, grid, Sc, C, D))); }
+            else { if (c.redo) TRY((launch_stream<true, false>(g, grid, Sc, C, D))); else TRY((launch_stream<false, false>(g, grid, Sc, C, D))); }
+        }
         CU(cudaEventRecord(c.ev_done, s));
         g->stats.kernel_launches++;
         g->stats.phases += c.phase_first ? 1 : 0;
@@ -1768,6 +1866,21 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         ++r_next;
     }
     for (int si = cur_stage + 1; si < (int)n_stages; ++si) TRY(begin_stage(si));
+    if (g->mgs_on && !chunks.empty() && chunks.back().sharded) {
+        // all-gather of the bands: every replica ends up complete (state and first-resolution scores)
+        TRY(mg_barrier());
+        const bool flip = g->d_state.p != g->mgs_A[g->mgs_rank];
+        for (int r = 0; r < g->mgs_world; ++r) {
+            if (r == g->mgs_rank) continue;
+            const int y0 = r * g->mgs_band_h, y1 = r == g->mgs_world - 1 ? g->H : std::min(g->H, y0 + g->mgs_band_h);
+            if (y1 <= y0) continue;
+            const size_t o = (size_t)y0 * g->W, cnt = (size_t)(y1 - y0) * g->W;
+            const uint4* src = flip ? g->mgs_B[r] : g->mgs_A[r];
+            CU(cudaMemcpyAsync(g->d_state.p + o, src + o, cnt * sizeof(uint4), cudaMemcpyDeviceToDevice, s));
+            CU(cudaMemcpyAsync(g->d_score.p + o, g->mgs_score[r] + o, cnt * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        }
+        TRY(mg_barrier());  // nobody changes its band before everybody has copied it
+    }
     CU(cudaEventRecord(ev_a1, s2));
     CU(cudaStreamWaitEvent(s, ev_a1, 0));
     CU(cudaMemcpyAsync(g->h_ctrl + 8, abort_flag, 4, cudaMemcpyDeviceToHost, s));
@@ -1820,9 +1933,12 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         cudaEventElapsedTime(&ms, c.ev_t0, c.ev_done);
         g->stats.gpu_ms_resolve += ms;
         if (dbg) {
-            float t0 = 0.f;
+            float t0 = 0.f, a0 = 0.f, a1 = 0.f;
             cudaEventElapsedTime(&t0, ev_begin, c.ev_t0);
-            fprintf(stderr, "[tsb] chunk stage %d %s first=%zu n=%zu start=%.3f ms resolve_ms=%.3f\n", c.stage, c.redo ? "redo" : "new", c.first, c.n, t0, ms);
+            cudaEventElapsedTime(&a0, ev_begin, c.ev_a0);
+            cudaEventElapsedTime(&a1, ev_begin, c.ev_ready);
+            fprintf(stderr, "[tsb] chunk stage %d %s first=%zu n=%zu | analysis %.3f..%.3f ms | resolve %.3f..%.3f ms (%.3f)\n", c.stage, c.redo ? "redo" : "new",
+                    c.first, c.items(), a0, a1, t0, t0 + ms, ms);
         }
     }
     float ms_a = 0.f, ms_total = 0.f;
@@ -2013,13 +2129,15 @@ int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
     TSB_FLOW_ATTR(true, false, false, false); TSB_FLOW_ATTR(true, false, true, false); TSB_FLOW_ATTR(true, false, false, true); TSB_FLOW_ATTR(true, false, true, true);
     TSB_FLOW_ATTR(false, true, false, false); TSB_FLOW_ATTR(false, true, true, false); TSB_FLOW_ATTR(true, true, false, false); TSB_FLOW_ATTR(true, true, true, false);
 #undef TSB_FLOW_ATTR
-#define TSB_STREAM_ATTR(G, O, R) cudaFuncSetAttribute(k_stream<G, O, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem))
+#define TSB_STREAM_ATTR(G, O, R)                                                                                          \
+    cudaFuncSetAttribute(k_stream<G, O, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem)); \
+    cudaFuncSetAttribute(k_stream<G, O, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem))
     TSB_STREAM_ATTR(false, false, false); TSB_STREAM_ATTR(false, true, false); TSB_STREAM_ATTR(false, false, true); TSB_STREAM_ATTR(false, true, true);
     TSB_STREAM_ATTR(true, false, false); TSB_STREAM_ATTR(true, true, false); TSB_STREAM_ATTR(true, false, true); TSB_STREAM_ATTR(true, true, true);
 #undef TSB_STREAM_ATTR
     cudaFuncSetAttribute(k_lists_chunk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(KnnScratch) * WARPS_PER_CTA));
     cudaFuncSetAttribute(k_lists_chunk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(KnnScratch) * WARPS_PER_CTA));
-    cudaFuncSetAttribute(k_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KW_WARPS * KMAX * 33 * sizeof(double)));
     cudaFuncSetAttribute(k_serial<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
     cudaFuncSetAttribute(k_serial<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_round<false>, CTA_THREADS, sizeof(RoundSmem)) != cudaSuccess || per_sm < 1) per_sm = 1;
@@ -2114,7 +2232,7 @@ int tsb_generator_upload_inputs(tsb_generator* g, const tsb_pyramid* examples, u
 static int resolve_dispatch(tsb_generator* g, const tsb_params* params, tsb_progress_fn cb, void* user) {
     // default: the in-order streaming scheduler; TSB_MODE selects the older schedulers (cross-checks), which the band-sharded
     // multi-GPU path still uses
-    if (g->mg_on || getenv("TSB_MODE")) return resolve_impl(g, params, cb, user);
+    if (!g->mgs_on && (g->mg_on || getenv("TSB_MODE"))) return resolve_impl(g, params, cb, user);
     return resolve_stream(g, params, cb, user);
 }
 
@@ -2329,31 +2447,29 @@ int tsb_generator_eval_items(tsb_generator* g, const tsb_params* prm, int32_t le
 }
 
 // ---- band-sharded multi-GPU execution: one process per GPU, replicas linked through CUDA IPC ----------------
-enum { MG_STATE = 0, MG_MASK, MG_MASK1, MG_SCORE, MG_R2, MG_NPRED, MG_NSUCC, MG_SUCC, MG_QUEUE, MG_CTL, MG_NBUF };
+// Shared with the peers: both state buffers (a neighbour outside this rank's band is read in its owner's replica), the
+// first-resolution scores (gathered at the end of a run) and the barrier flag block.
+enum { MG_STATE_A = 0, MG_STATE_B, MG_SCORE, MG_SYNC, MG_NBUF };
 enum { MG_ENTRY = 80 };  // bytes per exported buffer: IPC handle (64) + offset inside the allocation block (8) + padding
 
 static void* mg_local_ptr(tsb_generator* g, int which) {
     switch (which) {
-    case MG_STATE: return g->d_state.p;
-    case MG_MASK: return g->d_mask.p;
-    case MG_MASK1: return g->d_mask1.p;
+    case MG_STATE_A: return g->d_state.p;
+    case MG_STATE_B: return g->d_state2.p;
     case MG_SCORE: return g->d_score.p;
-    case MG_R2: return g->d_item_R2.p;
-    case MG_NPRED: return g->d_npred.p;
-    case MG_NSUCC: return g->d_nsucc.p;
-    case MG_SUCC: return g->d_succ.p;
-    case MG_QUEUE: return g->d_queue.p;
-    default: return g->d_fctl.p;
+    default: return g->d_mgs_sync.p;
     }
 }
 
 int tsb_generator_mg_prepare(tsb_generator* g, const tsb_params* params, uint32_t* n_handles) {
     if (!g || !params || !n_handles) return fail(TSB_ERR_INVALID, "null argument");
     TRY(set_device(g));
-    std::vector<StagePlan> plan;
-    size_t n_picks, max_stage_items, max_phase, total_items;
-    build_plan(g, params, plan, n_picks, max_stage_items, max_phase, total_items);
-    TRY(ensure_flow_buffers(g, max_phase));  // final sizes: the IPC mappings must stay valid for the whole run
+    // final sizes: the IPC mappings must stay valid for the lifetime of the generator
+    TRY(g->d_state2.ensure((size_t)g->W * g->H));
+    TRY(g->d_mgs_sync.ensure(64));
+    CU(cudaMemsetAsync(g->d_mgs_sync.p, 0, 64 * 4, g->stream));
+    CU(cudaStreamSynchronize(g->stream));
+    g->mgs_seq = 0;
     *n_handles = MG_NBUF;
     return 0;
 }
@@ -2383,6 +2499,7 @@ int tsb_generator_mg_export(tsb_generator* g, uint8_t* handles) {
     if (!g || !handles) return fail(TSB_ERR_INVALID, "null argument");
     TRY(set_device(g));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!g->d_state2.p || !g->d_mgs_sync.p) return fail(TSB_ERR_INVALID, "tsb_generator_mg_prepare has not been called");
     for (int i = 0; i < MG_NBUF; ++i) {
         uint64_t off = 0;
         TRY(ipc_offset_of(mg_local_ptr(g, i), &off));
@@ -2396,14 +2513,12 @@ int tsb_generator_mg_export(tsb_generator* g, uint8_t* handles) {
 }
 
 int tsb_generator_mg_attach(tsb_generator* g, uint32_t rank, uint32_t world, const uint8_t* all_handles, tsb_barrier_fn barrier, void* user) {
-    if (!g || !all_handles || !barrier) return fail(TSB_ERR_INVALID, "null argument");
+    if (!g || !all_handles) return fail(TSB_ERR_INVALID, "null argument");
     if (world < 2 || world > (uint32_t)MG_MAX || rank >= world) return fail(TSB_ERR_INVALID, "world size must be in [2,%d]", MG_MAX);
     TRY(set_device(g));
-    MgDev& m = g->h_mg;
-    memset(&m, 0, sizeof(m));
-    m.rank = (int)rank; m.world = (int)world;
-    m.band_h = (g->H + (int)world - 1) / (int)world;
-    if (m.band_h <= (int)((float)g->H * 0.05f) + 1) return fail(TSB_ERR_UNSUPPORTED, "output too small for %u bands", world);
+    g->mgs_rank = (int)rank; g->mgs_world = (int)world;
+    g->mgs_band_h = (g->H + (int)world - 1) / (int)world;
+    if (g->mgs_band_h < 8) return fail(TSB_ERR_UNSUPPORTED, "output too small for %u bands", world);
     for (uint32_t r = 0; r < world; ++r) {
         void* ptrs[MG_NBUF];
         for (int i = 0; i < MG_NBUF; ++i) {
@@ -2423,22 +2538,20 @@ int tsb_generator_mg_attach(tsb_generator* g, uint32_t rank, uint32_t world, con
             }
             ptrs[i] = (uint8_t*)base + off;
         }
-        m.state[r] = (uint4*)ptrs[MG_STATE]; m.mask[r] = (uint32_t*)ptrs[MG_MASK]; m.mask1[r] = (uint32_t*)ptrs[MG_MASK1];
-        m.score[r] = (float*)ptrs[MG_SCORE]; m.item_R2[r] = (uint32_t*)ptrs[MG_R2]; m.npred[r] = (uint32_t*)ptrs[MG_NPRED];
-        m.nsucc[r] = (uint32_t*)ptrs[MG_NSUCC]; m.succ[r] = (uint32_t*)ptrs[MG_SUCC]; m.queue[r] = (uint32_t*)ptrs[MG_QUEUE];
-        m.ctl[r] = (uint32_t*)ptrs[MG_CTL];
+        g->mgs_A[r] = (uint4*)ptrs[MG_STATE_A]; g->mgs_B[r] = (uint4*)ptrs[MG_STATE_B];
+        g->mgs_score[r] = (float*)ptrs[MG_SCORE]; g->mgs_sync[r] = (uint32_t*)ptrs[MG_SYNC];
     }
-    TRY(g->d_mg.upload(&m, 1, g->stream));
+    TRY(g->d_mgs_sync_ptrs.upload(g->mgs_sync, MG_MAX, g->stream));
     CU(cudaStreamSynchronize(g->stream));
-    g->mg_barrier = barrier; g->mg_barrier_user = user;
-    if (getenv("TSB_MG_MIN_PHASE")) g->mg_min_phase = (size_t)std::max(1, atoi(getenv("TSB_MG_MIN_PHASE")));
-    g->mg_on = true;
+    (void)barrier; (void)user;  // the ranks synchronise on the device (k_mg_signal / k_mg_wait); kept for ABI compatibility
+    if (getenv("TSB_MG_MIN_PHASE")) g->mgs_shard_min = (size_t)std::max(1, atoi(getenv("TSB_MG_MIN_PHASE")));
+    g->mgs_on = true;
     return 0;
 }
 
 int tsb_generator_mg_phases(tsb_generator* g, uint64_t* n) {
     if (!g || !n) return fail(TSB_ERR_INVALID, "null argument");
-    *n = g->mg_phases;
+    *n = g->mgs_sharded_chunks;
     return 0;
 }
 

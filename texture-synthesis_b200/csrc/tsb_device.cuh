@@ -1867,7 +1867,7 @@ __global__ void k_seed_queue(StageDev S, PhaseDev P, FlowDev F) {
 // ---------------------------------------------------------------------------------------------
 __global__ void k_rand_candidates(const DevEx* ex, int n_ex, int m, uint64_t seed_base, uint32_t n,
                                   uint32_t* rand_xy, uint8_t* rand_map, const uint32_t* own_pixel = nullptr, int W = 1,
-                                  int band_h = 1, int rank = 0, int world = 1) {
+                                  int band_h = 1, int rank = 0, int world = 1, const uint32_t* tidx = nullptr) {
     // each thread draws the m candidates of one item into shared memory; the block then writes its (contiguous)
     // slice of the two arrays with coalesced stores
     extern __shared__ __align__(16) unsigned char rc_smem[];
@@ -1883,7 +1883,8 @@ __global__ void k_rand_candidates(const DevEx* ex, int n_ex, int m, uint64_t see
     }
     sown[threadIdx.x] = mine ? 1 : 0;
     if (mine) {
-        Pcg32 rng = Pcg32::seed_from_u64(seed_base + (uint64_t)it);
+        // tidx: the items are a subset of the stage (band-sharded chunk); their stage indices select the random streams
+        Pcg32 rng = Pcg32::seed_from_u64(seed_base + (uint64_t)(tidx ? tidx[it] : it));
         uint32_t* oxy = sxy + (size_t)threadIdx.x * m;
         uint8_t* om = smap + (size_t)threadIdx.x * m;
         if (n_ex == 1) {

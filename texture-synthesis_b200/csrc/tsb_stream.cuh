@@ -59,7 +59,9 @@ struct ChunkDev {
     uint8_t* rand_map;      // [n][m]
     uint32_t n;             // items in the chunk
     uint32_t first;         // stage work-item index of item 0 (= its position in the pick array)
+    const uint32_t* tidx;   // band-sharded chunks hold this rank's items only: [n] stage work-item index of each (else nullptr)
 };
+__device__ __forceinline__ uint32_t chunk_item_index(const ChunkDev& C, uint32_t c) { return C.tidx ? __ldg(C.tidx + c) : C.first + c; }
 
 // pixel -> position in the pick array (= the work-item index of its first resolution in its stage); NONE32 for pixels
 // that are never picked (locked before the run)
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_lists_chunk(StageDev S, ChunkDe
     const uint32_t nwarps = gridDim.x * WARPS_PER_CTA;
     const double area = (double)S.W * (double)S.H;
     for (uint32_t c = blockIdx.x * WARPS_PER_CTA + warp; c < C.n; c += nwarps) {
-        const uint32_t i = C.first + c;
+        const uint32_t i = chunk_item_index(C, c);
         const uint32_t flat = C.pixel[c];
         const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
         uint32_t r2;
@@ -119,48 +121,57 @@ __global__ void __launch_bounds__(CTA_THREADS) k_lists_chunk(StageDev S, ChunkDe
     }
 }
 
-// get_distances_to_k_neighs + the gaussians of find_best_match (ms.rs:405-425, 1198-1203) for every item of a chunk, one
-// THREAD per item: d_j = fma(dx, dx, dy * dy) on the normalised coordinates (tables divx / divy hold the reference's
-// divisions), mean over the x4-duplicated list as a strictly sequential f64 sum, g_j = (f32) exp(-(d_j / mean)).
-// Offsets come in and weights go out through shared memory so that the global accesses stay coalesced.
-__global__ void k_weights(StageDev S, ChunkDev C) {
+// get_distances_to_k_neighs + the gaussians of find_best_match (ms.rs:405-425, 1198-1203) for every item of a chunk:
+// d_j = fma(dx, dx, dy * dy) on the normalised coordinates (tables divx / divy hold the reference's divisions), mean over the
+// x4-duplicated list as a strictly sequential f64 sum, g_j = (f32) exp(-(d_j / mean)).  Each warp takes 32 items at a time:
+//   1. item by item, lanes = neighbours: the distances (coalesced list reads, table reads that share sectors) -> shared memory
+//   2. lanes = items: the sequential sum -- 32 chains side by side, one lane each instead of one warp each
+//   3. (item, neighbour) pairs flattened over the lanes: division, exp, cast, coalesced store
+constexpr int KW_WARPS = 4;
+__global__ void __launch_bounds__(KW_WARPS * 32) k_weights(StageDev S, ChunkDev C) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* sm = reinterpret_cast<uint32_t*>(smem_raw);  // [blockDim.x][k]: offsets in, weights out
     const int k = S.k;
-    const uint32_t c0 = blockIdx.x * blockDim.x;
-    const uint32_t rows = min((uint32_t)blockDim.x, C.n - c0);
-    const uint32_t total = rows * (uint32_t)k;
-    const uint32_t* gin = reinterpret_cast<const uint32_t*>(C.nb + (size_t)c0 * k);
-    for (uint32_t f = threadIdx.x; f < total; f += blockDim.x) sm[f] = gin[f];
-    __syncthreads();
-    if (threadIdx.x < rows) {
-        const uint32_t c = c0 + threadIdx.x;
-        const int kk = (int)C.nbk[c];
-        const uint32_t flat = C.pixel[c];
-        const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
-        const double x2 = __ldg(S.divx + x + S.mx), y2 = __ldg(S.divy + y + S.my);
-        uint32_t* row = sm + (size_t)threadIdx.x * k;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* sd = reinterpret_cast<double*>(smem_raw) + (size_t)warp * (size_t)k * 33;  // [k][33]: (j, item) at j * 33 + item
+    const uint32_t ngroups = (C.n + 31u) / 32u;
+    for (uint32_t grp = blockIdx.x * KW_WARPS + warp; grp < ngroups; grp += gridDim.x * KW_WARPS) {
+        const uint32_t c0 = grp * 32u;
+        const int rows = (int)min(32u, C.n - c0);
+        int my_kk = 0;
+        if (lane < rows) my_kk = (int)C.nbk[c0 + lane];
+        for (int it = 0; it < rows; ++it) {
+            const uint32_t c = c0 + (uint32_t)it;
+            const int kk = __shfl_sync(FULL, my_kk, it);
+            const uint32_t flat = C.pixel[c];
+            const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
+            const double x2 = __ldg(S.divx + x + S.mx), y2 = __ldg(S.divy + y + S.my);
+            for (int j = lane; j < kk; j += 32) {
+                const short2 o = C.nb[(size_t)c * k + j];
+                const double ddx = __dsub_rn(__ldg(S.divx + x + o.x + S.mx), x2), ddy = __dsub_rn(__ldg(S.divy + y + o.y + S.my), y2);
+                sd[(size_t)j * 33 + it] = __fma_rn(ddx, ddx, __dmul_rn(ddy, ddy));
+            }
+        }
+        __syncwarp();
         double sum = 0.0;
-        for (int j = 0; j < kk; ++j) {
-            const uint32_t ov = row[j];
-            const int ox = (int)(short)(ov & 0xFFFFu), oy = (int)(short)(ov >> 16);
-            const double ddx = __dsub_rn(__ldg(S.divx + x + ox + S.mx), x2), ddy = __dsub_rn(__ldg(S.divy + y + oy + S.my), y2);
-            const double d = __fma_rn(ddx, ddx, __dmul_rn(ddy, ddy));
+        for (int j = 0; j < my_kk; ++j) {
+            const double d = sd[(size_t)j * 33 + lane];
             sum = __dadd_rn(sum, d); sum = __dadd_rn(sum, d); sum = __dadd_rn(sum, d); sum = __dadd_rn(sum, d);
         }
-        const double avg = __ddiv_rn(sum, (double)(kk * 4));
-        for (int j = 0; j < kk; ++j) {
-            const uint32_t ov = row[j];
-            const int ox = (int)(short)(ov & 0xFFFFu), oy = (int)(short)(ov >> 16);
-            const double ddx = __dsub_rn(__ldg(S.divx + x + ox + S.mx), x2), ddy = __dsub_rn(__ldg(S.divy + y + oy + S.my), y2);
-            const double d = __fma_rn(ddx, ddx, __dmul_rn(ddy, ddy));
-            row[j] = __float_as_uint((float)exp(-__ddiv_rn(d, avg)));  // avg == 0 (the pixel is its own only neighbour): NaN, as in the reference
+        const double my_avg = __ddiv_rn(sum, (double)(my_kk * 4));  // 0 / 0 = NaN for an empty list (never read)
+        const int total = rows * k;
+        for (int e = lane; e < ((total + 31) & ~31); e += 32) {
+            const int it = e / k, j = e - it * k;
+            const double avg = __shfl_sync(FULL, my_avg, it & 31);
+            const int kk = __shfl_sync(FULL, my_kk, it & 31);
+            if (e < total) {
+                float gv = 0.f;
+                // avg == 0 (the pixel is its own only neighbour): 0 / 0 -> NaN weights, as in the reference
+                if (j < kk) gv = (float)exp(-__ddiv_rn(sd[(size_t)j * 33 + it], avg));
+                C.g[(size_t)c0 * k + e] = gv;
+            }
         }
-        for (int j = kk; j < k; ++j) row[j] = 0u;
+        __syncwarp();
     }
-    __syncthreads();
-    uint32_t* gout = reinterpret_cast<uint32_t*>(C.g + (size_t)c0 * k);
-    for (uint32_t f = threadIdx.x; f < total; f += blockDim.x) gout[f] = sm[f];
 }
 
 // Control block of one k_stream launch
@@ -178,12 +189,17 @@ struct StreamDev {
     // per-item trace (tests)
     int32_t* tr_best; int32_t* tr_ncand; int32_t* tr_nneigh; float* tr_score;
     uint64_t trace_base;
+    // band-sharded execution (MG): the state of a pixel lives with the rank that owns its row; neighbours outside this rank's
+    // band are read (and polled) in the owner's replica over NVLink -- nothing is ever pushed
+    int world, rank, band_h, y0, y1;      // this rank owns rows [y0, y1)
+    const uint4* prev_r[MG_MAX];
+    const uint4* cur_r[MG_MAX];
 };
 
 // Persistent in-order resolve kernel for one chunk.  REDO: re-resolution of already resolved pixels (ms.rs:905-907) --
 // neighbours flagged "earlier" are read from `cur` once their tag is this phase's, all others from `prev`; the result goes
 // to `cur`.  Otherwise new pixels (ms.rs:909-915): every neighbour is read from `cur` once its tag is non-zero.
-template <bool GUIDED, bool OPAQUE, bool REDO>
+template <bool GUIDED, bool OPAQUE, bool REDO, bool MG = false>
 __global__ void __launch_bounds__(CTA_THREADS, 3) k_stream(StageDev S, ChunkDev C, StreamDev D) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RoundSmem& rs = *reinterpret_cast<RoundSmem*>(smem_raw);
@@ -209,7 +225,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_stream(StageDev S, ChunkDev 
         const int kk = (int)C.nbk[c];
         const uint32_t flat = C.pixel[c];
         const int x = (int)(flat % (uint32_t)W), y = (int)(flat / (uint32_t)W);
-        const uint32_t si = C.first + c;
+        const uint32_t si = chunk_item_index(C, c);
         const uint32_t* rand_xy = C.rand_xy + (size_t)c * S.m;
         const uint8_t* rand_map = C.rand_map + (size_t)c * S.m;
         uint4 lowm = make_uint4(0u, 0u, 0u, 0u);
@@ -246,8 +262,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_stream(StageDev S, ChunkDev 
                             const uint32_t wsel = (j >> 5) == 0 ? lowm.x : (j >> 5) == 1 ? lowm.y : (j >> 5) == 2 ? lowm.z : lowm.w;
                             low = (wsel >> (j & 31)) & 1u;
                         }
-                        src[q] = ((REDO && !low) ? D.prev : D.cur) + ((size_t)qy * W + qx);
-                        st[q] = ld_state(src[q]);
+                        if (MG && (qy < D.y0 || qy >= D.y1)) {  // the owner's replica holds the authoritative copy
+                            int r = qy / D.band_h;
+                            r = r < D.world - 1 ? r : D.world - 1;
+                            src[q] = ((REDO && !low) ? D.prev_r[r] : D.cur_r[r]) + ((size_t)qy * W + qx);
+                        } else src[q] = ((REDO && !low) ? D.prev : D.cur) + ((size_t)qy * W + qx);
+                        st[q] = MG ? ld_state_sys(src[q]) : ld_state(src[q]);
                         need[q] = REDO ? (low && st_tag(st[q].w) != D.tag) : (st_tag(st[q].w) == 0u);
                     }
                 }
@@ -262,7 +282,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_stream(StageDev S, ChunkDev 
 #pragma unroll
                         for (int q = 0; q < 2; ++q)
                             if (need[q]) {
-                                st[q] = ld_state(src[q]);
+                                st[q] = MG ? ld_state_sys(src[q]) : ld_state(src[q]);
                                 need[q] = REDO ? (st_tag(st[q].w) != D.tag) : (st_tag(st[q].w) == 0u);
                             }
                         if ((++polls & 255u) == 0u) {  // watchdog in wall-clock time: a stalled run is an error, never a hang
@@ -330,7 +350,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_stream(StageDev S, ChunkDev 
                 DevEx e = S.ex[o.bmap];
                 const uint32_t col = o.bcol_valid ? o.bcol : __ldg(e.px + (size_t)o.by * e.w + o.bx);
                 if (!REDO) S.score[flat] = o.score;  // first resolution only (ms.rs:365)
-                st_state(D.cur + flat, make_uint4(col, (uint32_t)o.bx | ((uint32_t)o.by << 16), o.bpatch, st_pack_w((uint32_t)o.bmap, (uint32_t)o.bmap, D.tag)));
+                const uint4 v = make_uint4(col, (uint32_t)o.bx | ((uint32_t)o.by << 16), o.bpatch, st_pack_w((uint32_t)o.bmap, (uint32_t)o.bmap, D.tag));
+                if (MG) st_state_sys(D.cur + flat, v); else st_state(D.cur + flat, v);
             }
             if (D.tr_best) {
                 const size_t ti = (size_t)(D.trace_base + si);
@@ -351,6 +372,44 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_stream(StageDev S, ChunkDev 
     }
     __syncthreads();
     if (S.counters && threadIdx.x < ST_COUNT && rs.stat[threadIdx.x]) atomicAdd(S.counters + threadIdx.x, rs.stat[threadIdx.x]);
+}
+
+// Device-side barrier between the ranks of a band-sharded run (one per phase): every rank stores its sequence number into
+// every peer's flag block (peer-mapped memory, release at system scope) and then waits, polling its OWN block, until all
+// peers have stored theirs.  Stream-ordered: no host synchronisation.
+__global__ void k_mg_signal(uint32_t* const* flags_of_rank, int world, int rank, uint32_t seq) {
+    const int r = threadIdx.x;
+    if (r < world) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags_of_rank[r] + rank), "r"(seq) : "memory");
+}
+__global__ void k_mg_wait(const uint32_t* my_flags, int world, uint32_t seq, uint32_t watchdog_ms, uint32_t* abort_flag) {
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    unsigned long long t0 = 0;
+    unsigned polls = 0;
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(my_flags + r) : "memory");
+        if ((int32_t)(v - seq) >= 0) break;
+        __nanosleep(200);
+        if ((++polls & 1023u) == 0u) {
+            const unsigned long long now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            if (*((volatile uint32_t*)abort_flag)) break;
+            if (now - t0 > (unsigned long long)watchdog_ms * 1000000ull) { atomicExch(abort_flag, 1u); break; }
+        }
+    }
+}
+// ownership flags of the picks for the ordered compaction (band-sharded runs)
+__global__ void k_own_flags(const uint32_t* picks, uint32_t n, int W, int band_h, int world, int rank, uint8_t* flag) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int r = (int)(picks[t] / (uint32_t)W) / band_h;
+    r = r < world - 1 ? r : world - 1;
+    flag[t] = r == rank ? 1 : 0;
+}
+__global__ void k_gather_u32(const uint32_t* src, const uint32_t* idx, uint32_t n, uint32_t* dst) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) dst[t] = src[idx[t]];
 }
 
 }  // namespace tsb
