@@ -25,8 +25,8 @@ sys.path.insert(0, ROOT)
 
 OUT, EX = 2048, 512
 WORKLOAD = f"{OUT}x{OUT} output from synthetic {EX}x{EX} example (synth_texture seed 1), k=50 m=50 cauchy=1.0 backtrack=0.5x5 seed=0"
-# dram bytes (read+write) of all k_flow launches of one step, from the ncu --set full capture summarised under profiles/
-TRAFFIC_PER_STEP = 14.48e9  # 14.06 GB read + 0.42 GB written over the 11 k_flow launches of one step (profiles/r1_kflow_all_launches_2048.txt)
+# dram bytes (read+write) of all k_stream launches of one step, from the ncu capture summarised under profiles/
+TRAFFIC_PER_STEP = None  # filled in from profiles/r2_kstream_all_launches_2048.txt
 CPU_SAMPLE_OUT = 2048  # CPU sample = the full workload (2048x2048 output, about 9 s on 16 host cores)
 
 
@@ -121,6 +121,68 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def headline_digest(g):
+    """SHA-256 digests of everything the run hands back, in the layout of tests/golden/fullsize_digests.json."""
+    from tests import fullsize_cases as F
+    flat, score = g.resolved()
+    return F.digest(g.color(), g.coord(), g.ids(), flat, score)
+
+
+def digest_matches(got, name):
+    from tests import fullsize_cases as F
+    want = F.load_digests().get(name)
+    if want is None:
+        return None
+    return all(got[k] == want[k] for k in ("n_resolved", "order", "coord", "id", "color", "score"))
+
+
+def band_sharded_c5(capi, dist, torch, rank, world, local_rank):
+    """BASELINE config C5 -- ONE 8192x8192 output from the synthetic 1024x1024 example -- band-sharded over all ranks
+    (SURVEY 8e): every rank resolves the work items of its horizontal band, neighbours across a band boundary are read in
+    the owner's replica over NVLink, ranks meet at device-side barriers.  Reports the device time (max over ranks), the
+    single-GPU time of the same run on rank 0, and whether the result is bit-identical (replicas, single GPU, oracle digest)."""
+    from texture_synthesis_b200.parallel import link_band_sharded, max_over_ranks
+    from texture_synthesis_b200.synth import synth_texture
+    out, ex_sz = 8192, 1024
+    pyr = capi.pyramid_build(synth_texture(ex_sz, ex_sz, 2), 5)
+    params = capi.make_params(seed=0)
+    g = capi.Generator(out, out, device=local_rank)
+    g.upload_inputs([pyr])
+    link_band_sharded(g, params, dist)
+    ms = None
+    for _ in range(2):  # the second run is the measured one (buffers allocated, clocks up)
+        g.reset()
+        dist.barrier()
+        torch.cuda.synchronize()
+        g.resolve_resident(params)
+        torch.cuda.synchronize()
+        ms = max_over_ranks(g.stats()["gpu_ms_total"], dist, "cuda")
+    dg = headline_digest(g)
+    all_dg = [None] * world
+    dist.all_gather_object(all_dg, dg["color"] + dg["coord"] + dg["score"] + dg["order"])
+    res = None
+    if rank == 0:
+        res = {"workload": f"{out}x{out} output from synthetic {ex_sz}x{ex_sz} example (synth_texture seed 2), defaults, seed 0",
+               "ms": ms, "px_s": out * out / (ms * 1e-3), "sharded_chunks": int(g.mg_phases()),
+               "replicas_identical": len(set(all_dg)) == 1, "digest_ok": digest_matches(dg, "c5_8192_from_1024")}
+    del g
+    if rank == 0:  # the same run on one GPU
+        g1 = capi.Generator(out, out, device=local_rank)
+        g1.upload_inputs([pyr])
+        n1 = None
+        for _ in range(2):
+            g1.reset()
+            g1.resolve_resident(params)
+            n1 = g1.stats()["gpu_ms_total"]
+        d1 = headline_digest(g1)
+        res["n1_ms"] = n1
+        res["speedup_vs_n1"] = n1 / ms
+        res["identical_to_single_gpu"] = all(d1[k] == dg[k] for k in d1)
+        del g1
+    dist.barrier()
+    return res
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     from texture_synthesis_b200 import capi
@@ -171,6 +233,7 @@ def run_ours(args, rank, world, local_rank):
     from texture_synthesis_b200.parallel import aggregate_throughput
     ms = np.array([s["gpu_ms_total"] for s in stats])
     value, _, t_max = aggregate_throughput(args.steps * OUT * OUT, float(ms.sum()) * 1e-3, dist, "cuda")
+    parity_ok = digest_matches(headline_digest(g), "headline_2048_from_512") if rank == 0 else None
 
     # end to end through the public C-ABI call with HOST buffers: H2D of the example pyramid and D2H of the result inside
     e2e_t = []
@@ -183,21 +246,30 @@ def run_ours(args, rank, world, local_rank):
         capi._check(g.L.tsb_generator_read_color(g.h, out_host.ctypes.data))
         e2e_t.append(time.perf_counter() - a)
     e2e_value, _, _ = aggregate_throughput(len(e2e_t) * OUT * OUT, float(np.sum(e2e_t)), dist, "cuda")
+    st = stats[-1]
+    del g
+    sharded = band_sharded_c5(capi, dist, torch, rank, world, local_rank) if world > 1 else None
 
     if rank != 0:
+        dist.destroy_process_group()
         return
-    st = stats[-1]
     peaks, peak_src = measured_peaks()
-    # dominant kernel: k_flow (K2+K3+K4+K5 fused, persistent).  Algorithmic bytes per launch set = texels actually gathered x 4 B
-    # + per pixel-resolution k*4 B target pattern + k*16 B neighbour state + k*4 B neighbour list + 16 B written.
+    # Dominant kernel: k_stream (K3 + K4 + K5 fused: candidates, cost + argmin, commit; persistent, in-order).  It is bound by
+    # gathers of 4-byte texels out of an L2-resident example level, so the roofline is the chip's L2-gather rate (own
+    # microbenchmark, tsb_microbench_gather: random 4-byte loads inside warp-coherent windows of a 1 MiB image).  Achieved =
+    # texels ACTUALLY fetched (instrumented; exact de-duplication and early-out remove ~93 % of the nominal (k+m)*k) x 4 B /
+    # the summed duration of the k_stream launches of a step (CUDA events on the launching stream).
     k = 50
-    alg_bytes = st["texels_fetched"] * 4 + st["work_items"] * (k * 4 + k * 16 + k * 4 + 16)  # + k*4: prepared neighbour list
     kern_s = st["gpu_ms_resolve"] * 1e-3
-    achieved = alg_bytes / kern_s / 1e9
     try:
         l2_gbs, l2_gps = capi.microbench_gather(EX * EX * 4, 0, 20)
     except Exception:
         l2_gbs, l2_gps = None, None
+    gather_gbs = st["texels_fetched"] * 4 / kern_s / 1e9
+    # HBM view: texels fetched x 4 B + per pixel-resolution k*4 (target pattern) + k*8 (source coordinate / id)
+    # + 16 B written = 616 B
+    alg_bytes = st["texels_fetched"] * 4 + st["work_items"] * (k * 4 + k * 8 + 16)
+    hbm_achieved = alg_bytes / kern_s / 1e9
     cores = os.cpu_count() or 1
     cpu_v, cpu_s = cpu_oracle_run(ex, CPU_SAMPLE_OUT, cores) if world == 1 else (None, None)
     line = {
@@ -205,23 +277,27 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": float(ms.mean()), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "parallelism": "1 session per GPU (independent sessions, no collective)" if world > 1 else "1 GPU",
-                   "l2": "256 MiB flush buffer written between timed iterations", "schedule": "exact 1-thread order: per phase one persistent dataflow kernel (k_flow)",
+                   "l2": "256 MiB flush buffer written between timed iterations",
+                   "schedule": "exact 1-thread order: analysis stream (k-NN lists, weights, random candidates) ahead of an in-order persistent resolve kernel (k_stream)",
                    "pixel_resolutions_per_step": int(st["work_items"]), "candidate_evals_per_s": st["candidates"] / (float(ms.mean()) * 1e-3),
                    "host_wall_ms_per_step": (t1 - t0) * 1e3 / args.steps},
+        "parity_digest_ok": parity_ok,
         "clocks": clk.summary(),
         "e2e": {"value": e2e_value, "unit": "px/s", "h2d_bytes_per_step": int(pyr.nbytes), "d2h_bytes_per_step": int(out_host.nbytes)},
         "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                     "traffic": TRAFFIC_PER_STEP, "peak_source": peak_src, "kernel": "k_flow", "kernel_ms_per_step": st["gpu_ms_resolve"],
+        "roofline": {"bound": "l2-gather", "achieved": gather_gbs, "peak": l2_gbs, "unit": "GB/s",
+                     "frac": (gather_gbs / l2_gbs) if l2_gbs else None,
+                     "traffic": TRAFFIC_PER_STEP, "peak_source": "own microbenchmark tsb_microbench_gather (useful bytes of random 4-byte gathers, 1 MiB window), measured in this run",
+                     "kernel": "k_stream", "kernel_ms_per_step": st["gpu_ms_resolve"], "analysis_stream_ms_per_step": st["gpu_ms_analysis"],
                      "texels_fetched": int(st["texels_fetched"]), "texels_nominal": int(st["texels_nominal"]),
-                     "l2_gather": {"note": "example level is L2 resident: own microbenchmark of random 4-byte gathers over a 1 MiB window",
-                                   "peak_gathers_per_s": l2_gps, "peak_useful_gbs": l2_gbs,
-                                   "achieved_gathers_per_s": st["texels_fetched"] / kern_s,
-                                   "frac": (st["texels_fetched"] / kern_s / l2_gps) if l2_gps else None,
-                                   "nominal_texel_evals_per_s": st["texels_nominal"] / kern_s,
-                                   "note2": "exact pruning (candidate de-duplication + early-out) removes ~90% of the nominal "
-                                            "(k+m)*k texel comparisons; frac uses texels actually fetched"}},
+                     "achieved_gathers_per_s": st["texels_fetched"] / kern_s, "peak_gathers_per_s": l2_gps,
+                     "nominal_texel_evals_per_s": st["texels_nominal"] / kern_s,
+                     "hbm": {"achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_achieved / peaks["hbm_gbs"],
+                             "peak_source": peak_src, "algorithmic_bytes_per_step": int(alg_bytes),
+                             "note": "SURVEY 8d bytes: texels fetched x 4 + 616 B per pixel resolution; the example level and most of the state are L2 resident"}},
     }
+    if sharded is not None:
+        line["band_sharded"] = sharded
     if cpu_v is not None:
         line["cpu_baseline"] = {"value": cpu_v, "unit": "px/s", "cores": cores, "kind": "port",
                                 "sample": f"{CPU_SAMPLE_OUT}x{CPU_SAMPLE_OUT} output, same example and parameters, {cpu_s:.1f} s"}

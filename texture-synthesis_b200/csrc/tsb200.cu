@@ -1542,15 +1542,32 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         // own band up to date).  Sparse phases are dependency bound anyway: every rank executes them on its own replica.
         bool latched = false;
         const double area = (double)g->W * (double)g->H;
+        // resolved pixels needed for r * 8 <= band height
+        const double rmax = std::max(1.0, (double)g->mgs_band_h / 8.0);
+        const size_t need = (size_t)std::ceil((double)k * area / (3.14159265358979 * rmax * rmax));
+        std::vector<ChunkPlan> out;
         for (auto& c : chunks) {
             const StagePlan& sp = plan[c.stage];
-            if (!latched && c.phase_first) {
-                const size_t phase_n = c.redo ? sp.n_redo : sp.n_new;
-                const double r = sqrt((double)k * area / (3.14159265358979 * (double)std::max<size_t>(sp.resolved_before, 1)));
-                if (phase_n >= g->mgs_shard_min && r * 8.0 <= (double)g->mgs_band_h) latched = true;
+            if (latched) { c.sharded = true; out.push_back(c); continue; }
+            const size_t before = sp.resolved_before + (c.redo ? 0 : c.first - sp.n_redo);  // resolved pixels when the chunk starts
+            if (c.redo) {  // the resolved set is static during a redo phase
+                if (before >= need && c.n >= g->mgs_shard_min) { latched = true; c.sharded = true; }
+                out.push_back(c);
+                continue;
             }
-            c.sharded = latched;
+            if (before >= need) {
+                if (c.n >= g->mgs_shard_min) { latched = true; c.sharded = true; }
+                out.push_back(c);
+            } else if (before + c.n > need && before + c.n - need >= g->mgs_shard_min) {
+                // the threshold is crossed inside this chunk: replicated head, sharded tail
+                ChunkPlan a = c, b = c;
+                a.n = need - before; a.phase_last = false;
+                b.first = c.first + a.n; b.n = c.n - a.n; b.phase_first = false; b.sharded = true;
+                latched = true;
+                out.push_back(a); out.push_back(b);
+            } else out.push_back(c);
         }
+        chunks.swap(out);
         const uint32_t T = (uint32_t)n_picks;
         TRY(g->d_own_flag.ensure(n_picks + 1)); TRY(g->d_own_pos.ensure(n_picks + 1)); TRY(g->d_own_t.ensure(n_picks)); TRY(g->d_own_pix.ensure(n_picks));
         TRY(g->d_own_cnt.ensure(4));
@@ -1795,7 +1812,9 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
     };
     auto enqueue_resolve = [&](ChunkPlan& c) -> int {
         const StagePlan& sp = plan[c.stage];
-        if (c.sharded && c.phase_first) TRY(mg_barrier());  // every rank has finished the previous phase: nobody reads what the prologue changes
+        const size_t ci0 = (size_t)(&c - chunks.data());
+        const bool shard_begins = c.sharded && ci0 > 0 && !chunks[ci0 - 1].sharded;  // the peers' replicas are read from here on
+        if (c.sharded && (c.phase_first || shard_begins)) TRY(mg_barrier());  // every rank has finished the previous phase: nobody reads what the prologue changes
         if (c.stage != cur_stage) {
             for (int si = cur_stage + 1; si <= c.stage; ++si) TRY(begin_stage(si));  // stages without work items still recolour
             cur_stage = c.stage;
@@ -1804,7 +1823,12 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         memset(&D, 0, sizeof(D));
         if (c.redo && c.phase_first) {
             // redo results go to the other buffer: pixels that are not re-resolved must be there too
-            CU(cudaMemcpyAsync(g->d_state2.p, g->d_state.p, npix * sizeof(uint4), cudaMemcpyDeviceToDevice, s));
+            size_t o = 0, cnt = npix;
+            if (c.sharded) {  // only this rank's band is ever read from this replica
+                const int y0 = g->mgs_rank * g->mgs_band_h, y1 = g->mgs_rank == g->mgs_world - 1 ? g->H : std::min(g->H, y0 + g->mgs_band_h);
+                o = (size_t)std::min(y0, g->H) * g->W; cnt = (size_t)std::max(0, y1 - y0) * g->W;
+            }
+            if (cnt) CU(cudaMemcpyAsync(g->d_state2.p + o, g->d_state.p + o, cnt * sizeof(uint4), cudaMemcpyDeviceToDevice, s));
         }
         if (c.redo) { D.prev = g->d_state.p; D.cur = g->d_state2.p; }
         else { D.prev = nullptr; D.cur = g->d_state.p; }
@@ -1882,6 +1906,7 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         TRY(mg_barrier());  // nobody changes its band before everybody has copied it
     }
     CU(cudaEventRecord(ev_a1, s2));
+    const double t_enqueued = now_ms();
     CU(cudaStreamWaitEvent(s, ev_a1, 0));
     CU(cudaMemcpyAsync(g->h_ctrl + 8, abort_flag, 4, cudaMemcpyDeviceToHost, s));
     CU(cudaEventRecord(ev_end, s));
@@ -1927,7 +1952,7 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
     unsigned long long cnt[ST_COUNT];
     CU(cudaMemcpy(cnt, g->d_counters.p, sizeof(cnt), cudaMemcpyDeviceToHost));
     g->stats.texels_fetched = cnt[ST_FETCHED]; g->stats.texels_nominal = cnt[ST_NOMINAL]; g->stats.candidates = cnt[ST_CANDS];
-    const bool dbg = getenv("TSB_DEBUG_PHASES") != nullptr;
+    const bool dbg = getenv("TSB_DEBUG_PHASES") != nullptr && g->mgs_rank == 0;
     for (auto& c : chunks) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, c.ev_t0, c.ev_done);
@@ -1937,7 +1962,7 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
             cudaEventElapsedTime(&t0, ev_begin, c.ev_t0);
             cudaEventElapsedTime(&a0, ev_begin, c.ev_a0);
             cudaEventElapsedTime(&a1, ev_begin, c.ev_ready);
-            fprintf(stderr, "[tsb] chunk stage %d %s first=%zu n=%zu | analysis %.3f..%.3f ms | resolve %.3f..%.3f ms (%.3f)\n", c.stage, c.redo ? "redo" : "new",
+            fprintf(stderr, "[tsb] chunk stage %d %s%s first=%zu n=%zu | analysis %.3f..%.3f ms | resolve %.3f..%.3f ms (%.3f)\n", c.stage, c.redo ? "redo" : "new", c.sharded ? " (sharded)" : "",
                     c.first, c.items(), a0, a1, t0, t0 + ms, ms);
         }
     }
@@ -1945,6 +1970,11 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
     cudaEventElapsedTime(&ms_a, ev_a0, ev_a1);
     cudaEventElapsedTime(&ms_total, ev_begin, ev_end);
     g->stats.gpu_ms_analysis = ms_a;  // overlapped with the resolve kernels
+    if (dbg) {
+        float tp = 0.f;
+        cudaEventElapsedTime(&tp, ev_begin, ev_a0);
+        fprintf(stderr, "[tsb] pixel order + plan: %.3f ms on the device, %.3f ms host wall until everything was enqueued\n", tp, t_enqueued - t_start);
+    }
     if (dbg && cnt[ST_ITEMS])
         fprintf(stderr, "[tsb] analysis stream %.3f ms (overlapped), total %.3f ms | cycles/item: wait %.0f lists %.0f neigh %.0f rand %.0f score %.0f commit %.0f (items %llu)\n",
                 ms_a, ms_total, (double)cnt[ST_CYC_READY] / cnt[ST_ITEMS], (double)cnt[ST_CYC_KNN] / cnt[ST_ITEMS], (double)cnt[ST_CYC_NEIGH] / cnt[ST_ITEMS],
