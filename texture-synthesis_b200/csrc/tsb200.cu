@@ -1468,8 +1468,8 @@ template <bool REDO, bool MG>
 int launch_stream(tsb_generator* g, int grid, const StageDev& S, const ChunkDev& C, const StreamDev& D) {
     cudaStream_t s = g->stream;
     const bool op = S.opaque != 0;
-    if (g->guided) { if (op) k_stream<true, true, REDO, MG><<<grid, CTA_THREADS, sizeof(RoundSmem), s>>>(S, C, D); else k_stream<true, false, REDO, MG><<<grid, CTA_THREADS, sizeof(RoundSmem), s>>>(S, C, D); }
-    else { if (op) k_stream<false, true, REDO, MG><<<grid, CTA_THREADS, sizeof(RoundSmem), s>>>(S, C, D); else k_stream<false, false, REDO, MG><<<grid, CTA_THREADS, sizeof(RoundSmem), s>>>(S, C, D); }
+    if (g->guided) { if (op) k_stream<true, true, REDO, MG><<<grid, CTA_THREADS, sizeof(StreamSmem), s>>>(S, C, D); else k_stream<true, false, REDO, MG><<<grid, CTA_THREADS, sizeof(StreamSmem), s>>>(S, C, D); }
+    else { if (op) k_stream<false, true, REDO, MG><<<grid, CTA_THREADS, sizeof(StreamSmem), s>>>(S, C, D); else k_stream<false, false, REDO, MG><<<grid, CTA_THREADS, sizeof(StreamSmem), s>>>(S, C, D); }
     CU(cudaGetLastError());
     return 0;
 }
@@ -1515,18 +1515,26 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
     CU(cudaMemcpyAsync(g->d_luts_all.p, g->h_luts_all.p, n_stages * 512 * sizeof(float), cudaMemcpyHostToDevice, s));
 
     // ---- chunks: runs of consecutive work items of one phase ----
-    size_t chunk_max = 2u << 20;
+    // Chunk size = granularity of the analysis -> resolve pipeline: the resolve kernel of a chunk starts when its lists are
+    // complete, so the first chunks of a run are small (the synthesis starts early) and no chunk is so large that the last
+    // one's resolve kernel -- which nothing overlaps -- matters.
+    size_t chunk_max = 2u << 20;  // (512 Ki-item chunks were tried: the shorter tail does not pay for 2.5x as many launches)
     if (const char* e = getenv("TSB_CHUNK")) chunk_max = std::max<size_t>(1024, (size_t)strtoull(e, nullptr, 10));
     std::vector<ChunkPlan> chunks;
     bool first_pixel_fixed = false;  // the very first pixel of a fresh run has no neighbour: resolve_at_random (ms.rs:1002-1009)
     for (size_t si = 0; si < n_stages; ++si) {
         const StagePlan& sp = plan[si];
         auto add_phase = [&](bool redo, size_t a, size_t b) {
-            for (size_t c0 = a; c0 < b; c0 += chunk_max) {
+            // (a ramp of small first chunks -- 4 Ki, 16 Ki, ... -- starts the synthesis 1.4 ms earlier but every chunk boundary
+            // drains the dependency pipeline of the sparse first phase: 51.0 instead of 49.8 ms per 2048^2 step)
+            size_t ramp = chunk_max;
+            for (size_t c0 = a; c0 < b;) {
                 ChunkPlan c;
-                c.stage = (int)si; c.redo = redo; c.first = c0; c.n = std::min(chunk_max, b - c0); c.slot = 0;
+                c.stage = (int)si; c.redo = redo; c.first = c0; c.n = std::min(std::min(ramp, chunk_max), b - c0); c.slot = 0;
                 c.phase_first = c0 == a; c.phase_last = c0 + c.n == b;
                 chunks.push_back(c);
+                c0 += c.n;
+                ramp = std::min(chunk_max, ramp * 4);
             }
         };
         if (sp.n_redo) add_phase(true, 0, sp.n_redo);
@@ -1733,8 +1741,8 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         }
         CU(cudaGetLastError());
         if (n) {
-            const unsigned wgroups = (n + 31u) / 32u;
-            k_weights<<<std::max(1u, std::min((wgroups + KW_WARPS - 1) / KW_WARPS, (unsigned)g->n_sms * 8u)), KW_WARPS * 32, (size_t)KW_WARPS * k * 33 * sizeof(double), s2>>>(S, C);
+            const unsigned wgroups = (n + KW_ITEMS - 1) / KW_ITEMS;
+            k_weights<<<std::max(1u, std::min((wgroups + KW_WARPS - 1) / KW_WARPS, (unsigned)g->n_sms * 16u)), KW_WARPS * 32, (size_t)KW_WARPS * k * (KW_ITEMS + 1) * sizeof(double), s2>>>(S, C);
             const unsigned rb = m <= 64 ? 128u : 32u;  // items per block: the staging area is rb * m * 5 bytes (< 48 KB)
             k_rand_candidates<<<(n + rb - 1) / rb, rb, (size_t)rb * m * 5 + rb, s2>>>(S.ex, S.n_ex, m, sp.seed + 1ull + (c.sharded ? 0ull : (uint64_t)c.first), n,
                                                                                    C.rand_xy, C.rand_map, nullptr, 1, 1, 0, 1, C.tidx);
@@ -1764,7 +1772,8 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         for (size_t si = 0; si < n_stages; ++si) { stage_trace_base[si] = tb; stage_progress_base[si] = pb; tb += plan[si].n_redo + plan[si].n_new; pb += plan[si].pixels_to_resolve; }
     }
     (void)progress_base; (void)trace_base;
-    const int grid_full = g->guided ? g->max_ctas_stream_guided : g->max_ctas_stream;
+    int grid_full = g->guided ? g->max_ctas_stream_guided : g->max_ctas_stream;
+    if (const char* e = getenv("TSB_STREAM_OCC")) grid_full = std::min(grid_full, g->n_sms * std::max(1, atoi(e)));
     bool stage_prologue_pending = false;  // a recolour happened since the last kernel of this rank
     auto mg_barrier = [&]() -> int {
         const uint32_t seq = ++g->mgs_seq;
@@ -1839,6 +1848,7 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         D.progress_base = (uint32_t)std::min<uint64_t>(stage_progress_base[c.stage] + c.first, 0xFFFFFFFFull);
         D.tag = (uint32_t)(2 * c.stage + (c.redo ? 1 : 2));
         D.watchdog_ms = watchdog_ms;
+        D.profile = getenv("TSB_DEBUG_PHASES") ? 1u : 0u;
         if (g->trace) { D.tr_best = g->d_tr_best.p; D.tr_ncand = g->d_tr_ncand.p; D.tr_nneigh = g->d_tr_nneigh.p; D.tr_score = g->d_tr_score.p; }
         D.trace_base = stage_trace_base[c.stage];
         StageDev Sc = S;
@@ -1847,8 +1857,7 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         int grid = std::max(1, std::min((int)((C.n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), grid_full));
         // a phase that multiplies the resolved set is bound by its dependency depth, not by throughput: one CTA per SM
         // leaves the rest of the machine to the analysis stream
-        const size_t before = sp.resolved_before + (c.redo ? 0 : (c.first - sp.n_redo));
-        if (!c.redo && before * 4 < c.n) grid = std::min(grid, g->n_sms);
+        if (!c.redo && std::max<size_t>(sp.resolved_before, 1) * 4 < sp.n_new) grid = std::min(grid, g->n_sms);
         if (c.sharded) {
             if (c.phase_first && (c.redo || stage_prologue_pending)) TRY(mg_barrier());  // ... and every replica is through its own prologue
             D.world = g->mgs_world; D.rank = g->mgs_rank; D.band_h = g->mgs_band_h;
@@ -2160,14 +2169,14 @@ int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
     TSB_FLOW_ATTR(false, true, false, false); TSB_FLOW_ATTR(false, true, true, false); TSB_FLOW_ATTR(true, true, false, false); TSB_FLOW_ATTR(true, true, true, false);
 #undef TSB_FLOW_ATTR
 #define TSB_STREAM_ATTR(G, O, R)                                                                                          \
-    cudaFuncSetAttribute(k_stream<G, O, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem)); \
-    cudaFuncSetAttribute(k_stream<G, O, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem))
+    cudaFuncSetAttribute(k_stream<G, O, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem)); \
+    cudaFuncSetAttribute(k_stream<G, O, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem))
     TSB_STREAM_ATTR(false, false, false); TSB_STREAM_ATTR(false, true, false); TSB_STREAM_ATTR(false, false, true); TSB_STREAM_ATTR(false, true, true);
     TSB_STREAM_ATTR(true, false, false); TSB_STREAM_ATTR(true, true, false); TSB_STREAM_ATTR(true, false, true); TSB_STREAM_ATTR(true, true, true);
 #undef TSB_STREAM_ATTR
     cudaFuncSetAttribute(k_lists_chunk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(KnnScratch) * WARPS_PER_CTA));
     cudaFuncSetAttribute(k_lists_chunk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(KnnScratch) * WARPS_PER_CTA));
-    cudaFuncSetAttribute(k_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KW_WARPS * KMAX * 33 * sizeof(double)));
+    cudaFuncSetAttribute(k_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KW_WARPS * KMAX * (KW_ITEMS + 1) * sizeof(double)));
     cudaFuncSetAttribute(k_serial<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
     cudaFuncSetAttribute(k_serial<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_round<false>, CTA_THREADS, sizeof(RoundSmem)) != cudaSuccess || per_sm < 1) per_sm = 1;
@@ -2182,8 +2191,8 @@ int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
     g->max_ctas_flow_guided = prop.multiProcessorCount * per_sm_flow_g;
     {
         int ps = 0, psg = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, k_stream<false, false, true>, CTA_THREADS, sizeof(RoundSmem)) != cudaSuccess || ps < 1) ps = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&psg, k_stream<true, false, true>, CTA_THREADS, sizeof(RoundSmem)) != cudaSuccess || psg < 1) psg = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, k_stream<false, false, true>, CTA_THREADS, sizeof(StreamSmem)) != cudaSuccess || ps < 1) ps = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&psg, k_stream<true, false, true>, CTA_THREADS, sizeof(StreamSmem)) != cudaSuccess || psg < 1) psg = 1;
         g->max_ctas_stream = prop.multiProcessorCount * ps;
         g->max_ctas_stream_guided = prop.multiProcessorCount * psg;
     }

@@ -778,17 +778,18 @@ __device__ __forceinline__ void score_candidates(const StageDev& S, WarpScratch&
                 if (s >= best) ok = false;
             }
         }
-        bool win = ok && (s < best);
-        float ms = win ? s : INFINITY;
-        int ma = a;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            float os = __shfl_xor_sync(FULL, ms, o);
-            int oa = __shfl_xor_sync(FULL, ma, o);
-            if (os < ms || (os == ms && oa < ma)) { ms = os; ma = oa; }
+        // first strict minimum in candidate order (q11): order-preserving integer image of the scores (a running sum that
+        // starts at +0 is never -0), one warp-wide minimum, lowest lane among the holders = lowest candidate index
+        const bool win = ok && (s < best);
+        const uint32_t sb = __float_as_uint(s);
+        const uint32_t key = win ? (sb ^ ((sb >> 31) ? 0xFFFFFFFFu : 0x80000000u)) : 0xFFFFFFFFu;
+        const uint32_t mk = __reduce_min_sync(FULL, key);
+        if (mk != 0xFFFFFFFFu) {
+            const int wl = __ffs(__ballot_sync(FULL, key == mk)) - 1;
+            best = __shfl_sync(FULL, s, wl);
+            bestcol = __shfl_sync(FULL, ccol, wl);
+            besti = base + wl;
         }
-        const uint32_t wcol = __shfl_sync(FULL, ccol, (ma - base) & 31);
-        if (ms < best) { best = ms; besti = ma; bestcol = wcol; }  // first strict minimum wins (q11)
     }
 }
 

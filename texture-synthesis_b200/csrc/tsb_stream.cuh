@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_lists_chunk(StageDev S, ChunkDe
             bool low = false;
             if (j < kk) {
                 const short2 o = ws.off[j];
-                out[j] = o;
+                __stcs(reinterpret_cast<uint32_t*>(out + j), (uint32_t)(uint16_t)o.x | ((uint32_t)(uint16_t)o.y << 16));  // written once, read once
                 if (REDO) {
                     int qx = x + o.x, qy = y + o.y;
                     if (S.tiling) { qx = imod(qx, S.W); qy = imod(qy, S.H); }
@@ -127,16 +127,17 @@ __global__ void __launch_bounds__(CTA_THREADS) k_lists_chunk(StageDev S, ChunkDe
 //   1. item by item, lanes = neighbours: the distances (coalesced list reads, table reads that share sectors) -> shared memory
 //   2. lanes = items: the sequential sum -- 32 chains side by side, one lane each instead of one warp each
 //   3. (item, neighbour) pairs flattened over the lanes: division, exp, cast, coalesced store
-constexpr int KW_WARPS = 4;
+constexpr int KW_WARPS = 4, KW_ITEMS = 16;  // items per warp and pass: 16 keeps the staging area at 6.6 KB per warp (k = 50)
 __global__ void __launch_bounds__(KW_WARPS * 32) k_weights(StageDev S, ChunkDev C) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int k = S.k;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* sd = reinterpret_cast<double*>(smem_raw) + (size_t)warp * (size_t)k * 33;  // [k][33]: (j, item) at j * 33 + item
-    const uint32_t ngroups = (C.n + 31u) / 32u;
+    constexpr int P = KW_ITEMS + 1;  // padded pitch: (j, item) at j * P + item
+    double* sd = reinterpret_cast<double*>(smem_raw) + (size_t)warp * (size_t)k * P;
+    const uint32_t ngroups = (C.n + KW_ITEMS - 1) / KW_ITEMS;
     for (uint32_t grp = blockIdx.x * KW_WARPS + warp; grp < ngroups; grp += gridDim.x * KW_WARPS) {
-        const uint32_t c0 = grp * 32u;
-        const int rows = (int)min(32u, C.n - c0);
+        const uint32_t c0 = grp * KW_ITEMS;
+        const int rows = (int)min((uint32_t)KW_ITEMS, C.n - c0);
         int my_kk = 0;
         if (lane < rows) my_kk = (int)C.nbk[c0 + lane];
         for (int it = 0; it < rows; ++it) {
@@ -148,13 +149,13 @@ __global__ void __launch_bounds__(KW_WARPS * 32) k_weights(StageDev S, ChunkDev 
             for (int j = lane; j < kk; j += 32) {
                 const short2 o = C.nb[(size_t)c * k + j];
                 const double ddx = __dsub_rn(__ldg(S.divx + x + o.x + S.mx), x2), ddy = __dsub_rn(__ldg(S.divy + y + o.y + S.my), y2);
-                sd[(size_t)j * 33 + it] = __fma_rn(ddx, ddx, __dmul_rn(ddy, ddy));
+                sd[(size_t)j * P + it] = __fma_rn(ddx, ddx, __dmul_rn(ddy, ddy));
             }
         }
         __syncwarp();
         double sum = 0.0;
-        for (int j = 0; j < my_kk; ++j) {
-            const double d = sd[(size_t)j * 33 + lane];
+        for (int j = 0; j < my_kk; ++j) {  // lanes >= rows have my_kk = 0
+            const double d = sd[(size_t)j * P + lane];
             sum = __dadd_rn(sum, d); sum = __dadd_rn(sum, d); sum = __dadd_rn(sum, d); sum = __dadd_rn(sum, d);
         }
         const double my_avg = __ddiv_rn(sum, (double)(my_kk * 4));  // 0 / 0 = NaN for an empty list (never read)
@@ -166,8 +167,8 @@ __global__ void __launch_bounds__(KW_WARPS * 32) k_weights(StageDev S, ChunkDev 
             if (e < total) {
                 float gv = 0.f;
                 // avg == 0 (the pixel is its own only neighbour): 0 / 0 -> NaN weights, as in the reference
-                if (j < kk) gv = (float)exp(-__ddiv_rn(sd[(size_t)j * 33 + it], avg));
-                C.g[(size_t)c0 * k + e] = gv;
+                if (j < kk) gv = (float)exp(-__ddiv_rn(sd[(size_t)j * P + it], avg));
+                __stcs(C.g + (size_t)c0 * k + e, gv);
             }
         }
         __syncwarp();
@@ -186,6 +187,7 @@ struct StreamDev {
     uint32_t progress_base;
     uint32_t tag;             // phase id written with every commit
     uint32_t watchdog_ms;     // a single wait longer than this aborts the run
+    uint32_t profile;         // 1: also accumulate the per-section cycle counters (TSB_DEBUG_PHASES)
     // per-item trace (tests)
     int32_t* tr_best; int32_t* tr_ncand; int32_t* tr_nneigh; float* tr_score;
     uint64_t trace_base;
@@ -199,10 +201,17 @@ struct StreamDev {
 // Persistent in-order resolve kernel for one chunk.  REDO: re-resolution of already resolved pixels (ms.rs:905-907) --
 // neighbours flagged "earlier" are read from `cur` once their tag is this phase's, all others from `prev`; the result goes
 // to `cur`.  Otherwise new pixels (ms.rs:909-915): every neighbour is read from `cur` once its tag is non-zero.
+struct __align__(16) StreamSmem {
+    CtaSmem c;
+    unsigned long long stat[ST_COUNT];
+};
+#ifndef TSB_STREAM_CTAS
+#define TSB_STREAM_CTAS 3   /* 4 (64 registers) was tried: every item takes longer, the L1 gather path is the limit */
+#endif
 template <bool GUIDED, bool OPAQUE, bool REDO, bool MG = false>
-__global__ void __launch_bounds__(CTA_THREADS, 3) k_stream(StageDev S, ChunkDev C, StreamDev D) {
+__global__ void __launch_bounds__(CTA_THREADS, TSB_STREAM_CTAS) k_stream(StageDev S, ChunkDev C, StreamDev D) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    RoundSmem& rs = *reinterpret_cast<RoundSmem*>(smem_raw);
+    StreamSmem& rs = *reinterpret_cast<StreamSmem*>(smem_raw);
     CtaSmem& sm = rs.c;
     if (threadIdx.x < ST_COUNT) rs.stat[threadIdx.x] = 0ull;
     load_luts(S, sm.lut, sm.lutg);
@@ -212,15 +221,20 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_stream(StageDev S, ChunkDev 
     if (lane < 16) ws.stat[lane] = 0ull;
     __syncwarp();
     const int k = S.k, W = S.W, H = S.H;
-    for (;;) {
+    // Items are claimed in order.  AHEAD (experiment, off): claim one item ahead and pull its lists into L2 while the current
+    // one is resolved -- safe (the lowest unfinished item is always somebody's CURRENT item) but a held item cannot start
+    // elsewhere, which costs more in waiting than the prefetch saves (measured: 50.7 -> 53.3 ms per 2048^2 step).
+    constexpr bool AHEAD = false;
+    uint32_t c = 0;
+    if (lane == 0) c = atomicAdd(D.ctl + SC_NEXT, 1u);
+    c = __shfl_sync(FULL, c, 0);
+    while (c < C.n) {
         long long tr0 = clock64();
-        uint32_t c = 0;
+        uint32_t c_next = 0;
         if (lane == 0) {
-            c = atomicAdd(D.ctl + SC_NEXT, 1u);
-            if (D.progress && (c & 1023u) == 0u && c < C.n) *D.progress = D.progress_base + c;
+            if (AHEAD) c_next = atomicAdd(D.ctl + SC_NEXT, 1u);  // consumed after the neighbour loads have been issued
+            if (D.progress && (c & 1023u) == 0u) *D.progress = D.progress_base + c;
         }
-        c = __shfl_sync(FULL, c, 0);
-        if (c >= C.n) break;
         // ---- the item's lists (prepared by the analysis) ----
         const int kk = (int)C.nbk[c];
         const uint32_t flat = C.pixel[c];
@@ -230,10 +244,15 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_stream(StageDev S, ChunkDev 
         const uint8_t* rand_map = C.rand_map + (size_t)c * S.m;
         uint4 lowm = make_uint4(0u, 0u, 0u, 0u);
         if (REDO) lowm = C.low[c];
-        for (int j = lane; j < kk; j += 32) { ws.off[j] = C.nb[(size_t)c * k + j]; ws.g[j] = C.g[(size_t)c * k + j]; }
+        // the lists are read exactly once: streaming loads (evict-first) keep the state and the example level in L2
+        for (int j = lane; j < kk; j += 32) {
+            const uint32_t ov = __ldcs(reinterpret_cast<const uint32_t*>(C.nb + (size_t)c * k + j));
+            ws.off[j] = make_short2((short)(ov & 0xFFFFu), (short)(ov >> 16));
+            ws.g[j] = __ldcs(C.g + (size_t)c * k + j);
+        }
         uint32_t rxy0 = 0, rxy1 = 0, rmp0 = 0, rmp1 = 0;
-        if (lane < S.m) { rxy0 = __ldg(rand_xy + lane); rmp0 = __ldg(rand_map + lane); }
-        if (lane + 32 < S.m) { rxy1 = __ldg(rand_xy + lane + 32); rmp1 = __ldg(rand_map + lane + 32); }
+        if (lane < S.m) { rxy0 = __ldcs(rand_xy + lane); rmp0 = __ldcs(rand_map + lane); }
+        if (lane + 32 < S.m) { rxy1 = __ldcs(rand_xy + lane + 32); rmp1 = __ldcs(rand_map + lane + 32); }
         __syncwarp();
         long long t1 = clock64();
         ItemOut o;
@@ -338,6 +357,21 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_stream(StageDev S, ChunkDev 
             if (aborted) break;
             __syncwarp();
             long long t2 = clock64();
+            // pull the next item's lists into L2 (eight 128-byte lines cover them for k = m = 50)
+            if (AHEAD) c_next = __shfl_sync(FULL, c_next, 0);
+            if (AHEAD && c_next < C.n) {
+                const char* base = nullptr;
+                size_t bytes = 0;
+                const int which = lane >> 3, line = lane & 7;
+                if (which == 0) { base = reinterpret_cast<const char*>(C.nb + (size_t)c_next * k); bytes = (size_t)k * 4; }
+                else if (which == 1) { base = reinterpret_cast<const char*>(C.g + (size_t)c_next * k); bytes = (size_t)k * 4; }
+                else if (which == 2) { base = reinterpret_cast<const char*>(C.rand_xy + (size_t)c_next * S.m); bytes = (size_t)S.m * 4; }
+                else { base = reinterpret_cast<const char*>(C.rand_map + (size_t)c_next * S.m); bytes = (size_t)S.m; }
+                if ((size_t)line * 128 < bytes + 127) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)line * 128));
+                if (lane == 31) asm volatile("prefetch.global.L2 [%0];" ::"l"(C.pixel + c_next));
+                if (lane == 30) asm volatile("prefetch.global.L2 [%0];" ::"l"(C.nbk + c_next));
+                if (REDO && lane == 29) asm volatile("prefetch.global.L2 [%0];" ::"l"(C.low + c_next));
+            }
             const float g0 = ws.g[0];
             const bool degenerate = !(g0 == g0);  // NaN weights: the pixel is its own only neighbour (see k_weights)
             resolve_tail<GUIDED, OPAQUE ? 1 : 0>(S, ws, sm.lut, sm.lutg, lane, kk, ncand, reach, degenerate, rand_xy, rand_map,
@@ -360,12 +394,16 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k_stream(StageDev S, ChunkDev 
             }
             ws.stat[ST_FETCHED] += o.fetched; ws.stat[ST_NOMINAL] += o.nominal; ws.stat[ST_CANDS] += (unsigned long long)o.ncand;
             ws.stat[ST_ITEMS] += 1ull;
-            ws.stat[ST_CYC_READY] += (unsigned long long)waited;
-            ws.stat[ST_CYC_KNN] += (unsigned long long)o.c_knn; ws.stat[ST_CYC_NEIGH] += (unsigned long long)o.c_neigh;
-            ws.stat[ST_CYC_WEIGHT] += (unsigned long long)o.c_weight; ws.stat[ST_CYC_SCORE] += (unsigned long long)o.c_score;
-            ws.stat[ST_CYC_COMMIT] += (unsigned long long)(clock64() - tc0);
+            if (D.profile) {
+                ws.stat[ST_CYC_READY] += (unsigned long long)waited;
+                ws.stat[ST_CYC_KNN] += (unsigned long long)o.c_knn; ws.stat[ST_CYC_NEIGH] += (unsigned long long)o.c_neigh;
+                ws.stat[ST_CYC_WEIGHT] += (unsigned long long)o.c_weight; ws.stat[ST_CYC_SCORE] += (unsigned long long)o.c_score;
+                ws.stat[ST_CYC_COMMIT] += (unsigned long long)(clock64() - tc0);
+            }
         }
         __syncwarp();
+        if (!AHEAD) { if (lane == 0) c_next = atomicAdd(D.ctl + SC_NEXT, 1u); c = __shfl_sync(FULL, c_next, 0); }
+        else c = kk > 0 ? c_next : __shfl_sync(FULL, c_next, 0);
     }
     if (lane == 0 && S.counters) {
         for (int i = 0; i < ST_COUNT; ++i) if (ws.stat[i]) atomicAdd(&rs.stat[i], ws.stat[i]);
