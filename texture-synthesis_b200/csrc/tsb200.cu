@@ -303,7 +303,7 @@ struct tsb_generator {
     uint32_t predl_stride = 0;
     DevBuf<uint8_t> d_cub_temp, d_sort_temp;
     DevBuf<unsigned long long> d_keys, d_keys_sorted;
-    DevBuf<uint32_t> d_v0;
+    DevBuf<uint32_t> d_v0, d_pick_first;
     cudaStream_t stream2 = nullptr;
     int max_ctas_flow = 0, max_ctas_flow_guided = 0, max_ctas_radius = 0, max_ctas_stream = 0, max_ctas_stream_guided = 0;
     bool use_rounds = false, force_csr = false;
@@ -353,6 +353,7 @@ struct tsb_generator {
     DevBuf<uint8_t> d_own_flag;
     DevBuf<uint32_t> d_own_pos, d_own_t, d_own_pix, d_own_cnt;
     uint64_t mgs_sharded_chunks = 0;
+    size_t l2_persist_bytes = 0;                    // persisting L2 carve-out set aside for the active example level (0: unavailable)
     bool state_init_opaque = true;                  // every colour in the state before the run has alpha 255
     bool inpaint_opaque = true;                     // the same for the locked inpaint pixels as created
 
@@ -744,8 +745,19 @@ void build_plan(const tsb_generator* g, const tsb_params* prm, std::vector<Stage
 // the work items of every stage are simply a PREFIX of the pick array: item i of a stage = picks[i].
 // Leaves the picks in g->d_item_pixel (device), their first 4096 in g->h_items (host; the rest arrives on stream2) and
 // the pixels never picked in g->unresolved.
+// TSB_DEBUG_PLAN=1: wall-clock attribution of the planning steps (synchronises after each, debugging only)
+void plan_mark(tsb_generator* g, const char* what) {
+    static thread_local double last = 0.0;
+    if (!getenv("TSB_DEBUG_PLAN")) return;
+    cudaStreamSynchronize(g->stream);
+    const double t = now_ms();
+    if (what) fprintf(stderr, "[tsb plan] %-28s %8.3f ms\n", what, t - last);
+    last = t;
+}
+
 int plan_pixel_order(tsb_generator* g, const std::vector<StagePlan>& plan, size_t n_picks, size_t total, size_t npix) {
     cudaStream_t s = g->stream;
+    plan_mark(g, nullptr);
     TRY(g->h_items.ensure(std::max<size_t>(n_picks, 1)));
     TRY(g->d_item_pixel.ensure(std::max<size_t>(n_picks, 1)));
     {
@@ -768,6 +780,7 @@ int plan_pixel_order(tsb_generator* g, const std::vector<StagePlan>& plan, size_
             if (identity && (g->inpaint || g->locked)) identity = false;
             const uint32_t* v0 = nullptr;
             if (!identity) { TRY(g->d_v0.upload(g->unresolved.data(), g->unresolved.size(), s)); v0 = g->d_v0.p; }
+            plan_mark(g, "pick indices");
             k_pick_keys<<<(T + 255) / 256, 256, 0, s>>>(g->d_pick_idx.p, T, g->d_keys.p);
             int end_bit = 33;
             while (end_bit < 64 && (total >> (end_bit - 32)) != 0) ++end_bit;
@@ -776,8 +789,22 @@ int plan_pixel_order(tsb_generator* g, const std::vector<StagePlan>& plan, size_
             TRY(g->d_sort_temp.ensure(tb + 256));
             tb = g->d_sort_temp.n;
             CU(cub::DeviceRadixSort::SortKeys(g->d_sort_temp.p, tb, g->d_keys.p, g->d_keys_sorted.p, (int)T, 0, end_bit, s));
-            k_resolve_picks<<<(T + 255) / 256, 256, 0, s>>>(g->d_keys_sorted.p, T, (uint64_t)total, v0, g->d_pick_idx.p, g->d_item_pixel.p);
+            plan_mark(g, "sort");
+            // directory of the runs of equal position: histogram of the drawn positions + exclusive scan
+            TRY(g->d_pick_first.ensure(total + 2));
+            CU(cudaMemsetAsync(g->d_pick_first.p, 0, (total + 2) * 4, s));
+            k_pick_histogram<<<(T + 255) / 256, 256, 0, s>>>(g->d_pick_idx.p, T, g->d_pick_first.p);
+            {
+                size_t sb = 0;
+                CU(cub::DeviceScan::ExclusiveSum(nullptr, sb, g->d_pick_first.p, g->d_pick_first.p, (int)(total + 1), s));
+                TRY(g->d_sort_temp.ensure(sb + 256));
+                sb = g->d_sort_temp.n;
+                CU(cub::DeviceScan::ExclusiveSum(g->d_sort_temp.p, sb, g->d_pick_first.p, g->d_pick_first.p, (int)(total + 1), s));
+            }
+            plan_mark(g, "run directory");
+            k_resolve_picks<<<(T + 255) / 256, 256, 0, s>>>(g->d_keys_sorted.p, g->d_pick_first.p, T, (uint64_t)total, v0, g->d_pick_idx.p, g->d_item_pixel.p);
             CU(cudaGetLastError());
+            plan_mark(g, "resolve picks");
             g->stats.kernel_launches += 4;
             // host mirrors: the whole order is needed only after the run (resolved list, trace); the first few picks
             // are needed right away (first random pixel, serial-prefix bookkeeping)
@@ -788,7 +815,7 @@ int plan_pixel_order(tsb_generator* g, const std::vector<StagePlan>& plan, size_
             const size_t left = total - n_picks;
             if (left) {
                 TRY(g->d_tmp_u32.ensure(left));
-                k_resolve_leftover<<<(uint32_t)((left + 255) / 256), 256, 0, s>>>(g->d_keys_sorted.p, T, (uint64_t)total, v0, (uint32_t)left, g->d_tmp_u32.p);
+                k_resolve_leftover<<<(uint32_t)((left + 255) / 256), 256, 0, s>>>(g->d_keys_sorted.p, g->d_pick_first.p, T, (uint64_t)total, v0, (uint32_t)left, g->d_tmp_u32.p);
                 CU(cudaGetLastError());
                 std::vector<uint32_t> rest(left);
                 CU(cudaMemcpyAsync(rest.data(), g->d_tmp_u32.p, left * 4, cudaMemcpyDeviceToHost, s));
@@ -1506,6 +1533,7 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
     if (n_picks) k_tmap_fill<<<(uint32_t)((n_picks + 255) / 256), 256, 0, s>>>(g->d_item_pixel.p, (uint32_t)n_picks, g->d_tmap.p);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ev_picks, s));
+    plan_mark(g, "head copy + tmap");
     g->stats.host_ms_schedule = now_ms() - t_plan0;
 
     // ---- cost tables of every stage (ms.rs:739-742, 853-858), one upload ----
@@ -1605,6 +1633,7 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         if (n_own_total) k_gather_u32<<<(n_own_total + 255) / 256, 256, 0, s>>>(g->d_item_pixel.p, g->d_own_t.p, n_own_total, g->d_own_pix.p);
         CU(cudaGetLastError());
         CU(cudaEventRecord(ev_picks, s));  // the analysis stream also needs the own-item lists
+        plan_mark(g, "own-item lists");
         for (size_t i = 0; i < chunks.size(); ++i) { chunks[i].own_lo = bpos[2 * i]; chunks[i].own_n = bpos[2 * i + 1] - bpos[2 * i]; }
     }
     // ---- list ring ----
@@ -1653,6 +1682,7 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         TRY(g->d_tr_best.ensure(total_items)); TRY(g->d_tr_ncand.ensure(total_items));
         TRY(g->d_tr_nneigh.ensure(total_items)); TRY(g->d_tr_score.ensure(total_items));
     }
+    plan_mark(g, "ring + buffers");
     for (auto& c : chunks) { TRY(events.get(&c.ev_ready, true)); TRY(events.get(&c.ev_done, true)); TRY(events.get(&c.ev_t0, true)); TRY(events.get(&c.ev_a0, true)); }
     uint32_t watchdog_ms = 20000;
     if (const char* e = getenv("TSB_WATCHDOG_MS")) watchdog_ms = (uint32_t)std::max(1, atoi(e));
@@ -1788,6 +1818,20 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         stage_inputs(g, S, sp.level, prm);
         S.state = g->d_state.p;
         S.lut_my = g->d_luts_all.p + (size_t)si * 512; S.lut_guide = S.lut_my + 256;
+        if (g->l2_persist_bytes) {
+            // L2 persisting window over the level every candidate of this stage gathers from (the framed copy of the first
+            // example): hits stay resident, everything else the resolve stream touches is ordinary / streaming traffic
+            const int e0 = g->filt[0];
+            const size_t lvl = framed_level_size(g->ex_w[e0], g->ex_h[e0]) * sizeof(uint32_t);
+            cudaStreamAttrValue av;
+            memset(&av, 0, sizeof(av));
+            av.accessPolicyWindow.base_ptr = (void*)(g->d_exf[e0].p + (size_t)sp.level * framed_level_size(g->ex_w[e0], g->ex_h[e0]));
+            av.accessPolicyWindow.num_bytes = std::min(lvl, g->l2_persist_bytes);
+            av.accessPolicyWindow.hitRatio = 1.0f;
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+            if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) { cudaGetLastError(); g->l2_persist_bytes = 0; }
+        }
         if (sp.recolour) {  // next_pyramid_level, ms.rs:687-700
             k_recolour<<<(uint32_t)((npix + 255) / 256), 256, 0, s>>>(S);
             CU(cudaGetLastError());
@@ -1913,6 +1957,11 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
             CU(cudaMemcpyAsync(g->d_score.p + o, g->mgs_score[r] + o, cnt * sizeof(float), cudaMemcpyDeviceToDevice, s));
         }
         TRY(mg_barrier());  // nobody changes its band before everybody has copied it
+    }
+    if (g->l2_persist_bytes) {  // release the window
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof(av));
+        cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av);
     }
     CU(cudaEventRecord(ev_a1, s2));
     const double t_enqueued = now_ms();
@@ -2186,6 +2235,11 @@ int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "cudaGetDeviceProperties failed"));
     g->n_sms = prop.multiProcessorCount;
+    if (!getenv("TSB_NO_L2_WINDOW") && prop.persistingL2CacheMaxSize > 0) {
+        // room for one framed example level (north_star: "keeps the active example level resident in an L2 persisting window")
+        size_t want = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, 32u << 20);
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) g->l2_persist_bytes = want; else cudaGetLastError();
+    }
     g->max_ctas = prop.multiProcessorCount * std::max(per_sm, 4);  // analysis kernels (k_radius: 47 KB smem) fit 4 CTAs per SM
     g->max_ctas_flow = prop.multiProcessorCount * per_sm_flow;  // persistent grid: co-resident CTAs only
     g->max_ctas_flow_guided = prop.multiProcessorCount * per_sm_flow_g;

@@ -1952,33 +1952,38 @@ __global__ void k_pick_keys(const uint32_t* idx, uint32_t T, unsigned long long*
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < T) keys[t] = ((unsigned long long)idx[t] << 32) | (unsigned long long)t;
 }
-__device__ __forceinline__ uint32_t chain_value(const unsigned long long* __restrict__ keys, uint32_t T, uint64_t n,
+// first[p] = index of the first sorted key whose position is >= p (first[n] = T): the writes to position p are the keys
+// [first[p], first[p+1]), ordered by step -- a run of one or two entries on average, so a chain step costs one 8-byte read
+// of the directory plus a look into the run instead of a 26-level binary search over the whole key array.
+__global__ void k_pick_histogram(const uint32_t* idx, uint32_t T, uint32_t* count) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T) atomicAdd(count + idx[t], 1u);
+}
+__device__ __forceinline__ uint32_t chain_value(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ first, uint64_t n,
                                                 const uint32_t* __restrict__ v0, uint32_t p, uint32_t tt) {
     for (;;) {
-        const unsigned long long q = ((unsigned long long)p << 32) | (unsigned long long)tt;
-        uint32_t lo = 0, hi = T;  // lower_bound(q): the entry before it is the last write to p before step tt, if any
+        uint32_t lo = __ldg(first + p), hi = __ldg(first + p + 1);  // writes to p, by step
+        // the last write before step tt: upper end of the run of steps < tt
         while (lo < hi) {
-            uint32_t mid = lo + ((hi - lo) >> 1);
-            if (__ldg(keys + mid) < q) lo = mid + 1; else hi = mid;
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if ((uint32_t)__ldg(keys + mid) < tt) lo = mid + 1; else hi = mid;
         }
-        if (lo == 0) break;
-        const unsigned long long kp = __ldg(keys + lo - 1);
-        if ((uint32_t)(kp >> 32) != p) break;
-        const uint32_t ts = (uint32_t)kp;
+        if (lo == __ldg(first + p)) break;  // no earlier write: the position still holds its initial value
+        const uint32_t ts = (uint32_t)__ldg(keys + lo - 1);
         p = (uint32_t)(n - (uint64_t)ts - 1ull);  // step ts copied the then-last element into position p
         tt = ts;
     }
     return v0 ? __ldg(v0 + p) : p;
 }
 // picks[t] for every step t (time T_query = t, position idx[t])
-__global__ void k_resolve_picks(const unsigned long long* keys, uint32_t T, uint64_t n, const uint32_t* v0, const uint32_t* idx, uint32_t* picks) {
+__global__ void k_resolve_picks(const unsigned long long* keys, const uint32_t* first, uint32_t T, uint64_t n, const uint32_t* v0, const uint32_t* idx, uint32_t* picks) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < T) picks[t] = chain_value(keys, T, n, v0, idx[t], t);
+    if (t < T) picks[t] = chain_value(keys, first, n, v0, idx[t], t);
 }
 // the elements left in `unresolved` after all T steps: positions [0, n - T) at time T
-__global__ void k_resolve_leftover(const unsigned long long* keys, uint32_t T, uint64_t n, const uint32_t* v0, uint32_t count, uint32_t* out) {
+__global__ void k_resolve_leftover(const unsigned long long* keys, const uint32_t* first, uint32_t T, uint64_t n, const uint32_t* v0, uint32_t count, uint32_t* out) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < count) out[p] = chain_value(keys, T, n, v0, p, T);
+    if (p < count) out[p] = chain_value(keys, first, n, v0, p, T);
 }
 
 // ---------------------------------------------------------------------------------------------
