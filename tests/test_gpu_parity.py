@@ -158,14 +158,13 @@ def test_session_mirror_runs_like_reference_example_01():
     assert (go.color() == img).all()
 
 
-@pytest.mark.parametrize("env", [{"TSB_MODE": "csr"}, {"TSB_MODE": "rounds"}, {"TSB_MODE": "epochs"}, {"TSB_MODE": "epochs", "TSB_SUCC_STRIDE": "6"},
-                                 {"TSB_MODE": "epochs", "TSB_LIST_MAX": "0"}, {"TSB_NO_FAST": "1"}],
-                         ids=["csr", "rounds", "epochs", "epochs_stride_overflow", "epochs_mask_search", "general_scoring"])
-def test_alternative_schedulers_give_the_same_result(env, monkeypatch):
-    """The dependency scheduler has interchangeable implementations (default: whole stages with exact timed
-    neighbour lists; doubling epochs with fixed-stride successor lists, with the CSR fallback on overflow, with or
-    without the analysis neighbour lists; host-visible rounds) and two scoring paths: all must reproduce the serial
-    order exactly."""
+@pytest.mark.parametrize("env", [{"TSB_CHUNK": "700"}, {"TSB_CHUNK": "2000", "TSB_RING_ITEMS": "4500"}, {"TSB_RING_ITEMS": "900"},
+                                 {"TSB_NO_FAST": "1"}, {"TSB_BRUTE_BELOW": "0"}, {"TSB_NO_L2_WINDOW": "1"}],
+                         ids=["small_chunks", "ring_wraps", "tiny_ring_resplit", "general_scoring", "mask_search_only", "no_l2_window"])
+def test_scheduler_variants_give_the_same_result(env, monkeypatch):
+    """The streaming scheduler cuts every phase into chunks whose lists live in a ring that the analysis stream refills
+    as the resolve stream frees it; chunk size, ring size (wrap-around, re-splitting), the scoring path and the k-NN search
+    variant must not change a single bit of the result."""
     cases = [Case("sched", 96, 80, [(64, 48)], seed=17, tiling=True).build(),
              Case("sched_big_tiling", 208, 176, [(64, 48)], seed=18, tiling=True).build(),
              Case("sched_big", 200, 168, [(72, 56)], seed=19).build()]

@@ -224,9 +224,6 @@ SpiralHost build_spiral(int RT) {
 }
 
 constexpr int SPIRAL_RT = 48;
-constexpr uint32_t PAIR_MAX = 4096;   // phases up to this size use the all-pairs dependency test
-constexpr int ROUNDS_PER_SYNC = 4;
-constexpr size_t SUCC_STRIDE = 160;   // fixed-stride successor lists (single analysis pass); overflow falls back to CSR
 
 struct StagePlan {
     int p_stage, level;
@@ -258,7 +255,6 @@ struct tsb_generator {
     DevBuf<float> d_score;
     DevBuf<uint32_t> d_mask, d_mask1;
     DevBuf<uint32_t> d_pmask, d_pmask1;            // the current stage's new pixels (+ mirror copies), geometry of d_mask
-    bool stage_lists = false;                       // new pixels of a stage as ONE dataflow phase with exact timed lists
     DevBuf<uint32_t> d_inp_mask, d_inp_color;
     int mx = 0, my = 0, wpr = 0, mrows = 0, wpr1 = 0;
     DevBuf<short2> d_spiral;
@@ -289,41 +285,16 @@ struct tsb_generator {
     DevBuf<unsigned long long> d_counters;
 
     // per-run buffers
-    DevBuf<uint32_t> d_item_pixel, d_item_R2, d_pred_cnt, d_preds, d_done, d_pend0, d_pend1, d_ctrl, d_pmap;
-    DevBuf<uint32_t> d_rand_xy, d_pick_idx, d_tmp_u32, d_read_color, d_read_coord, d_read_id;
-    DevBuf<uint8_t> d_rand_map;
-    DevBuf<uint32_t> d_npred, d_nsucc, d_succ_off, d_succ_cur, d_succ, d_queue, d_fctl;
-    DevBuf<short2> d_nb0, d_predl;                  // neighbour lists of the phase analysis (see PhaseDev)
-    DevBuf<uint32_t> d_npredl;
-    size_t list_max_items = 0, predl_max_items = 0; // phases up to this size use the lists (nb0 / predl)
-    size_t stage_list_max = 4u << 20;               // larger (dense, throughput-bound) stages keep the epoch scheduler: its analysis is cheaper
-    size_t cur_resolved = 0;                        // resolved pixels at the start of the phase being run
-    bool cur_resolved_redo_ok = false;              // the redo phase being run has more than k resolved points (finite radii everywhere)
-    double list_min_positions = 300.0;              // new phases use the lists when a mask walk would visit at least this many pixels
-    uint32_t predl_stride = 0;
+    DevBuf<uint32_t> d_item_pixel, d_pick_idx, d_tmp_u32, d_read_color, d_read_coord, d_read_id;
     DevBuf<uint8_t> d_cub_temp, d_sort_temp;
     DevBuf<unsigned long long> d_keys, d_keys_sorted;
     DevBuf<uint32_t> d_v0, d_pick_first;
     cudaStream_t stream2 = nullptr;
-    int max_ctas_flow = 0, max_ctas_flow_guided = 0, max_ctas_radius = 0, max_ctas_stream = 0, max_ctas_stream_guided = 0;
-    bool use_rounds = false, force_csr = false;
-    // band-sharded multi-GPU execution
-    bool mg_on = false;
-    MgDev h_mg{};
-    DevBuf<MgDev> d_mg;
-    tsb_barrier_fn mg_barrier = nullptr;
-    void* mg_barrier_user = nullptr;
+    int max_ctas_radius = 0, max_ctas_stream = 0, max_ctas_stream_guided = 0;
     std::vector<void*> mg_opened;
     std::vector<std::pair<cudaIpcMemHandle_t, void*>> mg_blocks;
-    size_t mg_min_phase = 32768;   // smaller phases are executed redundantly by every rank (no communication)
-    uint64_t mg_phases = 0;
-    std::function<int(size_t, size_t)> regen_rand;  // regenerates the random candidates of a phase for ALL its items
-    cudaEvent_t ev_rand = nullptr;                   // stage-wide candidate generation on stream2 (single GPU)
-    bool rand_pending = false;
-    size_t succ_stride = SUCC_STRIDE;
     uint32_t* h_ctrl = nullptr;  // pinned, 16 words
-    PinnedBuf<uint32_t> h_idx, h_items;  // pick indices (D2H) and per-stage work-item pixels (H2D)
-    bool pmap_ready = false;
+    PinnedBuf<uint32_t> h_items;  // host mirror of the pick array
 
     // in-order streaming scheduler (tsb_stream.cuh)
     DevBuf<uint4> d_state2;                         // second state buffer (redo phases write here, then the two swap)
@@ -375,7 +346,6 @@ struct tsb_generator {
         if (stream2) cudaStreamDestroy(stream2);
         if (stream3) cudaStreamDestroy(stream3);
         if (h_progress) cudaFreeHost(h_progress);
-        if (ev_rand) cudaEventDestroy(ev_rand);
     }
 };
 
@@ -605,104 +575,6 @@ uint32_t r2_hint_for(const tsb_generator* g, size_t resolved_now, uint32_t k) {
     return (uint32_t)std::min(std::max(r2, 8.0), cap);
 }
 
-template <typename K, typename... Args>
-int launch_resolve_kernel(tsb_generator* g, K kernel, int grid, size_t smem, Args... args) {
-    kernel<<<grid, CTA_THREADS, smem, g->stream>>>(args...);
-    CU(cudaGetLastError());
-    g->stats.kernel_launches++;
-    return 0;
-}
-
-// kernels without shared memory (dependency scans) are latency bound: allow twice as many resident CTAs
-int grid_light(const tsb_generator* g, uint32_t items) {
-    int need = (int)((items + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
-    return std::max(1, std::min(need, g->n_sms * 8));
-}
-
-int grid_for(const tsb_generator* g, uint32_t items) {
-    int need = (int)((items + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
-    return std::max(1, std::min(need, g->max_ctas));
-}
-
-struct PhaseTimers {
-    cudaEvent_t a0, a1, r0, r1;
-};
-
-// Execute work items [i0, i0+n) of the current stage.
-int run_phase(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, bool is_new, bool analyze, uint64_t trace_base) {
-    cudaStream_t s = g->stream;
-    PhaseDev P;
-    memset(&P, 0, sizeof(P));
-    P.item_pixel = g->d_item_pixel.p + i0;
-    P.item_R2 = g->d_item_R2.p; P.pred_cnt = g->d_pred_cnt.p; P.preds = g->d_preds.p; P.done = g->d_done.p;
-    P.pending[0] = g->d_pend0.p; P.pending[1] = g->d_pend1.p;
-    P.cnt = g->d_ctrl.p; P.minpend = g->d_ctrl.p + 4;
-    P.pmap = g->d_pmap.p;
-    P.rand_xy = g->d_rand_xy.p; P.rand_map = g->d_rand_map.p;
-    P.n = n; P.stage_base = i0; P.is_new = is_new ? 1u : 0u;
-    if (g->trace) { P.tr_best = g->d_tr_best.p; P.tr_ncand = g->d_tr_ncand.p; P.tr_nneigh = g->d_tr_nneigh.p; P.tr_score = g->d_tr_score.p; }
-    P.trace_base = trace_base;
-    g->stats.phases++;
-
-    cudaEvent_t e0, e1, e2;
-    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventCreate(&e2));
-    CU(cudaEventRecord(e0, s));
-    uint32_t ctrl[8] = {n, 0, 0, 0, 0, NONE32, NONE32, NONE32};
-    memcpy(g->h_ctrl, ctrl, sizeof(ctrl));
-    CU(cudaMemcpyAsync(g->d_ctrl.p, g->h_ctrl, sizeof(ctrl), cudaMemcpyHostToDevice, s));
-    if (analyze) {
-        FlowDev F0;
-        memset(&F0, 0, sizeof(F0));
-        TRY(launch_resolve_kernel(g, k_radius, grid_for(g, n), sizeof(KnnScratch) * WARPS_PER_CTA, S, P, F0));
-        if (n <= PAIR_MAX) k_preds_pairs<<<grid_for(g, n), CTA_THREADS, 0, s>>>(S, P);
-        else k_preds_scan<<<grid_for(g, n), CTA_THREADS, 0, s>>>(S, P);
-        CU(cudaGetLastError());
-        g->stats.kernel_launches++;
-    } else {
-        // single serial item: no predecessors, unbounded neighbour search
-        g->h_ctrl[8] = R2_INF;
-        CU(cudaMemcpyAsync(g->d_item_R2.p, g->h_ctrl + 8, 4, cudaMemcpyHostToDevice, s));
-        CU(cudaMemsetAsync(g->d_pred_cnt.p, 0, 4, s));
-        CU(cudaMemsetAsync(g->d_done.p, 0, 4, s));
-        CU(cudaMemsetAsync(g->d_pend0.p, 0, 4, s));
-    }
-    CU(cudaEventRecord(e1, s));
-    if (g->rand_pending) { CU(cudaStreamWaitEvent(s, g->ev_rand, 0)); g->rand_pending = false; }
-    uint32_t known = n, round = 0;
-    while (known > 0) {
-        int grid = grid_for(g, known);
-        for (int r = 0; r < ROUNDS_PER_SYNC; ++r) {
-            if (g->guided) TRY(launch_resolve_kernel(g, k_round<true>, grid, sizeof(RoundSmem), S, P, round));
-            else TRY(launch_resolve_kernel(g, k_round<false>, grid, sizeof(RoundSmem), S, P, round));
-            ++round;
-            g->stats.rounds++;
-            if (n == 1) break;
-        }
-        CU(cudaMemcpyAsync(g->h_ctrl, g->d_ctrl.p + (round & 3), 4, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
-        known = g->h_ctrl[0];
-        if (round > 4u * n + 16u) return fail(TSB_ERR_INTERNAL, "dependency rounds did not converge (phase of %u items)", n);
-    }
-    if (analyze) {
-        k_pmap_clear<<<(n + 255) / 256, 256, 0, s>>>(P);
-        CU(cudaGetLastError());
-        g->stats.kernel_launches++;
-    }
-    CU(cudaEventRecord(e2, s));
-    CU(cudaEventSynchronize(e2));
-    float ma = 0.f, mr = 0.f;
-    cudaEventElapsedTime(&ma, e0, e1);
-    cudaEventElapsedTime(&mr, e1, e2);
-    g->stats.gpu_ms_analysis += ma;
-    g->stats.gpu_ms_resolve += mr;
-    if (getenv("TSB_DEBUG_PHASES"))
-        fprintf(stderr, "[tsb] phase i0=%u n=%u new=%d analyze=%d rounds=%u analysis_ms=%.3f resolve_ms=%.3f\n", i0, n, (int)is_new,
-                (int)analyze, round, ma, mr);
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
-    return 0;
-}
-
-
 // Stage plan (ms.rs:786-812): levels, seeds and work-item counts of every stage follow from the parameters alone.
 void build_plan(const tsb_generator* g, const tsb_params* prm, std::vector<StagePlan>& plan, size_t& n_picks, size_t& max_stage_items,
                 size_t& max_phase, size_t& total_items) {
@@ -829,640 +701,6 @@ int plan_pixel_order(tsb_generator* g, const std::vector<StagePlan>& plan, size_
     return 0;
 }
 
-int ensure_flow_buffers(tsb_generator* g, size_t max_phase) {
-    TRY(g->d_item_R2.ensure(max_phase));
-    TRY(g->d_npred.ensure(max_phase + 1)); TRY(g->d_nsucc.ensure(max_phase + 1)); TRY(g->d_succ_off.ensure(max_phase + 1));
-    TRY(g->d_succ_cur.ensure(max_phase + 1)); TRY(g->d_queue.ensure(max_phase + 1)); TRY(g->d_fctl.ensure(FC_WORDS));
-    TRY(g->d_succ.ensure(max_phase * SUCC_STRIDE + 1024));
-    return 0;
-}
-
-// neighbour lists for phases of up to TSB_LIST_MAX items (default 4Mi): k + predl_stride offsets per item
-// Neighbour lists: k offsets per item (nb0) for phases of up to TSB_LIST_MAX items (default 64 Mi: 13 GB at k = 50), and
-// predl_stride in-disc predecessors per item (predl) for the new-pixel phases of the epoch scheduler (up to 4 Mi items).
-int ensure_list_buffers(tsb_generator* g, size_t max_phase, uint32_t k) {
-    size_t cap = 64u << 20, cap_predl = 4u << 20;
-    if (const char* e = getenv("TSB_LIST_MAX")) cap = cap_predl = (size_t)strtoull(e, nullptr, 10);
-    g->list_max_items = std::min(max_phase, cap);
-    g->predl_max_items = std::min(max_phase, cap_predl);
-    g->predl_stride = std::min<uint32_t>(((2 * k + 31) / 32) * 32, (uint32_t)KBUF - k);
-    if (const char* e = getenv("TSB_LIST_MIN_POS")) g->list_min_positions = atof(e);
-    if (const char* e = getenv("TSB_STAGE_LIST_MAX")) g->stage_list_max = (size_t)strtoull(e, nullptr, 10);
-    if (g->use_rounds || g->force_csr || g->predl_stride == 0) g->list_max_items = g->predl_max_items = 0;
-    if (g->list_max_items == 0) return 0;
-    TRY(g->d_nb0.ensure(g->list_max_items * k));
-    TRY(g->d_predl.ensure(std::max<size_t>(g->predl_max_items, 1) * g->predl_stride));  // never null: a null predl means "exact lists" to the kernels
-    TRY(g->d_npredl.ensure(g->list_max_items));
-    return 0;
-}
-
-PhaseDev make_phase(tsb_generator* g, uint32_t i0, uint32_t n, bool is_new, uint64_t trace_base) {
-    PhaseDev P;
-    memset(&P, 0, sizeof(P));
-    P.item_pixel = g->d_item_pixel.p + i0;
-    P.item_R2 = g->d_item_R2.p; P.pred_cnt = g->d_pred_cnt.p; P.preds = g->d_preds.p; P.done = g->d_done.p;
-    P.pending[0] = g->d_pend0.p; P.pending[1] = g->d_pend1.p;
-    P.cnt = g->d_ctrl.p; P.minpend = g->d_ctrl.p + 4;
-    P.pmap = g->d_pmap.p;
-    P.rand_xy = g->d_rand_xy.p; P.rand_map = g->d_rand_map.p;
-    P.n = n; P.stage_base = i0; P.is_new = is_new ? 1u : 0u;
-    if (g->trace) { P.tr_best = g->d_tr_best.p; P.tr_ncand = g->d_tr_ncand.p; P.tr_nneigh = g->d_tr_nneigh.p; P.tr_score = g->d_tr_score.p; }
-    P.trace_base = trace_base;
-    return P;
-}
-
-struct PhaseClock {
-    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
-    int begin(cudaStream_t s) { CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventCreate(&e2)); CU(cudaEventRecord(e0, s)); return 0; }
-    int mid(cudaStream_t s) { CU(cudaEventRecord(e1, s)); return 0; }
-    int end(tsb_generator* g, cudaStream_t s, const char* what, uint32_t i0, uint32_t n, bool is_new, uint64_t extra) {
-        CU(cudaEventRecord(e2, s));
-        CU(cudaEventSynchronize(e2));
-        float ma = 0.f, mr = 0.f;
-        cudaEventElapsedTime(&ma, e0, e1);
-        cudaEventElapsedTime(&mr, e1, e2);
-        g->stats.gpu_ms_analysis += ma;
-        g->stats.gpu_ms_resolve += mr;
-        if (getenv("TSB_DEBUG_PHASES")) {
-            // per-phase averages of the in-kernel cycle counters (difference to the previous phase)
-            static thread_local unsigned long long prev[ST_COUNT] = {0};
-            unsigned long long cnt[ST_COUNT] = {0};
-            if (g->d_counters.p) cudaMemcpy(cnt, g->d_counters.p, sizeof(cnt), cudaMemcpyDeviceToHost);
-            if (cnt[ST_ITEMS] < prev[ST_ITEMS]) memset(prev, 0, sizeof(prev));  // a new run reset the counters
-            const double it = (double)std::max<unsigned long long>(1, cnt[ST_ITEMS] - prev[ST_ITEMS]);
-            fprintf(stderr, "[tsb] %s i0=%u n=%u new=%d extra=%llu analysis_ms=%.3f resolve_ms=%.3f | cyc/item ready %.0f knn %.0f neigh %.0f "
-                    "weight %.0f score %.0f commit %.0f\n", what, i0, n, (int)is_new, (unsigned long long)extra, ma, mr,
-                    (cnt[ST_CYC_READY] - prev[ST_CYC_READY]) / it, (cnt[ST_CYC_KNN] - prev[ST_CYC_KNN]) / it,
-                    (cnt[ST_CYC_NEIGH] - prev[ST_CYC_NEIGH]) / it, (cnt[ST_CYC_WEIGHT] - prev[ST_CYC_WEIGHT]) / it,
-                    (cnt[ST_CYC_SCORE] - prev[ST_CYC_SCORE]) / it, (cnt[ST_CYC_COMMIT] - prev[ST_CYC_COMMIT]) / it);
-            memcpy(prev, cnt, sizeof(prev));
-        }
-        return 0;
-    }
-    ~PhaseClock() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); if (e2) cudaEventDestroy(e2); }
-};
-
-// Items [i0, i0+n) one after the other on one warp (start of a synthesis; fallback for degenerate phases).
-int run_serial(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, bool is_new, uint64_t trace_base) {
-    cudaStream_t s = g->stream;
-    PhaseDev P = make_phase(g, i0, n, is_new, trace_base);
-    g->stats.phases++;
-    PhaseClock clk;
-    TRY(clk.begin(s));
-    TRY(clk.mid(s));
-    if (g->rand_pending) { CU(cudaStreamWaitEvent(s, g->ev_rand, 0)); g->rand_pending = false; }
-    if (g->guided) k_serial<true><<<1, CTA_THREADS, sizeof(RoundSmem), s>>>(S, P);
-    else k_serial<false><<<1, CTA_THREADS, sizeof(RoundSmem), s>>>(S, P);
-    CU(cudaGetLastError());
-    g->stats.kernel_launches++;
-    g->stats.rounds++;
-    return clk.end(g, s, "serial", i0, n, is_new, 0);
-}
-
-// k_flow instantiations: <guided, band-sharded, all-alpha-255, lists-only>
-template <bool MG>
-int launch_flow(tsb_generator* g, int grid, const StageDev& S, const PhaseDev& P, const FlowDev& F, bool lists_only) {
-    cudaStream_t s = g->stream;
-    const bool op = S.opaque != 0;
-#define TSB_FLOW(G, O, L) k_flow<G, MG, O, L><<<grid, CTA_THREADS, sizeof(RoundSmem), s>>>(S, P, F)
-    if (MG || !lists_only) {
-        if (g->guided) { if (op) TSB_FLOW(true, true, false); else TSB_FLOW(true, false, false); }
-        else { if (op) TSB_FLOW(false, true, false); else TSB_FLOW(false, false, false); }
-    } else {
-        if (g->guided) { if (op) TSB_FLOW(true, true, (!MG)); else TSB_FLOW(true, false, (!MG)); }
-        else { if (op) TSB_FLOW(false, true, (!MG)); else TSB_FLOW(false, false, (!MG)); }
-    }
-#undef TSB_FLOW
-    CU(cudaGetLastError());
-    return 0;
-}
-
-// All remaining new pixels [i0, i0+n) of a stage as ONE dataflow phase (single GPU): exact neighbour lists "as of" every
-// item's serial time (k_lists_timed), read-after-write edges from those lists (CSR), persistent kernel.
-int run_stage_new(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, size_t resolved_before, uint64_t trace_base) {
-    cudaStream_t s = g->stream;
-    PhaseDev P = make_phase(g, i0, n, true, trace_base);
-    P.nb0 = g->d_nb0.p; P.npredl = g->d_npredl.p; P.predl = nullptr; P.predl_stride = 0;
-    FlowDev F;
-    F.npred = g->d_npred.p; F.nsucc = g->d_nsucc.p; F.succ_off = g->d_succ_off.p; F.succ_cur = g->d_succ_cur.p;
-    F.succ = g->d_succ.p; F.queue = g->d_queue.p; F.ctl = g->d_fctl.p; F.stride = 0;
-    g->stats.phases++;
-    PhaseClock clk;
-    TRY(clk.begin(s));
-    const int gl = grid_light(g, n);
-    const int gr = std::max(1, std::min((int)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), g->max_ctas_radius));
-    const int gf = std::max(1, std::min((int)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), g->guided ? g->max_ctas_flow_guided : g->max_ctas_flow));
-    const unsigned nb = (n + 255) / 256;
-    CU(cudaMemsetAsync(F.ctl, 0, FC_RELEASE * 4, s));
-    CU(cudaMemsetAsync(g->d_pmask.p, 0, (size_t)g->wpr * g->mrows * 4, s));
-    CU(cudaMemsetAsync(g->d_pmask1.p, 0, (size_t)g->wpr1 * g->mrows * 4, s));
-    k_mask_insert_flat_at<<<nb, 256, 0, s>>>(S, g->d_pmask.p, g->d_pmask1.p, P.item_pixel, n, S.tiling);
-    k_pmap_fill<<<nb, 256, 0, s>>>(P);
-    TimeFilter T;
-    T.pend = g->d_pmask.p; T.pend1 = g->d_pmask1.p; T.pmap = g->d_pmap.p; T.idx = 0; T.hint = 0; T.n_points_max = 0;
-    T.item_pixel = P.item_pixel;
-    // early items: the disc is large and the pixel mask inside it holds ~n*k/N later pixels; walking the <= idx earlier
-    // items is cheaper while idx^2 < n*k
-    T.brute_below = (uint32_t)std::min<double>(sqrt((double)n * (double)S.k), 65536.0);
-    if (const char* e = getenv("TSB_BRUTE_BELOW")) T.brute_below = (uint32_t)atoi(e);
-    k_lists_timed<<<gr, CTA_THREADS, sizeof(KnnScratch) * WARPS_PER_CTA, s>>>(S, P, F, T, (uint32_t)std::min<size_t>(resolved_before, 0xFFFFFFFFull));
-    k_edges_lists<0><<<gl, CTA_THREADS, 0, s>>>(S, P, F);
-    CU(cudaGetLastError());
-    size_t temp_bytes = g->d_cub_temp.n;
-    CU(cub::DeviceScan::ExclusiveSum(g->d_cub_temp.p, temp_bytes, F.nsucc, F.succ_off, (int)(n + 1), s));
-    CU(cudaMemcpyAsync(g->h_ctrl, F.succ_off + n, 4, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    const uint64_t edges = g->h_ctrl[0];
-    if (edges > g->d_succ.n) { TRY(g->d_succ.ensure(edges + edges / 4 + 1024)); F.succ = g->d_succ.p; }
-    k_edges_lists<1><<<gl, CTA_THREADS, 0, s>>>(S, P, F);
-    k_seed_queue<<<nb, 256, 0, s>>>(S, P, F);
-    CU(cudaGetLastError());
-    TRY(clk.mid(s));
-    if (g->rand_pending) { CU(cudaStreamWaitEvent(s, g->ev_rand, 0)); g->rand_pending = false; }
-    TRY(launch_flow<false>(g, gf, S, P, F, true));  // every item has its exact list
-    k_pmap_clear<<<nb, 256, 0, s>>>(P);
-    CU(cudaGetLastError());
-    g->stats.kernel_launches += 11;
-    g->stats.rounds++;
-    CU(cudaMemcpyAsync(g->h_ctrl, F.ctl, 12, cudaMemcpyDeviceToHost, s));
-    TRY(clk.end(g, s, "stage-new", i0, n, true, edges));
-    if (g->h_ctrl[FC_ABORT]) return fail(TSB_ERR_INTERNAL, "stage-wide dataflow phase of %u items stalled", n);
-    return 0;
-}
-
-// Does this phase use the neighbour lists of the analysis (PhaseDev::nb0 / predl) instead of walking the bit mask?
-bool use_lists(const tsb_generator* g, const StageDev& S, uint32_t n, bool is_new) {
-    if (n > (is_new ? g->predl_max_items : g->list_max_items)) return false;
-    if (S.tiling && (g->W < 100 || g->H < 100)) return false;  // tiny_torus(): one-sided edge registration, no lists
-    // new pixels in an already dense canvas: walking the bit mask (k / density pixels) is cheaper than merging lists
-    if (is_new && (double)S.k * (double)g->W * (double)g->H / (double)std::max<size_t>(1, g->cur_resolved) < g->list_min_positions) return false;
-    return true;
-}
-
-// Items [i0, i0+n) in dataflow order: radius -> CSR dependency graph -> persistent kernel.
-int run_phase_flow(tsb_generator* g, const StageDev& S, uint32_t i0, uint32_t n, bool is_new, uint64_t trace_base) {
-    cudaStream_t s = g->stream;
-    PhaseDev P = make_phase(g, i0, n, is_new, trace_base);
-    FlowDev F;
-    F.npred = g->d_npred.p; F.nsucc = g->d_nsucc.p; F.succ_off = g->d_succ_off.p; F.succ_cur = g->d_succ_cur.p;
-    F.succ = g->d_succ.p; F.queue = g->d_queue.p; F.ctl = g->d_fctl.p; F.stride = 0;
-    g->stats.phases++;
-    PhaseClock clk;
-    TRY(clk.begin(s));
-    const int ga = grid_for(g, n), gl = grid_light(g, n);
-    const int gr = std::max(1, std::min((int)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), g->max_ctas_radius));
-    // persistent grid: never more than the co-resident CTAs
-    const int gf = std::max(1, std::min((int)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), g->guided ? g->max_ctas_flow_guided : g->max_ctas_flow));
-    uint64_t edges = 0;
-    if (g->mg_on && n >= g->mg_min_phase) {
-        // ---- band-sharded phase: every rank resolves the items of its band; commits go to all replicas ----
-        StageDev Sm = S;
-        Sm.mg = g->d_mg.p;
-        F.stride = (uint32_t)g->succ_stride;
-        if (use_lists(g, S, n, is_new)) { P.nb0 = g->d_nb0.p; P.predl = g->d_predl.p; P.npredl = g->d_npredl.p; P.predl_stride = g->predl_stride; }
-        auto barrier = [&]() -> int { CU(cudaStreamSynchronize(s)); g->mg_barrier(g->mg_barrier_user); return 0; };
-        TRY(barrier());  // every rank has finished the previous phase before anybody writes into its replica
-        CU(cudaMemsetAsync(F.ctl, 0, FC_RELEASE * 4, s));
-        k_radius<<<gr, CTA_THREADS, sizeof(KnnScratch) * WARPS_PER_CTA, s>>>(Sm, P, F);
-        CU(cudaGetLastError());
-        TRY(barrier());  // radii of all items and zeroed counters are visible on every replica
-        if (getenv("TSB_MG_DEBUG")) {
-            std::vector<uint32_t> np(n), ns(n), px(n);
-            cudaMemcpy(np.data(), F.npred, n * 4, cudaMemcpyDeviceToHost);
-            cudaMemcpy(ns.data(), F.nsucc, n * 4, cudaMemcpyDeviceToHost);
-            cudaMemcpy(px.data(), P.item_pixel, n * 4, cudaMemcpyDeviceToHost);
-            unsigned long long a = 0, b = 0, nz = 0;
-            for (uint32_t i = 0; i < n; ++i) {
-                int owner = std::min((int)(px[i] / (uint32_t)g->W) / g->h_mg.band_h, g->h_mg.world - 1);
-                if (owner == g->h_mg.rank) { a += np[i]; b += ns[i]; nz += (np[i] || ns[i]) ? 1 : 0; }
-            }
-            fprintf(stderr, "[tsb mg rank %d] after k_radius: own npred sum %llu nsucc sum %llu nonzero items %llu; ptrs local nsucc %p mg nsucc[self] %p\n",
-                    g->h_mg.rank, a, b, nz, (void*)F.nsucc, (void*)g->h_mg.nsucc[g->h_mg.rank]);
-        }
-        k_edges_scan<2><<<gl, CTA_THREADS, 0, s>>>(Sm, P, F);
-        CU(cudaGetLastError());
-        TRY(barrier());  // all edges registered with their owners
-        bool overflow = false;
-        for (int r = 0; r < g->h_mg.world; ++r) {  // a successor list overflow anywhere invalidates the phase for everybody
-            uint32_t flag = 0;
-            CU(cudaMemcpy(&flag, g->h_mg.ctl[r] + FC_OVERFLOW, 4, cudaMemcpyDeviceToHost));
-            overflow |= flag != 0;
-        }
-        TRY(barrier());  // everybody has read the flags before anyone resets its control block
-        if (overflow) {
-            // every rank takes the same decision: execute this phase redundantly on its own replica (single-GPU path with
-            // the CSR fallback); nothing of the phase has been committed yet.  Candidates were generated for own items only.
-            k_pmap_clear<<<(n + 255) / 256, 256, 0, s>>>(P);
-            CU(cudaGetLastError());
-            TRY(g->regen_rand(i0, n));
-            const bool was = g->mg_on;
-            g->mg_on = false;
-            int rc = run_phase_flow(g, S, i0, n, is_new, trace_base);
-            g->mg_on = was;
-            return rc;
-        }
-        if (getenv("TSB_MG_DEBUG")) {  // invariant: sum of own npred over ranks == sum of own nsucc over ranks == #edges
-            std::vector<uint32_t> np(n), ns(n), px(n);
-            cudaMemcpy(np.data(), F.npred, n * 4, cudaMemcpyDeviceToHost);
-            cudaMemcpy(ns.data(), F.nsucc, n * 4, cudaMemcpyDeviceToHost);
-            cudaMemcpy(px.data(), P.item_pixel, n * 4, cudaMemcpyDeviceToHost);
-            unsigned long long a = 0, b = 0, own = 0, a2 = 0, b2 = 0;
-            for (uint32_t i = 0; i < n; ++i) {
-                int owner = std::min((int)(px[i] / (uint32_t)g->W) / g->h_mg.band_h, g->h_mg.world - 1);
-                if (owner == g->h_mg.rank) { a += np[i]; b += ns[i]; ++own; }
-                else { a2 += np[i] < 100000 ? np[i] : 0; b2 += ns[i] < 100000 ? ns[i] : 0; }
-            }
-            fprintf(stderr, "[tsb mg rank %d] phase n=%u own=%llu sum(npred)=%llu sum(nsucc)=%llu | non-own entries: npred %llu nsucc %llu\n",
-                    g->h_mg.rank, n, own, a, b, a2, b2);
-            if (n <= 8192) {  // brute-force expectation from the local view of the radii
-                std::vector<uint32_t> r2(n), enp(n, 0), ens(n, 0);
-                cudaMemcpy(r2.data(), P.item_R2, n * 4, cudaMemcpyDeviceToHost);
-                for (uint32_t i = 0; i < n; ++i) for (uint32_t j = 0; j < i; ++j) {
-                    long dx = (long)(px[i] % (uint32_t)g->W) - (long)(px[j] % (uint32_t)g->W), dy = (long)(px[i] / (uint32_t)g->W) - (long)(px[j] / (uint32_t)g->W);
-                    unsigned long long D = (unsigned long long)(dx * dx + dy * dy);
-                    if (D <= std::max(r2[i], r2[j])) { enp[i]++; ens[j]++; }
-                }
-                unsigned long long te = 0; int shown = 0;
-                for (uint32_t i = 0; i < n; ++i) te += enp[i];
-                fprintf(stderr, "[tsb mg rank %d] expected edges (local radius view) %llu\n", g->h_mg.rank, te);
-                for (uint32_t i = 0; i < n && shown < 10; ++i) {
-                    int owner = std::min((int)(px[i] / (uint32_t)g->W) / g->h_mg.band_h, g->h_mg.world - 1);
-                    if (owner == g->h_mg.rank && (np[i] != enp[i] || ns[i] != ens[i])) {
-                        fprintf(stderr, "[tsb mg rank %d] item %u y=%u R2=%u: npred %u (expected %u) nsucc %u (expected %u)\n", g->h_mg.rank, i,
-                                px[i] / (uint32_t)g->W, r2[i], np[i], enp[i], ns[i], ens[i]);
-                        ++shown;
-                    }
-                }
-            }
-        }
-        k_seed_queue<<<(n + 255) / 256, 256, 0, s>>>(Sm, P, F);
-        CU(cudaGetLastError());
-        TRY(barrier());  // every rank has seeded its queue before any rank starts publishing into it
-        TRY(clk.mid(s));
-        const int gfm = g->guided ? g->max_ctas_flow_guided : g->max_ctas_flow;
-        TRY(launch_flow<true>(g, gfm, Sm, P, F, false));
-        CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(g->h_ctrl, F.ctl, 32, cudaMemcpyDeviceToHost, s));
-        {
-            // bulk push of this rank's band (rows it owns) to every peer replica: state, and for new pixels score and
-            // the resolved mask (plus the tiling mirror rows in the margins, which belong to the first / last band)
-            const MgDev& m = g->h_mg;
-            const int y0 = m.rank * m.band_h, y1 = std::min(g->H, y0 + m.band_h);
-            for (int r = 0; r < m.world && y1 > y0; ++r) {
-                if (r == m.rank) continue;
-                const size_t o = (size_t)y0 * g->W, c = (size_t)(y1 - y0) * g->W;
-                CU(cudaMemcpyAsync(m.state[r] + o, g->d_state.p + o, c * sizeof(uint4), cudaMemcpyDeviceToDevice, s));
-                if (is_new) {
-                    CU(cudaMemcpyAsync(m.score[r] + o, g->d_score.p + o, c * sizeof(float), cudaMemcpyDeviceToDevice, s));
-                    auto push_rows = [&](int ra, int rb) -> int {  // mask rows [ra, rb) in extended coordinates
-                        if (rb <= ra) return 0;
-                        CU(cudaMemcpyAsync(m.mask[r] + (size_t)ra * g->wpr, g->d_mask.p + (size_t)ra * g->wpr, (size_t)(rb - ra) * g->wpr * 4, cudaMemcpyDeviceToDevice, s));
-                        CU(cudaMemcpyAsync(m.mask1[r] + (size_t)ra * g->wpr1, g->d_mask1.p + (size_t)ra * g->wpr1, (size_t)(rb - ra) * g->wpr1 * 4, cudaMemcpyDeviceToDevice, s));
-                        return 0;
-                    };
-                    TRY(push_rows(y0 + g->my, y1 + g->my));
-                    if (S.tiling && m.rank == 0) TRY(push_rows(g->H + g->my, g->mrows));   // mirrors y + H of the top rows
-                    if (S.tiling && m.rank == m.world - 1) TRY(push_rows(0, g->my));          // mirrors y - H of the bottom rows
-                }
-            }
-        }
-        TRY(barrier());  // every commit of the phase has landed on every replica
-        k_pmap_clear<<<(n + 255) / 256, 256, 0, s>>>(P);
-        CU(cudaGetLastError());
-        g->stats.kernel_launches += 5;
-        g->stats.rounds++;
-        g->mg_phases++;
-        TRY(clk.end(g, s, "flow-mg", i0, n, is_new, g->h_ctrl[FC_NOWN]));
-        if (g->h_ctrl[FC_ABORT] && getenv("TSB_MG_DEBUG")) {
-            std::vector<uint32_t> np(n), px(n), r2(n), ns(n), q(n);
-            cudaMemcpy(np.data(), F.npred, n * 4, cudaMemcpyDeviceToHost);
-            cudaMemcpy(ns.data(), F.nsucc, n * 4, cudaMemcpyDeviceToHost);
-            cudaMemcpy(px.data(), P.item_pixel, n * 4, cudaMemcpyDeviceToHost);
-            cudaMemcpy(r2.data(), P.item_R2, n * 4, cudaMemcpyDeviceToHost);
-            cudaMemcpy(q.data(), F.queue, n * 4, cudaMemcpyDeviceToHost);
-            std::vector<char> queued(n, 0);
-            for (uint32_t i = 0; i < n; ++i) if (q[i] != NONE32 && q[i] < n) queued[q[i]] = 1;
-            int shown = 0;
-            for (uint32_t i = 0; i < n && shown < 12; ++i) {
-                int y = (int)(px[i] / (uint32_t)g->W), x = (int)(px[i] % (uint32_t)g->W);
-                int owner = std::min(y / g->h_mg.band_h, g->h_mg.world - 1);
-                if (owner == g->h_mg.rank && !queued[i]) {
-                    fprintf(stderr, "[tsb mg rank %d] stuck item %u px (%d,%d) npred %u nsucc %u R2 %u\n", g->h_mg.rank, i, x, y, np[i], ns[i], r2[i]);
-                    ++shown;
-                }
-            }
-        }
-        if (g->h_ctrl[FC_ABORT]) return fail(TSB_ERR_INTERNAL, "band-sharded dataflow phase of %u items stalled on rank %d (head %u own %u)", n,
-                                             g->h_mg.rank, g->h_ctrl[FC_HEAD], g->h_ctrl[FC_NOWN]);
-        return 0;
-    }
-    bool use_csr = g->force_csr || (size_t)n * g->succ_stride > g->d_succ.n;
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        F.stride = use_csr ? 0u : (uint32_t)g->succ_stride;
-        if (!use_csr && use_lists(g, S, n, is_new)) {  // the lists are built by the fixed-stride edge pass only
-            P.nb0 = g->d_nb0.p; P.predl = g->d_predl.p; P.npredl = g->d_npredl.p; P.predl_stride = g->predl_stride;
-        } else { P.nb0 = nullptr; P.predl = nullptr; P.npredl = nullptr; P.predl_stride = 0; }
-        CU(cudaMemsetAsync(F.ctl, 0, FC_RELEASE * 4, s));
-        k_radius<<<gr, CTA_THREADS, sizeof(KnnScratch) * WARPS_PER_CTA, s>>>(S, P, F);
-        CU(cudaGetLastError());
-        g->stats.kernel_launches++;
-        if (use_csr) {
-            if (n <= PAIR_MAX) k_edges_pairs<0><<<ga, CTA_THREADS, 0, s>>>(S, P, F);
-            else k_edges_scan<0><<<gl, CTA_THREADS, 0, s>>>(S, P, F);
-            CU(cudaGetLastError());
-            size_t temp_bytes = g->d_cub_temp.n;
-            CU(cub::DeviceScan::ExclusiveSum(g->d_cub_temp.p, temp_bytes, F.nsucc, F.succ_off, (int)(n + 1), s));
-            CU(cudaMemcpyAsync(g->h_ctrl, F.succ_off + n, 4, cudaMemcpyDeviceToHost, s));
-            CU(cudaStreamSynchronize(s));
-            edges = g->h_ctrl[0];
-            g->stats.kernel_launches += 3;
-            if (edges > 400ull * n + (64ull << 20)) {  // degenerate conflict graph: run the phase serially instead
-                k_pmap_clear<<<(n + 255) / 256, 256, 0, s>>>(P);
-                CU(cudaGetLastError());
-                return run_serial(g, S, i0, n, is_new, trace_base);
-            }
-            if (edges > g->d_succ.n) { TRY(g->d_succ.ensure(edges + edges / 4 + 1024)); F.succ = g->d_succ.p; }
-            if (n <= PAIR_MAX) k_edges_pairs<1><<<ga, CTA_THREADS, 0, s>>>(S, P, F);
-            else k_edges_scan<1><<<gl, CTA_THREADS, 0, s>>>(S, P, F);
-        } else {
-            if (n <= PAIR_MAX) k_edges_pairs<2><<<ga, CTA_THREADS, 0, s>>>(S, P, F);
-            else k_edges_scan<2><<<gl, CTA_THREADS, 0, s>>>(S, P, F);
-        }
-        k_seed_queue<<<(n + 255) / 256, 256, 0, s>>>(S, P, F);
-        CU(cudaGetLastError());
-        if (attempt == 0) TRY(clk.mid(s));
-        if (g->rand_pending) { CU(cudaStreamWaitEvent(s, g->ev_rand, 0)); g->rand_pending = false; }
-        // a redo phase with lists never needs the mask search (every item has k neighbours when this path is taken with
-        // more than k resolved points); new-pixel epochs may (a predecessor list can overflow)
-        TRY(launch_flow<false>(g, gf, S, P, F, P.nb0 != nullptr && !is_new && g->cur_resolved_redo_ok));
-        k_pmap_clear<<<(n + 255) / 256, 256, 0, s>>>(P);
-        CU(cudaGetLastError());
-        g->stats.kernel_launches += 4;
-        g->stats.rounds++;
-        CU(cudaMemcpyAsync(g->h_ctrl, F.ctl, 16, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
-        if (!use_csr && g->h_ctrl[FC_OVERFLOW]) { use_csr = true; continue; }  // a successor list overflowed: nothing ran, redo with CSR
-        break;
-    }
-    CU(cudaMemcpyAsync(g->h_ctrl, F.ctl, 12, cudaMemcpyDeviceToHost, s));
-    TRY(clk.end(g, s, "flow", i0, n, is_new, edges));
-    if (g->h_ctrl[FC_ABORT]) return fail(TSB_ERR_INTERNAL, "dataflow phase of %u items stalled", n);
-    return 0;
-}
-
-int resolve_impl(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, void* user) {
-    if (!g->inputs_ready) return fail(TSB_ERR_INVALID, "inputs have not been uploaded");
-    TRY(check_params(g, prm));
-    TRY(set_device(g));
-    const double t_start = now_ms();
-    cudaStream_t s = g->stream;
-    memset(&g->stats, 0, sizeof(g->stats));
-    g->rand_pending = false;
-    cudaEvent_t ev_begin, ev_end;
-    CU(cudaEventCreate(&ev_begin)); CU(cudaEventCreate(&ev_end));
-    CU(cudaEventRecord(ev_begin, s));
-    const bool tiling = prm->tiling_mode != 0;
-    const uint32_t k = prm->nearest_neighbors;
-    const int m = (int)prm->random_sample_locations;
-    const size_t total = g->unresolved.size();  // ms.rs:710
-    const size_t npix = (size_t)g->W * g->H;
-    if (g->mg_on && g->trace) return fail(TSB_ERR_UNSUPPORTED, "per-item trace is not available in multi-GPU mode");
-    if (g->mg_on && g->use_rounds) return fail(TSB_ERR_UNSUPPORTED, "TSB_MODE=rounds is single-GPU only");
-
-    // ---- stage plan (ms.rs:786-812): everything that defines the pixel order is known up front ----
-    const double t_plan0 = now_ms();
-    std::vector<StagePlan> plan;
-    size_t n_picks = 0, max_stage_items = 1, max_phase = 1, total_items = 0;
-    build_plan(g, prm, plan, n_picks, max_stage_items, max_phase, total_items);
-    if (max_stage_items > 0xFFFFFFF0ull) return fail(TSB_ERR_UNSUPPORTED, "output too large");
-
-    // ---- rebuild the resolved set with tiling mirrors (ms.rs:747-779) ----
-    StageDev S;
-    fill_stage_geometry(g, S, tiling);
-    CU(cudaMemsetAsync(g->d_mask.p, 0, (size_t)g->wpr * g->mrows * 4, s));
-    CU(cudaMemsetAsync(g->d_mask1.p, 0, (size_t)g->wpr1 * g->mrows * 4, s));
-    if (g->have_loaded_points) {
-        TRY(g->d_tmp_u32.upload((const uint32_t*)g->loaded_points.data(), g->loaded_points.size(), s));
-        uint32_t np = (uint32_t)(g->loaded_points.size() / 2);
-        if (np) k_mask_insert_points<<<(np + 255) / 256, 256, 0, s>>>(S, (const int32_t*)g->d_tmp_u32.p, np);
-    } else if (!g->resolved_order.empty()) {
-        TRY(g->d_tmp_u32.upload(g->resolved_order.data(), g->resolved_order.size(), s));
-        uint32_t np = (uint32_t)g->resolved_order.size();
-        k_mask_insert_flat<<<(np + 255) / 256, 256, 0, s>>>(S, g->d_tmp_u32.p, np, tiling ? 1 : 0);
-    }
-    CU(cudaGetLastError());
-
-    TRY(plan_pixel_order(g, plan, n_picks, total, npix));
-    const uint32_t* stage_pixels = g->h_items.p;  // host mirror of the pick array (only its head is valid before the run ends)
-    g->stats.host_ms_schedule = now_ms() - t_plan0;
-
-    // ---- buffers ----
-    TRY(g->d_item_R2.ensure(max_phase));
-    TRY(g->d_pred_cnt.ensure(max_phase));
-    if (getenv("TSB_MODE") && !strcmp(getenv("TSB_MODE"), "rounds")) TRY(g->d_preds.ensure(max_phase * (size_t)PRED_CAP));
-    TRY(g->d_done.ensure(max_phase));
-    TRY(g->d_pend0.ensure(max_phase));
-    TRY(g->d_pend1.ensure(max_phase));
-    TRY(g->d_ctrl.ensure(8));
-    TRY(ensure_flow_buffers(g, max_phase));
-    {
-        size_t tb = 0;
-        CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, g->d_nsucc.p, g->d_succ_off.p, (int)(max_phase + 1), s));
-        TRY(g->d_cub_temp.ensure(tb + 256));
-    }
-    g->use_rounds = getenv("TSB_MODE") && !strcmp(getenv("TSB_MODE"), "rounds");
-    g->force_csr = getenv("TSB_MODE") && !strcmp(getenv("TSB_MODE"), "csr");
-    g->succ_stride = getenv("TSB_SUCC_STRIDE") ? std::max(1, atoi(getenv("TSB_SUCC_STRIDE"))) : SUCC_STRIDE;
-    g->stage_lists = !g->use_rounds && !g->force_csr && !(getenv("TSB_MODE") && !strcmp(getenv("TSB_MODE"), "epochs"));
-    if (g->stage_lists) {  // whole stages as one phase: the per-phase buffers must hold a stage's new pixels
-        size_t max_new = 1;
-        for (auto& sp : plan) max_new = std::max(max_new, sp.n_new);
-        max_phase = std::max(max_phase, max_new);
-        TRY(ensure_flow_buffers(g, max_phase));
-        size_t tb = 0;
-        CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, g->d_nsucc.p, g->d_succ_off.p, (int)(max_phase + 1), s));
-        TRY(g->d_cub_temp.ensure(tb + 256));
-        TRY(g->d_pmask.ensure((size_t)g->wpr * g->mrows));
-        TRY(g->d_pmask1.ensure((size_t)g->wpr1 * g->mrows));
-    }
-    TRY(ensure_list_buffers(g, max_phase, k));
-    TRY(g->d_rand_xy.ensure(max_stage_items * (size_t)m));
-    TRY(g->d_rand_map.ensure(max_stage_items * (size_t)m));
-    TRY(g->d_luts.ensure(512));
-    TRY(g->d_counters.ensure(ST_COUNT));
-    CU(cudaMemsetAsync(g->d_counters.p, 0, ST_COUNT * sizeof(unsigned long long), s));
-    if (!g->pmap_ready) {
-        TRY(g->d_pmap.ensure(npix));
-        CU(cudaMemsetAsync(g->d_pmap.p, 0xFF, npix * 4, s));
-        g->pmap_ready = true;
-    }
-    g->trace_n = 0;
-    g->tr_pixel.clear(); g->tr_fix_idx.clear();
-    if (g->trace) {
-        TRY(g->d_tr_best.ensure(total_items)); TRY(g->d_tr_ncand.ensure(total_items));
-        TRY(g->d_tr_nneigh.ensure(total_items)); TRY(g->d_tr_score.ensure(total_items));
-    }
-
-    S.counters = g->d_counters.p;
-    uint64_t overall_total = 0, overall_current = 0;
-    for (auto& sp : plan) overall_total += sp.pixels_to_resolve;
-    uint32_t last_pcnt = 0;
-    std::vector<uint8_t> progress_img;
-    uint64_t trace_base = 0;
-
-    for (auto& sp : plan) {
-        stage_inputs(g, S, sp.level, prm);
-        TRY(upload_luts(g, prm, sp.adaptive_alpha));
-        if (sp.recolour) {  // next_pyramid_level, ms.rs:687-700
-            k_recolour<<<(uint32_t)((npix + 255) / 256), 256, 0, s>>>(S);
-            CU(cudaGetLastError());
-            g->stats.kernel_launches++;
-        }
-        TRY(decide_opaque(g, sp.level));
-        S.opaque = g->run_opaque ? 1 : 0;
-        const size_t n_items = sp.n_redo + sp.n_new;
-        if (n_items == 0) continue;
-        // random candidates: rng seeded with loop_seed + 1 = stage seed + i + 1 (ms.rs:902,945); generated per phase, and in
-        // band-sharded phases only for the items this rank owns
-        auto launch_rand = [&](size_t i0, size_t n_, bool own_only, cudaStream_t st) -> int {
-            const unsigned rb = m <= 64 ? 128u : 32u;  // items per block: the staging area is rb * m * 5 bytes (< 48 KB)
-            k_rand_candidates<<<(uint32_t)((n_ + rb - 1) / rb), rb, (size_t)rb * m * 5 + rb, st>>>(S.ex, S.n_ex, m, sp.seed + 1ull + (uint64_t)i0, (uint32_t)n_,
-                                                                         g->d_rand_xy.p + i0 * (size_t)m, g->d_rand_map.p + i0 * (size_t)m,
-                                                                         own_only ? g->d_item_pixel.p + i0 : nullptr, g->W, g->h_mg.band_h,
-                                                                         g->h_mg.rank, g->h_mg.world);
-            CU(cudaGetLastError());
-            g->stats.kernel_launches++;
-            return 0;
-        };
-        g->regen_rand = [&](size_t i0, size_t n_) -> int { return launch_rand(i0, n_, false, s); };
-        if (!g->mg_on) {
-            // single GPU: the whole stage at once on the second stream, overlapped with the dependency analysis of the
-            // first phase; the resolve kernels wait for the event (run_phase_flow / run_serial)
-            TRY(launch_rand(0, n_items, false, g->stream2));
-            CU(cudaEventRecord(g->ev_rand, g->stream2));
-            g->rand_pending = true;
-        }
-        auto gen_rand = [&](size_t i0, size_t n_) -> int {
-            if (!g->mg_on) return 0;
-            return launch_rand(i0, n_, n_ >= g->mg_min_phase, s);
-        };
-
-        size_t resolved_now = sp.resolved_before;
-        // ---- redo phase: the resolved set is static, radii are exact ----
-        if (sp.n_redo) {
-            S.r2_hint = r2_hint_for(g, resolved_now, k);
-            S.n_points_max = (uint32_t)std::min<size_t>((tiling ? 3 : 1) * resolved_now, 0xFFFFFFFFull);
-            TRY(gen_rand(0, sp.n_redo));
-            if (g->use_rounds) TRY(run_phase(g, S, 0, (uint32_t)sp.n_redo, false, true, trace_base));
-            else { g->cur_resolved_redo_ok = resolved_now > (size_t)k; TRY(run_phase_flow(g, S, 0, (uint32_t)sp.n_redo, false, trace_base)); }
-        }
-        // ---- new pixels, in epochs over which the resolved count at most doubles ----
-        size_t cur = sp.n_redo;
-        while (cur < n_items) {
-            if (resolved_now == 0) {
-                // no resolved neighbour at all: resolve_at_random(seed = p_stage_seed), ms.rs:1002-1009 -> 447-475
-                uint32_t flat = stage_pixels[cur];
-                uint32_t rmap = (uint32_t)Pcg32::seed_from_u64(sp.seed).gen_range_usize((uint64_t)g->n_ex);
-                int e = g->filt[rmap];
-                uint32_t rx = Pcg32::seed_from_u64(sp.seed).gen_range_u32((uint32_t)g->ex_w[e]);
-                uint32_t ry = Pcg32::seed_from_u64(sp.seed).gen_range_u32((uint32_t)g->ex_h[e]);
-                uint32_t item[4] = {flat, rx, ry, rmap};
-                TRY(g->d_tmp_u32.upload(item, 4, s));
-                k_commit_fixed<<<1, 32, 0, s>>>(S, S.ex, g->d_tmp_u32.p, 1, 1);
-                CU(cudaGetLastError());
-                CU(cudaStreamSynchronize(s));
-                g->stats.kernel_launches++;
-                if (g->trace) g->tr_fix_idx.push_back(trace_base + cur);
-                cur += 1; resolved_now += 1;
-                continue;
-            }
-            size_t base = resolved_now - g->inpaint_locked;
-            bool whole_stage = false;
-            // band-sharded runs: only stages that are dependency bound (small, or growing the resolved set at least 4x) take
-            // this route -- every rank then executes the stage redundantly on its own replica, with no communication
-            const bool mg_ok = !g->mg_on || n_items - cur <= 2 * g->mg_min_phase || resolved_now * 4 <= n_items - cur;
-            if (g->stage_lists && mg_ok && base >= std::max<size_t>((size_t)k + 14, 64) && n_items - cur <= std::min(g->list_max_items, g->stage_list_max)) {
-                // the rest of the stage as one dataflow phase (exact timed neighbour lists, run_stage_new)
-                const size_t n_e = n_items - cur;
-                S.r2_hint = r2_hint_for(g, resolved_now, k);
-                S.n_points_max = (uint32_t)std::min<size_t>((tiling ? 3 : 1) * (resolved_now + n_e), 0xFFFFFFFFull);
-                if (g->mg_on) TRY(launch_rand(cur, n_e, false, s));  // executed redundantly by every rank: candidates for ALL items
-                TRY(run_stage_new(g, S, (uint32_t)cur, (uint32_t)n_e, resolved_now, trace_base));
-                cur += n_e; resolved_now += n_e;
-                whole_stage = true;
-            }
-            if (!whole_stage) {
-            // every item still depends on (almost) all earlier ones: one warp runs them in order, keeping the whole
-            // resolved set as a point list in shared memory while it fits the key buffer
-            // (the dataflow kernel overlaps the independent parts of consecutive items, so it takes over as soon as
-            // every item can find its k neighbours, i.e. the radii are finite)
-            size_t serial_until = std::max<size_t>((size_t)k + 14, 64);
-            if (const char* e = getenv("TSB_SERIAL_UNTIL")) serial_until = std::max<size_t>((size_t)k + 1, (size_t)atoi(e));
-            const bool serial = base < serial_until;
-            size_t n_e = serial ? (g->use_rounds ? 1 : std::min(n_items - cur, serial_until - base)) : std::min(n_items - cur, base);
-            S.r2_hint = r2_hint_for(g, resolved_now, k);
-            S.n_points_max = (uint32_t)std::min<size_t>((tiling ? 3 : 1) * (resolved_now + n_e), 0xFFFFFFFFull);
-            if (serial && tiling && resolved_now + n_e <= (size_t)KBUF) {
-                // exact upper bound of the point count (pixels + their mirror copies, ms.rs:306-327) so that the
-                // serial kernel can keep the whole set as a list; pixels resolved before this stage count 3x
-                size_t cnt = 3 * sp.resolved_before;
-                for (size_t i = sp.n_redo; i < cur + n_e; ++i) {
-                    int x = (int)(stage_pixels[i] % (uint32_t)g->W), y = (int)(stage_pixels[i] / (uint32_t)g->W);
-                    cnt += 1 + ((x < S.x_l || x > S.x_r) ? 1 : 0) + ((y < S.y_b || y > S.y_t) ? 1 : 0);
-                }
-                S.n_points_max = (uint32_t)cnt;
-            }
-            TRY(gen_rand(cur, n_e));
-            if (g->use_rounds) TRY(run_phase(g, S, (uint32_t)cur, (uint32_t)n_e, true, n_e > 1, trace_base));
-            else if (serial) TRY(run_serial(g, S, (uint32_t)cur, (uint32_t)n_e, true, trace_base));
-            else { g->cur_resolved = resolved_now; TRY(run_phase_flow(g, S, (uint32_t)cur, (uint32_t)n_e, true, trace_base)); }
-            cur += n_e; resolved_now += n_e;
-            }
-            if (cb) {
-                uint64_t cur_total = overall_current + cur;
-                uint32_t pcnt = (uint32_t)lroundf((float)cur_total / (float)overall_total * 100.0f);
-                if (pcnt != last_pcnt) {
-                    last_pcnt = pcnt;
-                    progress_img.resize(npix * 4);
-                    TRY(g->d_tmp_u32.ensure(npix));
-                    k_unpack_state<<<(uint32_t)((npix + 255) / 256), 256, 0, s>>>(g->d_state.p, (uint32_t)npix, g->d_tmp_u32.p, nullptr, nullptr);
-                    CU(cudaMemcpyAsync(progress_img.data(), g->d_tmp_u32.p, npix * 4, cudaMemcpyDeviceToHost, s));
-                    CU(cudaStreamSynchronize(s));
-                    cb(user, progress_img.data(), (uint32_t)g->W, (uint32_t)g->H, cur_total, overall_total, cur, sp.pixels_to_resolve);
-                }
-            }
-        }
-        overall_current += sp.pixels_to_resolve;
-        trace_base += n_items;
-    }
-    // host mirrors of the order: ms.rs:1043-1049 (newly resolved pixels join `resolved` in processing order)
-    CU(cudaStreamSynchronize(g->stream2));
-    CU(cudaStreamSynchronize(g->stream3));
-    g->resolved_order.insert(g->resolved_order.end(), g->h_items.p, g->h_items.p + n_picks);
-    if (g->trace) for (auto& sp : plan) g->tr_pixel.insert(g->tr_pixel.end(), g->h_items.p, g->h_items.p + sp.n_redo + sp.n_new);
-    g->trace_n = g->trace ? trace_base : 0;
-    unsigned long long cnt[ST_COUNT];
-    CU(cudaMemcpyAsync(cnt, g->d_counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    g->stats.texels_fetched = cnt[ST_FETCHED]; g->stats.texels_nominal = cnt[ST_NOMINAL]; g->stats.candidates = cnt[ST_CANDS];
-    if (getenv("TSB_DEBUG_PHASES") && cnt[ST_ITEMS])
-        fprintf(stderr, "[tsb] cycles/item: ready %.0f knn %.0f neigh %.0f weight+rand %.0f score %.0f commit %.0f (items %llu)\n",
-                (double)cnt[ST_CYC_READY] / cnt[ST_ITEMS], (double)cnt[ST_CYC_KNN] / cnt[ST_ITEMS], (double)cnt[ST_CYC_NEIGH] / cnt[ST_ITEMS],
-                (double)cnt[ST_CYC_WEIGHT] / cnt[ST_ITEMS], (double)cnt[ST_CYC_SCORE] / cnt[ST_ITEMS], (double)cnt[ST_CYC_COMMIT] / cnt[ST_ITEMS],
-                cnt[ST_ITEMS]);
-    g->stats.work_items = total_items;
-    CU(cudaEventRecord(ev_end, s));
-    CU(cudaEventSynchronize(ev_end));
-    float ms_total = 0.f;
-    cudaEventElapsedTime(&ms_total, ev_begin, ev_end);
-    cudaEventDestroy(ev_begin); cudaEventDestroy(ev_end);
-    g->stats.gpu_ms_total = ms_total;
-    g->stats.wall_ms_total = now_ms() - t_start;
-    g->stats.gpu_ms_other = ms_total - g->stats.gpu_ms_resolve - g->stats.gpu_ms_analysis;
-    g->have_loaded_points = false;
-    return 0;
-}
-
 // =============================================================================================
 // In-order streaming scheduler (default).  See tsb_stream.cuh for the device side.
 // Host: ONE pass that enqueues everything -- the analysis of every chunk on stream2 (it depends on (seed, size, parameters)
@@ -1547,9 +785,8 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
     // complete, so the first chunks of a run are small (the synthesis starts early) and no chunk is so large that the last
     // one's resolve kernel -- which nothing overlaps -- matters.
     size_t chunk_max = 2u << 20;  // (512 Ki-item chunks were tried: the shorter tail does not pay for 2.5x as many launches)
-    if (const char* e = getenv("TSB_CHUNK")) chunk_max = std::max<size_t>(1024, (size_t)strtoull(e, nullptr, 10));
+    if (const char* e = getenv("TSB_CHUNK")) chunk_max = std::max<size_t>(16, (size_t)strtoull(e, nullptr, 10));
     std::vector<ChunkPlan> chunks;
-    bool first_pixel_fixed = false;  // the very first pixel of a fresh run has no neighbour: resolve_at_random (ms.rs:1002-1009)
     for (size_t si = 0; si < n_stages; ++si) {
         const StagePlan& sp = plan[si];
         auto add_phase = [&](bool redo, size_t a, size_t b) {
@@ -1567,7 +804,7 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         };
         if (sp.n_redo) add_phase(true, 0, sp.n_redo);
         size_t a = sp.n_redo;
-        if (sp.n_new && sp.resolved_before == 0) { first_pixel_fixed = true; a += 1; }
+        if (sp.n_new && sp.resolved_before == 0) a += 1;  // the very first pixel of a fresh run has no neighbour: resolve_at_random (ms.rs:1002-1009), see begin_stage
         if (sp.n_redo + sp.n_new > a) add_phase(false, a, sp.n_redo + sp.n_new);
     }
     // ---- band-sharded run: which phases are sharded, and this rank's items of every sharded chunk ----
@@ -1649,11 +886,12 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
             ring_items = std::min(ring_items, std::max<size_t>(cap, 1));
         }
     }
+    if (const char* e = getenv("TSB_RING_ITEMS")) ring_items = std::max<size_t>(16, (size_t)strtoull(e, nullptr, 10));  // tests: force the ring to wrap
     size_t largest = 1;
     for (auto& c : chunks) largest = std::max(largest, c.items());
     if (g->mgs_on) ring_items = std::max(ring_items, 2 * largest);  // (own-item ranges are per chunk: no re-splitting)
     if (ring_items < 2 * largest) {  // smaller chunks so that two of them fit the ring
-        const size_t cm = std::max<size_t>(1024, ring_items / 3);
+        const size_t cm = std::max<size_t>(8, ring_items / 3);
         std::vector<ChunkPlan> split;
         for (auto& c : chunks)
             for (size_t o = 0; o < c.n; o += cm) {
@@ -1724,12 +962,16 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
     auto enqueue_analysis = [&](ChunkPlan& c) -> int {
         size_t off = ring_head;
         if (off + c.items() > ring_items) off = 0;
-        while (!live.empty()) {
-            const ChunkPlan& f = chunks[live.front()];
-            const bool overlap = off < f.slot + f.items() && f.slot < off + c.items();
-            if (!overlap) break;
-            if (live.front() >= r_next) return 1;  // its resolve kernel is not enqueued yet: no event to wait for
-            CU(cudaStreamWaitEvent(s2, f.ev_done, 0));
+        // slots are reclaimed in FIFO order: everything up to the LAST live chunk that overlaps the new range must be done
+        size_t reclaim = 0;
+        for (size_t i = 0; i < live.size(); ++i) {
+            const ChunkPlan& f = chunks[live[i]];
+            if (off < f.slot + f.items() && f.slot < off + c.items()) reclaim = i + 1;
+        }
+        for (size_t i = 0; i < reclaim; ++i)
+            if (live[i] >= r_next) return 1;  // its resolve kernel is not enqueued yet: no event to wait for
+        for (size_t i = 0; i < reclaim; ++i) {
+            CU(cudaStreamWaitEvent(s2, chunks[live.front()].ev_done, 0));
             live.pop_front();
         }
         c.slot = off;
@@ -1775,7 +1017,7 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
             k_weights<<<std::max(1u, std::min((wgroups + KW_WARPS - 1) / KW_WARPS, (unsigned)g->n_sms * 16u)), KW_WARPS * 32, (size_t)KW_WARPS * k * (KW_ITEMS + 1) * sizeof(double), s2>>>(S, C);
             const unsigned rb = m <= 64 ? 128u : 32u;  // items per block: the staging area is rb * m * 5 bytes (< 48 KB)
             k_rand_candidates<<<(n + rb - 1) / rb, rb, (size_t)rb * m * 5 + rb, s2>>>(S.ex, S.n_ex, m, sp.seed + 1ull + (c.sharded ? 0ull : (uint64_t)c.first), n,
-                                                                                   C.rand_xy, C.rand_map, nullptr, 1, 1, 0, 1, C.tidx);
+                                                                                   C.rand_xy, C.rand_map, C.tidx);
             CU(cudaGetLastError());
         }
         if (!c.redo && c.phase_last) {  // the stage's new pixels join the resolved set of the next stage's analysis
@@ -1794,14 +1036,11 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
     S.counters = g->d_counters.p;
     bool state_opaque = g->state_init_opaque;  // every resolved colour in the state has alpha 255
     int cur_stage = -1;
-    size_t progress_base = 0;
-    uint64_t trace_base = 0;
     std::vector<uint64_t> stage_trace_base(n_stages, 0), stage_progress_base(n_stages, 0);
     {
         uint64_t tb = 0, pb = 0;
         for (size_t si = 0; si < n_stages; ++si) { stage_trace_base[si] = tb; stage_progress_base[si] = pb; tb += plan[si].n_redo + plan[si].n_new; pb += plan[si].pixels_to_resolve; }
     }
-    (void)progress_base; (void)trace_base;
     int grid_full = g->guided ? g->max_ctas_stream_guided : g->max_ctas_stream;
     if (const char* e = getenv("TSB_STREAM_OCC")) grid_full = std::min(grid_full, g->n_sms * std::max(1, atoi(e)));
     bool stage_prologue_pending = false;  // a recolour happened since the last kernel of this rank
@@ -2043,7 +1282,6 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
     g->stats.gpu_ms_other = ms_total - g->stats.gpu_ms_resolve;
     g->have_loaded_points = false;
     g->state_init_opaque = state_opaque;
-    (void)first_pixel_fixed;
     return 0;
 }
 
@@ -2170,7 +1408,6 @@ int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
     if (cudaStreamCreateWithFlags(&g->stream3, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "stream creation failed"));
     if (cudaHostAlloc((void**)&g->h_progress, 64, cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer((void**)&g->d_progress, g->h_progress, 0) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "mapped allocation failed"));
-    if (cudaEventCreateWithFlags(&g->ev_rand, cudaEventDisableTiming) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "event creation failed"));
     if (cudaMallocHost((void**)&g->h_ctrl, 64) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "pinned allocation failed"));
     g->W = (int)desc->out_width; g->H = (int)desc->out_height;
     const size_t npix = (size_t)g->W * g->H;
@@ -2206,17 +1443,8 @@ int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
         g->unresolved0.resize(npix);
         for (size_t i = 0; i < npix; ++i) g->unresolved0[i] = (uint32_t)i;
     }
-    int per_sm = 0;
-    cudaFuncSetAttribute(k_round<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
-    cudaFuncSetAttribute(k_round<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
     cudaFuncSetAttribute(k_eval_items<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
     cudaFuncSetAttribute(k_eval_items<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaSmem));
-    cudaFuncSetAttribute(k_radius, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(KnnScratch) * WARPS_PER_CTA));
-#define TSB_FLOW_ATTR(G, M, O, L) cudaFuncSetAttribute(k_flow<G, M, O, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem))
-    TSB_FLOW_ATTR(false, false, false, false); TSB_FLOW_ATTR(false, false, true, false); TSB_FLOW_ATTR(false, false, false, true); TSB_FLOW_ATTR(false, false, true, true);
-    TSB_FLOW_ATTR(true, false, false, false); TSB_FLOW_ATTR(true, false, true, false); TSB_FLOW_ATTR(true, false, false, true); TSB_FLOW_ATTR(true, false, true, true);
-    TSB_FLOW_ATTR(false, true, false, false); TSB_FLOW_ATTR(false, true, true, false); TSB_FLOW_ATTR(true, true, false, false); TSB_FLOW_ATTR(true, true, true, false);
-#undef TSB_FLOW_ATTR
 #define TSB_STREAM_ATTR(G, O, R)                                                                                          \
     cudaFuncSetAttribute(k_stream<G, O, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem)); \
     cudaFuncSetAttribute(k_stream<G, O, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem))
@@ -2226,12 +1454,6 @@ int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
     cudaFuncSetAttribute(k_lists_chunk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(KnnScratch) * WARPS_PER_CTA));
     cudaFuncSetAttribute(k_lists_chunk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(KnnScratch) * WARPS_PER_CTA));
     cudaFuncSetAttribute(k_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KW_WARPS * KMAX * (KW_ITEMS + 1) * sizeof(double)));
-    cudaFuncSetAttribute(k_serial<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
-    cudaFuncSetAttribute(k_serial<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_round<false>, CTA_THREADS, sizeof(RoundSmem)) != cudaSuccess || per_sm < 1) per_sm = 1;
-    int per_sm_flow = 0, per_sm_flow_g = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_flow, k_flow<false, true, false, false>, CTA_THREADS, sizeof(RoundSmem)) != cudaSuccess || per_sm_flow < 1) per_sm_flow = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_flow_g, k_flow<true, true, false, false>, CTA_THREADS, sizeof(RoundSmem)) != cudaSuccess || per_sm_flow_g < 1) per_sm_flow_g = 1;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "cudaGetDeviceProperties failed"));
     g->n_sms = prop.multiProcessorCount;
@@ -2240,19 +1462,17 @@ int tsb_generator_create(const tsb_generator_desc* desc, tsb_generator** out) {
         size_t want = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, 32u << 20);
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) g->l2_persist_bytes = want; else cudaGetLastError();
     }
-    g->max_ctas = prop.multiProcessorCount * std::max(per_sm, 4);  // analysis kernels (k_radius: 47 KB smem) fit 4 CTAs per SM
-    g->max_ctas_flow = prop.multiProcessorCount * per_sm_flow;  // persistent grid: co-resident CTAs only
-    g->max_ctas_flow_guided = prop.multiProcessorCount * per_sm_flow_g;
     {
-        int ps = 0, psg = 0;
+        int ps = 0, psg = 0, pr = 0, pe = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, k_stream<false, false, true>, CTA_THREADS, sizeof(StreamSmem)) != cudaSuccess || ps < 1) ps = 1;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&psg, k_stream<true, false, true>, CTA_THREADS, sizeof(StreamSmem)) != cudaSuccess || psg < 1) psg = 1;
-        g->max_ctas_stream = prop.multiProcessorCount * ps;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pr, k_lists_chunk<false>, CTA_THREADS, sizeof(KnnScratch) * WARPS_PER_CTA) != cudaSuccess || pr < 1) pr = 4;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pe, k_eval_items<false>, CTA_THREADS, sizeof(CtaSmem)) != cudaSuccess || pe < 1) pe = 1;
+        g->max_ctas_stream = prop.multiProcessorCount * ps;         // persistent grids: co-resident CTAs only
         g->max_ctas_stream_guided = prop.multiProcessorCount * psg;
+        g->max_ctas_radius = prop.multiProcessorCount * pr;         // one wave of co-resident CTAs, grid-stride over the items
+        g->max_ctas = prop.multiProcessorCount * pe;
     }
-    int per_sm_radius = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_radius, k_radius, CTA_THREADS, sizeof(KnnScratch) * WARPS_PER_CTA) != cudaSuccess || per_sm_radius < 1) per_sm_radius = 4;
-    g->max_ctas_radius = prop.multiProcessorCount * per_sm_radius;  // one wave of co-resident CTAs, grid-stride over the items
     if ((rc = init_state(g))) return bail(rc);
     if (cudaStreamSynchronize(g->stream) != cudaSuccess) return bail(fail(TSB_ERR_CUDA, "generator initialisation failed: %s", cudaGetErrorString(cudaGetLastError())));
     *out = g;
@@ -2323,9 +1543,6 @@ int tsb_generator_upload_inputs(tsb_generator* g, const tsb_pyramid* examples, u
 }
 
 static int resolve_dispatch(tsb_generator* g, const tsb_params* params, tsb_progress_fn cb, void* user) {
-    // default: the in-order streaming scheduler; TSB_MODE selects the older schedulers (cross-checks), which the band-sharded
-    // multi-GPU path still uses
-    if (!g->mgs_on && (g->mg_on || getenv("TSB_MODE"))) return resolve_impl(g, params, cb, user);
     return resolve_stream(g, params, cb, user);
 }
 
@@ -2516,7 +1733,7 @@ int tsb_generator_eval_items(tsb_generator* g, const tsb_params* prm, int32_t le
         CU(cudaGetLastError());
         i = j;
     }
-    int grid = grid_for(g, n);
+    const int grid = std::max(1, std::min((int)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), g->max_ctas));
     if (g->guided) k_eval_items<true><<<grid, CTA_THREADS, sizeof(CtaSmem), s>>>(S, n, dpix.p, dxy.p, dmap.p, dneigh.p, dres.p, dscore.p);
     else k_eval_items<false><<<grid, CTA_THREADS, sizeof(CtaSmem), s>>>(S, n, dpix.p, dxy.p, dmap.p, dneigh.p, dres.p, dscore.p);
     CU(cudaGetLastError());

@@ -1,19 +1,16 @@
-// tsb_device.cuh -- sm_100a kernels of the texture-synthesis hot path.
+// tsb_device.cuh -- sm_100a device code of the texture-synthesis hot path shared by the kernels.
 //
 // One warp performs one "pixel resolution" (reference lib/src/ms.rs:887-1011):
-//   K2  k nearest resolved neighbours  : (replaces TreeGrid + rstar, ms.rs:1313-1531) prepared by the phase analysis as
-//                                         a per-item list -- spiral walk / disc scan over a bit-packed resolved mask,
-//                                         for new pixels "as of" the item's serial time (k_lists_timed) -- and only
-//                                         loaded by the resolve kernel (knn_from_lists); knn_search is the fallback
+//   K2  k nearest resolved neighbours  : (replaces TreeGrid + rstar, ms.rs:1313-1531) spiral walk / disc scan over a
+//                                         bit-packed resolved mask (knn_search); run ahead of the synthesis by the analysis
+//                                         kernels of tsb_stream.cuh, which leave one neighbour list per work item
 //   K3  candidates                      : coherence candidates from the neighbours' source coordinates, exactly
 //                                         de-duplicated (ms.rs:496-547) + pre-generated PCG-exact random ones (549-599)
 //   K4  cost + argmin                   : eight lanes per candidate with the f32 sum carried as a chain when few
 //                                         coherence candidates remain, else one lane per candidate; strict f32 order
 //                                         (ms.rs:1184-1288)
-//   K5  commit                          : ms.rs:334-377 / 296-331
-// Work items are executed in the exact serial-order semantics of the single-threaded reference by a persistent
-// dataflow kernel (k_flow): an item runs once every lower-index item it reads from (or that reads what it
-// overwrites) has committed.
+//   K5  commit                          : ms.rs:334-377 / 296-331 (one 128-bit store, see tsb_stream.cuh)
+// Also here: pixel order (ms.rs:380-389), K1 resampling (img_pyramid.rs:20-37), guide preprocessing, read-outs.
 #pragma once
 #include <cuda_runtime.h>
 #include <cfloat>
@@ -25,7 +22,6 @@ namespace tsb {
 constexpr int KMAX = 128;         // max nearest_neighbors
 constexpr int CANDMAX = 256;      // max nearest_neighbors + random_sample_locations
 constexpr int KBUF = 256;         // key buffer of the general k-NN path
-constexpr int PRED_CAP = 160;     // predecessor list capacity per work item
 constexpr int WARPS_PER_CTA = 8;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
 constexpr uint32_t NONE32 = 0xFFFFFFFFu;
@@ -37,7 +33,7 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 // pixel was last written: 0 = never resolved, TAG_LOCKED = present before the run (inpaint, random_init, loaded
 // snapshot), otherwise the id of the phase that committed it (stage s, counted from the first stage: redo phase 2s+1,
 // new-pixel phase 2s+2).  The in-order resolve kernel (k_stream) waits on these tags instead of a ready queue.
-constexpr uint32_t MAP_MASK = 0xFFFu, TAG_LOCKED = 255u, TAG_LEGACY = 254u;
+constexpr uint32_t MAP_MASK = 0xFFFu, TAG_LOCKED = 255u;
 __host__ __device__ __forceinline__ uint32_t st_idmap(uint32_t w) { return w & MAP_MASK; }
 __host__ __device__ __forceinline__ uint32_t st_coordmap(uint32_t w) { return (w >> 12) & MAP_MASK; }
 __host__ __device__ __forceinline__ uint32_t st_tag(uint32_t w) { return w >> 24; }
@@ -61,27 +57,9 @@ struct DevGuide {  // one example guide at the current level (NOT filtered, ms.r
     int w, h;
 };
 
-// Band-sharded execution of ONE output over several GPUs of a node.  Every rank keeps a full
-// replica of the synthesis state; work items are owned by the rank whose horizontal band contains their
-// pixel; a commit is written to every replica and successor notifications go to the owner's counters and
-// ready queue -- plain stores and system-scope atomics on peer memory (CUDA IPC mappings, NVLink).
-constexpr int MG_MAX = 8;
-struct MgDev {
-    int rank, world, band_h, pad;
-    uint4* state[MG_MAX];
-    uint32_t* mask[MG_MAX];
-    uint32_t* mask1[MG_MAX];
-    float* score[MG_MAX];
-    uint32_t* item_R2[MG_MAX];
-    uint32_t* npred[MG_MAX];
-    uint32_t* nsucc[MG_MAX];
-    uint32_t* succ[MG_MAX];
-    uint32_t* queue[MG_MAX];
-    uint32_t* ctl[MG_MAX];
-};
+constexpr int MG_MAX = 8;  // ranks of a band-sharded run (tsb_stream.cuh)
 
 struct StageDev {
-    const MgDev* mg;  // nullptr: single GPU, or a phase every rank executes redundantly on its own replica
     // synthesis state
     uint4* state;     // per output pixel {colour RGBA, src x|y<<16, patch id, id_map.map | coord_map.map<<16}
     uint32_t* mask;   // resolved set, bit packed, extended by the tiling margins
@@ -114,49 +92,6 @@ struct StageDev {
     unsigned long long* counters;  // [ST_COUNT] run statistics (see enum below), flushed once per CTA
 };
 
-struct PhaseDev {
-    const uint32_t* item_pixel;  // [n] flat output pixel of local item
-    uint32_t* item_R2;           // [n] conflict radius^2 (k-th neighbour distance at phase start)
-    uint32_t* pred_cnt;          // [n]
-    uint32_t* preds;             // [n][PRED_CAP] local indices of lower items that must commit first
-    uint32_t* done;              // [n]
-    uint32_t* pending[2];        // ping-pong pending lists
-    uint32_t* cnt;               // [4] pending counts ring (round r reads r&3, appends (r+1)&3, clears (r+2)&3)
-    uint32_t* minpend;           // [4] min pending local index ring
-    uint32_t* pmap;              // W*H: local item index or NONE32
-    const uint32_t* rand_xy;     // [n_stage][m] pre-generated random candidates (x | y<<16)
-    const uint8_t* rand_map;     // [n_stage][m]
-    uint32_t n;                  // items in phase
-    uint32_t stage_base;         // work-item index (within the stage) of local item 0
-    uint32_t is_new;             // 1: new pixels (insert into the resolved set), 0: redo
-    // trace (optional, indexed by stage work-item index + trace_base)
-    int32_t* tr_best; int32_t* tr_ncand; int32_t* tr_nneigh; float* tr_score;
-    uint64_t trace_base;
-    // neighbour lists prepared by the phase analysis (nullptr: every item searches the bit mask instead)
-    short2* nb0;            // [n][k] the k nearest resolved points at phase start, canonical order
-    short2* predl;          // [n][predl_stride] new phases: lower-index items of this phase inside the item's disc (offsets)
-    uint32_t* npredl;       // [n] entries in predl; anything above predl_stride = list unusable, search the mask
-    uint32_t predl_stride;
-};
-constexpr uint32_t PREDL_UNUSABLE = 0xFFFFFFFFu;
-
-// Dataflow execution of one phase: CSR successor lists + a ready queue (every item is enqueued exactly once,
-// so the queue is a plain array of n slots; NONE32 = slot not yet published).
-struct FlowDev {
-    uint32_t* npred;     // [n]   predecessors that have not committed yet
-    uint32_t* nsucc;     // [n+1] successor counts (entry n is 0 so that the scan yields the edge total)
-    uint32_t* succ_off;  // [n+1] exclusive scan of nsucc
-    uint32_t* succ_cur;  // [n]   fill cursors
-    uint32_t* succ;      // [edges]
-    uint32_t* queue;     // [n]
-    uint32_t* ctl;       // control block, see FC_*
-    uint32_t stride;     // > 0: successors of item a live in succ[a*stride ..] (single analysis pass); 0: CSR
-};
-// Control block (32-bit words).  Queue head, queue tail and the targets of the release stores are the hottest addresses of
-// the whole run (every work item touches each once), so each has a 128-byte line of its own; sharing one line cost 2 %.
-enum { FC_HEAD = 0, FC_ABORT = 2, FC_OVERFLOW = 3, FC_NOWN = 4,  // FC_NOWN: items owned by this rank (multi-GPU)
-       FC_TAIL = 64, FC_RELEASE = 128, FC_WORDS = FC_RELEASE + 32 * 32 };
-
 struct __align__(16) WarpScratch {
     union {
         unsigned long long keys[KBUF];  // general k-NN path (dead once the neighbour list is built)
@@ -169,8 +104,6 @@ struct __align__(16) WarpScratch {
     float g[KMAX];
     uint32_t tcol[KMAX];
     uint32_t gcol[KMAX];
-    uint32_t succ_pref[32];   // k_flow: the first 32 successors of the current item, copied in asynchronously
-    uint32_t nsucc_pref, nrem_pref;
     int cnt;
     int pad[1];
     unsigned long long stat[16];  // per-warp run statistics (ST_*), kept out of the registers
@@ -199,9 +132,6 @@ struct ItemOut {
     int bcol_valid;
 };
 
-__device__ __forceinline__ void cp_async_u32(uint32_t* smem_dst, const uint32_t* gmem_src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
-}
 __device__ __forceinline__ int imod(int a, int b) { int r = a % b; return r < 0 ? r + b : r; }
 
 __device__ __forceinline__ int isqrt_u32(uint32_t v) {
@@ -245,7 +175,6 @@ __device__ __forceinline__ bool mask_test(const StageDev& S, int x, int y) {
     if ((unsigned)X >= (unsigned)(S.wpr * 32) || (unsigned)Y >= (unsigned)S.mrows) return false;
     return (mask_word<STABLE>(S.mask + (size_t)Y * S.wpr + (X >> 5)) >> (X & 31)) & 1u;
 }
-__device__ __forceinline__ int mg_owner_y(const MgDev* mg, int y) { int r = y / mg->band_h; return r < mg->world - 1 ? r : mg->world - 1; }
 
 __device__ __forceinline__ void mask_set_at(const StageDev& S, uint32_t* mask, uint32_t* mask1, bool shared, int x, int y) {
     int X = x + S.mx, Y = y + S.my;
@@ -490,96 +419,6 @@ __device__ __forceinline__ int knn_search(const StageDev& S, WS& ws, int lane, i
     return kk;
 }
 
-// k nearest among an explicit point list held in shared memory (serial start of a synthesis, where the
-// resolved set is tiny and scanning the mask would cost more than looking at every point)
-__device__ __forceinline__ int knn_points(const StageDev& S, WarpScratch& ws, int lane, int x, int y, const short2* pts, int npts, uint32_t* r2_out) {
-    for (int i = lane; i < npts; i += 32) {
-        int dx = pts[i].x - x, dy = pts[i].y - y;
-        ws.u.keys[i] = ((unsigned long long)(uint32_t)(dx * dx + dy * dy) << 32) | ((unsigned long long)(uint32_t)(dy + 32768) << 16) |
-                       (unsigned long long)(uint32_t)(dx + 32768);
-    }
-    __syncwarp();
-    sort_keys(ws, lane, npts);
-    const int kk = npts < S.k ? npts : S.k;
-    unsigned long long kth = kk > 0 ? ws.u.keys[kk - 1] : 0ull;
-    __syncwarp();
-    for (int j = lane; j < kk; j += 32) {
-        unsigned long long key = ws.u.keys[j];
-        ws.off[j] = make_short2((short)((int)(key & 0xFFFF) - 32768), (short)((int)((key >> 16) & 0xFFFF) - 32768));
-    }
-    __syncwarp();
-    *r2_out = (kk == S.k) ? (uint32_t)(kth >> 32) : R2_INF;
-    return kk;
-}
-
-// Does the resolved set hold a point at the (unwrapped) position (ux, uy) once the pixel at the wrapped
-// position is resolved?  In-canvas: the pixel itself; outside: only the single-axis tiling mirror copies of
-// flush_resolved (ms.rs:308-331), no diagonal ones.
-__device__ __forceinline__ bool point_exists_at(const StageDev& S, int ux, int uy) {
-    const bool xin = (unsigned)ux < (unsigned)S.W, yin = (unsigned)uy < (unsigned)S.H;
-    if (xin && yin) return true;
-    if (!S.tiling || (!xin && !yin)) return false;
-    if (!xin) return ux >= S.W ? (ux - S.W < S.x_l) : (ux + S.W > S.x_r);
-    return uy >= S.H ? (uy - S.H < S.y_b) : (uy + S.H > S.y_t);
-}
-
-// k nearest from the lists the phase analysis prepared: the k nearest at phase start (sorted) merged with the
-// points this phase has added inside the item's disc before it (exactly its in-disc predecessors, all committed
-// by the time the item runs).  No access to the bit mask.
-__device__ __forceinline__ int knn_from_lists(const StageDev& S, WarpScratch& ws, int lane, const short2* __restrict__ nb0,
-                                              const short2* __restrict__ predl, int npl, uint32_t* r2_out, int nbk = -1) {
-    const int k = nbk >= 0 ? nbk : S.k;  // nbk: the list is the final neighbourhood and may be shorter than k (early pixels)
-    if (npl == 0) {
-        *r2_out = R2_INF;
-        if (k == 0) return 0;
-        for (int j = lane; j < k; j += 32) ws.off[j] = nb0[j];
-        __syncwarp();
-        const short2 last = ws.off[k - 1];
-        if (k == S.k) *r2_out = (uint32_t)(last.x * last.x + last.y * last.y);
-        return k;
-    }
-    for (int j = lane; j < k + npl; j += 32) {
-        const short2 o = j < k ? nb0[j] : predl[j - k];
-        ws.u.keys[j] = ((unsigned long long)(uint32_t)(o.x * o.x + o.y * o.y) << 32) | ((unsigned long long)(uint32_t)(o.y + 32768) << 16) |
-                       (unsigned long long)(uint32_t)(o.x + 32768);
-    }
-    __syncwarp();
-    // rank merge: the start list is already sorted and all keys are distinct, so the final position of a key is
-    // its rank in its own list plus the number of smaller keys in the other one; positions >= k drop out.
-    // Three keys per lane share every broadcast read of a phase key.
-    const unsigned long long* keys = ws.u.keys;
-    const int n = k + npl;
-    for (int e0 = 0; e0 < n; e0 += 96) {
-        unsigned long long key[3];
-        int pos[3];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            const int e = e0 + 32 * q + lane;
-            key[q] = e < n ? keys[e] : ~0ull;
-            pos[q] = e;
-            if (e >= k) {  // a phase key (or padding): number of start-list keys below it
-                int lo = 0, hi = k;
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < key[q]) lo = mid + 1; else hi = mid; }
-                pos[q] = lo;
-            }
-        }
-#pragma unroll 4
-        for (int c = 0; c < npl; ++c) {
-            const unsigned long long kc = keys[k + c];
-#pragma unroll
-            for (int q = 0; q < 3; ++q) pos[q] += kc < key[q] ? 1 : 0;
-        }
-#pragma unroll
-        for (int q = 0; q < 3; ++q)
-            if (key[q] != ~0ull && pos[q] < k)
-                ws.off[pos[q]] = make_short2((short)((int)(key[q] & 0xFFFF) - 32768), (short)((int)((key[q] >> 16) & 0xFFFF) - 32768));
-    }
-    __syncwarp();
-    const short2 last = ws.off[k - 1];
-    *r2_out = (uint32_t)(last.x * last.x + last.y * last.y);
-    return k;
-}
-
 // ---------------------------------------------------------------------------------------------
 // Coherence candidates when at most COOP_CANDS distinct ones remain (the common case: neighbours that agree
 // propose the same source pixel): eight lanes share one candidate.  Lane u of a group gathers and weighs the
@@ -816,19 +655,17 @@ __device__ __forceinline__ void resolve_tail(const StageDev& S, WarpScratch& ws,
 // One pixel resolution (steps 2-4 of ms.rs:917-986) by one warp.  No commit.
 // ---------------------------------------------------------------------------------------------
 // OPQ: 1 / 0 = the alpha term is known at compile time to be skipped / kept, -1 = decided at run time (S.opaque).
-// LISTS: the neighbourhood always comes from the analysis lists (nb0 != nullptr), the mask search is not compiled in.
-// Both only shrink the code of the persistent kernel (instruction fetch is a measurable share of its stalls).
-template <bool GUIDED, int OPQ = -1, bool LISTS = false>
+// This is the self-contained form (own k-NN search and weights), used by the frozen-snapshot harness k_eval_items; the
+// production kernel k_stream (tsb_stream.cuh) takes the neighbourhood and the weights from the analysis and shares
+// resolve_tail with it.
+template <bool GUIDED, int OPQ = -1>
 __device__ __forceinline__ void resolve_item(const StageDev& S, WarpScratch& ws, const float* __restrict__ s_lut,
                              const float* __restrict__ s_lutg, int lane, int x, int y, uint32_t R2bound,
-                             const uint32_t* __restrict__ rand_xy, const uint8_t* __restrict__ rand_map, ItemOut& out,
-                             const short2* pts = nullptr, int npts = 0, const short2* nb0 = nullptr,
-                             const short2* predl = nullptr, int npl = 0, int nbk = -1) {
+                             const uint32_t* __restrict__ rand_xy, const uint8_t* __restrict__ rand_map, ItemOut& out) {
     const unsigned lt = (1u << lane) - 1u;
     uint32_t r2;
     long long t0 = clock64();
-    const int kk = (LISTS || nb0) ? knn_from_lists(S, ws, lane, nb0, predl, npl, &r2, nbk)
-                 : pts ? knn_points(S, ws, lane, x, y, pts, npts, &r2) : knn_search(S, ws, lane, x, y, R2bound, &r2);
+    const int kk = knn_search(S, ws, lane, x, y, R2bound, &r2);
     long long t1 = clock64();
     out.c_knn = t1 - t0; out.c_neigh = out.c_weight = out.c_score = 0; out.fetched = out.nominal = 0;
     out.kk = kk;
@@ -1032,350 +869,11 @@ __device__ __forceinline__ void load_luts(const StageDev& S, float* s_lut, float
     __syncthreads();
 }
 
-constexpr int REQ_CAP = 1024;  // per-CTA staging of re-queued items (one global atomic per CTA and round)
-
 struct __align__(16) CtaSmem {
     float lut[256];
     float lutg[256];
     WarpScratch ws[WARPS_PER_CTA];
 };
-struct __align__(16) RoundSmem {
-    CtaSmem c;
-    uint32_t req[REQ_CAP];
-    unsigned long long stat[ST_COUNT];
-    uint32_t req_cnt, req_min, req_base, pad;
-};
-
-// update(), ms.rs:334-377 (+ flush_resolved's tree insert, ms.rs:296-331); called by lane 0
-template <bool MG = false>
-__device__ __forceinline__ void commit_item(const StageDev& S, const PhaseDev& P, uint32_t si, uint32_t flat, int x, int y, const ItemOut& o,
-                                            bool to_peers = false) {
-    if (o.kk > 0) {
-        DevEx e = S.ex[o.bmap];
-        const uint32_t col = o.bcol_valid ? o.bcol : __ldg(e.px + (size_t)o.by * e.w + o.bx);
-        const uint4 v = make_uint4(col, (uint32_t)o.bx | ((uint32_t)o.by << 16), o.bpatch, st_pack_w((uint32_t)o.bmap, (uint32_t)o.bmap, TAG_LEGACY));
-        if (!MG || !to_peers) {
-            // local replica only.  In a band-sharded phase the owner pushes its band rows to the peers in bulk after
-            // the kernel; the local mask is also written by other GPUs (their boundary items), hence system scope.
-            S.state[flat] = v;
-            if (P.is_new) {
-                S.score[flat] = o.score;
-                mask_insert(S, x, y, S.tiling != 0);
-            }
-        } else {  // an item with a successor on another GPU: the commit goes to every replica right away (peer stores)
-            const MgDev* mg = S.mg;
-            for (int r = 0; r < mg->world; ++r) {
-                mg->state[r][flat] = v;
-                if (P.is_new) {
-                    mg->score[r][flat] = o.score;
-                    mask_insert_at(S, mg->mask[r], mg->mask1[r], true, x, y, S.tiling != 0);
-                }
-            }
-        }
-    }
-    if (P.tr_best) {
-        size_t ti = (size_t)(P.trace_base + si);
-        P.tr_best[ti] = o.kk > 0 ? o.best : -1;
-        P.tr_ncand[ti] = o.ncand; P.tr_nneigh[ti] = o.kk; P.tr_score[ti] = o.score;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Round kernel: every pending item whose predecessors have committed is resolved and committed.
-// ---------------------------------------------------------------------------------------------
-template <bool GUIDED>
-__global__ void __launch_bounds__(CTA_THREADS) k_round(StageDev S, PhaseDev P, uint32_t round) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    RoundSmem& rs = *reinterpret_cast<RoundSmem*>(smem_raw);
-    CtaSmem& sm = rs.c;
-    if (threadIdx.x == 0) { rs.req_cnt = 0; rs.req_min = NONE32; }
-    if (threadIdx.x < ST_COUNT) rs.stat[threadIdx.x] = 0ull;
-    load_luts(S, sm.lut, sm.lutg);
-    unsigned long long st_acc[ST_COUNT];
-#pragma unroll
-    for (int i = 0; i < ST_COUNT; ++i) st_acc[i] = 0ull;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpScratch& ws = sm.ws[warp];
-    const uint32_t npend = P.cnt[round & 3];
-    const uint32_t minprev = P.minpend[round & 3];
-    if (blockIdx.x == 0 && threadIdx.x == 0) { P.cnt[(round + 2) & 3] = 0; P.minpend[(round + 2) & 3] = NONE32; }
-    const uint32_t* pend = P.pending[round & 1];
-    uint32_t* next = P.pending[(round + 1) & 1];
-    const uint32_t nwarps = gridDim.x * WARPS_PER_CTA;
-    for (uint32_t w = blockIdx.x * WARPS_PER_CTA + warp; w < npend; w += nwarps) {
-        long long tr0 = clock64();
-        const uint32_t it = pend[w];
-        const uint32_t pc = P.pred_cnt[it];
-        bool ready = true;
-        if (pc > (uint32_t)PRED_CAP) ready = (it == minprev);  // overflowed list: wait for every lower item
-        else {
-            const uint32_t* pl = P.preds + (size_t)it * PRED_CAP;
-            for (uint32_t base = 0; base < pc; base += 32) {
-                uint32_t j = base + lane;
-                bool nd = false;
-                if (j < pc) nd = *((volatile uint32_t*)(P.done + pl[j])) == 0u;
-                if (__any_sync(FULL, nd)) { ready = false; break; }
-            }
-        }
-        if (!ready) {
-            if (lane == 0) {
-                uint32_t slot = atomicAdd(&rs.req_cnt, 1u);
-                if (slot < (uint32_t)REQ_CAP) rs.req[slot] = it;
-                else next[atomicAdd(P.cnt + ((round + 1) & 3), 1u)] = it;  // staging full: direct append
-                atomicMin(&rs.req_min, it);
-            }
-            continue;
-        }
-        __threadfence();  // acquire: predecessors' commits are visible below
-        st_acc[ST_CYC_READY] += (unsigned long long)(clock64() - tr0);
-        const uint32_t flat = P.item_pixel[it];
-        const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
-        const uint32_t si = P.stage_base + it;
-        ItemOut o;
-        resolve_item<GUIDED>(S, ws, sm.lut, sm.lutg, lane, x, y, P.item_R2[it], P.rand_xy + (size_t)si * S.m,
-                             P.rand_map + (size_t)si * S.m, o);
-        long long tc0 = clock64();
-        if (lane == 0) {
-            commit_item(S, P, si, flat, x, y, o);
-            __threadfence();  // release
-            *((volatile uint32_t*)(P.done + it)) = 1u;
-        }
-        __syncwarp();
-        st_acc[ST_FETCHED] += o.fetched; st_acc[ST_NOMINAL] += o.nominal; st_acc[ST_CANDS] += (unsigned long long)o.ncand;
-        st_acc[ST_ITEMS] += 1ull;
-        st_acc[ST_CYC_KNN] += (unsigned long long)o.c_knn; st_acc[ST_CYC_NEIGH] += (unsigned long long)o.c_neigh;
-        st_acc[ST_CYC_WEIGHT] += (unsigned long long)o.c_weight; st_acc[ST_CYC_SCORE] += (unsigned long long)o.c_score;
-        st_acc[ST_CYC_COMMIT] += (unsigned long long)(clock64() - tc0);
-    }
-    if (lane == 0 && S.counters) {
-#pragma unroll
-        for (int i = 0; i < ST_COUNT; ++i) if (st_acc[i]) atomicAdd(&rs.stat[i], st_acc[i]);
-    }
-    // flush the staged re-queue list with one global atomic per CTA
-    __syncthreads();
-    const uint32_t nreq = min(rs.req_cnt, (uint32_t)REQ_CAP);
-    if (threadIdx.x == 0 && nreq) {
-        rs.req_base = atomicAdd(P.cnt + ((round + 1) & 3), nreq);
-        atomicMin(P.minpend + ((round + 1) & 3), rs.req_min);
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < nreq; i += blockDim.x) next[rs.req_base + i] = rs.req[i];
-    if (S.counters && threadIdx.x < ST_COUNT && rs.stat[threadIdx.x]) atomicAdd(S.counters + threadIdx.x, rs.stat[threadIdx.x]);
-}
-
-
-// ---------------------------------------------------------------------------------------------
-// Persistent dataflow kernel: one launch per phase.  Warps claim queue slots in order; a slot is
-// published when the last predecessor of an item commits.  Grid = co-resident CTAs only.
-// ---------------------------------------------------------------------------------------------
-template <bool GUIDED, bool MG, bool OPAQUE, bool LISTS>
-__global__ void __launch_bounds__(CTA_THREADS, 3) k_flow(StageDev S, PhaseDev P, FlowDev F) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    RoundSmem& rs = *reinterpret_cast<RoundSmem*>(smem_raw);
-    CtaSmem& sm = rs.c;
-    if (threadIdx.x < ST_COUNT) rs.stat[threadIdx.x] = 0ull;
-    load_luts(S, sm.lut, sm.lutg);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpScratch& ws = sm.ws[warp];
-    if (lane < 16) ws.stat[lane] = 0ull;  // statistics live in shared memory, updated by lane 0
-    __syncwarp();
-    const bool pref = !MG && F.stride != 0u;  // fixed-stride successor lists are complete before this kernel starts
-    volatile uint32_t* vq = F.queue;
-    volatile uint32_t* vctl = F.ctl;
-    const bool skip = F.stride && vctl[FC_OVERFLOW];  // incomplete successor lists: do nothing, the host re-plans the phase
-    const uint32_t n_mine = MG ? vctl[FC_NOWN] : P.n;
-    for (; !skip;) {
-        long long tr0 = clock64();
-        uint32_t slot = 0;
-        if (lane == 0) slot = atomicAdd(F.ctl + FC_HEAD, 1u);
-        slot = __shfl_sync(FULL, slot, 0);
-        if (slot >= n_mine) break;
-        uint32_t it = NONE32;
-        if (lane == 0) {
-            unsigned spins = 0, ns = 32;
-            while ((it = vq[slot]) == NONE32) {
-                __nanosleep(ns);
-                if (ns < 256) ns <<= 1;
-                if ((++spins & 1023u) == 0u) {
-                    if (vctl[FC_ABORT]) break;
-                    if (spins > (1u << 22)) { atomicExch(F.ctl + FC_ABORT, 1u); break; }  // watchdog: never hang the device
-                }
-            }
-        }
-        it = __shfl_sync(FULL, it, 0);
-        if (it == NONE32) break;
-        // Acquire.  Every read of mutable data below (state, resolved-set mask) is an L2 load (ld.cg) whose address
-        // depends on `it`, and every predecessor made its commit visible in L2 before it decremented this item's
-        // counter, so single-GPU phases need no fence here -- in particular not __threadfence(), which also
-        // invalidates the SM's whole L1 (CCTL.IVALL) and with it the cached example texels of all resident warps.
-        if (MG) __threadfence();
-        else asm volatile("" ::: "memory");
-        if (lane == 0) ws.stat[ST_CYC_READY] += (unsigned long long)(clock64() - tr0);
-        if (pref) {
-            // the item's successor list is needed only after its commit: start copying it to shared memory now
-            cp_async_u32(&ws.succ_pref[lane], F.succ + (size_t)it * F.stride + lane);
-            if (lane == 0) cp_async_u32(&ws.nsucc_pref, F.nsucc + it);
-            if (lane == 1) cp_async_u32(&ws.nrem_pref, F.succ_cur + it);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        }
-        const uint32_t flat = P.item_pixel[it];
-        const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
-        const uint32_t si = P.stage_base + it;
-        {   // the random candidates are read late (after the neighbourhood is built) and usually come from HBM: pull them in now
-            const char* rx = reinterpret_cast<const char*>(P.rand_xy + (size_t)si * S.m);
-            for (int b = lane * 128; b < S.m * 4; b += 32 * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(rx + b));
-            if (lane == 31) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.rand_map + (size_t)si * S.m));
-        }
-        ItemOut o;
-        const short2* nb0 = nullptr;
-        const short2* predl = nullptr;
-        int npl = 0;
-        int nbk = -1;
-        if (P.nb0) {  // neighbour lists from the phase analysis
-            const uint32_t c = P.npredl[it];
-            if (!P.predl) { nb0 = P.nb0 + (size_t)it * S.k; nbk = (int)c; }  // exact lists "as of" the item's serial time
-            else if (c <= P.predl_stride) { nb0 = P.nb0 + (size_t)it * S.k; predl = P.predl + (size_t)it * P.predl_stride; npl = (int)c; }
-        }
-        if (LISTS && !nb0) {  // the host promised a usable list for every item of this phase
-            if (lane == 0) atomicExch(F.ctl + FC_ABORT, 1u);
-            break;
-        }
-        resolve_item<GUIDED, OPAQUE ? 1 : 0, LISTS>(S, ws, sm.lut, sm.lutg, lane, x, y, P.item_R2[it], P.rand_xy + (size_t)si * S.m,
-                                                    P.rand_map + (size_t)si * S.m, o, nullptr, 0, nb0, predl, npl, nbk);
-        long long tc0 = clock64();
-        if (pref) { asm volatile("cp.async.wait_all;" ::: "memory"); __syncwarp(); }
-        const size_t s0 = F.stride ? (size_t)it * F.stride : (size_t)F.succ_off[it];
-        const size_t s1 = F.stride ? s0 + (pref ? ws.nsucc_pref : F.nsucc[it]) : (size_t)F.succ_off[it + 1];
-        bool remote_succ = false;
-        if (MG) {
-            // Only an item with a successor on another GPU needs its commit ordered at system scope (that successor is
-            // the only remote reader of this pixel during the phase); everybody else's peer stores just have to land
-            // by the end of the phase.  A system-scope fence costs ~15 us, a device-scope one well under 1 us.
-            const MgDev* mg = S.mg;
-            for (size_t e0 = s0; e0 < s1; e0 += 32) {
-                const size_t e = e0 + lane;
-                bool rem = false;
-                if (e < s1) rem = mg_owner_y(mg, (int)(P.item_pixel[F.succ[e]] / (uint32_t)S.W)) != mg->rank;
-                if (__any_sync(FULL, rem)) { remote_succ = true; break; }
-            }
-        }
-        if (lane == 0) {
-            commit_item<MG>(S, P, si, flat, x, y, o, remote_succ);
-            // release: the commit is visible device-wide before any successor counter is touched.  A release store
-            // (MEMBAR.ALL.GPU + store) instead of __threadfence() (MEMBAR.SC.GPU + L1 invalidation, see above).
-            if (MG) { if (remote_succ) __threadfence_system(); else __threadfence(); }
-            else asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(F.ctl + FC_RELEASE + 32 * (blockIdx.x & 31)), "r"(it) : "memory");
-        }
-        __syncwarp();
-        // notify successors; the one that drops a counter to zero publishes the item
-        if (!MG) {
-            // fixed-stride lists: own entries from the front, entries registered by other items from the back
-            const uint32_t n_back = F.stride ? (pref ? ws.nrem_pref : F.succ_cur[it]) : 0u;
-            const size_t n_all = (s1 - s0) + n_back;
-            for (size_t e = lane; e < n_all; e += 32) {
-                uint32_t sc;
-                if (e < s1 - s0) sc = (pref && e < 32) ? ws.succ_pref[lane] : F.succ[s0 + e];
-                else sc = F.succ[s0 + F.stride - 1u - (e - (s1 - s0))];
-                // every predecessor made its commit visible (fence) BEFORE its decrement and consumers read the
-                // mutable state with L2 loads, so the publisher needs no further fence
-                if (atomicSub(F.npred + sc, 1u) == 1u) vq[atomicAdd(F.ctl + FC_TAIL, 1u)] = sc;
-            }
-        } else {
-            const MgDev* mg = S.mg;
-            for (size_t e = s0 + lane; e < s1; e += 32) {
-                uint32_t sc = F.succ[e];
-                const int r = mg_owner_y(mg, (int)(P.item_pixel[sc] / (uint32_t)S.W));  // the successor's owner holds its counter and queue
-                if (r == mg->rank) {  // local successor: device-scope operations (all atomics resolve in this GPU's L2)
-                    if (atomicSub(F.npred + sc, 1u) == 1u) {
-                        __threadfence();
-                        uint32_t pos = atomicAdd(F.ctl + FC_TAIL, 1u);
-                        vq[pos] = sc;
-                    }
-                } else if (atomicSub_system(mg->npred[r] + sc, 1u) == 1u) {
-                    __threadfence_system();
-                    uint32_t pos = atomicAdd_system(mg->ctl[r] + FC_TAIL, 1u);
-                    *((volatile uint32_t*)(mg->queue[r] + pos)) = sc;
-                }
-            }
-        }
-        if (lane == 0) {
-            ws.stat[ST_FETCHED] += o.fetched; ws.stat[ST_NOMINAL] += o.nominal; ws.stat[ST_CANDS] += (unsigned long long)o.ncand;
-            ws.stat[ST_ITEMS] += 1ull;
-            ws.stat[ST_CYC_KNN] += (unsigned long long)o.c_knn; ws.stat[ST_CYC_NEIGH] += (unsigned long long)o.c_neigh;
-            ws.stat[ST_CYC_WEIGHT] += (unsigned long long)o.c_weight; ws.stat[ST_CYC_SCORE] += (unsigned long long)o.c_score;
-            ws.stat[ST_CYC_COMMIT] += (unsigned long long)(clock64() - tc0);
-        }
-        __syncwarp();
-    }
-    if (lane == 0 && S.counters) {
-        for (int i = 0; i < ST_COUNT; ++i) if (ws.stat[i]) atomicAdd(&rs.stat[i], ws.stat[i]);
-    }
-    __syncthreads();
-    if (S.counters && threadIdx.x < ST_COUNT && rs.stat[threadIdx.x]) atomicAdd(S.counters + threadIdx.x, rs.stat[threadIdx.x]);
-}
-
-// Strictly serial execution of items [0, n) by one warp: the start of a synthesis, where every item
-// depends on all earlier ones (the reference itself is serial there, ms.rs:815).
-template <bool GUIDED>
-__global__ void __launch_bounds__(CTA_THREADS) k_serial(StageDev S, PhaseDev P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    RoundSmem& rs = *reinterpret_cast<RoundSmem*>(smem_raw);
-    CtaSmem& sm = rs.c;
-    load_luts(S, sm.lut, sm.lutg);
-    if (threadIdx.x >= 32) return;
-    const int lane = threadIdx.x;
-    WarpScratch& ws = sm.ws[0];
-    unsigned long long fetched = 0, nominal = 0, cands = 0;
-    // While the whole resolved set fits the key buffer, keep it as a point list (read once from the mask,
-    // extended with every commit) instead of scanning the mask for every item.
-    short2* pts = reinterpret_cast<short2*>(rs.req);  // the re-queue staging area is unused by this kernel
-    const bool use_list = S.n_points_max <= (uint32_t)KBUF;
-    int npts = 0;
-    if (use_list) {
-        if (lane == 0) ws.cnt = 0;
-        __syncwarp();
-        uint32_t extw = (uint32_t)(S.wpr * 32), exth = (uint32_t)S.mrows;
-        npts = min((int)scan_disc<true>(S, ws, lane, 0, 0, extw * extw + exth * exth), KBUF);
-        for (int i = lane; i < npts; i += 32) {
-            unsigned long long key = ws.u.keys[i];
-            pts[i] = make_short2((short)((int)(key & 0xFFFF) - 32768), (short)((int)((key >> 16) & 0xFFFF) - 32768));
-        }
-        __syncwarp();
-    }
-    for (uint32_t it = 0; it < P.n; ++it) {
-        const uint32_t flat = P.item_pixel[it];
-        const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
-        const uint32_t si = P.stage_base + it;
-        ItemOut o;
-        resolve_item<GUIDED>(S, ws, sm.lut, sm.lutg, lane, x, y, R2_INF, P.rand_xy + (size_t)si * S.m, P.rand_map + (size_t)si * S.m, o,
-                             use_list ? pts : nullptr, npts);
-        if (lane == 0) {
-            commit_item(S, P, si, flat, x, y, o);
-            if (use_list && P.is_new && o.kk > 0) {  // same insertions as mask_insert (ms.rs:306-327)
-                int q = npts;
-                pts[q++] = make_short2((short)x, (short)y);
-                if (S.tiling) {
-                    if (x < S.x_l) pts[q++] = make_short2((short)(x + S.W), (short)y);
-                    else if (x > S.x_r) pts[q++] = make_short2((short)(x - S.W), (short)y);
-                    if (y < S.y_b) pts[q++] = make_short2((short)x, (short)(y + S.H));
-                    else if (y > S.y_t) pts[q++] = make_short2((short)x, (short)(y - S.H));
-                }
-            }
-            __threadfence();
-        }
-        if (use_list && P.is_new && o.kk > 0) {
-            npts += 1;
-            if (S.tiling) { npts += (x < S.x_l || x > S.x_r) ? 1 : 0; npts += (y < S.y_b || y > S.y_t) ? 1 : 0; }
-        }
-        __syncwarp();
-        fetched += o.fetched; nominal += o.nominal; cands += (unsigned long long)o.ncand;
-    }
-    if (lane == 0 && S.counters) {
-        atomicAdd(S.counters + ST_FETCHED, fetched); atomicAdd(S.counters + ST_NOMINAL, nominal);
-        atomicAdd(S.counters + ST_CANDS, cands); atomicAdd(S.counters + ST_ITEMS, (unsigned long long)P.n);
-    }
-}
-
 // Frozen-snapshot evaluation (test harness): resolve without committing.
 template <bool GUIDED>
 __global__ void __launch_bounds__(CTA_THREADS) k_eval_items(StageDev S, uint32_t n, const uint32_t* pixel_flat,
@@ -1408,457 +906,10 @@ __global__ void __launch_bounds__(CTA_THREADS) k_eval_items(StageDev S, uint32_t
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Dependency analysis
-// ---------------------------------------------------------------------------------------------
-// Conflict radius of every item: distance^2 of its k-th nearest resolved point at phase start.
-__global__ void __launch_bounds__(CTA_THREADS) k_radius(StageDev S, PhaseDev P, FlowDev F) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    KnnScratch* all_ws = reinterpret_cast<KnnScratch*>(smem_raw);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    KnnScratch& ws = all_ws[warp];
-    const uint32_t nwarps = gridDim.x * WARPS_PER_CTA;
-    for (uint32_t it = blockIdx.x * WARPS_PER_CTA + warp; it < P.n; it += nwarps) {
-        const uint32_t flat = P.item_pixel[it];
-        const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
-        if (lane == 0) {  // local bookkeeping for EVERY item (the pending-index map and the queue are per replica)
-            P.pmap[flat] = it;
-            if (F.npred) {
-                F.queue[it] = NONE32;
-                if (it == 0) F.nsucc[P.n] = 0;  // F.ctl is zeroed by the host before this kernel
-            }
-        }
-        if (S.mg && mg_owner_y(S.mg, y) != S.mg->rank) continue;  // band-sharded: the owner computes the radius
-        uint32_t r2;
-        knn_search<true>(S, ws, lane, x, y, R2_INF, &r2);
-        if (P.nb0) {
-            if (r2 != R2_INF) for (int j = lane; j < S.k; j += 32) P.nb0[(size_t)it * S.k + j] = ws.off[j];
-            if (lane == 0) P.npredl[it] = r2 != R2_INF ? 0u : PREDL_UNUSABLE;
-        }
-        if (lane == 0) {
-            if (!S.mg) P.item_R2[it] = r2;
-            else {
-                for (int r = 0; r < S.mg->world; ++r) S.mg->item_R2[r][it] = r2;
-                atomicAdd(F.ctl + FC_NOWN, 1u);
-            }
-            P.pred_cnt[it] = 0;
-            P.done[it] = 0;
-            P.pending[0][it] = it;
-            if (F.npred) { F.npred[it] = 0; F.nsucc[it] = 0; F.succ_cur[it] = 0; }
-        }
-        __syncwarp();
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Stage-wide analysis of the NEW pixels (single GPU).  Every item's neighbourhood is computed exactly "as of" its
-// own serial time -- the resolved set plus the stage's new pixels with a lower index -- so the resolve kernel needs
-// no search, and the dependency graph is the plain read-after-write relation (an item waits for the new pixels in
-// its own list): the whole stage is one dataflow phase, no epochs.
-// ---------------------------------------------------------------------------------------------
-__global__ void k_pmap_fill(PhaseDev P) {
-    uint32_t it = blockIdx.x * blockDim.x + threadIdx.x;
-    if (it < P.n) P.pmap[P.item_pixel[it]] = it;
-}
 __global__ void k_mask_insert_flat_at(StageDev S, uint32_t* mask, uint32_t* mask1, const uint32_t* flat, uint32_t n, int mirrors) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     mask_insert_at(S, mask, mask1, false, (int)(flat[i] % (uint32_t)S.W), (int)(flat[i] / (uint32_t)S.W), mirrors != 0);
-}
-__global__ void __launch_bounds__(CTA_THREADS) k_lists_timed(StageDev S, PhaseDev P, FlowDev F, TimeFilter T0, uint32_t n_before) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    KnnScratch* all_ws = reinterpret_cast<KnnScratch*>(smem_raw);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    KnnScratch& ws = all_ws[warp];
-    const uint32_t nwarps = gridDim.x * WARPS_PER_CTA;
-    const double area = (double)S.W * (double)S.H;
-    for (uint32_t it = blockIdx.x * WARPS_PER_CTA + warp; it < P.n; it += nwarps) {
-        const uint32_t flat = P.item_pixel[it];
-        const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
-        TimeFilter T = T0;
-        T.idx = it; T.idx_cmp = it;
-        const double npts = (double)n_before + (double)it;
-        T.hint = (uint32_t)fmin(fmax(1.5 * (double)S.k * area / (3.14159265358979 * fmax(npts, 1.0)), 8.0), 4.0e9);
-        T.n_points_max = (uint32_t)fmin((S.tiling ? 3.0 : 1.0) * npts, 4.0e9);
-        uint32_t r2;
-        const int kk = knn_search<true>(S, ws, lane, x, y, R2_INF, &r2, &T);
-        for (int j = lane; j < kk; j += 32) P.nb0[(size_t)it * S.k + j] = ws.off[j];
-        if (lane == 0) {
-            P.npredl[it] = (uint32_t)kk;
-            P.item_R2[it] = r2;
-            F.queue[it] = NONE32;
-            F.npred[it] = 0; F.nsucc[it] = 0; F.succ_cur[it] = 0;
-            if (it == 0) F.nsucc[P.n] = 0;
-        }
-        __syncwarp();
-    }
-}
-// edges j -> it for every new pixel j (of this stage, lower index) in the list of `it`.  PASS 0 counts, PASS 1 fills the CSR lists.
-template <int PASS>
-__global__ void __launch_bounds__(CTA_THREADS) k_edges_lists(StageDev S, PhaseDev P, FlowDev F) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t nwarps = gridDim.x * WARPS_PER_CTA;
-    for (uint32_t it = blockIdx.x * WARPS_PER_CTA + warp; it < P.n; it += nwarps) {
-        const uint32_t flat = P.item_pixel[it];
-        const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
-        const int kk = (int)P.npredl[it];
-        uint32_t cnt = 0;
-        for (int e = lane; e < kk; e += 32) {
-            const short2 o = P.nb0[(size_t)it * S.k + e];
-            int qx = x + o.x, qy = y + o.y;
-            if (S.tiling) { qx = imod(qx, S.W); qy = imod(qy, S.H); }
-            const uint32_t j = P.pmap[(size_t)qy * S.W + qx];
-            if (j < it) {  // NONE32 (a pixel resolved before this stage) is never below an index
-                if (PASS == 0) { atomicAdd(F.nsucc + j, 1u); ++cnt; }
-                else { const uint32_t slot = atomicAdd(F.succ_cur + j, 1u); F.succ[(size_t)F.succ_off[j] + slot] = it; }
-            }
-        }
-        if (PASS == 0) {
-            cnt = __reduce_add_sync(FULL, cnt);
-            if (lane == 0) F.npred[it] = cnt;
-        }
-    }
-}
-
-__global__ void k_pmap_clear(PhaseDev P) {
-    uint32_t it = blockIdx.x * blockDim.x + threadIdx.x;
-    if (it < P.n) P.pmap[P.item_pixel[it]] = NONE32;
-}
-
-__device__ __forceinline__ void pred_visit(const StageDev& S, const PhaseDev& P, uint32_t it, uint32_t R2i, int qx, int qy, uint32_t D) {
-    if (S.tiling) { qx = imod(qx, S.W); qy = imod(qy, S.H); }  // conservative: treat the canvas as a torus
-    else if ((unsigned)qx >= (unsigned)S.W || (unsigned)qy >= (unsigned)S.H) return;
-    uint32_t j = P.pmap[(size_t)qy * S.W + qx];
-    if (j == NONE32 || j == it) return;
-    if (j < it) {
-        uint32_t slot = atomicAdd(P.pred_cnt + it, 1u);
-        if (slot < (uint32_t)PRED_CAP) P.preds[(size_t)it * PRED_CAP + slot] = j;
-    } else if (D > P.item_R2[j]) {  // j does not see `it` from its side: register the edge for it
-        uint32_t slot = atomicAdd(P.pred_cnt + j, 1u);
-        if (slot < (uint32_t)PRED_CAP) P.preds[(size_t)j * PRED_CAP + slot] = it;
-    }
-    (void)R2i;
-}
-
-// Edges i -> j (i < j) for every pair with dist^2 <= max(R_i^2, R_j^2), found by scanning the dense
-// pending-index map over each item's own disc.
-__global__ void __launch_bounds__(CTA_THREADS) k_preds_scan(StageDev S, PhaseDev P) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t nwarps = gridDim.x * WARPS_PER_CTA;
-    for (uint32_t it = blockIdx.x * WARPS_PER_CTA + warp; it < P.n; it += nwarps) {
-        const uint32_t flat = P.item_pixel[it];
-        const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
-        const uint32_t R2 = P.item_R2[it];
-        if (R2 <= (uint32_t)S.RT2) {
-            int limit = (int)__ldg(S.cntLE + R2);
-            for (int idx = lane; idx < limit; idx += 32) {
-                short2 o = __ldg(S.spiral + idx);
-                pred_visit(S, P, it, R2, x + o.x, y + o.y, (uint32_t)(o.x * o.x + o.y * o.y));
-            }
-        } else {
-            int rmaxx = S.tiling ? S.W / 2 : S.W, rmaxy = S.tiling ? S.H / 2 : S.H;
-            int r = isqrt_u32(R2);
-            int ry = min(r, rmaxy);
-            for (int dy = -ry; dy <= ry; ++dy) {
-                int w = min(isqrt_u32(R2 - (uint32_t)(dy * dy)), rmaxx);
-                for (int dx = -w + lane; dx <= w; dx += 32)
-                    pred_visit(S, P, it, R2, x + dx, y + dy, (uint32_t)(dx * dx + dy * dy));
-            }
-        }
-    }
-}
-
-// Small phases: all-pairs test.
-__global__ void __launch_bounds__(CTA_THREADS) k_preds_pairs(StageDev S, PhaseDev P) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned lt = (1u << lane) - 1u;
-    const uint32_t nwarps = gridDim.x * WARPS_PER_CTA;
-    for (uint32_t it = blockIdx.x * WARPS_PER_CTA + warp; it < P.n; it += nwarps) {
-        const uint32_t flat = P.item_pixel[it];
-        const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
-        const uint32_t R2 = P.item_R2[it];
-        uint32_t cnt = 0;
-        for (uint32_t base = 0; base < it; base += 32) {
-            uint32_t j = base + lane;
-            bool edge = false;
-            if (j < it) {
-                uint32_t fj = P.item_pixel[j];
-                int dx = abs((int)(fj % (uint32_t)S.W) - x), dy = abs((int)(fj / (uint32_t)S.W) - y);
-                if (S.tiling) { dx = min(dx, S.W - dx); dy = min(dy, S.H - dy); }
-                unsigned long long D = (unsigned long long)dx * dx + (unsigned long long)dy * dy;
-                uint32_t Rm = max(R2, P.item_R2[j]);
-                edge = (Rm == R2_INF) || (D <= (unsigned long long)Rm);
-            }
-            unsigned b = __ballot_sync(FULL, edge);
-            if (edge) {
-                uint32_t slot = cnt + __popc(b & lt);
-                if (slot < (uint32_t)PRED_CAP) P.preds[(size_t)it * PRED_CAP + slot] = j;
-            }
-            cnt += __popc(b);
-        }
-        if (lane == 0) P.pred_cnt[it] = cnt;
-    }
-}
-
-
-// ---- CSR dependency graph for the dataflow kernel: edge a -> b (a < b) for every pair with
-// dist^2 <= max(R_a^2, R_b^2).  PASS 0 counts, PASS 1 fills (after an exclusive scan of nsucc). ----
-template <int PASS>
-__device__ __forceinline__ void edge_emit(const FlowDev& F, uint32_t a, uint32_t b) {
-    if (PASS == 0) { atomicAdd(F.nsucc + a, 1u); atomicAdd(F.npred + b, 1u); }
-    else if (PASS == 1) { uint32_t slot = atomicAdd(F.succ_cur + a, 1u); F.succ[F.succ_off[a] + slot] = b; }
-    else {  // PASS 2: single pass into fixed-stride lists; an overflow makes the host redo the phase with the CSR passes
-        uint32_t slot = atomicAdd(F.nsucc + a, 1u);
-        if (slot < F.stride) F.succ[(size_t)a * F.stride + slot] = b;
-        else F.ctl[FC_OVERFLOW] = 1u;
-        atomicAdd(F.npred + b, 1u);
-    }
-}
-// band-sharded variant: the successor list lives with the owner of a, the counter with the owner of b
-__device__ __forceinline__ void edge_emit_mg(const MgDev* mg, const FlowDev& F, uint32_t a, int ra, uint32_t b, int rb) {
-    uint32_t slot = atomicAdd_system(mg->nsucc[ra] + a, 1u);
-    if (slot < F.stride) mg->succ[ra][(size_t)a * F.stride + slot] = b;
-    else mg->ctl[ra][FC_OVERFLOW] = 1u;
-    atomicAdd_system(mg->npred[rb] + b, 1u);
-}
-template <int PASS>
-__device__ __forceinline__ void edge_visit(const StageDev& S, const PhaseDev& P, const FlowDev& F, uint32_t it, int qx, int qy, uint32_t D) {
-    if (S.tiling) { qx = imod(qx, S.W); qy = imod(qy, S.H); }  // conservative: treat the canvas as a torus
-    else if ((unsigned)qx >= (unsigned)S.W || (unsigned)qy >= (unsigned)S.H) return;
-    uint32_t j = P.pmap[(size_t)qy * S.W + qx];
-    if (j == NONE32 || j == it) return;
-    if (S.mg) {  // `it` is owned by this rank; j's owner follows from its row
-        const int rj = mg_owner_y(S.mg, qy), ri = S.mg->rank;
-        if (j < it) edge_emit_mg(S.mg, F, j, rj, it, ri);
-        else if (D > P.item_R2[j]) edge_emit_mg(S.mg, F, it, ri, j, rj);
-        return;
-    }
-    if (j < it) edge_emit<PASS>(F, j, it);                       // `it` sees j from its own disc
-    else if (D > P.item_R2[j]) edge_emit<PASS>(F, it, j);        // j does not see `it`: registered from this side
-}
-// A tiling canvas so small that one disc of the dense walk can meet the same pixel through two wrapped offsets while
-// the (clipped) large-radius walk meets it once: the split bookkeeping below needs both sides to agree, so such
-// canvases keep the one-sided registration (and no neighbour lists, see run_phase_flow).
-__device__ __forceinline__ bool tiny_torus(const StageDev& S) { return S.tiling && (S.W < 100 || S.H < 100); }
-// the bookkeeping scheme of the single-GPU fixed-stride pass (see k_edges_scan) for one visited pixel, plain atomics
-__device__ __forceinline__ void edge_visit_own(const StageDev& S, const PhaseDev& P, const FlowDev& F, uint32_t it, int qx, int qy, uint32_t D) {
-    if (S.tiling) { qx = imod(qx, S.W); qy = imod(qy, S.H); }
-    else if ((unsigned)qx >= (unsigned)S.W || (unsigned)qy >= (unsigned)S.H) return;
-    const uint32_t j = P.pmap[(size_t)qy * S.W + qx];
-    if (j == NONE32 || j == it) return;
-    const bool blind = D > P.item_R2[j];
-    if (j < it) {
-        atomicAdd(F.npred + it, 1u);
-        if (blind) {  // remote entries fill j's list from the back
-            const uint32_t back = atomicAdd(F.succ_cur + j, 1u);
-            if (back < F.stride) F.succ[(size_t)j * F.stride + (F.stride - 1u - back)] = it;
-            else F.ctl[FC_OVERFLOW] = 1u;
-        }
-    } else {
-        const uint32_t slot = atomicAdd(F.nsucc + it, 1u);
-        if (slot < F.stride) F.succ[(size_t)it * F.stride + slot] = j;
-        else F.ctl[FC_OVERFLOW] = 1u;
-        if (blind) atomicAdd(F.npred + j, 1u);
-    }
-}
-template <int PASS>
-__global__ void __launch_bounds__(CTA_THREADS) k_edges_scan(StageDev S, PhaseDev P, FlowDev F) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t nwarps = gridDim.x * WARPS_PER_CTA;
-    for (uint32_t it = blockIdx.x * WARPS_PER_CTA + warp; it < P.n; it += nwarps) {
-        const uint32_t flat = P.item_pixel[it];
-        const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
-        if (S.mg && mg_owner_y(S.mg, y) != S.mg->rank) continue;  // band-sharded: every rank scans its own items
-        const uint32_t R2 = P.item_R2[it];
-        if (R2 <= (uint32_t)S.RT2) {
-            // row-major walk over the bounding square of the disc: consecutive lanes read consecutive pixels of
-            // the pending-index map (coalesced), unlike the distance-ordered spiral table
-            const int r = isqrt_u32(R2), side = 2 * r + 1, cells = side * side;
-            if (PASS == 2 && !S.mg && !tiny_torus(S)) {
-                // Single-GPU fixed-stride build.  Whoever SEES the other end of an edge does its own half of the
-                // bookkeeping: the lower item appends the higher one to the FRONT of its own successor list (no
-                // atomics: only this warp writes there), the higher item counts the lower one in its own predecessor
-                // counter (one atomic per item).  Only the half that belongs to an item which does NOT see this one
-                // (its radius is smaller than the distance) needs a remote atomic; remote successor entries fill the
-                // list from the BACK (counter succ_cur), k_seed_queue flags a list whose two ends met.
-                uint32_t n_in = 0, n_pl = 0, n_own = 0;
-                const bool want_pl = P.nb0 != nullptr && P.is_new != 0u;
-                const uint32_t inv = 0xFFFFFFFFu / (uint32_t)side + 1u;  // c / side == __umulhi(c, inv) while c * side < 2^32
-                const unsigned lt = (1u << lane) - 1u;
-                uint32_t* my_succ = F.succ + (size_t)it * F.stride;
-                // Redo phase without tiling: every resolved point is a pixel of the canvas, so the items inside the disc
-                // are found among the k nearest stored by k_radius (those closer than the k-th) plus the pixels at exactly
-                // the k-th distance (a short run of the spiral table) -- k + a few lookups instead of (2r+1)^2.
-                const bool from_list = P.nb0 != nullptr && P.is_new == 0u && !S.tiling;
-                const int ring0 = from_list ? (R2 ? (int)__ldg(S.cntLE + R2 - 1u) : 0) : 0;
-                const int n_visit = from_list ? S.k + ((int)__ldg(S.cntLE + R2) - ring0) : cells;
-                for (int c0 = 0; c0 < n_visit; c0 += 64) {  // two chunks per turn: their loads overlap
-                    uint32_t j[2], D[2], r2j[2];
-                    int dxs[2], dys[2];
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const int c = c0 + 32 * q + lane;
-                        j[q] = NONE32; D[q] = 0; r2j[q] = 0; dxs[q] = 0; dys[q] = 0;
-                        if (c < n_visit) {
-                            int dx, dy;
-                            bool take;
-                            if (from_list) {
-                                const short2 o = c < S.k ? P.nb0[(size_t)it * S.k + c] : __ldg(S.spiral + ring0 + (c - S.k));
-                                dx = o.x; dy = o.y;
-                                D[q] = (uint32_t)(dx * dx + dy * dy);
-                                take = c < S.k ? D[q] < R2 : true;  // list entries at exactly R2 are covered by the ring
-                            } else {
-                                const int row = (int)__umulhi((uint32_t)c, inv);
-                                dy = row - r; dx = c - row * side - r;
-                                D[q] = (uint32_t)(dx * dx + dy * dy);
-                                take = D[q] <= R2;
-                            }
-                            dxs[q] = dx; dys[q] = dy;
-                            if (take) {
-                                int qx = x + dx, qy = y + dy;
-                                bool in = true;
-                                if (S.tiling) { qx = imod(qx, S.W); qy = imod(qy, S.H); }
-                                else in = (unsigned)qx < (unsigned)S.W && (unsigned)qy < (unsigned)S.H;
-                                if (in) j[q] = P.pmap[(size_t)qy * S.W + qx];
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        if (j[q] == it) j[q] = NONE32;
-                        if (j[q] != NONE32) r2j[q] = P.item_R2[j[q]];
-                    }
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const bool found = j[q] != NONE32;
-                        const bool lower = found && j[q] < it, higher = found && !lower;
-                        const bool blind = found && D[q] > r2j[q];  // the other item does not see this one
-                        if (lower) {
-                            ++n_in;
-                            if (blind) {  // j cannot know about this successor: put it on j's list from here
-                                const uint32_t back = atomicAdd(F.succ_cur + j[q], 1u);
-                                if (back < F.stride) F.succ[(size_t)j[q] * F.stride + (F.stride - 1u - back)] = it;
-                                else F.ctl[FC_OVERFLOW] = 1u;
-                            }
-                        }
-                        if (want_pl) {
-                            // a lower item whose pixel (or mirror copy) will be a point inside this disc
-                            const bool pl = lower && point_exists_at(S, x + dxs[q], y + dys[q]);
-                            const uint32_t bpl = __ballot_sync(FULL, pl);
-                            if (pl) {
-                                const uint32_t slot = n_pl + __popc(bpl & lt);
-                                if (slot < P.predl_stride) P.predl[(size_t)it * P.predl_stride + slot] = make_short2((short)dxs[q], (short)dys[q]);
-                            }
-                            n_pl += __popc(bpl);
-                        }
-                        const uint32_t bout = __ballot_sync(FULL, higher);
-                        if (higher) {
-                            const uint32_t slot = n_own + __popc(bout & lt);
-                            if (slot < F.stride) my_succ[slot] = j[q];
-                            else F.ctl[FC_OVERFLOW] = 1u;
-                            if (blind) atomicAdd(F.npred + j[q], 1u);  // j does not count this predecessor itself
-                        }
-                        n_own += __popc(bout);
-                    }
-                }
-                if (lane == 0) F.nsucc[it] = n_own;
-                n_in = __reduce_add_sync(FULL, n_in);
-                if (lane == 0 && n_in) atomicAdd(F.npred + it, n_in);
-                if (want_pl && lane == 0) P.npredl[it] = n_pl;
-                continue;
-            }
-            const bool want_pl_mg = PASS == 2 && S.mg != nullptr && P.nb0 != nullptr && P.is_new != 0u;
-            for (int c = lane; c < cells; c += 32) {
-                const int dy = c / side - r, dx = c % side - r;
-                const uint32_t D = (uint32_t)(dx * dx + dy * dy);
-                if (D <= R2) {
-                    edge_visit<PASS>(S, P, F, it, x + dx, y + dy, D);
-                    if (want_pl_mg) {  // band-sharded phase: in-disc predecessor list of this (owned) item
-                        int qx = x + dx, qy = y + dy;
-                        bool in = true;
-                        if (S.tiling) { qx = imod(qx, S.W); qy = imod(qy, S.H); }
-                        else in = (unsigned)qx < (unsigned)S.W && (unsigned)qy < (unsigned)S.H;
-                        if (in && P.pmap[(size_t)qy * S.W + qx] < it && point_exists_at(S, x + dx, y + dy)) {  // NONE32 is never below an index
-                            const uint32_t slot = atomicAdd(P.npredl + it, 1u);
-                            if (slot < P.predl_stride) P.predl[(size_t)it * P.predl_stride + slot] = make_short2((short)dx, (short)dy);
-                        }
-                    }
-                }
-            }
-        } else {
-            int rmaxx = S.tiling ? S.W / 2 : S.W, rmaxy = S.tiling ? S.H / 2 : S.H;
-            int r = isqrt_u32(R2);
-            int ry = min(r, rmaxy);
-            // in-disc predecessor list: not for the torus walk (it does not enumerate the mirror copies) and not for R2_INF
-            const bool want_pl = PASS == 2 && P.nb0 != nullptr && P.is_new != 0u;
-            const bool can_pl = want_pl && !S.tiling && R2 != R2_INF;
-            if (want_pl && !can_pl && lane == 0) P.npredl[it] = PREDL_UNUSABLE;
-            for (int dy = -ry; dy <= ry; ++dy) {
-                int w = min(isqrt_u32(R2 - (uint32_t)(dy * dy)), rmaxx);
-                for (int dx = -w + lane; dx <= w; dx += 32) {
-                    if (PASS == 2 && !S.mg && !tiny_torus(S)) edge_visit_own(S, P, F, it, x + dx, y + dy, (uint32_t)(dx * dx + dy * dy));
-                    else edge_visit<PASS>(S, P, F, it, x + dx, y + dy, (uint32_t)(dx * dx + dy * dy));
-                    if (can_pl) {
-                        const int qx = x + dx, qy = y + dy;
-                        if ((unsigned)qx < (unsigned)S.W && (unsigned)qy < (unsigned)S.H) {
-                            const uint32_t j = P.pmap[(size_t)qy * S.W + qx];
-                            if (j < it) {  // NONE32 is never below an item index
-                                const uint32_t slot = atomicAdd(P.npredl + it, 1u);
-                                if (slot < P.predl_stride) P.predl[(size_t)it * P.predl_stride + slot] = make_short2((short)dx, (short)dy);
-                            }
-                        }
-                    }
-                }
-            }
-        }
-    }
-}
-template <int PASS>
-__global__ void __launch_bounds__(CTA_THREADS) k_edges_pairs(StageDev S, PhaseDev P, FlowDev F) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t nwarps = gridDim.x * WARPS_PER_CTA;
-    for (uint32_t it = blockIdx.x * WARPS_PER_CTA + warp; it < P.n; it += nwarps) {
-        const uint32_t flat = P.item_pixel[it];
-        const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
-        const uint32_t R2 = P.item_R2[it];
-        const bool want_pl = PASS == 2 && !S.mg && P.nb0 != nullptr && P.is_new != 0u;
-        const bool can_pl = want_pl && !S.tiling && R2 != R2_INF;
-        uint32_t n_pl = 0;
-        for (uint32_t base = 0; base < it; base += 32) {
-            uint32_t j = base + lane;
-            bool pl = false; short2 plo = make_short2(0, 0);
-            if (j < it) {
-                uint32_t fj = P.item_pixel[j];
-                const int sdx = (int)(fj % (uint32_t)S.W) - x, sdy = (int)(fj / (uint32_t)S.W) - y;
-                int dx = abs(sdx), dy = abs(sdy);
-                if (S.tiling) { dx = min(dx, S.W - dx); dy = min(dy, S.H - dy); }
-                unsigned long long D = (unsigned long long)dx * dx + (unsigned long long)dy * dy;
-                uint32_t Rm = max(R2, P.item_R2[j]);
-                if ((Rm == R2_INF) || (D <= (unsigned long long)Rm)) edge_emit<PASS>(F, j, it);
-                if (can_pl && D <= (unsigned long long)R2) { pl = true; plo = make_short2((short)sdx, (short)sdy); }
-            }
-            if (can_pl) {
-                const uint32_t bpl = __ballot_sync(FULL, pl);
-                if (pl) {
-                    const uint32_t slot = n_pl + __popc(bpl & ((1u << lane) - 1u));
-                    if (slot < P.predl_stride) P.predl[(size_t)it * P.predl_stride + slot] = plo;
-                }
-                n_pl += __popc(bpl);
-            }
-        }
-        if (want_pl && lane == 0) P.npredl[it] = can_pl ? n_pl : PREDL_UNUSABLE;
-    }
-}
-__global__ void k_seed_queue(StageDev S, PhaseDev P, FlowDev F) {
-    uint32_t it = blockIdx.x * blockDim.x + threadIdx.x;
-    if (it >= P.n) return;
-    if (S.mg) {  // band-sharded: own items only; the tail counter is also advanced by other GPUs -> system scope
-        if (mg_owner_y(S.mg, (int)(P.item_pixel[it] / (uint32_t)S.W)) != S.mg->rank) return;
-        if (F.npred[it] == 0u) F.queue[atomicAdd_system(F.ctl + FC_TAIL, 1u)] = it;
-        return;
-    }
-    if (F.stride && F.nsucc[it] + F.succ_cur[it] > F.stride) F.ctl[FC_OVERFLOW] = 1u;  // the two ends of the successor list met
-    if (F.npred[it] == 0u) F.queue[atomicAdd(F.ctl + FC_TAIL, 1u)] = it;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1867,8 +918,7 @@ __global__ void k_seed_queue(StageDev S, PhaseDev P, FlowDev F) {
 // stream depends only on (stage seed, work-item index) so a whole stage is generated ahead of the rounds.
 // ---------------------------------------------------------------------------------------------
 __global__ void k_rand_candidates(const DevEx* ex, int n_ex, int m, uint64_t seed_base, uint32_t n,
-                                  uint32_t* rand_xy, uint8_t* rand_map, const uint32_t* own_pixel = nullptr, int W = 1,
-                                  int band_h = 1, int rank = 0, int world = 1, const uint32_t* tidx = nullptr) {
+                                  uint32_t* rand_xy, uint8_t* rand_map, const uint32_t* tidx = nullptr) {
     // each thread draws the m candidates of one item into shared memory; the block then writes its (contiguous)
     // slice of the two arrays with coalesced stores
     extern __shared__ __align__(16) unsigned char rc_smem[];
@@ -1877,11 +927,7 @@ __global__ void k_rand_candidates(const DevEx* ex, int n_ex, int m, uint64_t see
     uint8_t* sown = smap + (size_t)blockDim.x * m;                           // [blockDim.x]
     const uint32_t it0 = blockIdx.x * blockDim.x;
     const uint32_t it = it0 + threadIdx.x;
-    bool mine = it < n;
-    if (mine && own_pixel) {  // band-sharded phase: only the owner of the item needs its candidates
-        int r = (int)(own_pixel[it] / (uint32_t)W) / band_h;
-        mine = (r < world - 1 ? r : world - 1) == rank;
-    }
+    const bool mine = it < n;
     sown[threadIdx.x] = mine ? 1 : 0;
     if (mine) {
         // tidx: the items are a subset of the stage (band-sharded chunk); their stage indices select the random streams
@@ -2007,7 +1053,6 @@ __global__ void k_recolour(StageDev S) {
 __global__ void k_frame_levels(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int w, int h, int levels, uint32_t* flag) {
     const int pw = w + 2 * EX_PAD, ph = h + 2 * EX_PAD;
     const size_t per = (size_t)pw * ph, n = per * (size_t)levels;
-    bool bad = false;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int l = (int)(i / per);
         const size_t r = i - (size_t)l * per;
@@ -2019,7 +1064,6 @@ __global__ void k_frame_levels(const uint32_t* __restrict__ src, uint32_t* __res
         }
         dst[i] = v;
     }
-    (void)bad;
 }
 __global__ void k_alpha_check(const uint32_t* __restrict__ src, size_t n, size_t per_level, uint32_t* flag) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
