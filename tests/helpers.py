@@ -24,7 +24,8 @@ class Case:
     """One synthesis configuration, expressed in the terms of Session::builder()."""
 
     def __init__(self, name, out_w, out_h, ex_sizes, seed=0, k=50, m=50, stages=5, p=0.5, cauchy=1.0, alpha=0.8,
-                 tiling=False, random_init=0, inpaint=False, methods=None, sample_masks=False, guided=False, tex_seed=1):
+                 tiling=False, random_init=0, inpaint=False, methods=None, sample_masks=False, guided=False, tex_seed=1,
+                 guide_sizes=None):
         self.name = name
         self.out_w, self.out_h = out_w, out_h
         self.ex_sizes = ex_sizes
@@ -33,6 +34,7 @@ class Case:
         self.methods = methods
         self.sample_masks = sample_masks
         self.guided = guided
+        self.guide_sizes = guide_sizes   # example-guide sizes when they differ from the examples' (the reference keeps them as loaded)
         self.tex_seed = tex_seed
         self._built = False
 
@@ -65,7 +67,7 @@ class Case:
             tg[..., 1] = tg[..., 0]
             tg[..., 2] = tg[..., 0]
             exg = []
-            for i, (w, h) in enumerate(self.ex_sizes):
+            for i, (w, h) in enumerate(self.guide_sizes or self.ex_sizes):
                 gimg = synth_texture(w, h, self.tex_seed + 200 + i)
                 gimg[..., 1] = gimg[..., 0]
                 gimg[..., 2] = gimg[..., 0]
@@ -169,4 +171,12 @@ def edge_cases():
         Case("k100_m100", 64, 64, [(40, 40)], seed=9, k=100, m=100, stages=3),
         Case("out_smaller_than_ex", 24, 24, [(96, 96)], seed=10),
         Case("tiling_tiny", 20, 20, [(16, 16)], seed=11, tiling=True),
+        # q14: cauchy_dispersion = 0 passes the reference's validation (session.rs:451); x / 0 gives inf / NaN cost tables
+        Case("cauchy0", 40, 40, [(24, 24)], seed=12, cauchy=0.0, stages=3),
+        Case("cauchy0_multi", 36, 36, [(24, 24), (20, 28)], seed=13, cauchy=0.0, stages=2, k=12, m=9),
+        # q13: mostly locked inpaint + guides drives adaptive_alpha negative (ms.rs:846-851), costs can be negative
+        Case("neg_alpha", 64, 64, [(64, 64)], seed=14, inpaint=True, guided=True, stages=4),
+        # an example guide smaller than its example keeps its own bounds (ms.rs:1265-1273)
+        Case("guide_shorter", 64, 64, [(48, 48)], seed=15, guided=True, guide_sizes=[(48, 30)]),
+        Case("guide_narrower", 64, 64, [(48, 48)], seed=16, guided=True, guide_sizes=[(31, 48)], stages=3),
     ]

@@ -272,7 +272,7 @@ struct tsb_generator {
     DevBuf<uint32_t> d_alpha_flag;                  // [level] set when an input texel of that pyramid level has alpha != 255, [64] same for the state
     std::vector<uint8_t> level_opaque;              // per pyramid level: every input texel has alpha 255
     int pad_pitch = 0;                              // common row pitch of the framed copies, 0 when the sizes differ
-    bool run_opaque = false, no_fast = false;
+    bool run_opaque = false, no_fast = false, luts_exact_mode = false;
     std::vector<DevBuf<uint8_t>> d_smask;           // per (all) example
     DevBuf<DevEx> d_exdesc;                         // [levels][n_ex] filtered
     bool guided = false;
@@ -307,6 +307,8 @@ struct tsb_generator {
     DevBuf<float> d_luts_all;                       // [stage][512]
     PinnedBuf<float> h_luts_all;
     DevBuf<uint32_t> d_sctl;                        // [chunk][SC_WORDS] + abort flag
+    DevBuf<uint32_t> d_live_color;                  // colour plane mirrored for progress snapshots
+    PinnedBuf<uint32_t> h_snap;
     cudaStream_t stream3 = nullptr;                 // host copies that must not delay the analysis stream
     uint32_t* h_progress = nullptr;                 // mapped pinned word: work items claimed so far
     uint32_t* d_progress = nullptr;                 // its device alias
@@ -530,7 +532,6 @@ int check_params(const tsb_generator* g, const tsb_params* p) {
     if (p->nearest_neighbors + p->random_sample_locations > (uint64_t)CANDMAX)
         return fail(TSB_ERR_UNSUPPORTED, "nearest_neighbors + random_sample_locations must be <= %d", CANDMAX);
     if (p->random_sample_locations == 0) return fail(TSB_ERR_INVALID, "random_sample_locations must be at least 1 (session.rs:489-496; without random candidates a pixel can be left with no candidate at all)");
-    if (p->cauchy_dispersion == 0.0f) return fail(TSB_ERR_UNSUPPORTED, "cauchy_dispersion == 0 yields NaN costs in the reference (quirk q14); not supported");
     int need_levels = p->p_stages == 0 ? 1 : p->p_stages;
     if (g->n_levels < need_levels) return fail(TSB_ERR_INVALID, "example pyramids have %d levels, %d needed", g->n_levels, need_levels);
     return 0;
@@ -550,6 +551,11 @@ void stage_inputs(tsb_generator* g, StageDev& S, int level, const tsb_params* p)
 }
 
 // PrerenderedU8Function tables (ms.rs:739-742, 853-858, 1110-1120) reduced to |a-b| (256 entries)
+// are pruning and early-outs result neutral for these cost tables?  (all entries finite and >= 0)
+bool luts_well_behaved(const float* h) {
+    for (int i = 0; i < 512; ++i) if (!(h[i] >= 0.0f) || std::isinf(h[i])) return false;
+    return true;
+}
 void fill_luts(const tsb_generator* g, const tsb_params* p, float adaptive_alpha, float* h) {
     float sig2 = p->cauchy_dispersion * p->cauchy_dispersion;
     for (int d = 0; d < 256; ++d) {
@@ -563,6 +569,7 @@ void fill_luts(const tsb_generator* g, const tsb_params* p, float adaptive_alpha
 int upload_luts(tsb_generator* g, const tsb_params* p, float adaptive_alpha) {
     float h[512];
     fill_luts(g, p, adaptive_alpha, h);
+    g->luts_exact_mode = !luts_well_behaved(h);
     CU(cudaMemcpyAsync(g->d_luts.p, h, sizeof(h), cudaMemcpyHostToDevice, g->stream));
     CU(cudaStreamSynchronize(g->stream));
     return 0;
@@ -1037,6 +1044,7 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
     bool state_opaque = g->state_init_opaque;  // every resolved colour in the state has alpha 255
     int cur_stage = -1;
     std::vector<uint64_t> stage_trace_base(n_stages, 0), stage_progress_base(n_stages, 0);
+    std::vector<const uint4*> stage_buf(n_stages, nullptr);  // the state buffer each stage writes (progress snapshots)
     {
         uint64_t tb = 0, pb = 0;
         for (size_t si = 0; si < n_stages; ++si) { stage_trace_base[si] = tb; stage_progress_base[si] = pb; tb += plan[si].n_redo + plan[si].n_new; pb += plan[si].pixels_to_resolve; }
@@ -1073,6 +1081,7 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         }
         if (sp.recolour) {  // next_pyramid_level, ms.rs:687-700
             k_recolour<<<(uint32_t)((npix + 255) / 256), 256, 0, s>>>(S);
+            if (cb) k_snapshot_color<<<(unsigned)std::min<size_t>((npix + 255) / 256, 4096), 256, 0, s>>>(g->d_state.p, (uint32_t)npix, g->d_live_color.p);
             CU(cudaGetLastError());
             g->stats.kernel_launches++;
             // recoloured pixels take the level's alphas; a pixel whose source is out of range keeps its colour
@@ -1080,7 +1089,8 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
             state_opaque = (may_keep ? state_opaque : true) && g->level_opaque[sp.level];
         }
         g->no_fast = getenv("TSB_NO_FAST") != nullptr;
-        g->run_opaque = !g->no_fast && state_opaque && sp.level < (int)g->level_opaque.size() && g->level_opaque[sp.level];
+        S.seq_exact = luts_well_behaved(g->h_luts_all.p + (size_t)si * 512) ? 0 : 1;  // q13 / q14: literal candidate loop
+        g->run_opaque = !g->no_fast && !S.seq_exact && state_opaque && sp.level < (int)g->level_opaque.size() && g->level_opaque[sp.level];
         S.opaque = g->run_opaque ? 1 : 0;
         S.pad_pitch = g->no_fast ? 0 : g->pad_pitch;
         state_opaque = state_opaque && g->level_opaque[sp.level];  // this stage commits texels of this level
@@ -1096,6 +1106,7 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
             TRY(g->d_tmp_u32.ensure(4));
             CU(cudaMemcpyAsync(g->d_tmp_u32.p, item, 16, cudaMemcpyHostToDevice, s));
             k_commit_fixed<<<1, 32, 0, s>>>(S, S.ex, g->d_tmp_u32.p, 1, 0);
+            if (cb) k_snapshot_color<<<(unsigned)std::min<size_t>((npix + 255) / 256, 4096), 256, 0, s>>>(g->d_state.p, (uint32_t)npix, g->d_live_color.p);
             CU(cudaGetLastError());
             g->stats.kernel_launches++;
             if (g->trace) g->tr_fix_idx.push_back(stage_trace_base[si] + sp.n_redo);
@@ -1125,9 +1136,11 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         if (c.redo) { D.prev = g->d_state.p; D.cur = g->d_state2.p; }
         else { D.prev = nullptr; D.cur = g->d_state.p; }
         const size_t ci = (size_t)(&c - chunks.data());
+        stage_buf[c.stage] = D.cur;
         D.ctl = g->d_sctl.p + ci * SC_WORDS;
         D.abort_flag = abort_flag;
         D.progress = cb ? g->d_progress : nullptr;
+        D.live_color = cb ? g->d_live_color.p : nullptr;
         D.progress_base = (uint32_t)std::min<uint64_t>(stage_progress_base[c.stage] + c.first, 0xFFFFFFFFull);
         D.tag = (uint32_t)(2 * c.stage + (c.redo ? 1 : 2));
         D.watchdog_ms = watchdog_ms;
@@ -1169,7 +1182,38 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         return 0;
     };
 
+    // ---- progress (ProgressNotifier, ms.rs:1054-1107): the calling thread polls the claim counter, as the reference's main
+    // thread does (ms.rs:1026-1034), and reports every change of the integer percentage with a snapshot of the colours.
+    // Polled between the enqueue calls too: on a cold start (lazy kernel loading) the device runs while the host still enqueues.
+    uint64_t overall_total = 0;
+    for (auto& sp : plan) overall_total += sp.pixels_to_resolve;
+    uint32_t last_pcnt = 0;
+    if (cb) {
+        // A plain colour plane mirrors the commits while a callback is registered (the counterpart of the reference's shared
+        // color_map): a snapshot is then ONE copy-engine transfer into pinned memory -- no kernel has to squeeze in beside the
+        // persistent resolve grid, nothing is stalled.
+        TRY(g->d_live_color.ensure(npix)); TRY(g->h_snap.ensure(npix));
+        k_snapshot_color<<<(unsigned)std::min<size_t>((npix + 255) / 256, 4096), 256, 0, s>>>(g->d_state.p, (uint32_t)npix, g->d_live_color.p);
+        CU(cudaGetLastError());
+    }
+    auto report = [&](uint64_t cur_total) -> int {
+        if (!cb || overall_total == 0) return 0;
+        const uint32_t pcnt = (uint32_t)lroundf((float)cur_total / (float)overall_total * 100.0f);
+        if (pcnt == last_pcnt) return 0;
+        size_t si = 0;
+        while (si + 1 < n_stages && cur_total >= stage_progress_base[si + 1]) ++si;
+        while (si > 0 && !stage_buf[si]) --si;
+        if (!stage_buf[si]) return 0;  // nothing of that stage is enqueued yet
+        last_pcnt = pcnt;
+        // snapshot on the copy stream: racy by design, like the reference's read of the shared colour map
+        CU(cudaMemcpyAsync(g->h_snap.p, g->d_live_color.p, npix * 4, cudaMemcpyDeviceToHost, g->stream3));
+        CU(cudaStreamSynchronize(g->stream3));
+        cb(user, (const uint8_t*)g->h_snap.p, (uint32_t)g->W, (uint32_t)g->H, cur_total, overall_total, cur_total - stage_progress_base[si], plan[si].pixels_to_resolve);
+        return 0;
+    };
+
     while (r_next < chunks.size()) {
+        if (cb) TRY(report(*(volatile uint32_t*)g->h_progress));
         while (a_next < chunks.size()) {
             int rc = enqueue_analysis(chunks[a_next]);
             if (rc == 1) break;
@@ -1211,26 +1255,6 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
     // ---- progress (ProgressNotifier, ms.rs:1054-1107): the calling thread polls the claim counter, as the reference's main
     // thread does (ms.rs:1026-1034), and reports every change of the integer percentage with a snapshot of the colours ----
     if (cb) {
-        uint64_t overall_total = 0;
-        for (auto& sp : plan) overall_total += sp.pixels_to_resolve;
-        std::vector<uint8_t> img(npix * 4);
-        DevBuf<uint32_t> snap;
-        TRY(snap.ensure(npix));
-        uint32_t last_pcnt = 0;
-        auto report = [&](uint64_t cur_total) -> int {
-            if (overall_total == 0) return 0;
-            const uint32_t pcnt = (uint32_t)lroundf((float)cur_total / (float)overall_total * 100.0f);
-            if (pcnt == last_pcnt) return 0;
-            last_pcnt = pcnt;
-            // snapshot on the copy stream: racy by design, like the reference's read of the shared colour map
-            k_unpack_state<<<(uint32_t)((npix + 255) / 256), 256, 0, g->stream3>>>(g->d_state.p, (uint32_t)npix, snap.p, nullptr, nullptr);
-            CU(cudaMemcpyAsync(img.data(), snap.p, npix * 4, cudaMemcpyDeviceToHost, g->stream3));
-            CU(cudaStreamSynchronize(g->stream3));
-            size_t si = 0;
-            while (si + 1 < n_stages && cur_total >= stage_progress_base[si + 1]) ++si;
-            cb(user, img.data(), (uint32_t)g->W, (uint32_t)g->H, cur_total, overall_total, cur_total - stage_progress_base[si], plan[si].pixels_to_resolve);
-            return 0;
-        };
         while (cudaEventQuery(ev_end) == cudaErrorNotReady) {
             TRY(report(*(volatile uint32_t*)g->h_progress));
             std::this_thread::sleep_for(std::chrono::microseconds(200));
@@ -1715,6 +1739,8 @@ int tsb_generator_eval_items(tsb_generator* g, const tsb_params* prm, int32_t le
     fill_stage_geometry(g, S, prm->tiling_mode != 0);
     stage_inputs(g, S, level, prm);
     TRY(upload_luts(g, prm, adaptive_alpha));
+    S.seq_exact = g->luts_exact_mode ? 1 : 0;
+    if (S.seq_exact) S.opaque = 0;
     S.r2_hint = r2_hint_for(g, g->resolved_order.size(), (uint32_t)k);
     DevBuf<uint32_t> dpix, dxy;
     DevBuf<uint8_t> dmap;

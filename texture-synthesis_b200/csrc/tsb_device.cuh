@@ -88,6 +88,8 @@ struct StageDev {
     int k, m;
     int pad_pitch;     // row pitch of the framed copies when every example (and guide) shares it, else 0
     int opaque;        // 1: every texel this stage can read has alpha 255, so the alpha term is lut[0] = +0 and is skipped
+    int seq_exact;     // 1: a cost table holds NaN / inf / negative entries (cauchy_dispersion == 0, q14; guide alpha outside [0,1],
+                       //    q13): pruning and early-outs are not result neutral then -- literal candidate-by-candidate evaluation
     uint32_t r2_hint;  // starting radius^2 of the general k-NN search
     unsigned long long* counters;  // [ST_COUNT] run statistics (see enum below), flushed once per CTA
 };
@@ -644,6 +646,60 @@ __device__ __noinline__ ScoreOut score_unframed(const StageDev& S, WarpScratch& 
     return r;
 }
 
+// find_best_match / better_match exactly as written (ms.rs:1205-1221, 1259-1283) for cost tables that are not "non-negative and
+// finite": a candidate is rejected iff some PREFIX of its weighted sum compares >= the best so far -- comparisons with NaN are
+// false, so a NaN score is accepted and from then on everything is -- and acceptance is sequential in candidate order.  One lane
+// per candidate evaluates the whole neighbourhood, keeping the largest non-NaN prefix M and the final score s; the acceptance
+// scan then runs over the candidates in order: accept iff !(M >= best).
+template <bool GUIDED>
+__device__ __noinline__ ScoreOut score_sequential(const StageDev& S, WarpScratch& ws, const float* __restrict__ s_lut,
+                                                  const float* __restrict__ s_lutg, int lane, int kk, int ncand) {
+    ScoreOut r;
+    r.best = FLT_MAX; r.besti = 0; r.fetched = 0; r.bestcol = 0;
+    for (int base = 0; base < ncand; base += 32) {
+        const int a = base + lane;
+        float s = 0.f, M = -INFINITY;
+        if (a < ncand) {
+            const uint32_t cxy = ws.u.c.cxy[a], meta = ws.cmeta[a];
+            const int cx = (int)(cxy & 0xFFFFu), cy = (int)(cxy >> 16);
+            const int sgn = (meta & 0x8000u) ? -1 : 1;
+            const uint32_t map = meta & 0x7FFFu;
+            const DevEx e = S.ex[map];
+            DevGuide ge;
+            if (GUIDED) ge = S.exg[map];
+            for (int j = 0; j < kk; ++j) {
+                const short2 o = ws.off[j];
+                const int X = cx + sgn * o.x, Y = cy + sgn * o.y;
+                uint32_t tex = OUTSIDE_RGBA;
+                if ((unsigned)X < (unsigned)e.w && (unsigned)Y < (unsigned)e.h) tex = __ldg(e.px + (size_t)Y * e.w + X);
+                const uint32_t dd = __vabsdiffu4(ws.tcol[j], tex);
+                float t = s_lut[dd & 0xFFu];
+                t = __fadd_rn(t, s_lut[(dd >> 8) & 0xFFu]);
+                t = __fadd_rn(t, s_lut[(dd >> 16) & 0xFFu]);
+                t = __fadd_rn(t, s_lut[dd >> 24]);
+                if (GUIDED) {
+                    uint32_t gtex = OUTSIDE_RGBA;
+                    if ((unsigned)X < (unsigned)ge.w && (unsigned)Y < (unsigned)ge.h) gtex = __ldg(ge.px + (size_t)Y * ge.w + X);
+                    const uint32_t dg = __vabsdiffu4(ws.gcol[j], gtex);
+                    t = __fadd_rn(t, s_lutg[dg & 0xFFu]);
+                    t = __fadd_rn(t, s_lutg[(dg >> 8) & 0xFFu]);
+                    t = __fadd_rn(t, s_lutg[(dg >> 16) & 0xFFu]);
+                    t = __fadd_rn(t, s_lutg[dg >> 24]);
+                }
+                s = __fadd_rn(s, __fmul_rn(t, ws.g[j]));
+                if (s == s && s > M) M = s;
+            }
+            r.fetched += (uint32_t)kk;
+        }
+        const int cnt = min(32, ncand - base);
+        for (int l = 0; l < cnt; ++l) {
+            const float Ml = __shfl_sync(FULL, M, l), sl = __shfl_sync(FULL, s, l);
+            if (!(Ml >= r.best)) { r.best = sl; r.besti = base + l; }
+        }
+    }
+    return r;
+}
+
 template <bool GUIDED, int OPQ>
 __device__ __forceinline__ void resolve_tail(const StageDev& S, WarpScratch& ws, const float* __restrict__ s_lut,
                                              const float* __restrict__ s_lutg, int lane, int kk, int ncand, int reach, bool degenerate,
@@ -771,7 +827,11 @@ __device__ __forceinline__ void resolve_tail(const StageDev& S, WarpScratch& ws,
         // chunk by chunk: __match_any groups equal keys inside the chunk (the lowest lane is the first occurrence),
         // then the survivors are checked against the unique keys of earlier chunks (dk[0..nuniq), compacted in place)
         int nuniq = 0;
-        for (int base = 0; base < ncoh; base += 32) {
+        if (S.seq_exact) {  // every proposal is kept: with NaN scores a duplicate is accepted again and changes the winning index
+            for (int a = lane; a < ncoh; a += 32) ws.corig[a] = (uint8_t)a;
+            nuniq = ncoh;
+        }
+        for (int base = 0; base < ncoh && !S.seq_exact; base += 32) {
             const int a = base + lane;
             const bool valid = a < ncoh;
             const unsigned long long key = valid ? dk[a] : (0xFFFF000000000000ull | (unsigned long long)lane);  // distinct dummies
@@ -828,7 +888,11 @@ __device__ __forceinline__ void resolve_tail(const StageDev& S, WarpScratch& ws,
         if (shared_round) score_coherent_shared<GUIDED, FR, OP>(S, ws, s_lut, s_lutg, lane, kk, kk8, nuniq_coh, best, besti, fetched, bestcol); \
         score_candidates<GUIDED, FR, OP>(S, ws, s_lut, s_lutg, lane, kk, kk8, ncand, nuniq_coh, base0, best, besti, fetched, bestcol); \
     } while (0)
-    if (OPQ == 1 || OPQ == 0) {
+    if (S.seq_exact) {
+        const ScoreOut r = score_sequential<GUIDED>(S, ws, s_lut, s_lutg, lane, kk, ncand);
+        best = r.best; besti = r.besti; fetched = r.fetched; bestcol = 0;
+    }
+    else if (OPQ == 1 || OPQ == 0) {
         // persistent kernel: the framed path is the hot one (fine stages); the bounds-tested one is kept out of line so
         // that it does not dilute the instruction cache
         if (framed) TSB_SCORE(true, (OPQ == 1));
@@ -859,7 +923,7 @@ __device__ __forceinline__ void resolve_tail(const StageDev& S, WarpScratch& ws,
     out.bmap = (int)(ws.cmeta[besti] & 0x7FFFu);
     out.bpatch = ws.u.c.cpatch[besti];
     out.bcol = bestcol;
-    out.bcol_valid = (!degenerate && best != FLT_MAX) ? 1 : 0;
+    out.bcol_valid = (!degenerate && !S.seq_exact && best != FLT_MAX) ? 1 : 0;
     out.score = best;
     __syncwarp();
 }
@@ -1125,6 +1189,11 @@ __global__ void k_unpack_state(const uint4* state, uint32_t n, uint32_t* color, 
     if (color) color[p] = st.x;
     if (coord) { coord[3 * p] = st.y & 0xFFFFu; coord[3 * p + 1] = st.y >> 16; coord[3 * p + 2] = st_coordmap(st.w); }
     if (idm) { idm[2 * p] = st.z; idm[2 * p + 1] = st_idmap(st.w); }
+}
+// progress snapshots: a handful of CTAs that fit next to the persistent resolve kernel (which leaves a few CTA slots free when
+// a callback is registered) walk the whole state
+__global__ void k_snapshot_color(const uint4* state, uint32_t n, uint32_t* color) {
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) color[p] = state[p].x;
 }
 __global__ void k_pack_state(uint4* state, uint32_t n, const uint32_t* color, const uint32_t* coord, const uint32_t* idm) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;

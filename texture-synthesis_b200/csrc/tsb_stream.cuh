@@ -184,6 +184,7 @@ struct StreamDev {
     uint32_t* ctl;            // SC_*
     uint32_t* abort_flag;     // sticky per-run abort flag (watchdog)
     volatile uint32_t* progress;  // mapped host word (or nullptr): work items claimed so far in this run
+    uint32_t* live_color;     // progress callback registered: plain colour plane kept up to date for copy-engine snapshots
     uint32_t progress_base;
     uint32_t tag;             // phase id written with every commit
     uint32_t watchdog_ms;     // a single wait longer than this aborts the run
@@ -386,6 +387,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TSB_STREAM_CTAS) k_stream(StageDe
                 if (!REDO) S.score[flat] = o.score;  // first resolution only (ms.rs:365)
                 const uint4 v = make_uint4(col, (uint32_t)o.bx | ((uint32_t)o.by << 16), o.bpatch, st_pack_w((uint32_t)o.bmap, (uint32_t)o.bmap, D.tag));
                 if (MG) st_state_sys(D.cur + flat, v); else st_state(D.cur + flat, v);
+                if (D.live_color) D.live_color[flat] = col;
             }
             if (D.tr_best) {
                 const size_t ti = (size_t)(D.trace_base + si);
