@@ -26,7 +26,7 @@ sys.path.insert(0, ROOT)
 OUT, EX = 2048, 512
 WORKLOAD = f"{OUT}x{OUT} output from synthetic {EX}x{EX} example (synth_texture seed 1), k=50 m=50 cauchy=1.0 backtrack=0.5x5 seed=0"
 # dram bytes (read+write) of all k_stream launches of one step, from the ncu capture summarised under profiles/
-TRAFFIC_PER_STEP = None  # filled in from profiles/r2_kstream_all_launches_2048.txt
+TRAFFIC_PER_STEP = 9.91e9  # 9.59 GB read + 0.32 GB written over the 11 k_stream launches of one step (profiles/r2_kstream_all_launches_2048.txt)
 CPU_SAMPLE_OUT = 2048  # CPU sample = the full workload (2048x2048 output, about 9 s on 16 host cores)
 
 

@@ -50,3 +50,10 @@ extern "C" {
     pub fn tsb_generator_reset(g: *mut tsb_generator) -> c_int;
     pub fn tsb_device_count() -> c_int;
 }
+
+impl tsb_sampling {
+    // SamplingMethod, lib.rs:458-468
+    pub fn all() -> Self { tsb_sampling { kind: 0, _pad: 0, rgba: std::ptr::null() } }
+    pub fn ignore() -> Self { tsb_sampling { kind: 1, _pad: 0, rgba: std::ptr::null() } }
+    pub fn image(rgba: *const u8) -> Self { tsb_sampling { kind: 2, _pad: 0, rgba } }
+}

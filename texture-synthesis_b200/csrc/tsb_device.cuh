@@ -1254,6 +1254,10 @@ struct TapTable {
     const float* weights;
 };
 
+// u8 -> f32 without the quarter-rate I2F: 0x4B0000bb is the float 8388608 + bb, exactly (one PRMT + one FADD per channel)
+__device__ __forceinline__ float u8_to_f32(uint32_t p, int c) {
+    return __fsub_rn(__uint_as_float(__byte_perm(p, 0x4B000000u, 0x7540u + (uint32_t)c)), 8388608.0f);
+}
 __device__ __forceinline__ uint32_t resample_finish(float a0, float a1, float a2, float a3, float sum) {
     float v[4] = {__fdiv_rn(a0, sum), __fdiv_rn(a1, sum), __fdiv_rn(a2, sum), __fdiv_rn(a3, sum)};
     uint32_t r = 0;
@@ -1275,10 +1279,10 @@ __global__ void k_resample_v(const uint32_t* __restrict__ src, int w, int h, uin
     for (int i = 0; i < n; ++i) {
         uint32_t p = __ldg(src + (size_t)(left + i) * w + x);
         float wv = wt[i];
-        a0 = __fadd_rn(a0, __fmul_rn((float)(p & 0xFFu), wv));
-        a1 = __fadd_rn(a1, __fmul_rn((float)((p >> 8) & 0xFFu), wv));
-        a2 = __fadd_rn(a2, __fmul_rn((float)((p >> 16) & 0xFFu), wv));
-        a3 = __fadd_rn(a3, __fmul_rn((float)(p >> 24), wv));
+        a0 = __fadd_rn(a0, __fmul_rn(u8_to_f32(p, 0), wv));
+        a1 = __fadd_rn(a1, __fmul_rn(u8_to_f32(p, 1), wv));
+        a2 = __fadd_rn(a2, __fmul_rn(u8_to_f32(p, 2), wv));
+        a3 = __fadd_rn(a3, __fmul_rn(u8_to_f32(p, 3), wv));
     }
     dst[(size_t)oy * w + x] = resample_finish(a0, a1, a2, a3, t.sum[oy]);
 }
@@ -1293,10 +1297,10 @@ __global__ void k_resample_h(const uint32_t* __restrict__ src, int w, int h, uin
     for (int i = 0; i < n; ++i) {
         uint32_t p = __ldg(row + i);
         float wv = wt[i];
-        a0 = __fadd_rn(a0, __fmul_rn((float)(p & 0xFFu), wv));
-        a1 = __fadd_rn(a1, __fmul_rn((float)((p >> 8) & 0xFFu), wv));
-        a2 = __fadd_rn(a2, __fmul_rn((float)((p >> 16) & 0xFFu), wv));
-        a3 = __fadd_rn(a3, __fmul_rn((float)(p >> 24), wv));
+        a0 = __fadd_rn(a0, __fmul_rn(u8_to_f32(p, 0), wv));
+        a1 = __fadd_rn(a1, __fmul_rn(u8_to_f32(p, 1), wv));
+        a2 = __fadd_rn(a2, __fmul_rn(u8_to_f32(p, 2), wv));
+        a3 = __fadd_rn(a3, __fmul_rn(u8_to_f32(p, 3), wv));
     }
     dst[(size_t)y * nw + ox] = resample_finish(a0, a1, a2, a3, t.sum[ox]);
 }
