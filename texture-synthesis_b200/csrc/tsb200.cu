@@ -799,14 +799,15 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         auto add_phase = [&](bool redo, size_t a, size_t b) {
             // (a ramp of small first chunks -- 4 Ki, 16 Ki, ... -- starts the synthesis 1.4 ms earlier but every chunk boundary
             // drains the dependency pipeline of the sparse first phase: 51.0 instead of 49.8 ms per 2048^2 step)
-            size_t ramp = chunk_max;
+            // (cutting a large sparse first phase -- 8192^2: 2 Mi items -- into eighths so that its analysis overlaps its own
+            // resolution was tried as well: 696 -> 706 ms)
+            const size_t ramp = chunk_max;
             for (size_t c0 = a; c0 < b;) {
                 ChunkPlan c;
                 c.stage = (int)si; c.redo = redo; c.first = c0; c.n = std::min(std::min(ramp, chunk_max), b - c0); c.slot = 0;
                 c.phase_first = c0 == a; c.phase_last = c0 + c.n == b;
                 chunks.push_back(c);
                 c0 += c.n;
-                ramp = std::min(chunk_max, ramp * 4);
             }
         };
         if (sp.n_redo) add_phase(true, 0, sp.n_redo);
