@@ -235,6 +235,25 @@ struct StagePlan {
 
 }  // namespace
 
+// CUDA events are created once and reused by every run of a generator
+struct EventPool {
+    std::vector<cudaEvent_t> timing, plain;
+    size_t nt = 0, np = 0;
+    ~EventPool() { for (auto e : timing) cudaEventDestroy(e); for (auto e : plain) cudaEventDestroy(e); }
+    void rewind() { nt = np = 0; }
+    int get(cudaEvent_t* out, bool with_timing) {
+        std::vector<cudaEvent_t>& v = with_timing ? timing : plain;
+        size_t& n = with_timing ? nt : np;
+        if (n == v.size()) {
+            cudaEvent_t e;
+            if (cudaEventCreateWithFlags(&e, with_timing ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess) return TSB_ERR_CUDA;
+            v.push_back(e);
+        }
+        *out = v[n++];
+        return 0;
+    }
+};
+
 struct tsb_generator {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -307,6 +326,7 @@ struct tsb_generator {
     DevBuf<float> d_luts_all;                       // [stage][512]
     PinnedBuf<float> h_luts_all;
     DevBuf<uint32_t> d_sctl;                        // [chunk][SC_WORDS] + abort flag
+    EventPool events;
     DevBuf<uint32_t> d_live_color;                  // colour plane mirrored for progress snapshots
     PinnedBuf<uint32_t> h_snap;
     cudaStream_t stream3 = nullptr;                 // host copies that must not delay the analysis stream
@@ -324,7 +344,7 @@ struct tsb_generator {
     uint32_t mgs_seq = 0;                           // barrier sequence number (identical on all ranks)
     size_t mgs_shard_min = 32768;                   // smaller phases are executed redundantly by every rank
     DevBuf<uint8_t> d_own_flag;
-    DevBuf<uint32_t> d_own_pos, d_own_t, d_own_pix, d_own_cnt;
+    DevBuf<uint32_t> d_own_pos, d_own_t, d_own_pix, d_own_cnt, d_own_bidx, d_own_bpos, d_init_points;
     uint64_t mgs_sharded_chunks = 0;
     size_t l2_persist_bytes = 0;                    // persisting L2 carve-out set aside for the active example level (0: unavailable)
     bool state_init_opaque = true;                  // every colour in the state before the run has alpha 255
@@ -726,16 +746,6 @@ struct ChunkPlan {
     cudaEvent_t ev_ready = nullptr, ev_done = nullptr, ev_t0 = nullptr, ev_a0 = nullptr;
 };
 
-struct EventPool {
-    std::vector<cudaEvent_t> all;
-    ~EventPool() { for (auto e : all) cudaEventDestroy(e); }
-    int get(cudaEvent_t* out, bool timing) {
-        CU(cudaEventCreateWithFlags(out, timing ? cudaEventDefault : cudaEventDisableTiming));
-        all.push_back(*out);
-        return 0;
-    }
-};
-
 template <bool REDO, bool MG>
 int launch_stream(tsb_generator* g, int grid, const StageDev& S, const ChunkDev& C, const StreamDev& D) {
     cudaStream_t s = g->stream;
@@ -753,7 +763,8 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
     const double t_start = now_ms();
     cudaStream_t s = g->stream, s2 = g->stream2;
     memset(&g->stats, 0, sizeof(g->stats));
-    EventPool events;
+    EventPool& events = g->events;
+    events.rewind();
     cudaEvent_t ev_begin, ev_end, ev_a0, ev_a1, ev_picks;
     TRY(events.get(&ev_begin, true)); TRY(events.get(&ev_end, true)); TRY(events.get(&ev_a0, true)); TRY(events.get(&ev_a1, true));
     TRY(events.get(&ev_picks, false));
@@ -824,7 +835,9 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         bool latched = false;
         const double area = (double)g->W * (double)g->H;
         // resolved pixels needed for r * 8 <= band height
-        const double rmax = std::max(1.0, (double)g->mgs_band_h / 8.0);
+        double rfactor = 8.0;
+        if (const char* e = getenv("TSB_MG_RFACTOR")) rfactor = std::max(1.0, atof(e));
+        const double rmax = std::max(1.0, (double)g->mgs_band_h / rfactor);
         const size_t need = (size_t)std::ceil((double)k * area / (3.14159265358979 * rmax * rmax));
         std::vector<ChunkPlan> out;
         for (auto& c : chunks) {
@@ -866,7 +879,9 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         // own counts at the chunk boundaries
         std::vector<uint32_t> bidx;
         for (auto& c : chunks) { bidx.push_back((uint32_t)c.first); bidx.push_back((uint32_t)(c.first + c.n)); }
-        DevBuf<uint32_t> d_bidx, d_bpos;
+        // (no allocation in the steady state: with peer mappings enabled every cudaMalloc / cudaFree is a cross-process affair)
+        DevBuf<uint32_t>& d_bidx = g->d_own_bidx;
+        DevBuf<uint32_t>& d_bpos = g->d_own_bpos;
         std::vector<uint32_t> bpos(bidx.size());
         TRY(d_bidx.upload(bidx.data(), bidx.size(), s)); TRY(d_bpos.ensure(bidx.size()));
         k_gather_u32<<<(uint32_t)((bidx.size() + 255) / 256), 256, 0, s>>>(g->d_own_pos.p, d_bidx.p, (uint32_t)bidx.size(), d_bpos.p);
@@ -886,7 +901,7 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
     size_t ring_mb = 24576;
     if (const char* e = getenv("TSB_RING_MB")) ring_mb = std::max<size_t>(64, (size_t)strtoull(e, nullptr, 10));
     size_t ring_items = std::min(std::max<size_t>(total_items, 1), ring_mb * (1u << 20) / bytes_per_item);
-    {
+    if (g->r_nbk.n < ring_items) {  // only when the ring has to grow (a repeated run allocates nothing)
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
             size_t have = g->r_nb.n * sizeof(short2) + g->r_g.n * 4 + g->r_low.n * 16 + g->r_rand_xy.n * 4 + g->r_rand_map.n + g->r_nbk.n;
@@ -942,7 +957,7 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
     A.k = (int)k; A.m = m;
     CU(cudaMemsetAsync(g->d_mask.p, 0, (size_t)g->wpr * g->mrows * 4, s2));
     CU(cudaMemsetAsync(g->d_mask1.p, 0, (size_t)g->wpr1 * g->mrows * 4, s2));
-    DevBuf<uint32_t> d_init_points;
+    DevBuf<uint32_t>& d_init_points = g->d_init_points;
     if (g->have_loaded_points) {
         TRY(d_init_points.upload((const uint32_t*)g->loaded_points.data(), g->loaded_points.size(), s2));
         uint32_t np = (uint32_t)(g->loaded_points.size() / 2);

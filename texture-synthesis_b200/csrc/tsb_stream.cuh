@@ -246,10 +246,15 @@ __global__ void __launch_bounds__(CTA_THREADS, TSB_STREAM_CTAS) k_stream(StageDe
         uint4 lowm = make_uint4(0u, 0u, 0u, 0u);
         if (REDO) lowm = C.low[c];
         // the lists are read exactly once: streaming loads (evict-first) keep the state and the example level in L2
-        for (int j = lane; j < kk; j += 32) {
-            const uint32_t ov = __ldcs(reinterpret_cast<const uint32_t*>(C.nb + (size_t)c * k + j));
-            ws.off[j] = make_short2((short)(ov & 0xFFFFu), (short)(ov >> 16));
-            ws.g[j] = __ldcs(C.g + (size_t)c * k + j);
+        // (all k slots, so that these loads do not wait for the neighbour count: one round trip to memory instead of two)
+        for (int j0 = 0; j0 < k; j0 += 64) {
+            const int ja = j0 + lane, jb = ja + 32;
+            uint32_t ova = 0u, ovb = 0u;
+            float ga = 0.f, gb = 0.f;
+            if (ja < k) { ova = __ldcs(reinterpret_cast<const uint32_t*>(C.nb + (size_t)c * k + ja)); ga = __ldcs(C.g + (size_t)c * k + ja); }
+            if (jb < k) { ovb = __ldcs(reinterpret_cast<const uint32_t*>(C.nb + (size_t)c * k + jb)); gb = __ldcs(C.g + (size_t)c * k + jb); }
+            if (ja < k) { ws.off[ja] = make_short2((short)(ova & 0xFFFFu), (short)(ova >> 16)); ws.g[ja] = ga; }
+            if (jb < k) { ws.off[jb] = make_short2((short)(ovb & 0xFFFFu), (short)(ovb >> 16)); ws.g[jb] = gb; }
         }
         uint32_t rxy0 = 0, rxy1 = 0, rmp0 = 0, rmp1 = 0;
         if (lane < S.m) { rxy0 = __ldcs(rand_xy + lane); rmp0 = __ldcs(rand_map + lane); }
