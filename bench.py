@@ -44,26 +44,31 @@ class ClockSampler:
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.rows, self.stop = index, [], False
+        self.index, self.rows, self.proc = index, [], None
         self.t = threading.Thread(target=self.run, daemon=True)
 
     def run(self):
-        while not self.stop:
-            try:
-                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([c.strip() for c in o.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+        # ONE nvidia-smi process in loop mode (a sample every 100 ms) instead of one process per sample: the timed region of a
+        # default run lasts well under a second
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                line = line.strip()
+                if line:
+                    self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
 
     def __enter__(self):
         self.t.start()
+        time.sleep(0.3)  # let the sampler come up before the timed region starts
         return self
 
     def __exit__(self, *a):
-        self.stop = True
+        time.sleep(0.06)
+        if self.proc is not None:
+            self.proc.terminate()
         self.t.join(timeout=6)
 
     def summary(self):
