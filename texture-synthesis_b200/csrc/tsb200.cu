@@ -710,7 +710,7 @@ int plan_pixel_order(tsb_generator* g, const std::vector<StagePlan>& plan, size_
             const size_t head = std::min<size_t>(n_picks, 4096);
             CU(cudaMemcpyAsync(g->h_items.p, g->d_item_pixel.p, head * 4, cudaMemcpyDeviceToHost, s));
             CU(cudaStreamSynchronize(s));
-            if (n_picks > head) CU(cudaMemcpyAsync(g->h_items.p + head, g->d_item_pixel.p + head, (n_picks - head) * 4, cudaMemcpyDeviceToHost, g->stream3));
+            // (the rest of the host mirror is copied by copy_picks_tail once nothing small has to cross PCIe any more)
             const size_t left = total - n_picks;
             if (left) {
                 TRY(g->d_tmp_u32.ensure(left));
@@ -725,6 +725,17 @@ int plan_pixel_order(tsb_generator* g, const std::vector<StagePlan>& plan, size_
             }
         }
     }
+    return 0;
+}
+
+// The host mirror of the whole pick array is needed only after the run (resolved list, trace): a large device->host copy on the
+// copy stream.  Issued AFTER the planning's own small read-backs -- a 4-byte copy queued behind 268 MB on the same copy engine
+// waits 10-20 ms (measured on 8 GPUs sharing the host's PCIe).
+int copy_picks_tail(tsb_generator* g, size_t n_picks, cudaEvent_t picks_ready) {
+    const size_t head = std::min<size_t>(n_picks, 4096);
+    if (n_picks <= head) return 0;
+    CU(cudaStreamWaitEvent(g->stream3, picks_ready, 0));
+    CU(cudaMemcpyAsync(g->h_items.p + head, g->d_item_pixel.p + head, (n_picks - head) * 4, cudaMemcpyDeviceToHost, g->stream3));
     return 0;
 }
 
@@ -896,6 +907,7 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         plan_mark(g, "own-item lists");
         for (size_t i = 0; i < chunks.size(); ++i) { chunks[i].own_lo = bpos[2 * i]; chunks[i].own_n = bpos[2 * i + 1] - bpos[2 * i]; }
     }
+    TRY(copy_picks_tail(g, n_picks, ev_picks));
     // ---- list ring ----
     const size_t bytes_per_item = 1 + (size_t)k * 8 + 16 + (size_t)m * 5;
     size_t ring_mb = 24576;
