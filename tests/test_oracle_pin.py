@@ -8,9 +8,12 @@ Measured Hamming distances (of 135 bits; two unrelated images differ in ~67):
   1-4 bits : multi_example, guided, style_transfer, inpaint_channel
   14-15    : inpaint, tiling -- both threshold a JPEG mask at exactly 255 / 0 (ms.rs:272, 1546), so the +-1 LSB difference
              between Pillow's and jpeg-decoder 0.1.22's IDCT moves mask pixels
-The residual bits are explained by the two things the oracle cannot restate offline: the JPEG decoder (inputs are Pillow
-decodes) and rstar's order among equidistant neighbours (the oracle uses ascending (d^2, dy, dx)): running the oracle with
-the REVERSED tie order changes these distances by 0-2 bits per PNG-only case.
+The residual bits come from two things: the JPEG decoder (inputs are Pillow decodes, which the oracle cannot restate
+offline) and rstar's order among equidistant neighbours.  The canonical oracle (the parity reference of the CUDA path) uses
+ascending (d^2, dy, dx).  With ORC_KNN=rstar the oracle answers its k-NN queries from a restatement of rstar 0.7.1's R*-tree
+(oracle/rstar_port.hpp: insertion with forced reinsertion, split, best-first nearest-neighbour iterator) and then reproduces
+SIX of the nine constants character for character -- every configuration whose inputs are PNG only -- and the three left are
+the ones that read a JPEG (guided: 1 bit; inpaint 16, tiling 9: JPEG masks thresholded at exactly 255 / 0).
 """
 import pytest
 
@@ -23,6 +26,28 @@ MAX_DISTANCE = {
     "diff_multi_example": 3, "diff_guided": 2, "diff_style_transfer": 1, "diff_inpaint_channel": 4,
     "diff_inpaint": 15, "diff_tiling": 14,
 }
+
+
+# the same nine runs with the k-NN answered by the restated rstar tree (ORC_KNN=rstar)
+MAX_DISTANCE_RSTAR = {
+    "diff_single_example": 0, "diff_multi_example": 0, "diff_style_transfer": 0, "diff_inpaint_channel": 0,
+    "diff_sample_masks": 0, "diff_sample_masks_ignore": 0,
+    "diff_guided": 1, "diff_inpaint": 16, "diff_tiling": 9,
+}
+
+
+@pytest.mark.parametrize("name", sorted(F.DIFF_HASHES))
+def test_oracle_with_rstar_order_reproduces_reference_hash(name, monkeypatch):
+    """The oracle reads ORC_KNN when a run builds its neighbour index, so the mode is scoped to this test."""
+    monkeypatch.setenv("ORC_KNN", "rstar")
+    monkeypatch.delenv("ORC_RSTAR_VARIANT", raising=False)
+    spec = F.SPECS[name]()
+    out = F.to_oracle(spec).run().color()
+    d = H.distance(out, F.DIFF_HASHES[name])
+    print(f"{name} [rstar order]: hash {H.hash_image(out)} expected {F.DIFF_HASHES[name]} distance {d}/135")
+    assert d <= MAX_DISTANCE_RSTAR[name]
+    if MAX_DISTANCE_RSTAR[name] == 0:
+        assert H.hash_image(out) == F.DIFF_HASHES[name]
 
 
 @pytest.mark.parametrize("name", sorted(F.DIFF_HASHES))
