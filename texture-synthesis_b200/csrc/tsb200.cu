@@ -1181,7 +1181,8 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         int grid = std::max(1, std::min((int)((C.n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), grid_full));
         // a phase that multiplies the resolved set is bound by its dependency depth, not by throughput: one CTA per SM
         // leaves the rest of the machine to the analysis stream
-        if (!c.redo && std::max<size_t>(sp.resolved_before, 1) * 4 < sp.n_new) grid = std::min(grid, g->n_sms);
+        const bool dependency_bound = !c.redo && std::max<size_t>(sp.resolved_before, 1) * 4 < sp.n_new;
+        if (dependency_bound) grid = std::min(grid, g->n_sms);
         if (c.sharded) {
             if (c.phase_first && (c.redo || stage_prologue_pending)) TRY(mg_barrier());  // ... and every replica is through its own prologue
             D.world = g->mgs_world; D.rank = g->mgs_rank; D.band_h = g->mgs_band_h;
@@ -1248,6 +1249,7 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
             if (rc != 0) return rc;
             live.push_back(a_next);
             ++a_next;
+            if (cb) TRY(report(*(volatile uint32_t*)g->h_progress));
         }
         if (a_next <= r_next) return fail(TSB_ERR_INTERNAL, "list ring too small for chunk %zu", r_next);
         TRY(enqueue_resolve(chunks[r_next]));
@@ -1283,9 +1285,15 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
     // ---- progress (ProgressNotifier, ms.rs:1054-1107): the calling thread polls the claim counter, as the reference's main
     // thread does (ms.rs:1026-1034), and reports every change of the integer percentage with a snapshot of the colours ----
     if (cb) {
-        while (cudaEventQuery(ev_end) == cudaErrorNotReady) {
+        // busy poll of the mapped counter, like the reference's main thread (a plain load per iteration); the event is
+        // queried every ~20 us only
+        double t_query = now_ms();
+        for (;;) {
             TRY(report(*(volatile uint32_t*)g->h_progress));
-            std::this_thread::sleep_for(std::chrono::microseconds(200));
+            const double t = now_ms();
+            if (t - t_query < 0.02) continue;
+            t_query = t;
+            if (cudaEventQuery(ev_end) != cudaErrorNotReady) break;
         }
         TRY(report(overall_total));
     }

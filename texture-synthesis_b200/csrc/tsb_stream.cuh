@@ -225,6 +225,9 @@ __global__ void __launch_bounds__(CTA_THREADS, TSB_STREAM_CTAS) k_stream(StageDe
     // Items are claimed in order.  AHEAD (experiment, off): claim one item ahead and pull its lists into L2 while the current
     // one is resolved -- safe (the lowest unfinished item is always somebody's CURRENT item) but a held item cannot start
     // elsewhere, which costs more in waiting than the prefetch saves (measured: 50.7 -> 53.3 ms per 2048^2 step).
+    // Also measured and dropped (2048^2 step, 46.4 ms): claiming 2 / 4 consecutive items per atomic in the throughput phases
+    // -- 49.3 / 64.6 ms, the held items are exactly the ones other warps end up waiting for; an L2 prefetch of the lists of
+    // the item one generation of resident warps ahead (no claim involved) -- 46.35 ms, the list latency is already hidden.
     constexpr bool AHEAD = false;
     uint32_t c = 0;
     if (lane == 0) c = atomicAdd(D.ctl + SC_NEXT, 1u);
