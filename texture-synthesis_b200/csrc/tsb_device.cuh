@@ -335,6 +335,8 @@ __device__ __forceinline__ int knn_search(const StageDev& S, WS& ws, int lane, i
     if (bounded || R2bound == R2_INF) {
         int limit = bounded ? (int)__ldg(S.cntLE + R2bound) : S.spiralN;
         // unbounded search: do not walk the whole table when the hint says the set is sparse
+        // (a lower switch point was measured: 1024 / 512 / 256 change nothing, 128 / 64 cost 1 - 6 ms per 2048^2 step -- the sort
+        // of the disc path outweighs the longer walk)
         if (!bounded && hint > (uint32_t)S.RT2) limit = 0;
         int cnt = 0;
         for (int base = 0; base < limit && cnt < k; base += 128) {
@@ -980,7 +982,9 @@ __global__ void k_mask_insert_flat_at(StageDev S, uint32_t* mask, uint32_t* mask
 // Random candidates (ms.rs:549-599): rng = Pcg32::seed_from_u64(loop_seed + 1); per candidate one usize draw
 // for the map, then (x, y) u32 draws until the sampling mask accepts.  One thread per work item; the
 // stream depends only on (stage seed, work-item index) so a whole stage is generated ahead of the rounds.
+// SINGLE: one example (the common case).
 // ---------------------------------------------------------------------------------------------
+template <bool SINGLE>
 __global__ void k_rand_candidates(const DevEx* ex, int n_ex, int m, uint64_t seed_base, uint32_t n,
                                   uint32_t* rand_xy, uint8_t* rand_map, const uint32_t* tidx = nullptr) {
     // each thread draws the m candidates of one item into shared memory; the block then writes its (contiguous)
@@ -988,51 +992,66 @@ __global__ void k_rand_candidates(const DevEx* ex, int n_ex, int m, uint64_t see
     extern __shared__ __align__(16) unsigned char rc_smem[];
     uint32_t* sxy = reinterpret_cast<uint32_t*>(rc_smem);                    // [blockDim.x][m]
     uint8_t* smap = rc_smem + (size_t)blockDim.x * m * 4;                    // [blockDim.x][m]
-    uint8_t* sown = smap + (size_t)blockDim.x * m;                           // [blockDim.x]
     const uint32_t it0 = blockIdx.x * blockDim.x;
     const uint32_t it = it0 + threadIdx.x;
     const bool mine = it < n;
-    sown[threadIdx.x] = mine ? 1 : 0;
     if (mine) {
         // tidx: the items are a subset of the stage (band-sharded chunk); their stage indices select the random streams
-        Pcg32 rng = Pcg32::seed_from_u64(seed_base + (uint64_t)(tidx ? tidx[it] : it));
+        const Pcg32 rng = Pcg32::seed_from_u64(seed_base + (uint64_t)(tidx ? tidx[it] : it));
         uint32_t* oxy = sxy + (size_t)threadIdx.x * m;
         uint8_t* om = smap + (size_t)threadIdx.x * m;
-        if (n_ex == 1) {
-            // One example (the common case): gen_range(0..1) still consumes 64-bit draws until v <= 2^63 - 1, i.e. until
-            // the top bit of the high word is clear, and always yields 0; the zones of the coordinate draws are fixed.
-            const DevEx e = ex[0];
-            const uint32_t w = (uint32_t)e.w, h = (uint32_t)e.h;
-            const uint32_t zw = (w << Pcg32::clz32(w)) - 1u, zh = (h << Pcg32::clz32(h)) - 1u;
-            // (a one-draw-per-iteration state machine, which removes the per-loop divergence of the three rejection loops, was
-            // measured twice -- round 1 and round 2 -- and is slower: 712 instead of 558 warp instructions per item)
-            for (int r = 0; r < m; ++r) {
-                uint32_t hi;
-                do { rng.step(); hi = rng.next_u32(); } while (hi >> 31);  // low word drawn and dropped, high word tested
-                uint32_t rx, ry;
-                for (;;) {
-                    uint64_t mm;
-                    do { mm = (uint64_t)rng.next_u32() * (uint64_t)w; } while ((uint32_t)mm > zw);
-                    rx = (uint32_t)(mm >> 32);
-                    do { mm = (uint64_t)rng.next_u32() * (uint64_t)h; } while ((uint32_t)mm > zh);
-                    ry = (uint32_t)(mm >> 32);
-                    if (!e.smask || e.smask[(size_t)ry * e.w + rx] != 0) break;
+        // The three nested rejection loops of the reference (64-bit map draw until it falls into the zone, x and y draws
+        // until they do, all again until the sampling mask accepts) as ONE loop with a per-lane phase: every trip advances
+        // every lane's generator, so the lanes of a warp never wait for the slowest draw of each candidate -- only for the
+        // slowest ITEM (~8 % more trips than the mean).  With one example gen_range(0..1) still consumes 64-bit draws until
+        // v <= 2^63 - 1, i.e. until the top bit of the high word is clear, and yields 0; the low word is drawn and dropped.
+        uint64_t st = rng.state;
+        const uint64_t inc = rng.inc;
+        const uint64_t nn = (uint64_t)n_ex, zone_n = (nn << Pcg32::clz64(nn)) - 1ull;
+        DevEx e = ex[0];
+        uint32_t w = (uint32_t)e.w, h = (uint32_t)e.h;
+        uint32_t zw = (w << Pcg32::clz32(w)) - 1u, zh = (h << Pcg32::clz32(h)) - 1u;
+        const uint8_t* smask = e.smask;
+        uint32_t lo_word = 0, rx = 0, map = 0;
+        uint32_t* po = oxy;
+        uint32_t* const pend = oxy + m;
+        int phase = 0;  // 0: map draw, 1: x, 2: y
+        while (po < pend) {
+            const bool p0 = phase == 0;
+            // the map draw is a 64-bit draw: its low word comes first (SINGLE: drawn and dropped)
+            const uint64_t s1 = st * Pcg32::MUL + inc;
+            if (!SINGLE && p0) lo_word = Pcg32::rotr((uint32_t)(((st >> 18) ^ st) >> 27), (uint32_t)(st >> 59));
+            const uint64_t old = p0 ? s1 : st;
+            st = old * Pcg32::MUL + inc;
+            const uint32_t out = Pcg32::rotr((uint32_t)(((old >> 18) ^ old) >> 27), (uint32_t)(old >> 59));
+            const bool p1 = phase == 1;
+            const uint64_t mm = (uint64_t)out * (uint64_t)(p1 ? w : h);
+            bool acc;
+            if (SINGLE) acc = (p0 ? out : (uint32_t)mm) <= (p0 ? 0x7FFFFFFFu : (p1 ? zw : zh));
+            else {
+                const uint64_t v64 = ((uint64_t)out << 32) | (uint64_t)lo_word;
+                acc = p0 ? (v64 * nn <= zone_n) : ((uint32_t)mm <= (p1 ? zw : zh));
+                if (p0 && acc) {
+                    map = (uint32_t)Pcg32::mulhi64(v64, nn);
+                    e = ex[map];
+                    w = (uint32_t)e.w; h = (uint32_t)e.h;
+                    zw = (w << Pcg32::clz32(w)) - 1u; zh = (h << Pcg32::clz32(h)) - 1u;
+                    smask = e.smask;
                 }
-                oxy[r] = rx | (ry << 16);
-                om[r] = 0;
             }
-        } else {
-            for (int r = 0; r < m; ++r) {
-                uint32_t map = (uint32_t)rng.gen_range_usize((uint64_t)n_ex);
-                DevEx e = ex[map];
-                uint32_t rx, ry;
-                for (;;) {
-                    rx = rng.gen_range_u32((uint32_t)e.w);
-                    ry = rng.gen_range_u32((uint32_t)e.h);
-                    if (!e.smask || e.smask[(size_t)ry * e.w + rx] != 0) break;
+            if (acc) {
+                const uint32_t v = (uint32_t)(mm >> 32);
+                if (phase == 2) {
+                    if (!smask || smask[(size_t)v * w + rx] != 0) {
+                        *po = rx | (v << 16);
+                        if (!SINGLE) om[po - oxy] = (uint8_t)map;
+                        ++po;
+                        phase = 0;
+                    } else phase = 1;
+                } else {
+                    if (p1) rx = v;
+                    ++phase;
                 }
-                oxy[r] = rx | (ry << 16);
-                om[r] = (uint8_t)map;
             }
         }
     }
@@ -1041,9 +1060,8 @@ __global__ void k_rand_candidates(const DevEx* ex, int n_ex, int m, uint64_t see
     const uint32_t total = rows * (uint32_t)m;
     uint32_t* gxy = rand_xy + (size_t)it0 * m;
     uint8_t* gmap = rand_map + (size_t)it0 * m;
-    for (uint32_t f = threadIdx.x; f < total; f += blockDim.x) {
-        if (sown[f / (uint32_t)m]) { gxy[f] = sxy[f]; gmap[f] = smap[f]; }
-    }
+    // (the first `rows` threads are exactly the ones that own an item)
+    for (uint32_t f = threadIdx.x; f < total; f += blockDim.x) { gxy[f] = sxy[f]; gmap[f] = SINGLE ? (uint8_t)0 : smap[f]; }
 }
 
 // pick_random_unresolved's index draw (ms.rs:386): idx[t] = Pcg32::seed_from_u64(seed_base + t).gen_range(0..len0 - t)
