@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_lists_chunk(StageDev S, ChunkDe
     for (uint32_t c = blockIdx.x * WARPS_PER_CTA + warp; c < C.n; c += nwarps) {
         const uint32_t i = chunk_item_index(C, c);
         const uint32_t flat = C.pixel[c];
-        const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
+        const int y = (int)(flat / (uint32_t)S.W), x = (int)(flat - (uint32_t)y * (uint32_t)S.W);
         uint32_t r2;
         int kk;
         if (REDO) kk = knn_search<true>(S, ws, lane, x, y, R2_INF, &r2);
@@ -138,14 +138,19 @@ __global__ void __launch_bounds__(KW_WARPS * 32) k_weights(StageDev S, ChunkDev 
     for (uint32_t grp = blockIdx.x * KW_WARPS + warp; grp < ngroups; grp += gridDim.x * KW_WARPS) {
         const uint32_t c0 = grp * KW_ITEMS;
         const int rows = (int)min((uint32_t)KW_ITEMS, C.n - c0);
-        int my_kk = 0;
-        if (lane < rows) my_kk = (int)C.nbk[c0 + lane];
+        int my_kk = 0, my_x = 0, my_y = 0;
+        double my_x2 = 0.0, my_y2 = 0.0;
+        if (lane < rows) {  // lanes = items: the per-item set-up once, side by side
+            my_kk = (int)C.nbk[c0 + lane];
+            const uint32_t flat = C.pixel[c0 + lane];
+            my_y = (int)(flat / (uint32_t)S.W); my_x = (int)(flat - (uint32_t)my_y * (uint32_t)S.W);
+            my_x2 = __ldg(S.divx + my_x + S.mx); my_y2 = __ldg(S.divy + my_y + S.my);
+        }
         for (int it = 0; it < rows; ++it) {
             const uint32_t c = c0 + (uint32_t)it;
             const int kk = __shfl_sync(FULL, my_kk, it);
-            const uint32_t flat = C.pixel[c];
-            const int x = (int)(flat % (uint32_t)S.W), y = (int)(flat / (uint32_t)S.W);
-            const double x2 = __ldg(S.divx + x + S.mx), y2 = __ldg(S.divy + y + S.my);
+            const int x = __shfl_sync(FULL, my_x, it), y = __shfl_sync(FULL, my_y, it);
+            const double x2 = __shfl_sync(FULL, my_x2, it), y2 = __shfl_sync(FULL, my_y2, it);
             for (int j = lane; j < kk; j += 32) {
                 const short2 o = C.nb[(size_t)c * k + j];
                 const double ddx = __dsub_rn(__ldg(S.divx + x + o.x + S.mx), x2), ddy = __dsub_rn(__ldg(S.divy + y + o.y + S.my), y2);
@@ -160,8 +165,9 @@ __global__ void __launch_bounds__(KW_WARPS * 32) k_weights(StageDev S, ChunkDev 
         }
         const double my_avg = __ddiv_rn(sum, (double)(my_kk * 4));  // 0 / 0 = NaN for an empty list (never read)
         const int total = rows * k;
-        for (int e = lane; e < ((total + 31) & ~31); e += 32) {
-            const int it = e / k, j = e - it * k;
+        int it = lane / k, j = lane - it * k;  // (item, neighbour) of element e, advanced without a division per trip
+        for (int e = lane; e < ((total + 31) & ~31); e += 32, j += 32) {
+            while (j >= k) { j -= k; ++it; }
             const double avg = __shfl_sync(FULL, my_avg, it & 31);
             const int kk = __shfl_sync(FULL, my_kk, it & 31);
             if (e < total) {
@@ -242,7 +248,7 @@ __global__ void __launch_bounds__(CTA_THREADS, TSB_STREAM_CTAS) k_stream(StageDe
         // ---- the item's lists (prepared by the analysis) ----
         const int kk = (int)C.nbk[c];
         const uint32_t flat = C.pixel[c];
-        const int x = (int)(flat % (uint32_t)W), y = (int)(flat / (uint32_t)W);
+        const int y = (int)(flat / (uint32_t)W), x = (int)(flat - (uint32_t)y * (uint32_t)W);
         const uint32_t si = chunk_item_index(C, c);
         const uint32_t* rand_xy = C.rand_xy + (size_t)c * S.m;
         const uint8_t* rand_map = C.rand_map + (size_t)c * S.m;
