@@ -984,6 +984,12 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
     std::deque<size_t> live;       // chunks whose lists occupy the ring (analysis enqueued, slots not yet reclaimed)
     size_t ring_head = 0;
     size_t a_next = 0, r_next = 0;  // next chunk to analyse / to resolve
+    // Exclusive batches: beside a throughput-bound resolve chunk the analysis kernels only take turns with it -- both get slower
+    // (a 2048^2 step: resolve launches +5 ms, the analysis 38 instead of 16 ms) -- so analysis and resolve alternate in batches
+    // as large as the list ring allows; only the dependency-bound first phase, which leaves most of the machine idle, runs
+    // beside the analysis.  TSB_EXCLUSIVE=0 restores free overlap.
+    static const bool exclusive = !(getenv("TSB_EXCLUSIVE") && atoi(getenv("TSB_EXCLUSIVE")) == 0);
+    bool batch_open = false;  // an analysis batch is being enqueued (its first chunk has waited for the resolve stream)
     auto chunk_dev = [&](const ChunkPlan& c) {
         ChunkDev C;
         C.pixel = g->d_item_pixel.p + c.first;
@@ -1009,6 +1015,8 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
             CU(cudaStreamWaitEvent(s2, chunks[live.front()].ev_done, 0));
             live.pop_front();
         }
+        if (exclusive && !batch_open && r_next > 0) CU(cudaStreamWaitEvent(s2, chunks[r_next - 1].ev_done, 0));  // after everything resolved so far
+        batch_open = true;
         c.slot = off;
         ring_head = off + c.items();
         CU(cudaEventRecord(c.ev_a0, s2));
@@ -1202,6 +1210,7 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
         }
         stage_prologue_pending = false;
         CU(cudaStreamWaitEvent(s, c.ev_ready, 0));
+        if (exclusive && !dependency_bound && a_next > 0) CU(cudaStreamWaitEvent(s, chunks[a_next - 1].ev_ready, 0));  // after the whole analysis batch
         CU(cudaEventRecord(c.ev_t0, s));
         if (C.n) {
             if (c.sharded) { if (c.redo) TRY((launch_stream<true, true>(g, grid, Sc, C, D))); else TRY((launch_stream<false, true>(g, grid, Sc, C, D))); }
@@ -1256,8 +1265,13 @@ int resolve_stream(tsb_generator* g, const tsb_params* prm, tsb_progress_fn cb, 
             if (cb) TRY(report(*(volatile uint32_t*)g->h_progress));
         }
         if (a_next <= r_next) return fail(TSB_ERR_INTERNAL, "list ring too small for chunk %zu", r_next);
-        TRY(enqueue_resolve(chunks[r_next]));
-        ++r_next;
+        batch_open = false;
+        const size_t batch_end = exclusive ? a_next : r_next + 1;
+        while (r_next < batch_end) {
+            TRY(enqueue_resolve(chunks[r_next]));
+            ++r_next;
+            if (cb) TRY(report(*(volatile uint32_t*)g->h_progress));
+        }
     }
     for (int si = cur_stage + 1; si < (int)n_stages; ++si) TRY(begin_stage(si));
     if (g->mgs_on && !chunks.empty() && chunks.back().sharded) {
