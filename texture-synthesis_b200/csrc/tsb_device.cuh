@@ -335,9 +335,9 @@ __device__ __forceinline__ int knn_search(const StageDev& S, WS& ws, int lane, i
     if (bounded || R2bound == R2_INF) {
         int limit = bounded ? (int)__ldg(S.cntLE + R2bound) : S.spiralN;
         // unbounded search: do not walk the whole table when the hint says the set is sparse
-        // (a lower switch point was measured: 1024 / 512 / 256 change nothing, 128 / 64 cost 1 - 6 ms per 2048^2 step -- the sort
-        // of the disc path outweighs the longer walk)
-        if (!bounded && hint > (uint32_t)S.RT2) limit = 0;
+        // (switch point measured on a 2048^2 step: at 1024 the sparse first stage's lists take 1.65 instead of 2.0 ms and the
+        // rest is unchanged; 256 and below cost 1 - 6 ms -- the sort of the disc path outweighs the longer walk)
+        if (!bounded && hint > min((uint32_t)S.RT2, 1024u)) limit = 0;
         int cnt = 0;
         for (int base = 0; base < limit && cnt < k; base += 128) {
             short2 o[4];
@@ -383,6 +383,16 @@ __device__ __forceinline__ int knn_search(const StageDev& S, WS& ws, int lane, i
         __syncwarp();
         n = (int)scan_disc<true, STABLE>(S, ws, lane, x, y, R2, T);
         if (n > KBUF || (n < k && R2 < R2max)) n = -1;  // overflow (or a stale bound): search below
+    }
+    if (n < 0 && R2bound == R2_INF) {
+        // unbounded search: the hinted radius holds 1.5 k points on average -- collect there at once; the counting passes
+        // below are only needed when that disc turns out to hold fewer than k or more than KBUF points
+        R2 = max(hint, 4u);
+        if (R2 > R2max) R2 = R2max;
+        if (lane == 0) ws.cnt = 0;
+        __syncwarp();
+        n = (int)scan_disc<true, STABLE>(S, ws, lane, x, y, R2, T);
+        if (n > KBUF || (n < k && R2 < R2max)) n = -1;
     }
     if (n < 0) {
         uint32_t lo = 0;

@@ -127,7 +127,9 @@ __global__ void __launch_bounds__(CTA_THREADS) k_lists_chunk(StageDev S, ChunkDe
 //   1. item by item, lanes = neighbours: the distances (coalesced list reads, table reads that share sectors) -> shared memory
 //   2. lanes = items: the sequential sum -- 32 chains side by side, one lane each instead of one warp each
 //   3. (item, neighbour) pairs flattened over the lanes: division, exp, cast, coalesced store
-constexpr int KW_WARPS = 4, KW_ITEMS = 16;  // items per warp and pass: 16 keeps the staging area at 6.6 KB per warp (k = 50)
+// items per warp and pass: 16 keeps the staging area at 6.6 KB per warp (k = 50); measured per 2048^2 step: 8 -> 4.29 ms,
+// 16 -> 4.24 ms, 32 -> 6.8 ms
+constexpr int KW_WARPS = 4, KW_ITEMS = 16;
 __global__ void __launch_bounds__(KW_WARPS * 32) k_weights(StageDev S, ChunkDev C) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int k = S.k;
