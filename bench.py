@@ -26,7 +26,7 @@ sys.path.insert(0, ROOT)
 OUT, EX = 2048, 512
 WORKLOAD = f"{OUT}x{OUT} output from synthetic {EX}x{EX} example (synth_texture seed 1), k=50 m=50 cauchy=1.0 backtrack=0.5x5 seed=0"
 # dram bytes (read+write) of all k_stream launches of one step, from the ncu capture summarised under profiles/
-TRAFFIC_PER_STEP = 9.91e9  # 9.59 GB read + 0.32 GB written over the 11 k_stream launches of one step (profiles/r2_kstream_all_launches_2048.txt)
+TRAFFIC_PER_STEP = 9.76e9  # 9.43 GB read + 0.33 GB written over the 11 k_stream launches of one step (profiles/r2_kstream_all_launches_2048.txt)
 CPU_SAMPLE_OUT = 2048  # CPU sample = the full workload (2048x2048 output, about 9 s on 16 host cores)
 
 
@@ -283,7 +283,7 @@ def run_ours(args, rank, world, local_rank):
         "dtype": "u8/f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "parallelism": "1 session per GPU (independent sessions, no collective)" if world > 1 else "1 GPU",
                    "l2": "256 MiB flush buffer written between timed iterations",
-                   "schedule": "exact 1-thread order: analysis stream (k-NN lists, weights, random candidates) ahead of an in-order persistent resolve kernel (k_stream)",
+                   "schedule": "exact 1-thread order: analysis (k-NN lists, weights, random candidates) ahead of an in-order persistent resolve kernel (k_stream), in exclusive batches after the first phase",
                    "pixel_resolutions_per_step": int(st["work_items"]), "candidate_evals_per_s": st["candidates"] / (float(ms.mean()) * 1e-3),
                    "host_wall_ms_per_step": (t1 - t0) * 1e3 / args.steps},
         "parity_digest_ok": parity_ok,
