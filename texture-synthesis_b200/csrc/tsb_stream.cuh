@@ -230,23 +230,19 @@ __global__ void __launch_bounds__(CTA_THREADS, TSB_STREAM_CTAS) k_stream(StageDe
     if (lane < 16) ws.stat[lane] = 0ull;
     __syncwarp();
     const int k = S.k, W = S.W, H = S.H;
-    // Items are claimed in order.  AHEAD (experiment, off): claim one item ahead and pull its lists into L2 while the current
-    // one is resolved -- safe (the lowest unfinished item is always somebody's CURRENT item) but a held item cannot start
-    // elsewhere, which costs more in waiting than the prefetch saves (measured: 50.7 -> 53.3 ms per 2048^2 step).
-    // Also measured and dropped (2048^2 step, 46.4 ms): claiming 2 / 4 consecutive items per atomic in the throughput phases
-    // -- 49.3 / 64.6 ms, the held items are exactly the ones other warps end up waiting for; an L2 prefetch of the lists of
-    // the item one generation of resident warps ahead (no claim involved) -- 46.35 ms, the list latency is already hidden.
-    constexpr bool AHEAD = false;
+    // Items are claimed in order, one per atomic, and nothing is claimed ahead.  Measured and dropped (2048^2 step): claiming one
+    // item ahead and pulling its lists into L2 while the current one is resolved -- safe (the lowest unfinished item is always
+    // somebody's CURRENT item) but a held item cannot start elsewhere, which costs more in waiting than the prefetch saves
+    // (50.7 -> 53.3 ms); claiming 2 / 4 consecutive items per atomic in the throughput phases -- 46.4 -> 49.3 / 64.6 ms, the held
+    // items are exactly the ones other warps end up waiting for; an L2 prefetch of the lists of the item one generation of
+    // resident warps ahead (no claim involved) -- 46.35 ms, the list latency is already hidden.
     uint32_t c = 0;
     if (lane == 0) c = atomicAdd(D.ctl + SC_NEXT, 1u);
     c = __shfl_sync(FULL, c, 0);
     while (c < C.n) {
         long long tr0 = clock64();
         uint32_t c_next = 0;
-        if (lane == 0) {
-            if (AHEAD) c_next = atomicAdd(D.ctl + SC_NEXT, 1u);  // consumed after the neighbour loads have been issued
-            if (D.progress && (c & 1023u) == 0u) *D.progress = D.progress_base + c;
-        }
+        if (lane == 0 && D.progress && (c & 1023u) == 0u) *D.progress = D.progress_base + c;
         // ---- the item's lists (prepared by the analysis) ----
         const int kk = (int)C.nbk[c];
         const uint32_t flat = C.pixel[c];
@@ -374,21 +370,6 @@ __global__ void __launch_bounds__(CTA_THREADS, TSB_STREAM_CTAS) k_stream(StageDe
             if (aborted) break;
             __syncwarp();
             long long t2 = clock64();
-            // pull the next item's lists into L2 (eight 128-byte lines cover them for k = m = 50)
-            if (AHEAD) c_next = __shfl_sync(FULL, c_next, 0);
-            if (AHEAD && c_next < C.n) {
-                const char* base = nullptr;
-                size_t bytes = 0;
-                const int which = lane >> 3, line = lane & 7;
-                if (which == 0) { base = reinterpret_cast<const char*>(C.nb + (size_t)c_next * k); bytes = (size_t)k * 4; }
-                else if (which == 1) { base = reinterpret_cast<const char*>(C.g + (size_t)c_next * k); bytes = (size_t)k * 4; }
-                else if (which == 2) { base = reinterpret_cast<const char*>(C.rand_xy + (size_t)c_next * S.m); bytes = (size_t)S.m * 4; }
-                else { base = reinterpret_cast<const char*>(C.rand_map + (size_t)c_next * S.m); bytes = (size_t)S.m; }
-                if ((size_t)line * 128 < bytes + 127) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)line * 128));
-                if (lane == 31) asm volatile("prefetch.global.L2 [%0];" ::"l"(C.pixel + c_next));
-                if (lane == 30) asm volatile("prefetch.global.L2 [%0];" ::"l"(C.nbk + c_next));
-                if (REDO && lane == 29) asm volatile("prefetch.global.L2 [%0];" ::"l"(C.low + c_next));
-            }
             const float g0 = ws.g[0];
             const bool degenerate = !(g0 == g0);  // NaN weights: the pixel is its own only neighbour (see k_weights)
             resolve_tail<GUIDED, OPAQUE ? 1 : 0>(S, ws, sm.lut, sm.lutg, lane, kk, ncand, reach, degenerate, rand_xy, rand_map,
@@ -420,8 +401,8 @@ __global__ void __launch_bounds__(CTA_THREADS, TSB_STREAM_CTAS) k_stream(StageDe
             }
         }
         __syncwarp();
-        if (!AHEAD) { if (lane == 0) c_next = atomicAdd(D.ctl + SC_NEXT, 1u); c = __shfl_sync(FULL, c_next, 0); }
-        else c = kk > 0 ? c_next : __shfl_sync(FULL, c_next, 0);
+        if (lane == 0) c_next = atomicAdd(D.ctl + SC_NEXT, 1u);
+        c = __shfl_sync(FULL, c_next, 0);
     }
     if (lane == 0 && S.counters) {
         for (int i = 0; i < ST_COUNT; ++i) if (ws.stat[i]) atomicAdd(&rs.stat[i], ws.stat[i]);
