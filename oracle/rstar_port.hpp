@@ -7,8 +7,9 @@
 // (choose_subtree by inclusion / overlap increase / area increase, forced reinsertion of the two children farthest from the node
 // centre once per level, split along the axis of minimum perimeter sum at the position of minimum overlap then area).  Five details
 // I could not recall with certainty are switchable through ORC_RSTAR_VARIANT (see variant()); all 32 combinations were run against
-// the nine hash constants of lib/tests/diff.rs and the default is the one that reproduces six of them exactly (0 0 1 0 16 0 9 0 0;
-// tests/test_oracle_pin.py::test_oracle_with_rstar_order_reproduces_reference_hash).
+// the nine hash constants of lib/tests/diff.rs; the default is the one that reproduces six of them exactly on Pillow decodes
+// (0 0 1 0 16 0 9 0 0) and ALL NINE on inputs decoded as jpeg-decoder 0.1.22 does (oracle/jpeg_port.py;
+// tests/test_oracle_pin.py::test_oracle_reproduces_every_reference_hash).
 // The CUDA path and its parity tests use the oracle's canonical order, not this one.
 #pragma once
 #include <algorithm>

@@ -9,14 +9,14 @@
 // legs may load this library.  The product (texture-synthesis_b200/csrc) never links,
 // includes or calls anything in this directory.
 //
-// PARITY STATUS: PINNED to golden vectors the reference owns -- the nine perceptual-hash
+// PARITY STATUS: PINNED to every golden vector the reference owns -- the nine perceptual-hash
 // constants of lib/tests/diff.rs:163-252 (tests/test_oracle_pin.py, oracle/dgrad_hash.py):
-//   * with the canonical neighbour tie order (below): 3 constants reproduced exactly,
-//     4 within 1-4 of 135 bits, the two JPEG-mask cases 14-15;
-//   * with ORC_KNN=rstar (rstar_port.hpp, a restatement of rstar 0.7.1's R*-tree and
-//     nearest-neighbour iterator): 6 constants reproduced exactly -- every PNG-only
-//     configuration -- the three that read JPEGs at 1, 9 and 16 bits (inputs are Pillow
-//     decodes; jpeg-decoder 0.1.22 differs by +-1 LSB).
+//   * with the JPEG inputs decoded as jpeg-decoder 0.1.22 does (oracle/jpeg_port.py) and the
+//     k-NN answered in rstar 0.7.1's order (ORC_KNN=rstar, rstar_port.hpp): ALL NINE constants
+//     are reproduced character for character;
+//   * with Pillow decodes and the canonical neighbour tie order (below) -- what every committed
+//     digest and CUDA parity test uses: 3 constants exact, 4 within 1-4 of 135 bits, the two
+//     JPEG-mask cases 14-15.
 // No Rust toolchain and no crate sources exist in the build container, so the reference
 // itself cannot be compiled or run here (rust/patches/lib/tests/dump_snapshots.rs is the
 // test a maintainer with cargo runs).  Also pinned:

@@ -16,20 +16,34 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 DIGESTS = os.path.join(HERE, "golden", "fullsize_digests.json")
-_IMGS = None
+_IMGS = {}
+_DECODER = "pillow"
+
+
+def set_decoder(name):
+    """"pillow": the libjpeg decodes every digest and every CUDA parity test is built on (default).  "jpegport": the same
+    images with the JPEG-derived ones as the restated jpeg-decoder 0.1.22 delivers them (oracle/jpeg_port.py; stored as
+    differences in tests/golden/ref_imgs_jpegport.npz) -- used by tests/test_oracle_pin.py only."""
+    global _DECODER
+    assert name in ("pillow", "jpegport")
+    _DECODER = name
 
 
 def imgs():
-    global _IMGS
-    if _IMGS is None:
+    if _DECODER not in _IMGS:
         z = np.load(os.path.join(HERE, "golden", "ref_imgs_full.npz"))
-        _IMGS = {}
+        delta = np.load(os.path.join(HERE, "golden", "ref_imgs_jpegport.npz")) if _DECODER == "jpegport" else None
+        d = {}
         for k in z.files:
             a = z[k]
+            if delta is not None and k in delta.files:
+                a = a.copy()
+                a[..., :3] = (a[..., :3].astype(np.int16) + delta[k]).astype(np.uint8)
             if a.shape[2] == 3:  # alpha == 255 everywhere: stored as RGB
                 a = np.concatenate([a, np.full(a.shape[:2] + (1,), 255, np.uint8)], axis=-1)
-            _IMGS[k] = np.ascontiguousarray(a, np.uint8)
-    return _IMGS
+            d[k] = np.ascontiguousarray(a, np.uint8)
+        _IMGS[_DECODER] = d
+    return _IMGS[_DECODER]
 
 
 def _synth(w, h, seed):

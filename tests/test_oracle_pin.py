@@ -1,19 +1,22 @@
 """Pins the CPU oracle (and, through the bit-exact digests, the CUDA path) to golden vectors the REFERENCE owns: the nine
 perceptual-hash constants of lib/tests/diff.rs:163-252.  Every configuration runs at the reference's real size on frozen
-decodes of the reference's own images (tests/golden/ref_imgs_full.npz); the output is hashed with the restated
-DoubleGradient hash (oracle/dgrad_hash.py) and compared with the constant.
+decodes of the reference's own images; the output is hashed with the restated DoubleGradient hash (oracle/dgrad_hash.py) and
+compared with the constant.
 
-Measured Hamming distances (of 135 bits; two unrelated images differ in ~67):
-  exact (0): single_example, sample_masks, sample_masks_ignore
-  1-4 bits : multi_example, guided, style_transfer, inpaint_channel
-  14-15    : inpaint, tiling -- both threshold a JPEG mask at exactly 255 / 0 (ms.rs:272, 1546), so the +-1 LSB difference
-             between Pillow's and jpeg-decoder 0.1.22's IDCT moves mask pixels
-The residual bits come from two things: the JPEG decoder (inputs are Pillow decodes, which the oracle cannot restate
-offline) and rstar's order among equidistant neighbours.  The canonical oracle (the parity reference of the CUDA path) uses
-ascending (d^2, dy, dx).  With ORC_KNN=rstar the oracle answers its k-NN queries from a restatement of rstar 0.7.1's R*-tree
-(oracle/rstar_port.hpp: insertion with forced reinsertion, split, best-first nearest-neighbour iterator) and then reproduces
-SIX of the nine constants character for character -- every configuration whose inputs are PNG only -- and the three left are
-the ones that read a JPEG (guided: 1 bit; inpaint 16, tiling 9: JPEG masks thresholded at exactly 255 / 0).
+ALL NINE constants are reproduced character for character (test_oracle_reproduces_every_reference_hash) when the two
+things the reference inherits from un-vendored crates are restated as well:
+  * the JPEG pixel pipeline of jpeg-decoder 0.1.22 (oracle/jpeg_port.py: stb_image's fixed-point IDCT, f32 YCbCr -> RGB;
+    it differs from Pillow's libjpeg by +-1..3 in 0.1-0.9 % of the samples) -- F.set_decoder("jpegport");
+  * the order in which rstar 0.7.1 yields equidistant neighbours (oracle/rstar_port.hpp: R*-tree insertion with forced
+    reinsertion, split, best-first nearest-neighbour iterator) -- ORC_KNN=rstar.
+The other two tests keep the separation of causes measurable (Hamming distances of 135 bits; unrelated images: ~67):
+                                   single multi guided style inpaint inpaint_channel tiling sample_masks masks_ignore
+  Pillow decodes, canonical order     0     3     2      1     15          4           14        0            0
+  Pillow decodes, rstar order         0     0     1      0     16          0            9        0            0
+  jpeg-decoder restated, canonical    0     3     2      2      4          4           14        0            0
+  jpeg-decoder restated, rstar order  0     0     0      0      0          0            0        0            0
+The canonical order (ascending (d^2, dy, dx)) on Pillow decodes is the configuration every committed digest and every CUDA
+parity test is built on: the first row is what the CUDA path itself scores against the reference's constants.
 """
 import pytest
 
@@ -28,7 +31,25 @@ MAX_DISTANCE = {
 }
 
 
-# the same nine runs with the k-NN answered by the restated rstar tree (ORC_KNN=rstar)
+@pytest.fixture
+def jpegport_decodes():
+    F.set_decoder("jpegport")
+    yield
+    F.set_decoder("pillow")
+
+
+@pytest.mark.parametrize("name", sorted(F.DIFF_HASHES))
+def test_oracle_reproduces_every_reference_hash(name, monkeypatch, jpegport_decodes):
+    """jpeg-decoder 0.1.22's pixels + rstar 0.7.1's neighbour order: the reference's constant, character for character."""
+    monkeypatch.setenv("ORC_KNN", "rstar")
+    monkeypatch.delenv("ORC_RSTAR_VARIANT", raising=False)
+    spec = F.SPECS[name]()
+    out = F.to_oracle(spec).run().color()
+    print(f"{name}: hash {H.hash_image(out)} expected {F.DIFF_HASHES[name]}")
+    assert H.hash_image(out) == F.DIFF_HASHES[name]
+
+
+# the same nine runs on the Pillow decodes with the k-NN answered by the restated rstar tree (ORC_KNN=rstar)
 MAX_DISTANCE_RSTAR = {
     "diff_single_example": 0, "diff_multi_example": 0, "diff_style_transfer": 0, "diff_inpaint_channel": 0,
     "diff_sample_masks": 0, "diff_sample_masks_ignore": 0,
