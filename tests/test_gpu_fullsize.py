@@ -34,3 +34,26 @@ def test_fullsize_digest_c5_8192():
     got, want = _run(name), DIGESTS[name]
     for key in ("n_resolved", "order", "coord", "id", "color", "score"):
         assert got[key] == want[key], f"{name}: {key} differs from the oracle's digest"
+
+
+# What the CUDA path itself scores against the golden vectors the reference owns (lib/tests/diff.rs:163-252): the hash of its
+# output image against the reference's constant.  Inputs are the Pillow decodes, the neighbour tie order is the canonical one
+# (the CPU oracle reproduces all nine constants exactly with jpeg-decoder's pixels and rstar's order,
+# tests/test_oracle_pin.py), so three configurations match character for character and the others by the stated distances.
+GPU_HASH_DISTANCE = {
+    "diff_single_example": 0, "diff_sample_masks": 0, "diff_sample_masks_ignore": 0,
+    "diff_multi_example": 3, "diff_guided": 2, "diff_style_transfer": 1, "diff_inpaint_channel": 4,
+    "diff_inpaint": 15, "diff_tiling": 14,
+}
+
+
+@pytest.mark.parametrize("name", sorted(F.DIFF_HASHES))
+def test_cuda_output_against_the_reference_hash(name):
+    from oracle import dgrad_hash as H   # the checker: hashing is not part of the product
+    spec = F.SPECS[name]()
+    out = F.to_gpu(spec).build().run(None).into_image()
+    d = H.distance(out, F.DIFF_HASHES[name])
+    print(f"{name}: CUDA output hash {H.hash_image(out)} expected {F.DIFF_HASHES[name]} distance {d}/135")
+    assert d == GPU_HASH_DISTANCE[name]
+    if GPU_HASH_DISTANCE[name] == 0:
+        assert H.hash_image(out) == F.DIFF_HASHES[name]
