@@ -1,12 +1,15 @@
 """Canonical neighbour tie order (ascending (d^2, dy, dx): the oracle default and the CUDA path) against the restated rstar 0.7.1
 order (ORC_KNN=rstar, oracle/rstar_port.hpp) on the nine diff.rs configurations and BASELINE C1-C3: fraction of output pixels
 whose colour / source coordinate differ, mean neighbourhood cost, and the total-variation distance between the two 64-bin
-histograms of per-pixel cost.  CPU only; writes tests/golden/tie_order_compare.json (quoted in DESIGN.md section 2).
+histograms of per-pixel cost.  Inputs: the reference's images with its JPEGs decoded as jpeg-decoder 0.1.22 does.  CPU only; writes tests/golden/tie_order_compare.json (quoted in DESIGN.md section 2).
 Usage: python tests/golden/compare_tie_orders.py [case ...]"""
 import sys, os, json, time
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', '..'))
 import numpy as np
 from tests import fullsize_cases as F
+# inputs as the reference decodes them (jpeg-decoder restated, oracle/jpeg_port.py): with the rstar order this side of the
+# comparison reproduces the reference's nine hashes exactly, the canonical side is bit-identical to the CUDA path
+F.set_decoder("jpegport")
 names = sys.argv[1:] or list(F.DIFF_HASHES) + ["c1_single_example_500", "c2_multi_example_500", "c3_guided_500", "c3_style_transfer_500"]
 def hist_distance(a, b):
     a = a[np.isfinite(a)]; b = b[np.isfinite(b)]
