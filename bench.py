@@ -242,14 +242,15 @@ def run_ours(args, rank, world, local_rank):
 
     # end to end through the public C-ABI call with HOST buffers: H2D of the example pyramid and D2H of the result inside
     e2e_t = []
-    for _ in range(max(1, args.steps)):
+    for it in range(1 + max(1, args.steps)):  # the first pass is this path's own warm-up (first use of the host-buffer entry point)
         g.reset()
         flush.fill_(1)
         torch.cuda.synchronize()
         a = time.perf_counter()
         g.resolve(params, [pyr_pinned])
         capi._check(g.L.tsb_generator_read_color(g.h, out_host.ctypes.data))
-        e2e_t.append(time.perf_counter() - a)
+        if it:
+            e2e_t.append(time.perf_counter() - a)
     e2e_value, _, _ = aggregate_throughput(len(e2e_t) * OUT * OUT, float(np.sum(e2e_t)), dist, "cuda")
     st = stats[-1]
     del g
