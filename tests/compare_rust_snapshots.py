@@ -4,7 +4,12 @@ toolchain) with the CUDA path and with the CPU oracle, on exactly the decoded in
     python tests/compare_rust_snapshots.py <dir with one sub-directory per diff.rs configuration> [--oracle-only]
 
 Reports, per configuration, the mismatched-pixel fraction of the output image and of the coordinate transform (the end-to-end
-criterion of BASELINE.json's north_star).  Not a pytest file: the snapshots cannot be produced in the build image."""
+criterion of BASELINE.json's north_star), three ways:
+  * oracle with the restated rstar neighbour order (ORC_KNN=rstar) vs the crate -- expected 0 everywhere: this is the
+    configuration that reproduces all nine hash constants of lib/tests/diff.rs (tests/test_oracle_pin.py);
+  * oracle with the canonical order vs the crate, and the CUDA path (bit-identical to it) vs the crate -- expected to differ
+    where equidistant neighbours straddle the k-cut (DESIGN.md section 2 has the table).
+Not a pytest file: the snapshots cannot be produced in the build image."""
 import os
 import struct
 import sys
@@ -58,8 +63,13 @@ def main():
             continue
         want_img, want_tx = rgba(d, "output"), transform(os.path.join(d, "transform.bin"))
         spec = spec_for(name, d)
+        os.environ["ORC_KNN"] = "rstar"
+        r = F.to_oracle(spec).run()
+        os.environ.pop("ORC_KNN")
         o = F.to_oracle(spec).run()
-        line = f"{name:22s} oracle vs crate: colour mismatch {np.mean((o.color() != want_img).any(axis=2)):.4f}, coord mismatch {np.mean((o.coord() != want_tx).any(axis=2)):.4f}"
+        line = (f"{name:22s} oracle (rstar order) vs crate: colour mismatch {np.mean((r.color() != want_img).any(axis=2)):.4f}, coord mismatch "
+                f"{np.mean((r.coord() != want_tx).any(axis=2)):.4f} | oracle (canonical) vs crate: colour {np.mean((o.color() != want_img).any(axis=2)):.4f}, "
+                f"coord {np.mean((o.coord() != want_tx).any(axis=2)):.4f}")
         if not oracle_only:
             g = F.to_gpu(spec).build().run(None)
             line += f" | CUDA vs crate: colour {np.mean((g.into_image() != want_img).any(axis=2)):.4f}, coord {np.mean((g.get_coordinate_transform().buffer != want_tx).any(axis=2)):.4f}"
